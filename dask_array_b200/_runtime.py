@@ -1,0 +1,304 @@
+"""Launch runtime: JIT cache, block canonicalisation, persistent launch tables.
+
+One ``FusedLaunch`` = one kernel launch covering every resident block of one fused
+expression on this device -- the B200 counterpart of the per-block task dictionary the
+reference emits in ``FusedBlockwise._layer`` (``dask_array/_blockwise.py:1690-1728``) and of
+the Rust records emitter that expands a layer natively (``crates/dask-array-python``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import threading
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _codegen as cg
+from . import _lib
+from ._device import DeviceChunk, alloc_bytes, current_stream_ptr
+
+_CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_jit_cache")
+_lock = threading.Lock()
+_cubins: dict[str, bytes] = {}
+_handles: dict[tuple, int] = {}
+
+
+def compile_kernel(program: cg.Program, spec: cg.KernelSpec) -> bytes:
+    """cubin of (program, spec); memoised in memory and under ``_jit_cache/`` (works on CPU)."""
+    dig = spec.digest()
+    with _lock:
+        if dig in _cubins:
+            return _cubins[dig]
+    path = os.path.join(_CACHE_DIR, dig + ".cubin")
+    if os.path.exists(path):
+        with open(path, "rb") as f:
+            cubin = f.read()
+    else:
+        cubin = _lib.jit_compile(cg.render(program, spec), f"b2_fused_{dig}.cu")
+        try:
+            os.makedirs(_CACHE_DIR, exist_ok=True)
+            tmp = f"{path}.{os.getpid()}.tmp"
+            with open(tmp, "wb") as f:
+                f.write(cubin)
+            os.replace(tmp, path)
+        except OSError:
+            pass
+    with _lock:
+        _cubins[dig] = cubin
+    return cubin
+
+
+def load_kernel(program: cg.Program, spec: cg.KernelSpec) -> int:
+    """b2_kernel* for the current device."""
+    key = (spec.digest(), torch.cuda.current_device())
+    with _lock:
+        if key in _handles:
+            return _handles[key]
+    cubin = compile_kernel(program, spec)
+    geom = _lib.Geom(spec.mode, spec.redop, spec.vec, spec.tx, spec.ty, spec.rpt,
+                     cg.packed_bytes(spec, program.out_dtype), 0)
+    out = C.c_void_p()
+    _lib.check(_lib.lib.b2_kernel_load(cubin, len(cubin), b"b2_fused", C.byref(geom), C.byref(out)))
+    with _lock:
+        _handles[key] = out.value
+    return out.value
+
+
+# ----------------------------------------------------------------------------- canonical views
+@dataclass
+class Canon:
+    """One block canonicalised to (B, R, C)."""
+    mode: int
+    B: int
+    R: int
+    C: int
+    in_strides: list          # per input (sb, sr, sc) in elements
+    lead: list = field(default_factory=list)   # extra leading (EW) dims expanded on the host: [(n, [stride per input])]
+
+
+def canonicalize(shape, in_strides, reduce_axes) -> Canon:
+    """Collapse an N-d block (+ per-input element strides, 0 = broadcast) to (B, R, C).
+
+    ``reduce_axes``: set of reduced dims (empty = element-wise).  Adjacent dims of the
+    same kind are merged when every input is contiguous across them.
+    """
+    nd = len(shape)
+    red = set(a % nd for a in reduce_axes) if nd else set()
+    dims = []   # [n, kind, [stride per input]]
+    for d in range(nd):
+        if shape[d] == 1:
+            continue
+        dims.append([int(shape[d]), "X" if d in red else "K", [int(s[d]) for s in in_strides]])
+    merged = []
+    for n, kind, st in dims:
+        if merged and merged[-1][1] == kind and all(p == q * n for p, q in zip(merged[-1][2], st)):
+            merged[-1][0] *= n
+            merged[-1][2] = st
+        else:
+            merged.append([n, kind, list(st)])
+    nin = len(in_strides)
+    zero = [0] * nin
+
+    def pack(b, r, c, mode, lead=()):
+        return Canon(mode, b[0], r[0], c[0], [(b[2][k], r[2][k], c[2][k]) for k in range(nin)], list(lead))
+
+    one = [1, "K", zero]
+    kinds = "".join(m[1] for m in merged)
+    if not red or "X" not in kinds:
+        if not red:
+            if len(merged) == 1 and all(s in (0, 1) for s in merged[0][2]):
+                # one flat contiguous run: give it rows so each thread keeps several loads in flight
+                n, _, st = merged[0]
+                for cc in (4096, 2048, 1024, 512, 256, 128, 64, 32, 16):
+                    if n % cc == 0 and n > cc:
+                        return pack(one, [n // cc, "K", [s * cc for s in st]], [cc, "K", st], _lib.MODE_EW)
+            lead = [(m[0], m[2]) for m in merged[:-3]]
+            tail = merged[-3:]
+            while len(tail) < 3:
+                tail.insert(0, one)
+            return pack(tail[0], tail[1], tail[2], _lib.MODE_EW, lead)
+        # reduction over size-1 axes only: a copy, expressed as mode C with one column
+        if len(merged) > 1:
+            raise NotImplementedError("degenerate reduction over non-contiguous kept dims")
+        r = merged[0] if merged else one
+        return pack(one, r, one, _lib.MODE_C)
+    if kinds == "X":
+        n, _, st = merged[0]
+        if all(s in (0, 1) for s in st):
+            for cc in (8192, 4096, 2048, 1024, 512, 256, 128, 64, 32, 16):
+                if n % cc == 0 and n > cc:
+                    return pack(one, [n // cc, "X", [s * cc for s in st]], [cc, "X", st], _lib.MODE_RC)
+        return pack(one, one, merged[0], _lib.MODE_RC)
+    if kinds == "XX":
+        return pack(one, merged[0], merged[1], _lib.MODE_RC)
+    if kinds == "KX":
+        return pack(one, merged[0], merged[1], _lib.MODE_C)
+    if kinds == "XK":
+        return pack(one, merged[0], merged[1], _lib.MODE_R)
+    if kinds == "KXK":
+        return pack(merged[0], merged[1], merged[2], _lib.MODE_R)
+    if kinds == "KXX":
+        return pack(merged[0], merged[1], merged[2], _lib.MODE_RC)
+    raise NotImplementedError(
+        f"reduction pattern {kinds!r} (shape {tuple(shape)}, axes {sorted(red)}) is not supported by the B200 kernels yet"
+    )
+
+
+@dataclass
+class BlockArgs:
+    """Arguments of one block of a fused launch (all device pointers are ints)."""
+    shape: tuple                      # logical N-d shape of the block the chain is evaluated on
+    inputs: list                      # [(ptr, strides-in-elements per logical dim)]
+    out0: int
+    out1: int = 0
+    arg_offset: int = 0
+    arg_ravel: tuple | None = None    # (block_shape, block_start, total_shape) for axis=None arg reductions
+
+
+class FusedLaunch:
+    """Persistent launch table of one fused expression over its resident blocks."""
+
+    def __init__(self, program: cg.Program, redop: int, reduce_axes, blocks: list[BlockArgs],
+                 acc_dtype=None, out_is_contiguous: bool = True):
+        if not blocks:
+            raise ValueError("FusedLaunch needs at least one block")
+        self.program = program
+        self.redop = redop
+        nin = len(program.inputs)
+        canons = [canonicalize(b.shape, [st for _, st in b.inputs], reduce_axes) for b in blocks]
+        modes = {c.mode for c in canons}
+        if len(modes) != 1:
+            raise NotImplementedError(f"blocks of one launch canonicalise to different modes {modes}")
+        self.mode = modes.pop()
+        out_dt = program.out_dtype
+        acc_dtype = np.dtype(acc_dtype) if acc_dtype is not None else out_dt
+        # ---- layout class per input and the widest vector every block allows
+        layouts = []
+        for k in range(nin):
+            cls = {("S" if c.in_strides[k][2] == 0 else "V" if c.in_strides[k][2] == 1 else "G")
+                   for c in canons if c.C > 1} or {"V"}
+            layouts.append(cls.pop() if len(cls) == 1 else "G")
+        sizes = [d.itemsize for d in program.inputs] + ([out_dt.itemsize] if self.mode == _lib.MODE_EW else [])
+        vmax = max(1, 16 // max(sizes or [out_dt.itemsize]))
+
+        def vec_fits(v):
+            for b, c in zip(blocks, canons):
+                if c.C % v:
+                    return False
+                for k, (ptr, _) in enumerate(b.inputs):
+                    sb, sr, sc = c.in_strides[k]
+                    if layouts[k] == "V":
+                        it = program.inputs[k].itemsize
+                        if ptr % (v * it) or (c.B > 1 and sb % v) or (c.R > 1 and sr % v):
+                            return False
+                if self.mode == _lib.MODE_EW and b.out0 % (v * out_dt.itemsize):
+                    return False
+                for n, sts in c.lead:
+                    if any(layouts[k] == "V" and s % v for k, s in enumerate(sts)):
+                        return False
+            return True
+
+        v = vmax
+        while v > 1 and not vec_fits(v):
+            v //= 2
+        if v == 1:
+            layouts = ["S" if l == "S" else "G" for l in layouts]
+        shapes = [(c.B, c.R, c.C) for c in canons]
+        geo = cg.choose_geometry(program, self.mode, shapes, v)
+        self.spec = cg.KernelSpec(program.key(), tuple(layouts), self.mode, redop,
+                                  acc_dtype=acc_dtype.name, **geo)
+        self.kernel = load_kernel(program, self.spec)
+
+        # ---- descriptor table (leading EW dims expanded into extra descriptors)
+        descs = []
+        for b, c in zip(blocks, canons):
+            lead_ranges = [range(n) for n, _ in c.lead]
+            lead_elems = math.prod(n for n, _ in c.lead) if c.lead else 1
+            inner = c.B * c.R * c.C
+            for li, idx in enumerate(np.ndindex(*[len(r) for r in lead_ranges]) if c.lead else [()]):
+                d = _lib.Block()
+                for k, (ptr, _) in enumerate(b.inputs):
+                    off = sum(i * c.lead[j][1][k] for j, i in enumerate(idx))
+                    d.in_[k] = ptr + off * program.inputs[k].itemsize
+                    d.in_sb[k], d.in_sr[k], d.in_sc[k] = c.in_strides[k]
+                d.out0 = b.out0 + (li * inner * out_dt.itemsize if self.mode == _lib.MODE_EW else 0)
+                d.out1 = b.out1
+                d.B, d.R, d.C = c.B, c.R, c.C
+                d.arg_offset = b.arg_offset
+                if b.arg_ravel is not None:
+                    bshape, bstart, total = b.arg_ravel
+                    if len(bshape) > _lib.B2_MAX_ND:
+                        raise NotImplementedError(f"ravelled arg reduction over {len(bshape)} dims")
+                    d.arg_ndim = len(bshape)
+                    for j in range(len(bshape)):
+                        d.arg_shape[j], d.arg_start[j], d.arg_total[j] = bshape[j], bstart[j], total[j]
+                descs.append(d)
+            assert lead_elems >= 1
+        self.nblocks = len(descs)
+        arr = (_lib.Block * self.nblocks)(*descs)
+        need = C.c_size_t()
+        tiles = C.c_int64()
+        _lib.check(_lib.lib.b2_fused_plan(self.kernel, arr, self.nblocks, None, 0, C.byref(need), C.byref(tiles)))
+        self.workspace = alloc_bytes(need.value, zero=True) if need.value else None
+        if need.value:
+            _lib.check(_lib.lib.b2_fused_plan(self.kernel, arr, self.nblocks, self.workspace.data_ptr(),
+                                              need.value, C.byref(need), C.byref(tiles)))
+        self.total_tiles = tiles.value
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8)
+        self.table = torch.from_numpy(raw.copy()).to(torch.device("cuda", torch.cuda.current_device()))
+        self.scalars = _lib.Scalars()
+
+    def run(self, stream: int | None = None) -> None:
+        st = current_stream_ptr() if stream is None else stream
+        _lib.check(_lib.lib.b2_fused_launch(self.kernel, self.table.data_ptr(), self.nblocks,
+                                            self.total_tiles, C.byref(self.scalars), st))
+
+
+# ----------------------------------------------------------------------------- AOT helpers
+def combine(redop: int, dtype, parts: list[int], parts1: list[int] | None, nelem: int,
+            out0: int, out1: int = 0, post: int = _lib.POST_NONE, out_dtype=None,
+            count: float = 0.0, ddof: float = 0.0, table: torch.Tensor | None = None) -> torch.Tensor:
+    """One PartialReduce level (reductions/_reduction.py:968-983) on the device."""
+    fanin = len(parts)
+    ptrs = list(parts) + (list(parts1) if parts1 else [0] * fanin)
+    host = torch.tensor(ptrs, dtype=torch.int64)
+    tab = host.to(torch.device("cuda", torch.cuda.current_device())) if table is None else table
+    base = tab.data_ptr()
+    _lib.check(_lib.lib.b2_combine(redop, _lib.dtype_code(dtype), base, base + 8 * fanin, fanin, nelem,
+                                   out0, out1, post, _lib.dtype_code(out_dtype if out_dtype is not None else dtype),
+                                   float(count), float(ddof), current_stream_ptr()))
+    return tab   # caller keeps the table alive until the stream has consumed it
+
+
+class GatherLaunch:
+    """Persistent tiled gather (rechunk / slicing / concatenation) -- b2_gather_*."""
+
+    def __init__(self, copies: list[tuple]):
+        """copies: (src_ptr, dst_ptr, rows, row_bytes, src_pitch, dst_pitch)"""
+        copies = [c for c in copies if c[2] > 0 and c[3] > 0]
+        self.n = len(copies)
+        if not self.n:
+            return
+        arr = (_lib.Copy * self.n)()
+        for d, c in zip(arr, copies):
+            d.src, d.dst, d.rows, d.row_bytes, d.src_pitch, d.dst_pitch = c
+        tiles = C.c_int64()
+        _lib.check(_lib.lib.b2_gather_plan(arr, self.n, C.byref(tiles)))
+        self.total_tiles = tiles.value
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8)
+        self.table = torch.from_numpy(raw.copy()).to(torch.device("cuda", torch.cuda.current_device()))
+
+    def run(self, stream: int | None = None) -> None:
+        if not self.n:
+            return
+        st = current_stream_ptr() if stream is None else stream
+        _lib.check(_lib.lib.b2_gather_launch(self.table.data_ptr(), self.n, self.total_tiles, st))
+
+
+def fill(chunk: DeviceChunk, value) -> None:
+    v = np.asarray(value).astype(chunk.dtype)
+    buf = (C.c_char * chunk.itemsize).from_buffer_copy(v.tobytes())
+    _lib.check(_lib.lib.b2_fill(chunk.ptr, chunk.size, chunk.itemsize, C.addressof(buf), current_stream_ptr()))

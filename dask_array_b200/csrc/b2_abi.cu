@@ -1,0 +1,463 @@
+// b2_abi.cu -- the C ABI of libb200da.so (declared in include/b200da.h).
+//
+// Host side of the B200 backend: error handling, NVRTC JIT of generated fused kernels,
+// module loading through the CUDA driver API (resolved with dlopen so the library also
+// loads -- for symbol / JIT-compile checks -- on a machine without a GPU driver), launch
+// planning, and the small ahead-of-time kernels (tree-level combine, tiled gather, fill).
+//
+// Reference interfaces replaced (paths under /root/reference/dask_array/): see the
+// per-function comments in include/b200da.h.
+#include "../../include/b200da.h"
+#include "b2_device.cuh"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// the device header text is embedded at build time (see Makefile: b2_device_text.inc)
+static const char kDeviceHeader[] = {
+#include "b2_device_text.inc"
+    , 0};
+
+// ---- layout checks: B2Block (device) == b2_block (ABI)
+static_assert(sizeof(B2Block) == sizeof(b2_block), "B2Block/b2_block size mismatch");
+static_assert(offsetof(B2Block, out0) == offsetof(b2_block, out0), "out0");
+static_assert(offsetof(B2Block, B) == offsetof(b2_block, B), "B");
+static_assert(offsetof(B2Block, tile_begin) == offsetof(b2_block, tile_begin), "tile_begin");
+static_assert(offsetof(B2Block, work) == offsetof(b2_block, work), "work");
+static_assert(offsetof(B2Block, counter) == offsetof(b2_block, counter), "counter");
+static_assert(offsetof(B2Block, arg_offset) == offsetof(b2_block, arg_offset), "arg_offset");
+static_assert(offsetof(B2Block, arg_shape) == offsetof(b2_block, arg_shape), "arg_shape");
+static_assert(offsetof(B2Block, arg_total) == offsetof(b2_block, arg_total), "arg_total");
+static_assert(sizeof(B2Scalars) == sizeof(b2_scalars), "scalars");
+static_assert(sizeof(B2Block) % 4 == 0, "descriptor copied as u32 words");
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return fail(B2_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));      \
+    } while (0)
+
+extern "C" int b2_abi_version(void) { return B2_ABI_VERSION; }
+extern "C" const char* b2_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t b2_launch_count(void) { return g_launches.load(); }
+extern "C" void b2_free(void* p) { free(p); }
+extern "C" const char* b2_device_header(void) { return kDeviceHeader; }
+
+extern "C" int b2_device_sm_count(int* out) {
+    if (!out) return fail(B2_ERR_INVALID, "out is NULL");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------ driver API (dlopen)
+struct DriverApi {
+    void* handle = nullptr;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+static DriverApi& driver() {
+    static DriverApi d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        d.handle = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!d.handle) { d.why = "libcuda.so.1 not found (no NVIDIA driver): there is no CPU fallback"; return; }
+#define LOAD(field, sym)                                                    \
+        *(void**)(&d.field) = dlsym(d.handle, sym);                         \
+        if (!d.field) { d.why = std::string("missing driver symbol ") + sym; return; }
+        LOAD(ModuleLoadData, "cuModuleLoadData");
+        LOAD(ModuleUnload, "cuModuleUnload");
+        LOAD(ModuleGetFunction, "cuModuleGetFunction");
+        LOAD(LaunchKernel, "cuLaunchKernel");
+        LOAD(GetErrorString, "cuGetErrorString");
+        LOAD(FuncGetAttribute, "cuFuncGetAttribute");
+#undef LOAD
+        d.ok = true;
+    });
+    return d;
+}
+static const char* cu_err(CUresult r) {
+    const char* s = nullptr;
+    if (driver().GetErrorString) driver().GetErrorString(r, &s);
+    return s ? s : "unknown CUDA driver error";
+}
+
+// ------------------------------------------------------------------ JIT
+extern "C" int b2_jit_compile(const char* source, const char* name, void** cubin, size_t* cubin_size) {
+    if (!source || !cubin || !cubin_size) return fail(B2_ERR_INVALID, "NULL argument");
+    *cubin = nullptr;
+    *cubin_size = 0;
+    nvrtcProgram prog;
+    const char* hdr_src[] = {kDeviceHeader};
+    const char* hdr_names[] = {"b2_device.cuh"};
+    nvrtcResult r = nvrtcCreateProgram(&prog, source, name ? name : "b2_fused.cu", 1, hdr_src, hdr_names);
+    if (r != NVRTC_SUCCESS) return fail(B2_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+    // --fmad=false: a*b+c stays two roundings, as in NumPy's separate ufunc loops, so float
+    // chains are bit-identical to the reference; the kernels call fma() where they want one.
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--restrict",
+                          "-default-device", "--fmad=false"};
+    r = nvrtcCompileProgram(prog, (int)(sizeof opts / sizeof *opts), opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        nvrtcGetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) nvrtcGetProgramLog(prog, &log[0]);
+        nvrtcDestroyProgram(&prog);
+        if (log.size() > 3500) log.resize(3500);
+        return fail(B2_ERR_NVRTC, "nvrtcCompileProgram: %s\n%s", nvrtcGetErrorString(r), log.c_str());
+    }
+    size_t n = 0;
+    r = nvrtcGetCUBINSize(prog, &n);
+    if (r != NVRTC_SUCCESS || n == 0) {
+        nvrtcDestroyProgram(&prog);
+        return fail(B2_ERR_NVRTC, "nvrtcGetCUBINSize: %s", nvrtcGetErrorString(r));
+    }
+    void* buf = malloc(n);
+    if (!buf) { nvrtcDestroyProgram(&prog); return fail(B2_ERR_INVALID, "out of host memory"); }
+    r = nvrtcGetCUBIN(prog, (char*)buf);
+    nvrtcDestroyProgram(&prog);
+    if (r != NVRTC_SUCCESS) { free(buf); return fail(B2_ERR_NVRTC, "nvrtcGetCUBIN: %s", nvrtcGetErrorString(r)); }
+    *cubin = buf;
+    *cubin_size = n;
+    return B2_OK;
+}
+
+struct b2_kernel {
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    b2_geom g{};
+};
+
+extern "C" int b2_kernel_load(const void* cubin, size_t cubin_size, const char* entry,
+                              const b2_geom* geom, b2_kernel** out) {
+    if (!cubin || !cubin_size || !entry || !geom || !out) return fail(B2_ERR_INVALID, "NULL argument");
+    if (geom->vec < 1 || geom->tx < 1 || geom->ty < 1 || geom->tx * geom->ty > 1024 || geom->rpt < 1)
+        return fail(B2_ERR_INVALID, "bad geometry vec=%d tx=%d ty=%d rpt=%d", geom->vec, geom->tx, geom->ty, geom->rpt);
+    DriverApi& d = driver();
+    if (!d.ok) return fail(B2_ERR_CUDA, "%s", d.why.c_str());
+    CUDA_TRY(cudaFree(0));   // make sure the primary context of the caller's device is current
+    b2_kernel* k = new b2_kernel();
+    CUresult r = d.ModuleLoadData(&k->mod, cubin);
+    if (r != CUDA_SUCCESS) { delete k; return fail(B2_ERR_CUDA, "cuModuleLoadData: %s", cu_err(r)); }
+    r = d.ModuleGetFunction(&k->fn, k->mod, entry);
+    if (r != CUDA_SUCCESS) { d.ModuleUnload(k->mod); delete k; return fail(B2_ERR_CUDA, "cuModuleGetFunction(%s): %s", entry, cu_err(r)); }
+    k->g = *geom;
+    *out = k;
+    return B2_OK;
+}
+
+extern "C" int b2_kernel_free(b2_kernel* k) {
+    if (!k) return B2_OK;
+    if (k->mod && driver().ok) driver().ModuleUnload(k->mod);
+    delete k;
+    return B2_OK;
+}
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+extern "C" int b2_fused_plan(const b2_kernel* k, b2_block* blocks, int nblocks,
+                             void* workspace, size_t workspace_bytes, size_t* needed,
+                             int64_t* total_tiles) {
+    if (!k || !blocks || nblocks <= 0 || !total_tiles) return fail(B2_ERR_INVALID, "bad argument");
+    const b2_geom& g = k->g;
+    const int64_t tile_cols = (int64_t)g.tx * g.vec;
+    int64_t tiles = 0;
+    size_t ncounters = 0, work_bytes = 0;
+    std::vector<size_t> ctr_off(nblocks, 0), work_off(nblocks, 0);
+    for (int i = 0; i < nblocks; ++i) {
+        b2_block& b = blocks[i];
+        if (b.B <= 0 || b.R <= 0 || b.C <= 0)
+            return fail(B2_ERR_INVALID, "block %d has an empty extent (%lld,%lld,%lld): skip it on the host",
+                        i, (long long)b.B, (long long)b.R, (long long)b.C);
+        b.tiles_r = cdiv(b.R, g.rpt);
+        b.tiles_c = (g.mode == B2_MODE_C) ? 1 : cdiv(b.C, tile_cols);
+        b.tile_begin = tiles;
+        tiles += b.B * b.tiles_r * b.tiles_c;
+        ctr_off[i] = ncounters;
+        work_off[i] = work_bytes;
+        if (g.mode == B2_MODE_R && b.tiles_r > 1) {
+            ncounters += (size_t)(b.B * b.tiles_c);
+            work_bytes += align_up((size_t)(b.B * b.tiles_r * b.tiles_c * tile_cols) * g.packed_bytes, 256);
+        } else if (g.mode == B2_MODE_RC && b.tiles_r * b.tiles_c > 1) {
+            ncounters += (size_t)b.B;
+            work_bytes += align_up((size_t)(b.B * b.tiles_r * b.tiles_c) * g.packed_bytes, 256);
+        }
+    }
+    if (tiles > 0x7fffffffLL) return fail(B2_ERR_UNSUPPORTED, "launch needs %lld tiles (> 2^31-1)", (long long)tiles);
+    const size_t ctr_bytes = align_up(ncounters * sizeof(unsigned), 256);
+    const size_t need = ctr_bytes + work_bytes;
+    if (needed) *needed = need;
+    *total_tiles = tiles;
+    if (need > 0 && (!workspace || workspace_bytes < need)) {
+        if (!workspace) return B2_OK;   // size query
+        return fail(B2_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    }
+    for (int i = 0; i < nblocks; ++i) {
+        blocks[i].counter = need ? (unsigned*)workspace + ctr_off[i] : nullptr;
+        blocks[i].work = need ? (char*)workspace + ctr_bytes + work_off[i] : nullptr;
+    }
+    return B2_OK;
+}
+
+extern "C" int b2_fused_launch(const b2_kernel* k, const b2_block* d_blocks, int nblocks,
+                               int64_t total_tiles, const b2_scalars* scalars, void* stream) {
+    if (!k || !d_blocks || nblocks <= 0 || total_tiles <= 0) return fail(B2_ERR_INVALID, "bad argument");
+    DriverApi& d = driver();
+    if (!d.ok) return fail(B2_ERR_CUDA, "%s", d.why.c_str());
+    b2_scalars zero;
+    memset(&zero, 0, sizeof zero);
+    const b2_scalars* sc = scalars ? scalars : &zero;
+    void* params[] = {(void*)&d_blocks, (void*)&nblocks, (void*)sc};
+    CUresult r = d.LaunchKernel(k->fn, (unsigned)total_tiles, 1, 1, (unsigned)(k->g.tx * k->g.ty), 1, 1,
+                                0, (CUstream)stream, params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(B2_ERR_CUDA, "cuLaunchKernel: %s", cu_err(r));
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------ tree-level combine (AOT)
+template <typename T, typename OUT>
+__device__ __forceinline__ void b2_post_store(void* out0, i64 e, T total, int post, double count) {
+    if (post == B2_POST_MEAN) ((OUT*)out0)[e] = (OUT)total / (OUT)count;   // divide(total, n, dtype)
+    else ((T*)out0)[e] = total;
+}
+
+template <typename T, int OP, typename OUT>
+__global__ void __launch_bounds__(256)
+b2_combine_kernel(const void* const* __restrict__ parts, const void* const* __restrict__ parts1, int fanin,
+                  i64 nelem, void* out0, void* out1, int post, double count, double ddof) {
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nelem) return;
+    if constexpr (OP == B2R_SUM || OP == B2R_PROD) {
+        T acc = ((const T*)parts[0])[e];
+        for (int g = 1; g < fanin; ++g) { T v = ((const T*)parts[g])[e]; acc = (OP == B2R_SUM) ? (T)(acc + v) : (T)(acc * v); }
+        b2_post_store<T, OUT>(out0, e, acc, post, count);
+    } else if constexpr (OP == B2R_MIN || OP == B2R_MAX) {
+        T acc = ((const T*)parts[0])[e];
+        for (int g = 1; g < fanin; ++g) { T v = ((const T*)parts[g])[e]; acc = (OP == B2R_MAX) ? b2_np_max(acc, v) : b2_np_min(acc, v); }
+        ((T*)out0)[e] = acc;
+    } else if constexpr (OP == B2R_ANY || OP == B2R_ALL) {
+        unsigned char acc = ((const unsigned char*)parts[0])[e];
+        for (int g = 1; g < fanin; ++g) { unsigned char v = ((const unsigned char*)parts[g])[e]; acc = (OP == B2R_ALL) ? (acc & v) : (acc | v); }
+        ((unsigned char*)out0)[e] = acc;
+    } else if constexpr (OP == B2R_ARGMIN || OP == B2R_ARGMAX) {
+        B2AccArg<T, OP == B2R_ARGMAX> acc;
+        acc.v = ((const T*)parts[0])[e]; acc.i = ((const i64*)parts1[0])[e];
+        for (int g = 1; g < fanin; ++g) {
+            B2AccArg<T, OP == B2R_ARGMAX> o;
+            o.v = ((const T*)parts[g])[e]; o.i = ((const i64*)parts1[g])[e];
+            acc.merge(o);
+        }
+        ((T*)out0)[e] = acc.v;
+        ((i64*)out1)[e] = acc.i;
+    } else {   // MOMENT: packed (n, mean, M2) fp64 triples
+        B2AccMoment<double, double> acc; acc.init();
+        for (int g = 0; g < fanin; ++g) {
+            const double* q = (const double*)parts[g] + 3 * e;
+            acc.chan(q[0], q[1], q[2]);
+        }
+        if (post == B2_POST_NONE) {
+            double* q = (double*)out0 + 3 * e;
+            q[0] = acc.n; q[1] = acc.mean; q[2] = acc.m2;
+        } else {
+            double den = acc.n - ddof;
+            double var = (den < 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : acc.m2 / den;
+            if (post == B2_POST_STD) var = sqrt(var);
+            ((OUT*)out0)[e] = (OUT)var;
+        }
+    }
+}
+
+template <typename T, typename OUT>
+static int launch_combine_t(int redop, const void* const* p0, const void* const* p1, int fanin, int64_t n,
+                            void* o0, void* o1, int post, double count, double ddof, cudaStream_t st) {
+    const unsigned grid = (unsigned)cdiv(n, 256);
+#define B2_CASE(OPC)                                                                                  \
+    case OPC:                                                                                         \
+        b2_combine_kernel<T, OPC, OUT><<<grid, 256, 0, st>>>(p0, p1, fanin, n, o0, o1, post, count, ddof); \
+        break;
+    switch (redop) {
+        B2_CASE(B2R_SUM) B2_CASE(B2R_PROD) B2_CASE(B2R_MIN) B2_CASE(B2R_MAX)
+        B2_CASE(B2R_ARGMIN) B2_CASE(B2R_ARGMAX) B2_CASE(B2R_ANY) B2_CASE(B2R_ALL)
+        default: return fail(B2_ERR_UNSUPPORTED, "combine: redop %d", redop);
+    }
+#undef B2_CASE
+    return B2_OK;
+}
+
+extern "C" int b2_combine(int redop, int dtype, const void* const* d_parts, const void* const* d_parts1,
+                          int fanin, int64_t nelem, void* out0, void* out1,
+                          int post, int out_dtype, double count, double ddof, void* stream) {
+    if (!d_parts || fanin <= 0 || nelem < 0 || !out0) return fail(B2_ERR_INVALID, "bad argument");
+    if (nelem == 0) return B2_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = B2_OK;
+    if (redop == B2R_MOMENT) {
+        const unsigned grid = (unsigned)cdiv(nelem, 256);
+        if (post != B2_POST_NONE && out_dtype == B2_F32)
+            b2_combine_kernel<double, B2R_MOMENT, float><<<grid, 256, 0, st>>>(d_parts, d_parts1, fanin, nelem, out0, out1, post, count, ddof);
+        else
+            b2_combine_kernel<double, B2R_MOMENT, double><<<grid, 256, 0, st>>>(d_parts, d_parts1, fanin, nelem, out0, out1, post, count, ddof);
+    } else {
+        const bool mean = (post == B2_POST_MEAN);
+        if (mean && redop != B2R_SUM) return fail(B2_ERR_INVALID, "POST_MEAN needs SUM");
+        if (mean && out_dtype != B2_F32 && out_dtype != B2_F64) return fail(B2_ERR_INVALID, "mean output must be f32/f64");
+#define B2_T(DT, T)                                                                                                   \
+    case DT:                                                                                                          \
+        rc = (mean && out_dtype == B2_F32)                                                                            \
+                 ? launch_combine_t<T, float>(redop, d_parts, d_parts1, fanin, nelem, out0, out1, post, count, ddof, st)   \
+                 : launch_combine_t<T, double>(redop, d_parts, d_parts1, fanin, nelem, out0, out1, post, count, ddof, st); \
+        break;
+        switch (dtype) {
+            B2_T(B2_BOOL, unsigned char) B2_T(B2_I8, signed char) B2_T(B2_U8, unsigned char)
+            B2_T(B2_I16, short) B2_T(B2_U16, unsigned short) B2_T(B2_I32, int) B2_T(B2_U32, unsigned)
+            B2_T(B2_I64, long long) B2_T(B2_U64, unsigned long long) B2_T(B2_F32, float) B2_T(B2_F64, double)
+            default: return fail(B2_ERR_UNSUPPORTED, "combine: dtype %d", dtype);
+        }
+#undef B2_T
+    }
+    if (rc != B2_OK) return rc;
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------ tiled gather (AOT)
+// One CTA copies one tile = tile_rows x (<= B2_GATHER_COL_BYTES) of one rectangle; a warp
+// takes a row, lanes move the widest aligned word.
+template <typename W>
+__device__ __forceinline__ void b2_copy_row(const char* s, char* d, i64 nbytes, int lane) {
+    const i64 n = nbytes / (i64)sizeof(W);
+    const W* sw = reinterpret_cast<const W*>(s);
+    W* dw = reinterpret_cast<W*>(d);
+    for (i64 i = lane; i < n; i += 32) dw[i] = sw[i];
+}
+
+__global__ void __launch_bounds__(256) b2_gather_kernel(const b2_copy* __restrict__ copies, int n) {
+    __shared__ b2_copy cp;
+    {
+        const i64 tile = blockIdx.x;
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (copies[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+        }
+        const unsigned* src = reinterpret_cast<const unsigned*>(copies + lo);
+        unsigned* dst = reinterpret_cast<unsigned*>(&cp);
+        for (int i = threadIdx.x; i < (int)(sizeof(b2_copy) / 4); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const i64 t = (i64)blockIdx.x - cp.tile_begin;
+    const i64 tc = t % cp.tiles_c, tr = t / cp.tiles_c;
+    const i64 r0 = tr * cp.tile_rows;
+    const i64 r1 = (r0 + cp.tile_rows < cp.rows) ? r0 + cp.tile_rows : cp.rows;
+    const i64 c0 = tc * B2_GATHER_COL_BYTES;
+    const i64 cb = (c0 + B2_GATHER_COL_BYTES < cp.row_bytes) ? B2_GATHER_COL_BYTES : cp.row_bytes - c0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (i64 r = r0 + warp; r < r1; r += nwarp) {
+        const char* s = (const char*)cp.src + r * cp.src_pitch + c0;
+        char* d = (char*)cp.dst + r * cp.dst_pitch + c0;
+        switch (cp.vec_bytes) {
+            case 16: b2_copy_row<uint4>(s, d, cb, lane); break;
+            case 8: b2_copy_row<uint2>(s, d, cb, lane); break;
+            case 4: b2_copy_row<unsigned>(s, d, cb, lane); break;
+            case 2: b2_copy_row<unsigned short>(s, d, cb, lane); break;
+            default: b2_copy_row<unsigned char>(s, d, cb, lane); break;
+        }
+    }
+}
+
+extern "C" int b2_gather_plan(b2_copy* copies, int n, int64_t* total_tiles) {
+    if (!copies || n <= 0 || !total_tiles) return fail(B2_ERR_INVALID, "bad argument");
+    int64_t tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        b2_copy& c = copies[i];
+        if (c.rows <= 0 || c.row_bytes <= 0) return fail(B2_ERR_INVALID, "copy %d is empty: skip it on the host", i);
+        uintptr_t bits = (uintptr_t)c.src | (uintptr_t)c.dst | (uintptr_t)c.row_bytes;
+        if (c.rows > 1) bits |= (uintptr_t)c.src_pitch | (uintptr_t)c.dst_pitch;
+        c.vec_bytes = (bits % 16 == 0) ? 16 : (bits % 8 == 0) ? 8 : (bits % 4 == 0) ? 4 : (bits % 2 == 0) ? 2 : 1;
+        const int64_t colb = c.row_bytes < B2_GATHER_COL_BYTES ? c.row_bytes : B2_GATHER_COL_BYTES;
+        int64_t tr = 65536 / colb;            // ~64 KiB per CTA
+        if (tr < 8) tr = 8;
+        if (tr > 256) tr = 256;
+        if (tr > c.rows) tr = c.rows;
+        c.tile_rows = (int32_t)tr;
+        c.tiles_c = (int32_t)cdiv(c.row_bytes, B2_GATHER_COL_BYTES);
+        c.tile_begin = tiles;
+        tiles += cdiv(c.rows, tr) * c.tiles_c;
+    }
+    if (tiles > 0x7fffffffLL) return fail(B2_ERR_UNSUPPORTED, "gather needs %lld tiles", (long long)tiles);
+    *total_tiles = tiles;
+    return B2_OK;
+}
+
+extern "C" int b2_gather_launch(const b2_copy* d_copies, int n, int64_t total_tiles, void* stream) {
+    if (!d_copies || n <= 0 || total_tiles <= 0) return fail(B2_ERR_INVALID, "bad argument");
+    b2_gather_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>(d_copies, n);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------ fill (AOT)
+template <typename W>
+__global__ void __launch_bounds__(256) b2_fill_kernel(W* dst, i64 n, W value) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i] = value;
+}
+
+extern "C" int b2_fill(void* dst, int64_t nelem, int itemsize, const void* value, void* stream) {
+    if (!dst || !value || nelem < 0) return fail(B2_ERR_INVALID, "bad argument");
+    if (nelem == 0) return B2_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t g = cdiv(nelem, 256);
+    if (g > 148 * 16) g = 148 * 16;
+    switch (itemsize) {
+        case 1: { unsigned char v; memcpy(&v, value, 1); b2_fill_kernel<<<(unsigned)g, 256, 0, st>>>((unsigned char*)dst, nelem, v); break; }
+        case 2: { unsigned short v; memcpy(&v, value, 2); b2_fill_kernel<<<(unsigned)g, 256, 0, st>>>((unsigned short*)dst, nelem, v); break; }
+        case 4: { unsigned v; memcpy(&v, value, 4); b2_fill_kernel<<<(unsigned)g, 256, 0, st>>>((unsigned*)dst, nelem, v); break; }
+        case 8: { unsigned long long v; memcpy(&v, value, 8); b2_fill_kernel<<<(unsigned)g, 256, 0, st>>>((unsigned long long*)dst, nelem, v); break; }
+        default: return fail(B2_ERR_UNSUPPORTED, "fill: itemsize %d", itemsize);
+    }
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
+// shared with the other translation units of the library
+extern "C" int b2_set_error_(int code, const char* msg) { return fail(code, "%s", msg); }
+extern "C" void b2_count_launch_(void) { g_launches.fetch_add(1); }

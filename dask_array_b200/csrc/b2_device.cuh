@@ -1,0 +1,699 @@
+// b2_device.cuh -- device-side kernel templates of libb200da (sm_100a).
+//
+// This header is compiled two ways:
+//   * by nvcc, ahead of time, into libb200da.so (b2_abi.cu);
+//   * by NVRTC at run time, as the body of every fused kernel: the host-side generator
+//     (dask_array_b200/_codegen.py) emits a `Chain` functor for one FusedBlockwise
+//     expression plus a handful of #defines and then includes this file.
+// It therefore uses no host or libstdc++ headers.
+//
+// What it replaces in the reference (paths under /root/reference/dask_array/):
+//   * the per-block NumPy calls run by FusedBlockwise._task (_blockwise.py:1697-1728):
+//     one temporary per operator becomes registers of one kernel;
+//   * the reduction chunk step fused behind the chain (reductions/_reduction.py:154-226,
+//     chunk kernels reductions/_common.py:92-105,270-281,368-404,704-732).
+//
+// Canonical block view: (B, R, C), C innermost.  A CTA owns one tile =
+// (B2_RPT rows) x (B2_TX*B2_V columns) of one block [modes EW, R, RC] or
+// (B2_RPT rows) x (all columns) [mode C].  Thread (tx, ty) walks rows ty, ty+TY, ...
+// of the tile with B2_V consecutive columns, B2_U row-loads in flight.
+#pragma once
+
+typedef long long i64;
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define B2_MAX_IN 6
+#define B2_MAX_ND 4
+
+// layout-identical to `b2_block` / `b2_scalars` in include/b200da.h (checked by
+// static_asserts in b2_abi.cu)
+struct B2Block {
+    const void* in[B2_MAX_IN];
+    i64 in_sb[B2_MAX_IN];
+    i64 in_sr[B2_MAX_IN];
+    i64 in_sc[B2_MAX_IN];
+    void* out0;
+    void* out1;
+    i64 B, R, C;
+    i64 tile_begin;
+    i64 tiles_r, tiles_c;
+    void* work;
+    u32* counter;
+    i64 arg_offset;
+    int arg_ndim;
+    int _pad;
+    i64 arg_shape[B2_MAX_ND];
+    i64 arg_start[B2_MAX_ND];
+    i64 arg_total[B2_MAX_ND];
+};
+
+struct B2Scalars {
+    double f[8];
+    i64 i[8];
+};
+
+enum { B2M_EW = 0, B2M_R = 1, B2M_C = 2, B2M_RC = 3 };
+enum { B2R_NONE = 0, B2R_SUM = 1, B2R_MIN = 2, B2R_MAX = 3, B2R_ARGMIN = 4, B2R_ARGMAX = 5,
+       B2R_MOMENT = 6, B2R_PROD = 7, B2R_ANY = 8, B2R_ALL = 9 };
+
+// ------------------------------------------------------------------ loads / stores
+// 128-bit (or narrower) read-only streaming loads: every input byte is touched once,
+// so keep it out of L1.
+__device__ __forceinline__ void b2_ldg16(const void* p, u32 (&w)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+}
+__device__ __forceinline__ void b2_ldg8(const void* p, u32 (&w)[2]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];"
+                 : "=r"(w[0]), "=r"(w[1]) : "l"(p));
+}
+__device__ __forceinline__ u32 b2_ldg4(const void* p) {
+    u32 w;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(w) : "l"(p));
+    return w;
+}
+
+template <int BYTES> struct B2Raw { u32 w[(BYTES + 3) / 4]; };
+
+// V consecutive elements of T starting at p (p is V*sizeof(T)-aligned by host contract)
+template <typename T, int V>
+__device__ __forceinline__ void b2_load_vec(const T* p, T (&dst)[V]) {
+    constexpr int BYTES = V * (int)sizeof(T);
+    if constexpr (BYTES == 16) {
+        union { u32 w[4]; T t[V]; } u;
+        b2_ldg16(p, u.w);
+#pragma unroll
+        for (int v = 0; v < V; ++v) dst[v] = u.t[v];
+    } else if constexpr (BYTES == 8) {
+        union { u32 w[2]; T t[V]; } u;
+        b2_ldg8(p, u.w);
+#pragma unroll
+        for (int v = 0; v < V; ++v) dst[v] = u.t[v];
+    } else if constexpr (BYTES == 4) {
+        union { u32 w; T t[V]; } u;
+        u.w = b2_ldg4(p);
+#pragma unroll
+        for (int v = 0; v < V; ++v) dst[v] = u.t[v];
+    } else if constexpr (BYTES == 32) {
+        union { u32 w[8]; T t[V]; } u;
+        u32 a[4], b[4];
+        b2_ldg16(p, a);
+        b2_ldg16((const char*)p + 16, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { u.w[i] = a[i]; u.w[4 + i] = b[i]; }
+#pragma unroll
+        for (int v = 0; v < V; ++v) dst[v] = u.t[v];
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) dst[v] = __ldg(p + v);
+    }
+}
+// one element broadcast to the V lanes (column stride 0)
+template <typename T, int V>
+__device__ __forceinline__ void b2_load_bcast(const T* p, T (&dst)[V]) {
+    T x = __ldg(p);
+#pragma unroll
+    for (int v = 0; v < V; ++v) dst[v] = x;
+}
+// arbitrary column stride (transposed views)
+template <typename T, int V>
+__device__ __forceinline__ void b2_load_strided(const T* p, i64 sc, T (&dst)[V]) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) dst[v] = __ldg(p + v * sc);
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void b2_store_vec(T* p, const T (&src)[V]) {
+    constexpr int BYTES = V * (int)sizeof(T);
+    if constexpr (BYTES == 16) {
+        union { uint4 q; T t[V]; } u;
+#pragma unroll
+        for (int v = 0; v < V; ++v) u.t[v] = src[v];
+        *reinterpret_cast<uint4*>(p) = u.q;
+    } else if constexpr (BYTES == 8) {
+        union { uint2 q; T t[V]; } u;
+#pragma unroll
+        for (int v = 0; v < V; ++v) u.t[v] = src[v];
+        *reinterpret_cast<uint2*>(p) = u.q;
+    } else if constexpr (BYTES == 4) {
+        union { u32 q; T t[V]; } u;
+#pragma unroll
+        for (int v = 0; v < V; ++v) u.t[v] = src[v];
+        *reinterpret_cast<u32*>(p) = u.q;
+    } else if constexpr (BYTES == 32) {
+        union { uint4 q[2]; T t[V]; } u;
+#pragma unroll
+        for (int v = 0; v < V; ++v) u.t[v] = src[v];
+        reinterpret_cast<uint4*>(p)[0] = u.q[0];
+        reinterpret_cast<uint4*>(p)[1] = u.q[1];
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) p[v] = src[v];
+    }
+}
+
+// ------------------------------------------------------------------ NumPy scalar semantics
+template <typename T> struct b2_is_float { static constexpr bool value = false; };
+template <> struct b2_is_float<float> { static constexpr bool value = true; };
+template <> struct b2_is_float<double> { static constexpr bool value = true; };
+
+template <typename T> __device__ __forceinline__ bool b2_isnan(T v) {
+    if constexpr (b2_is_float<T>::value) return v != v; else return false;
+}
+
+// Python/NumPy floor division and modulo (sign follows the divisor; x // 0 == 0 for ints)
+template <typename T> __device__ __forceinline__ T b2_floordiv_int(T a, T b) {
+    if (b == 0) return 0;
+    T q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+    return q;
+}
+template <typename T> __device__ __forceinline__ T b2_mod_int(T a, T b) {
+    if (b == 0) return 0;
+    T r = a % b;
+    if (r != 0 && ((r < 0) != (b < 0))) r += b;
+    return r;
+}
+template <typename T> __device__ __forceinline__ T b2_floordiv_uint(T a, T b) { return b == 0 ? 0 : a / b; }
+template <typename T> __device__ __forceinline__ T b2_mod_uint(T a, T b) { return b == 0 ? 0 : a % b; }
+__device__ __forceinline__ double b2_mod_f(double a, double b) {
+    double r = fmod(a, b);
+    if (b == 0.0) return r;               // nan
+    if (r != 0.0) { if ((b < 0.0) != (r < 0.0)) r += b; }
+    else r = copysign(0.0, b);
+    return r;
+}
+__device__ __forceinline__ float b2_mod_f(float a, float b) {
+    float r = fmodf(a, b);
+    if (b == 0.0f) return r;
+    if (r != 0.0f) { if ((b < 0.0f) != (r < 0.0f)) r += b; }
+    else r = copysignf(0.0f, b);
+    return r;
+}
+__device__ __forceinline__ double b2_floordiv_f(double a, double b) {
+    if (b == 0.0) return a / b;
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0 && ((b < 0.0) != (mod < 0.0))) div -= 1.0;
+    if (div != 0.0) { double fl = floor(div); if (div - fl > 0.5) fl += 1.0; return fl; }
+    return copysign(0.0, a / b);
+}
+__device__ __forceinline__ float b2_floordiv_f(float a, float b) {
+    if (b == 0.0f) return a / b;
+    float mod = fmodf(a, b);
+    float div = (a - mod) / b;
+    if (mod != 0.0f && ((b < 0.0f) != (mod < 0.0f))) div -= 1.0f;
+    if (div != 0.0f) { float fl = floorf(div); if (div - fl > 0.5f) fl += 1.0f; return fl; }
+    return copysignf(0.0f, a / b);
+}
+// integer power by squaring, wrap-around like NumPy
+template <typename T> __device__ __forceinline__ T b2_ipow(T base, i64 e) {
+    T r = 1;
+    while (e > 0) { if (e & 1) r *= base; base *= base; e >>= 1; }
+    return r;
+}
+// np.maximum / np.minimum propagate NaN
+template <typename T> __device__ __forceinline__ T b2_np_max(T a, T b) {
+    if constexpr (b2_is_float<T>::value) return (a != a) ? a : ((b != b) ? b : (a >= b ? a : b));
+    else return a >= b ? a : b;
+}
+template <typename T> __device__ __forceinline__ T b2_np_min(T a, T b) {
+    if constexpr (b2_is_float<T>::value) return (a != a) ? a : ((b != b) ? b : (a <= b ? a : b));
+    else return a <= b ? a : b;
+}
+template <typename T> __device__ __forceinline__ T b2_sign(T a) {
+    if constexpr (b2_is_float<T>::value) return (a != a) ? a : (T)((a > 0) - (a < 0));
+    else return (T)((a > 0) - (a < 0));
+}
+
+// ------------------------------------------------------------------ accumulators
+// An accumulator `A` offers: init(), add(value, index), merge(other) [other comes LATER
+// in index order unless the op is commutative], and Packed <-> A for the two-stage
+// partials.  Merges are deterministic: fixed shuffle pattern, fixed tile order.
+
+template <typename T> __device__ __forceinline__ T b2_shfl_down(T v, int off, int width) {
+    return __shfl_down_sync(0xffffffffu, v, off, width);
+}
+__device__ __forceinline__ unsigned char b2_shfl_down(unsigned char v, int off, int width) {
+    return (unsigned char)__shfl_down_sync(0xffffffffu, (int)v, off, width);
+}
+__device__ __forceinline__ signed char b2_shfl_down(signed char v, int off, int width) {
+    return (signed char)__shfl_down_sync(0xffffffffu, (int)v, off, width);
+}
+__device__ __forceinline__ short b2_shfl_down(short v, int off, int width) {
+    return (short)__shfl_down_sync(0xffffffffu, (int)v, off, width);
+}
+__device__ __forceinline__ unsigned short b2_shfl_down(unsigned short v, int off, int width) {
+    return (unsigned short)__shfl_down_sync(0xffffffffu, (int)v, off, width);
+}
+__device__ __forceinline__ bool b2_shfl_down(bool v, int off, int width) {
+    return (bool)__shfl_down_sync(0xffffffffu, (int)v, off, width);
+}
+
+template <typename T, typename ACC>
+struct B2AccSum {   // np.sum(x, dtype=ACC)  (_chunk.py:172; ints widen to 64 bit)
+    typedef ACC Packed;
+    ACC s;
+    __device__ __forceinline__ void init() { s = (ACC)0; }
+    __device__ __forceinline__ void prime(T) {}
+    __device__ __forceinline__ void add(T v, i64) { s += (ACC)v; }
+    __device__ __forceinline__ void merge(const B2AccSum& o) { s += o.s; }
+    __device__ __forceinline__ void shfl(int off, int width) { B2AccSum o; o.s = b2_shfl_down(s, off, width); merge(o); }
+    __device__ __forceinline__ Packed pack() const { return s; }
+    __device__ __forceinline__ void unpack(const Packed& p) { s = p; }
+};
+template <typename T, typename ACC>
+struct B2AccProd {
+    typedef ACC Packed;
+    ACC s;
+    __device__ __forceinline__ void init() { s = (ACC)1; }
+    __device__ __forceinline__ void prime(T) {}
+    __device__ __forceinline__ void add(T v, i64) { s *= (ACC)v; }
+    __device__ __forceinline__ void merge(const B2AccProd& o) { s *= o.s; }
+    __device__ __forceinline__ void shfl(int off, int width) { B2AccProd o; o.s = b2_shfl_down(s, off, width); merge(o); }
+    __device__ __forceinline__ Packed pack() const { return s; }
+    __device__ __forceinline__ void unpack(const Packed& p) { s = p; }
+};
+template <typename T, bool ALL>
+struct B2AccAnyAll {   // np.any / np.all -> bool
+    typedef unsigned char Packed;
+    unsigned char s;
+    __device__ __forceinline__ void init() { s = ALL ? 1 : 0; }
+    __device__ __forceinline__ void prime(T) {}
+    __device__ __forceinline__ void add(T v, i64) { bool t = (v != (T)0); s = ALL ? (s & (unsigned char)t) : (s | (unsigned char)t); }
+    __device__ __forceinline__ void merge(const B2AccAnyAll& o) { s = ALL ? (s & o.s) : (s | o.s); }
+    __device__ __forceinline__ void shfl(int off, int width) { B2AccAnyAll o; o.s = b2_shfl_down(s, off, width); merge(o); }
+    __device__ __forceinline__ Packed pack() const { return s; }
+    __device__ __forceinline__ void unpack(const Packed& p) { s = p; }
+};
+template <typename T, bool ISMAX>
+struct B2AccMinMax {   // np.min / np.max: NaN propagates (chunk_min/chunk_max _common.py:92-105)
+    struct Packed { T m; int has; };
+    T m; bool has;
+    __device__ __forceinline__ void init() { has = false; m = (T)0; }
+    __device__ __forceinline__ void prime(T) {}
+    __device__ __forceinline__ void add(T v, i64) {
+        if (!has) { m = v; has = true; return; }
+        m = ISMAX ? b2_np_max(m, v) : b2_np_min(m, v);
+    }
+    __device__ __forceinline__ void merge(const B2AccMinMax& o) {
+        if (!o.has) return;
+        if (!has) { m = o.m; has = true; return; }
+        m = ISMAX ? b2_np_max(m, o.m) : b2_np_min(m, o.m);
+    }
+    __device__ __forceinline__ void shfl(int off, int width) {
+        B2AccMinMax o; o.m = b2_shfl_down(m, off, width); o.has = b2_shfl_down(has, off, width); merge(o);
+    }
+    __device__ __forceinline__ Packed pack() const { Packed p; p.m = m; p.has = has ? 1 : 0; return p; }
+    __device__ __forceinline__ void unpack(const Packed& p) { m = p.m; has = (p.has != 0); }
+};
+// index-carrying argmin/argmax with np.argmax semantics: first occurrence wins ties,
+// the first NaN wins outright (arg_chunk _common.py:704-732; keepdims_wrapper _chunk.py:137).
+template <typename T, bool ISMAX>
+struct B2AccArg {
+    struct Packed { T v; i64 i; };
+    T v; i64 i;    // i < 0: empty
+    __device__ __forceinline__ void init() { v = (T)0; i = -1; }
+    __device__ __forceinline__ void prime(T) {}
+    // `a` strictly better than `b` (both valid)?
+    __device__ __forceinline__ static bool better(T av, i64 ai, T bv, i64 bi) {
+        bool an = b2_isnan(av), bn = b2_isnan(bv);
+        if (an || bn) { if (an && bn) return ai < bi; return an; }
+        if (av == bv) return ai < bi;
+        return ISMAX ? (av > bv) : (av < bv);
+    }
+    __device__ __forceinline__ void add(T x, i64 idx) {
+        if (i < 0 || better(x, idx, v, i)) { v = x; i = idx; }
+    }
+    __device__ __forceinline__ void merge(const B2AccArg& o) {
+        if (o.i < 0) return;
+        if (i < 0 || better(o.v, o.i, v, i)) { v = o.v; i = o.i; }
+    }
+    __device__ __forceinline__ void shfl(int off, int width) {
+        B2AccArg o; o.v = b2_shfl_down(v, off, width); o.i = b2_shfl_down(i, off, width); merge(o);
+    }
+    __device__ __forceinline__ Packed pack() const { Packed p; p.v = v; p.i = i; return p; }
+    __device__ __forceinline__ void unpack(const Packed& p) { v = p.v; i = p.i; }
+};
+// Single-pass second moment.  Per thread: sums of (x-K) and (x-K)^2 around a pivot K
+// taken from the data (kills the catastrophic cancellation of the naive sum of squares);
+// across threads / tiles / blocks: Chan's pairwise merge of (n, mean, M2) in fp64 -- the
+// same algebra as moment_combine (_common.py:415-453), which the reference applies
+// between blocks after a two-pass moment_chunk (:368-404).
+template <typename T, typename W>   // W: working type (float for fp32 data, double otherwise)
+struct B2AccMoment {
+    struct Packed { double n, mean, m2; };
+    W K, s1, s2; int cnt;        // thread-local phase
+    double n, mean, m2;          // merged phase
+    __device__ __forceinline__ void init() { K = (W)0; s1 = (W)0; s2 = (W)0; cnt = 0; n = 0.0; mean = 0.0; m2 = 0.0; }
+    __device__ __forceinline__ void prime(T v) { K = (W)v; }
+    __device__ __forceinline__ void add(T v, i64) { W d = (W)v - K; s1 += d; s2 = fma(d, d, s2); ++cnt; }
+    // fold the thread-local sums into (n, mean, M2)
+    __device__ __forceinline__ void finish_local() {
+        if (cnt > 0) {
+            double dn = (double)cnt, a = (double)s1, b = (double)s2;
+            Packed p; p.n = dn; p.mean = (double)K + a / dn; p.m2 = b - a * a / dn;
+            if (p.m2 < 0.0) p.m2 = 0.0;
+            chan(p.n, p.mean, p.m2);
+            s1 = (W)0; s2 = (W)0; cnt = 0;
+        }
+    }
+    __device__ __forceinline__ void chan(double on, double omean, double om2) {
+        if (on == 0.0) return;
+        if (n == 0.0) { n = on; mean = omean; m2 = om2; return; }
+        double tot = n + on, delta = omean - mean;
+        mean = mean + delta * (on / tot);
+        m2 = m2 + om2 + delta * delta * (n * on / tot);
+        n = tot;
+    }
+    __device__ __forceinline__ void merge(const B2AccMoment& o) { chan(o.n, o.mean, o.m2); }
+    __device__ __forceinline__ void shfl(int off, int width) {
+        double on = b2_shfl_down(n, off, width), om = b2_shfl_down(mean, off, width), o2 = b2_shfl_down(m2, off, width);
+        chan(on, om, o2);
+    }
+    __device__ __forceinline__ Packed pack() const { Packed p; p.n = n; p.mean = mean; p.m2 = m2; return p; }
+    __device__ __forceinline__ void unpack(const Packed& p) { init(); n = p.n; mean = p.mean; m2 = p.m2; }
+};
+
+template <int REDOP, typename T, typename ACC> struct B2AccSel;
+template <typename T, typename ACC> struct B2AccSel<B2R_SUM, T, ACC> { typedef B2AccSum<T, ACC> type; };
+template <typename T, typename ACC> struct B2AccSel<B2R_PROD, T, ACC> { typedef B2AccProd<T, ACC> type; };
+template <typename T, typename ACC> struct B2AccSel<B2R_MIN, T, ACC> { typedef B2AccMinMax<T, false> type; };
+template <typename T, typename ACC> struct B2AccSel<B2R_MAX, T, ACC> { typedef B2AccMinMax<T, true> type; };
+template <typename T, typename ACC> struct B2AccSel<B2R_ARGMIN, T, ACC> { typedef B2AccArg<T, false> type; };
+template <typename T, typename ACC> struct B2AccSel<B2R_ARGMAX, T, ACC> { typedef B2AccArg<T, true> type; };
+template <typename T, typename ACC> struct B2AccSel<B2R_MOMENT, T, ACC> { typedef B2AccMoment<T, ACC> type; };
+template <typename T, typename ACC> struct B2AccSel<B2R_ANY, T, ACC> { typedef B2AccAnyAll<T, false> type; };
+template <typename T, typename ACC> struct B2AccSel<B2R_ALL, T, ACC> { typedef B2AccAnyAll<T, true> type; };
+
+// final store of one reduced element
+template <int REDOP, typename T, typename ACC, typename A>
+__device__ __forceinline__ void b2_store_result(const B2Block& blk, i64 o, A& a, i64 idx_fix) {
+    if constexpr (REDOP == B2R_SUM || REDOP == B2R_PROD) {
+        ((ACC*)blk.out0)[o] = a.s;
+    } else if constexpr (REDOP == B2R_MIN || REDOP == B2R_MAX) {
+        ((T*)blk.out0)[o] = a.m;
+    } else if constexpr (REDOP == B2R_ARGMIN || REDOP == B2R_ARGMAX) {
+        ((T*)blk.out0)[o] = a.v;
+        ((i64*)blk.out1)[o] = a.i + idx_fix;
+    } else if constexpr (REDOP == B2R_MOMENT) {
+        double* q = (double*)blk.out0 + 3 * o;
+        q[0] = a.n; q[1] = a.mean; q[2] = a.m2;
+    } else {
+        ((unsigned char*)blk.out0)[o] = a.s;
+    }
+}
+
+// local flat index of a ravelled arg reduction -> index into the WHOLE array
+// (arg_chunk ravel branch, _common.py:709-713: unravel_index + offset + ravel_multi_index)
+__device__ __forceinline__ i64 b2_ravel_fix(const B2Block& blk, i64 local) {
+    i64 coords[B2_MAX_ND];
+    i64 rem = local;
+    for (int d = blk.arg_ndim - 1; d >= 0; --d) { coords[d] = rem % blk.arg_shape[d]; rem /= blk.arg_shape[d]; }
+    i64 g = 0;
+    for (int d = 0; d < blk.arg_ndim; ++d) g = g * blk.arg_total[d] + (coords[d] + blk.arg_start[d]);
+    return g;
+}
+
+// ------------------------------------------------------------------ tile lookup
+__device__ __forceinline__ int b2_find_block(const B2Block* __restrict__ blocks, int nblocks, i64 tile) {
+    int lo = 0, hi = nblocks - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (blocks[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------ the fused kernel body
+// partials written by other CTAs: read through L2 (never a stale L1 line)
+template <typename P> __device__ __forceinline__ P b2_load_cg(const P* p) {
+    union { P v; u32 w[(sizeof(P) + 3) / 4]; unsigned char c[sizeof(P)]; } u;
+    if constexpr (sizeof(P) % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(P) / 4); ++i) u.w[i] = __ldcg(reinterpret_cast<const u32*>(p) + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < (int)sizeof(P); ++i) u.c[i] = __ldcg(reinterpret_cast<const unsigned char*>(p) + i);
+    }
+    return u.v;
+}
+
+// Chain supplies:  out_t;  Regs;  load(blk, b, r, c, Regs&);  compute(Regs, scalars, out_t(&)[V]).
+template <typename Chain, int MODE, int REDOP, int V, int TX, int TY, int RPT, int U, typename ACC>
+__device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars& sc) {
+    typedef typename Chain::out_t T;
+    constexpr int NT = TX * TY;
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+
+    __shared__ B2Block sblk;
+    {
+        const i64 tile = blockIdx.x;
+        const int bi = b2_find_block(blocks, nblocks, tile);
+        const int nw = (int)(sizeof(B2Block) / 4);
+        const u32* src = reinterpret_cast<const u32*>(blocks + bi);
+        u32* dst = reinterpret_cast<u32*>(&sblk);
+        for (int i = tid; i < nw; i += NT) dst[i] = src[i];
+        __syncthreads();
+    }
+    const B2Block& blk = sblk;
+    i64 t = (i64)blockIdx.x - blk.tile_begin;
+    const i64 tc = t % blk.tiles_c; t /= blk.tiles_c;
+    const i64 tr = t % blk.tiles_r; t /= blk.tiles_r;
+    const i64 b = t;
+    const i64 R = blk.R, C = blk.C;
+    const i64 r0 = tr * RPT;
+    const i64 rend = (r0 + RPT < R) ? (r0 + RPT) : R;
+
+    if constexpr (MODE == B2M_EW) {
+        const i64 c = (tc * TX + tx) * V;
+        if (c < C) {
+            T* outp = (T*)blk.out0 + b * R * C;
+            for (i64 rb = r0 + ty; rb < rend; rb += (i64)TY * U) {
+                typename Chain::Regs g[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { i64 r = rb + (i64)u * TY; if (r < rend) Chain::load(blk, b, r, c, g[u]); }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    i64 r = rb + (i64)u * TY;
+                    if (r < rend) { T o[V]; Chain::compute(g[u], sc, o); b2_store_vec<T, V>(outp + r * C + c, o); }
+                }
+            }
+        }
+        return;
+    } else {
+        typedef typename B2AccSel<REDOP, T, ACC>::type A;
+        typedef typename A::Packed P;
+        __shared__ bool last;
+
+        if constexpr (MODE == B2M_R || MODE == B2M_RC) {
+            // ---- accumulate this thread's rows of the tile
+            const i64 c = (tc * TX + tx) * V;
+            A acc[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v].init();
+            if (c < C) {
+                if constexpr (REDOP == B2R_MOMENT) {
+                    // pivot: the first element this thread (mode R) / this tile (mode RC) sees
+                    typename Chain::Regs g0; T o0[V];
+                    if constexpr (MODE == B2M_R) {
+                        i64 rp = (r0 + ty < rend) ? (r0 + ty) : r0;
+                        Chain::load(blk, b, rp, c, g0);
+                        Chain::compute(g0, sc, o0);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc[v].prime(o0[v]);
+                    } else {
+                        Chain::load(blk, b, r0, tc * TX * V, g0);
+                        Chain::compute(g0, sc, o0);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc[v].prime(o0[0]);
+                    }
+                }
+                for (i64 rb = r0 + ty; rb < rend; rb += (i64)TY * U) {
+                    typename Chain::Regs g[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) { i64 r = rb + (i64)u * TY; if (r < rend) Chain::load(blk, b, r, c, g[u]); }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        i64 r = rb + (i64)u * TY;
+                        if (r < rend) {
+                            T o[V]; Chain::compute(g[u], sc, o);
+#pragma unroll
+                            for (int v = 0; v < V; ++v) {
+                                i64 idx = (MODE == B2M_R) ? r : (r * C + c + v);
+                                acc[v].add(o[v], idx);
+                            }
+                        }
+                    }
+                }
+            }
+            if constexpr (REDOP == B2R_MOMENT) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v].finish_local();
+            }
+
+            if constexpr (MODE == B2M_R) {
+                // ---- fold the TY row-lanes of each column (fixed order), then tiles_r partials
+                if constexpr (TY > 1) {
+                    __shared__ P sm[NT * V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) sm[(ty * TX + tx) * V + v] = acc[v].pack();
+                    __syncthreads();
+                    if (ty == 0) {
+                        const int ny = (rend - r0 < TY) ? (int)(rend - r0) : TY;   // lanes that saw a row
+                        for (int y = 1; y < ny; ++y) {
+#pragma unroll
+                            for (int v = 0; v < V; ++v) { A o; o.unpack(sm[(y * TX + tx) * V + v]); acc[v].merge(o); }
+                        }
+                    }
+                }
+                const i64 tiles_r = blk.tiles_r;
+                const i64 Cpad = blk.tiles_c * TX * V;
+                if (tiles_r == 1) {
+                    if (ty == 0 && c < C) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) b2_store_result<REDOP, T, ACC>(blk, b * C + c + v, acc[v], blk.arg_offset);
+                    }
+                    return;
+                }
+                P* work = (P*)blk.work;
+                if (ty == 0 && c < C) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) work[(b * tiles_r + tr) * Cpad + c + v] = acc[v].pack();
+                    __threadfence();
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    u32* ctr = blk.counter + (b * blk.tiles_c + tc);
+                    u32 prev = atomicAdd(ctr, 1u);
+                    last = (prev == (u32)(tiles_r - 1));
+                    if (last) *ctr = 0u;      // self-reset: the workspace is reusable
+                }
+                __syncthreads();
+                if (!last) return;
+                __threadfence();
+                if (ty == 0 && c < C) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        A tot; tot.unpack(b2_load_cg(&work[(b * tiles_r) * Cpad + c + v]));
+                        for (i64 k = 1; k < tiles_r; ++k) {
+                            A part; part.unpack(b2_load_cg(&work[(b * tiles_r + k) * Cpad + c + v]));
+                            tot.merge(part);
+                        }
+                        b2_store_result<REDOP, T, ACC>(blk, b * C + c + v, tot, blk.arg_offset);
+                    }
+                }
+                return;
+            } else {
+                // ---- MODE RC: one value per tile, then all tiles of (block, b) in order
+                A a = acc[0];
+#pragma unroll
+                for (int v = 1; v < V; ++v) a.merge(acc[v]);
+                // warp reduce (lower lane = earlier), then across warps in order
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) a.shfl(off, 32);
+                constexpr int NW = (NT + 31) / 32;
+                __shared__ A smw[NW];
+                const int lane = tid & 31, wid = tid >> 5;
+                if constexpr (NW > 1) {
+                    if (lane == 0) smw[wid] = a;
+                    __syncthreads();
+                    if (tid == 0) { for (int w = 1; w < NW; ++w) a.merge(smw[w]); }
+                }
+                const i64 ntile = blk.tiles_r * blk.tiles_c;
+                const i64 tslot = tr * blk.tiles_c + tc;
+                i64 fix = 0;
+                if (ntile == 1) {
+                    if (tid == 0) {
+                        if constexpr (REDOP == B2R_ARGMIN || REDOP == B2R_ARGMAX) {
+                            fix = (blk.arg_ndim > 0) ? (b2_ravel_fix(blk, a.i) - a.i) : blk.arg_offset;
+                        }
+                        b2_store_result<REDOP, T, ACC>(blk, b, a, fix);
+                    }
+                    return;
+                }
+                P* work = (P*)blk.work;
+                if (tid == 0) {
+                    work[b * ntile + tslot] = a.pack();
+                    __threadfence();
+                    u32* ctr = blk.counter + b;
+                    u32 prev = atomicAdd(ctr, 1u);
+                    last = (prev == (u32)(ntile - 1));
+                    if (last) *ctr = 0u;
+                }
+                __syncthreads();
+                if (!last) return;
+                __threadfence();
+                // last CTA: fold the tile partials.  Lanes take contiguous runs of tiles so
+                // the fold order stays "earlier tiles first".
+                A tot; tot.init();
+                {
+                    const i64 per = (ntile + NT - 1) / NT;
+                    const i64 k0 = (i64)tid * per;
+                    const i64 k1 = (k0 + per < ntile) ? (k0 + per) : ntile;
+                    for (i64 k = k0; k < k1; ++k) { A part; part.unpack(b2_load_cg(&work[b * ntile + k])); tot.merge(part); }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) tot.shfl(off, 32);
+                if constexpr (NW > 1) {
+                    __syncthreads();
+                    if (lane == 0) smw[wid] = tot;
+                    __syncthreads();
+                    if (tid == 0) { for (int w = 1; w < NW; ++w) tot.merge(smw[w]); }
+                }
+                if (tid == 0) {
+                    if constexpr (REDOP == B2R_ARGMIN || REDOP == B2R_ARGMAX) {
+                        fix = (blk.arg_ndim > 0) ? (b2_ravel_fix(blk, tot.i) - tot.i) : blk.arg_offset;
+                    }
+                    b2_store_result<REDOP, T, ACC>(blk, b, tot, fix);
+                }
+                return;
+            }
+        } else {
+            // ---- MODE C: every row of the tile is reduced over ALL columns by its TX lanes
+            static_assert(MODE == B2M_C, "mode");
+            constexpr int WPR = (TX + 31) / 32;     // warps per row
+            constexpr int SW = TX < 32 ? TX : 32;   // shuffle width
+            __shared__ A smc[TY * WPR];
+            for (i64 rr = r0; rr < rend; rr += TY) {       // uniform trip count (barriers inside)
+                const i64 r = rr + ty;
+                const bool rok = r < rend;
+                A acc; acc.init();
+                if (rok) {
+                    if constexpr (REDOP == B2R_MOMENT) {
+                        typename Chain::Regs g0; T o0[V];
+                        Chain::load(blk, b, r, 0, g0); Chain::compute(g0, sc, o0); acc.prime(o0[0]);
+                    }
+                    for (i64 cb = (i64)tx * V; cb < C; cb += (i64)TX * V * U) {
+                        typename Chain::Regs g[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) { i64 c = cb + (i64)u * TX * V; if (c < C) Chain::load(blk, b, r, c, g[u]); }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            i64 c = cb + (i64)u * TX * V;
+                            if (c < C) {
+                                T o[V]; Chain::compute(g[u], sc, o);
+#pragma unroll
+                                for (int v = 0; v < V; ++v) acc.add(o[v], c + v);
+                            }
+                        }
+                    }
+                    if constexpr (REDOP == B2R_MOMENT) acc.finish_local();
+                }
+#pragma unroll
+                for (int off = SW / 2; off > 0; off >>= 1) acc.shfl(off, SW);
+                if constexpr (WPR > 1) {
+                    const int lane = tid & 31, w = tx >> 5;
+                    __syncthreads();
+                    if (lane == 0) smc[ty * WPR + w] = acc;
+                    __syncthreads();
+                    if (tx == 0) { for (int k = 1; k < WPR; ++k) acc.merge(smc[ty * WPR + k]); }
+                }
+                if (tx == 0 && rok) b2_store_result<REDOP, T, ACC>(blk, b * R + r, acc, blk.arg_offset);
+            }
+            return;
+        }
+    }
+}

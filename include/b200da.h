@@ -1,0 +1,221 @@
+/*
+ * b200da.h -- C ABI of libb200da.so, the B200-native execution backend for the
+ * data-parallel hot path of dask-array.
+ *
+ * The reference (mrocklin/dask-array) has NO FFI for this path: every hot loop is a
+ * per-block Python call of a NumPy function.  Each entry point below therefore cites
+ * the reference *Python* interface it replaces (file:line under /root/reference/).
+ * The binding a maintainer would add on the reference side (ctypes stub registered
+ * through dask_array/_chunk_types.py:31 and dask_array/_dispatch.py:145-151) is shown
+ * in INTEGRATION.md.
+ *
+ * Conventions
+ *  - Every function returns 0 on success or a negative b2_status; the message for the
+ *    calling thread is returned by b2_last_error().  No C++ exception crosses the ABI.
+ *  - The caller owns every buffer (device memory allocated by the host runtime, e.g.
+ *    torch.empty) and passes raw device pointers.  The library never allocates output
+ *    memory; scratch comes from a caller-provided workspace.
+ *  - All launches are asynchronous on the caller's stream (a cudaStream_t passed as
+ *    void*); the library never synchronises the device.
+ *  - The current CUDA device is the caller's (cudaSetDevice before the call).
+ *  - Re-entrant; the only shared state is the JIT module cache (mutex protected).
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point fails
+ *    with B2_ERR_CUDA.
+ */
+#ifndef B200DA_H
+#define B200DA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ABI_VERSION 1
+#define B2_MAX_IN 6      /* external inputs of one fused kernel                         */
+#define B2_MAX_ND 4      /* dims kept for arg-reduction index bookkeeping               */
+
+typedef enum b2_status {
+    B2_OK = 0,
+    B2_ERR_INVALID = -1,      /* bad argument                                            */
+    B2_ERR_CUDA = -2,         /* CUDA runtime / driver error (includes "no device")      */
+    B2_ERR_NVRTC = -3,        /* JIT compilation failed; log in b2_last_error()          */
+    B2_ERR_UNSUPPORTED = -4,  /* layout / dtype combination not implemented              */
+    B2_ERR_WORKSPACE = -5     /* caller workspace too small                              */
+} b2_status;
+
+/* element types (NumPy kinds the reference's chunk kernels see) */
+typedef enum b2_dtype {
+    B2_BOOL = 0, B2_I8 = 1, B2_U8 = 2, B2_I16 = 3, B2_U16 = 4, B2_I32 = 5, B2_U32 = 6,
+    B2_I64 = 7, B2_U64 = 8, B2_F32 = 9, B2_F64 = 10, B2_BF16 = 11, B2_F16 = 12
+} b2_dtype;
+
+/* reduction operators: the chunk / combine / aggregate kernels of
+ * dask_array/reductions/_common.py:57-167 (sum/min/max), :270-320 (mean),
+ * :368-505 (moment -> var/std), :675-750 (arg reductions). */
+typedef enum b2_redop {
+    B2_RED_NONE = 0, B2_RED_SUM = 1, B2_RED_MIN = 2, B2_RED_MAX = 3,
+    B2_RED_ARGMIN = 4, B2_RED_ARGMAX = 5, B2_RED_MOMENT = 6,
+    B2_RED_PROD = 7, B2_RED_ANY = 8, B2_RED_ALL = 9
+} b2_redop;
+
+/* which canonical axes of a (B, R, C) block are reduced */
+typedef enum b2_redmode {
+    B2_MODE_EW = 0,   /* element-wise, full (B,R,C) output                              */
+    B2_MODE_R = 1,    /* reduce rows   -> (B, C)   e.g. x.sum(axis=0) of a 2-D block      */
+    B2_MODE_C = 2,    /* reduce cols   -> (B, R)   e.g. x.argmax(axis=1)                  */
+    B2_MODE_RC = 3    /* reduce both   -> (B,)     e.g. x.std() chunk step               */
+} b2_redmode;
+
+/* what the last level of a tree reduction applies after combining
+ * (mean_agg _common.py:308-320, moment_agg :456-505, std's sqrt :625-653) */
+typedef enum b2_post {
+    B2_POST_NONE = 0, B2_POST_MEAN = 1, B2_POST_VAR = 2, B2_POST_STD = 3
+} b2_post;
+
+/*
+ * One output block of a fused launch, canonicalised by the host to a 3-D view
+ * (B, R, C) with C innermost.  Strides are in ELEMENTS of the operand's dtype;
+ * 0 = broadcast (creation/_utils.py:65-72 zero-stride constant blocks, NumPy
+ * broadcasting inside Elemwise, _blockwise.py:1030-1074); swapped strides express
+ * np.transpose views (manipulation/_transpose.py:14-75).
+ * Replaces: the per-block argument tuple of FusedBlockwise._task
+ * (_blockwise.py:1697-1728).
+ */
+typedef struct b2_block {
+    const void* in[B2_MAX_IN];
+    int64_t in_sb[B2_MAX_IN];
+    int64_t in_sr[B2_MAX_IN];
+    int64_t in_sc[B2_MAX_IN];
+    void* out0;            /* EW: (B,R,C) contiguous.  Reductions: values / totals       */
+    void* out1;            /* arg reductions: int64 indices; moment: unused              */
+    int64_t B, R, C;
+    int64_t tile_begin;    /* exclusive prefix sum of this block's tiles in the launch   */
+    int64_t tiles_r, tiles_c; /* tile grid of this block (filled by b2_fused_plan)      */
+    void* work;            /* two-stage partials for this block (from the workspace)     */
+    unsigned int* counter; /* arrival counters for this block (from the workspace)       */
+    /* arg reductions (arg_chunk, _common.py:704-732): offset along the reduced axis,
+     * or -- ravel mode -- the block's N-d shape/offset inside the whole array.         */
+    int64_t arg_offset;
+    int32_t arg_ndim;      /* 0 = plain axis mode; >0 = ravel mode with the fields below */
+    int32_t _pad;
+    int64_t arg_shape[B2_MAX_ND];
+    int64_t arg_start[B2_MAX_ND];
+    int64_t arg_total[B2_MAX_ND];
+} b2_block;
+
+/* scalar operands of the chain (Python scalars of elemwise(), _blockwise.py:1030) */
+typedef struct b2_scalars {
+    double f[8];
+    int64_t i[8];
+} b2_scalars;
+
+/* ------------------------------------------------------------------ housekeeping */
+int b2_abi_version(void);
+const char* b2_last_error(void);
+/* number of kernels this library has launched in this process (bench `gpu_launches`) */
+int64_t b2_launch_count(void);
+/* SM count of the current device (grid sizing) */
+int b2_device_sm_count(int* out);
+
+/* ------------------------------------------------------------------ fused kernels
+ * FusedBlockwise (_blockwise.py:1574-1738) + the reduction chunk step
+ * (reductions/_reduction.py:154-226): one JIT-compiled kernel per fused expression,
+ * one launch per (expression, device) covering every resident block.               */
+typedef struct b2_kernel b2_kernel;
+
+/* Compile CUDA C++ `source` (produced by the host-side generator; it includes the
+ * library's own device header "b2_device.cuh", supplied in-memory) for sm_100a and
+ * return the cubin.  Works without a GPU.  *cubin is malloc'ed; free with b2_free. */
+int b2_jit_compile(const char* source, const char* name, void** cubin, size_t* cubin_size);
+void b2_free(void* p);
+/* text of the device header (for diagnostics / offline nvcc builds) */
+const char* b2_device_header(void);
+
+/* compile-time geometry the generator baked into a kernel (must match its #defines) */
+typedef struct b2_geom {
+    int32_t mode;          /* b2_redmode                                                  */
+    int32_t redop;         /* b2_redop                                                    */
+    int32_t vec;           /* elements per thread per load (B2_V)                         */
+    int32_t tx, ty;        /* thread layout: tx over columns, ty over rows (B2_TX, B2_TY) */
+    int32_t rpt;           /* rows per tile (B2_RPT)                                      */
+    int32_t packed_bytes;  /* sizeof of one two-stage partial (0 for EW / mode C)         */
+    int32_t _pad;
+} b2_geom;
+
+/* Load a cubin on the current device and look up `entry` (needs a GPU). */
+int b2_kernel_load(const void* cubin, size_t cubin_size, const char* entry,
+                   const b2_geom* geom, b2_kernel** out);
+int b2_kernel_free(b2_kernel* k);
+
+/* Fill tile_begin / tiles_r / tiles_c / work / counter of every block and return the
+ * launch geometry.  `blocks` is HOST memory; workspace pointers are device pointers
+ * carved from [workspace, workspace + workspace_bytes).  Returns B2_ERR_WORKSPACE and
+ * the required size in *needed when the workspace is too small (call with NULL to
+ * query). */
+int b2_fused_plan(const b2_kernel* k, b2_block* blocks, int nblocks,
+                  void* workspace, size_t workspace_bytes, size_t* needed,
+                  int64_t* total_tiles);
+
+/* Launch over `nblocks` blocks whose descriptors (already planned) live in DEVICE
+ * memory at d_blocks.  The counters region of the workspace must be zero on entry;
+ * the kernel leaves it zero on exit (self-resetting), so it is reusable.            */
+int b2_fused_launch(const b2_kernel* k, const b2_block* d_blocks, int nblocks,
+                    int64_t total_tiles, const b2_scalars* scalars, void* stream);
+
+/* ------------------------------------------------------------------ tree levels
+ * PartialReduce (reductions/_reduction.py:900-983): one level of the
+ * chunk -> combine -> aggregate tree.  For every output element e in [0, nelem) the
+ * `fanin` partials are folded IN THE GIVEN ORDER (the lol_tuples nesting order of
+ * :968-983).  parts[g] / parts1[g] are device pointers listed in a DEVICE table.
+ *  - SUM/MIN/MAX/PROD/ANY/ALL: parts[g] -> dtype values.
+ *  - ARGMIN/ARGMAX: parts[g] values, parts1[g] int64 indices (_arg_combine :675-701).
+ *  - MOMENT: parts[g] -> packed (n, mean, M2) fp64 triples (Chan merge of
+ *    moment_combine :415-453 carried in fp64).
+ * post != NONE finishes mean/var/std (count = elements per output, ddof as given) and
+ * writes `out_dtype` values.                                                        */
+int b2_combine(int redop, int dtype, const void* const* d_parts, const void* const* d_parts1,
+               int fanin, int64_t nelem, void* out0, void* out1,
+               int post, int out_dtype, double count, double ddof, void* stream);
+
+/* ------------------------------------------------------------------ data movement
+ * Rechunk / slicing / concatenation (_rechunk.py:1252-1323 split+merge tasks,
+ * _chunk.py:285-317 getitem, _core_utils.py:1182-1248 concatenate3) as ONE tiled
+ * gather: each descriptor copies a (rows x row_bytes) rectangle.                     */
+typedef struct b2_copy {
+    const void* src;
+    void* dst;
+    int64_t rows;
+    int64_t row_bytes;
+    int64_t src_pitch;   /* bytes between consecutive rows */
+    int64_t dst_pitch;
+    /* filled by b2_gather_plan: */
+    int64_t tile_begin;  /* exclusive prefix sum of tiles                                 */
+    int32_t tile_rows;   /* rows per tile                                                 */
+    int32_t tiles_c;     /* column tiles per row band (each B2_GATHER_COL_BYTES wide)     */
+    int32_t vec_bytes;   /* widest aligned access: 16, 8, 4, 2 or 1                       */
+    int32_t _pad;
+} b2_copy;
+#define B2_GATHER_COL_BYTES 4096
+
+int b2_gather_plan(b2_copy* copies, int n, int64_t* total_tiles);
+int b2_gather_launch(const b2_copy* d_copies, int n, int64_t total_tiles, void* stream);
+
+/* fill a contiguous buffer with one element (Ones/Zeros/Full materialisation,
+ * creation/_ones_zeros.py:17-137) */
+int b2_fill(void* dst, int64_t nelem, int itemsize, const void* value, void* stream);
+
+/* ------------------------------------------------------------------ contraction
+ * matmul / tensordot block GEMM (linalg/_tensordot.py:194-249): C (+)= A @ B^T with
+ * A (M,K) and B (N,K) row-major ("TN"), accumulating over the k block index instead
+ * of materialising the (M,1,N) partials.  dtype B2_BF16: tcgen05 bf16 x bf16 -> fp32;
+ * B2_F32: 3xBF16 split on tcgen05 (documented tolerance).                            */
+int b2_gemm_tn(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb,
+               float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+               int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DA_H */
