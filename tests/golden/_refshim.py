@@ -261,13 +261,30 @@ def parse_bytes(s):
     return int(float(s[:i] or 1) * units[s[i:].lower()])
 
 
+def ndimlist(seq):
+    if not isinstance(seq, (list, tuple)):
+        return 0
+    if len(seq) == 0:
+        return 1
+    return 1 + ndimlist(seq[0])
+
+
+def concrete(seq):
+    if isinstance(seq, Iterator_):
+        seq = list(seq)
+    if isinstance(seq, (tuple, list)):
+        seq = list(map(concrete, seq))
+    return seq
+
+
 _UTILS = dict(
+    ndimlist=ndimlist, concrete=concrete,
     Dispatch=Dispatch, deepmap=deepmap, derived_from=derived_from, funcname=funcname,
     getargspec=getargspec, has_keyword=has_keyword, is_arraylike=is_arraylike,
     cached_cumsum=cached_cumsum, parse_bytes=parse_bytes, cached_property=functools.cached_property,
     is_cupy_type=lambda x: False, is_series_like=lambda x: False, is_dataframe_like=lambda x: False,
-    is_index_like=lambda x: False, format_bytes=lambda n: f"{n} B", ndeepmap=None,
-    typename=lambda t: getattr(t, "__name__", str(t)), concrete=None,
+    is_index_like=lambda x: False, format_bytes=lambda n: f"{n} B",
+    typename=lambda t: getattr(t, "__name__", str(t)),
 )
 
 
