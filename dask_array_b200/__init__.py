@@ -1,1 +1,22 @@
-"""dask_array_b200 -- B200-native execution backend for dask-array's data-parallel hot path."""
+"""dask_array_b200 -- B200-native execution backend for dask-array's data-parallel hot path.
+
+``import dask_array_b200 as da`` gives the subset of ``import dask_array as da`` that
+BASELINE.json's north star names: fused element-wise chains, tree reductions
+(sum/mean/var/std/min/max/argmin/argmax), rechunk / transpose / basic slicing and the blocked
+matmul.  Every result is computed by hand-written sm_100a CUDA kernels behind the C ABI of
+``include/b200da.h``; there is no CPU fallback (importing without the built library fails).
+"""
+from . import _lib  # noqa: F401  (fails loudly when libb200da.so is missing)
+from ._collection import (  # noqa: F401
+    UFUNC_NAMES, Array, _method, _ufunc, asarray, elemwise, from_array, full, matmul, ones, random,
+    rechunk, transpose, where, zeros,
+)
+
+for _n in UFUNC_NAMES:
+    globals()[_n] = _ufunc(_n)
+for _n in ("sum", "prod", "mean", "var", "std", "min", "max", "any", "all", "argmin", "argmax"):
+    globals()[_n] = _method(_n)
+del _n
+
+__all__ = ["Array", "from_array", "asarray", "ones", "zeros", "full", "random", "elemwise", "where",
+           "transpose", "rechunk", "matmul"] + UFUNC_NAMES

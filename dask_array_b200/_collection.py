@@ -1,0 +1,344 @@
+"""``Array`` -- the user-facing collection, API-compatible with ``dask_array.Array`` for the
+hot path (``dask_array/_collection.py:110-1761``): operators build ``Elemwise`` nodes
+(:715-877), methods build reductions (:1300-1500), ``.T`` / ``rechunk`` / basic slices build
+the data-movement nodes, ``compute()`` optimises and runs on the GPU(s), ``persist()`` keeps
+the blocks device-resident under the same expression name (:285-300).
+"""
+from __future__ import annotations
+
+import operator
+from numbers import Integral, Number
+
+import numpy as np
+
+from . import _codegen as cg
+from ._blockwise import Elemwise, Transpose
+from ._expr import ArrayExpr, BroadcastTrick, FromArray, Random, Resident, normalize_chunks
+from ._reductions import Reduction, validate_axis
+
+
+def _as_operand(x):
+    if isinstance(x, Array):
+        return x.expr
+    if isinstance(x, (bool, int, float, np.generic)):
+        return x
+    if isinstance(x, np.ndarray):
+        if x.ndim == 0:
+            return x[()]
+        return FromArray(x, normalize_chunks(x.shape, x.shape))
+    raise TypeError(f"cannot use {type(x).__name__} as an operand of a dask_array_b200 Array")
+
+
+def elemwise(op, *args, **kwargs):
+    """``elemwise()`` (``core/_blockwise_funcs.py:207``)."""
+    name = cg.canonical_name(op)
+    ops = tuple(_as_operand(a) for a in args)
+    if not any(isinstance(o, ArrayExpr) for o in ops):
+        raise TypeError("elemwise needs at least one Array operand")
+    return Array(Elemwise(name, ops, tuple(sorted(kwargs.items()))))
+
+
+class Array:
+    __array_priority__ = 11
+
+    def __init__(self, expr: ArrayExpr):
+        self.expr = expr
+
+    # ---- metadata
+    shape = property(lambda self: self.expr.shape)
+    dtype = property(lambda self: self.expr.dtype)
+    chunks = property(lambda self: self.expr.chunks)
+    ndim = property(lambda self: self.expr.ndim)
+    numblocks = property(lambda self: self.expr.numblocks)
+    size = property(lambda self: self.expr.size)
+    nbytes = property(lambda self: self.expr.nbytes)
+    name = property(lambda self: self.expr._name)
+
+    def __len__(self):
+        if not self.shape:
+            raise TypeError("len() of unsized object")
+        return self.shape[0]
+
+    def __repr__(self):
+        return f"dask_array_b200.Array<{self.name}, shape={self.shape}, dtype={self.dtype}, chunks={self.chunks}>"
+
+    # ---- optimisation / execution
+    def optimize(self, fuse=True):
+        return Array(self.expr.optimize(fuse=fuse))
+
+    def pprint(self):
+        self.expr.pprint()
+
+    def _execute(self):
+        from ._executor import Executor
+
+        opt = self.expr.optimize()
+        ex = Executor()
+        return ex, opt, ex.run(opt)
+
+    def compute(self, **kwargs):
+        from ._executor import gather_to_host
+
+        ex, opt, store = self._execute()
+        return gather_to_host(ex, opt, store)
+
+    def persist(self, **kwargs):
+        """Blocks stay on the GPU(s); the returned Array reads them in place."""
+        ex, opt, store = self._execute()
+        if store.kind != "array":
+            raise NotImplementedError("persist of a partial reduction state")
+        # keep dependencies' buffers alive through the store itself
+        store.keepalive.append([s for s in ex.results.values() if s is not store])
+        return Array(Resident(store, opt.chunks, opt.dtype, self.expr._name))
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.compute()
+        return np.asarray(out, dtype=dtype)
+
+    # ---- element-wise operators (``_collection.py:715-877``)
+    def _bin(self, op, other, reverse=False):
+        if not isinstance(other, (Array, Number, np.generic, np.ndarray, bool)):
+            return NotImplemented
+        return elemwise(op, other, self) if reverse else elemwise(op, self, other)
+
+    __add__ = lambda s, o: s._bin(operator.add, o)
+    __radd__ = lambda s, o: s._bin(operator.add, o, True)
+    __sub__ = lambda s, o: s._bin(operator.sub, o)
+    __rsub__ = lambda s, o: s._bin(operator.sub, o, True)
+    __mul__ = lambda s, o: s._bin(operator.mul, o)
+    __rmul__ = lambda s, o: s._bin(operator.mul, o, True)
+    __truediv__ = lambda s, o: s._bin(operator.truediv, o)
+    __rtruediv__ = lambda s, o: s._bin(operator.truediv, o, True)
+    __floordiv__ = lambda s, o: s._bin(operator.floordiv, o)
+    __rfloordiv__ = lambda s, o: s._bin(operator.floordiv, o, True)
+    __mod__ = lambda s, o: s._bin(operator.mod, o)
+    __rmod__ = lambda s, o: s._bin(operator.mod, o, True)
+    __pow__ = lambda s, o: s._bin(operator.pow, o)
+    __rpow__ = lambda s, o: s._bin(operator.pow, o, True)
+    __and__ = lambda s, o: s._bin(operator.and_, o)
+    __rand__ = lambda s, o: s._bin(operator.and_, o, True)
+    __or__ = lambda s, o: s._bin(operator.or_, o)
+    __ror__ = lambda s, o: s._bin(operator.or_, o, True)
+    __xor__ = lambda s, o: s._bin(operator.xor, o)
+    __rxor__ = lambda s, o: s._bin(operator.xor, o, True)
+    __lshift__ = lambda s, o: s._bin(operator.lshift, o)
+    __rshift__ = lambda s, o: s._bin(operator.rshift, o)
+    __lt__ = lambda s, o: s._bin(operator.lt, o)
+    __le__ = lambda s, o: s._bin(operator.le, o)
+    __gt__ = lambda s, o: s._bin(operator.gt, o)
+    __ge__ = lambda s, o: s._bin(operator.ge, o)
+    __eq__ = lambda s, o: s._bin(operator.eq, o)
+    __ne__ = lambda s, o: s._bin(operator.ne, o)
+    __neg__ = lambda s: elemwise(operator.neg, s)
+    __pos__ = lambda s: elemwise(operator.pos, s)
+    __abs__ = lambda s: elemwise(operator.abs, s)
+    __invert__ = lambda s: elemwise(operator.invert, s)
+    __hash__ = None
+
+    def __matmul__(self, other):
+        from ._matmul import matmul
+
+        return matmul(self, other)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        """``Array.__array_ufunc__`` (:1702): NumPy ufuncs on Arrays stay lazy."""
+        if method != "__call__" or kwargs:
+            return NotImplemented
+        return elemwise(ufunc.__name__, *inputs)
+
+    def astype(self, dtype, **kwargs):
+        """``Array.astype`` (:1569-1609)."""
+        dtype = np.dtype(dtype)
+        if dtype == self.dtype:
+            return self
+        return Array(Elemwise("astype", (self.expr,), (("dtype", dtype.name),)))
+
+    # ---- data movement
+    def transpose(self, *axes):
+        """``Array.transpose`` (:934-953)."""
+        if len(axes) == 1 and isinstance(axes[0], (tuple, list)):
+            axes = tuple(axes[0])
+        if not axes or axes == (None,):
+            axes = tuple(reversed(range(self.ndim)))
+        axes = tuple(a % self.ndim for a in axes)
+        if sorted(axes) != list(range(self.ndim)):
+            raise ValueError("axes don't match array")
+        return Array(Transpose(self.expr, axes))
+
+    T = property(lambda self: self.transpose())
+
+    def rechunk(self, chunks, **kwargs):
+        """``Array.rechunk`` (:1056)."""
+        from ._rechunk import rechunk
+
+        return Array(rechunk(self.expr, chunks))
+
+    def __getitem__(self, index):
+        from ._slicing import SliceSlicesIntegers, normalize_index
+
+        return Array(SliceSlicesIntegers(self.expr, normalize_index(index, self.shape)))
+
+    # ---- reductions (``_collection.py:1300-1500`` -> ``reductions/_common.py``)
+    def _reduce(self, kind, axis=None, keepdims=False, dtype=None, split_every=None, ddof=0):
+        if kind in ("argmin", "argmax") and axis is not None and not isinstance(axis, Integral):
+            raise TypeError(f"axis must be either `None` or int, got '{axis}'")
+        ax = validate_axis(axis, self.ndim)
+        return Array(Reduction(self.expr, kind, ax, bool(keepdims), None if dtype is None else np.dtype(dtype).name,
+                               _freeze(split_every), ddof))
+
+    def sum(self, axis=None, dtype=None, keepdims=False, split_every=None):
+        return self._reduce("sum", axis, keepdims, dtype, split_every)
+
+    def prod(self, axis=None, dtype=None, keepdims=False, split_every=None):
+        return self._reduce("prod", axis, keepdims, dtype, split_every)
+
+    def mean(self, axis=None, dtype=None, keepdims=False, split_every=None):
+        return self._reduce("mean", axis, keepdims, dtype, split_every)
+
+    def var(self, axis=None, dtype=None, keepdims=False, ddof=0, split_every=None):
+        return self._reduce("var", axis, keepdims, dtype, split_every, ddof)
+
+    def std(self, axis=None, dtype=None, keepdims=False, ddof=0, split_every=None):
+        """``std = sqrt(var)`` as an Elemwise on the aggregate (``_common.py:625-653``)."""
+        return elemwise("sqrt", self.var(axis, dtype, keepdims, ddof, split_every))
+
+    def min(self, axis=None, keepdims=False, split_every=None):
+        return self._reduce("min", axis, keepdims, None, split_every)
+
+    def max(self, axis=None, keepdims=False, split_every=None):
+        return self._reduce("max", axis, keepdims, None, split_every)
+
+    def any(self, axis=None, keepdims=False, split_every=None):
+        return self._reduce("any", axis, keepdims, None, split_every)
+
+    def all(self, axis=None, keepdims=False, split_every=None):
+        return self._reduce("all", axis, keepdims, None, split_every)
+
+    def argmin(self, axis=None, keepdims=False, split_every=None):
+        return self._reduce("argmin", axis, keepdims, None, split_every)
+
+    def argmax(self, axis=None, keepdims=False, split_every=None):
+        return self._reduce("argmax", axis, keepdims, None, split_every)
+
+
+def _freeze(split_every):
+    if isinstance(split_every, dict):
+        return dict(split_every)
+    return split_every
+
+
+# ----------------------------------------------------------------------------- creation
+def from_array(x, chunks="auto", **kwargs):
+    """``da.from_array`` (``io/_from_array.py``)."""
+    x = np.asarray(x)
+    if chunks == "auto":
+        chunks = x.shape
+    return Array(FromArray(x, normalize_chunks(chunks, x.shape)))
+
+
+def asarray(x, **kwargs):
+    return x if isinstance(x, Array) else from_array(x, **kwargs)
+
+
+def _creation(value, shape, chunks, dtype):
+    shape = (shape,) if isinstance(shape, Integral) else tuple(shape)
+    if chunks is None:
+        chunks = shape
+    dtype = np.dtype(dtype if dtype is not None else np.float64)
+    return Array(BroadcastTrick(value, shape, normalize_chunks(chunks, shape), dtype.name))
+
+
+def ones(shape, dtype=None, chunks=None, **kw):
+    """``da.ones`` (``creation/_ones_zeros.py:124``)."""
+    return _creation(1, shape, chunks, dtype)
+
+
+def zeros(shape, dtype=None, chunks=None, **kw):
+    return _creation(0, shape, chunks, dtype)
+
+
+def full(shape, fill_value, dtype=None, chunks=None, **kw):
+    if dtype is None:
+        dtype = np.asarray(fill_value).dtype
+    return _creation(fill_value, shape, chunks, dtype)
+
+
+class _RandomGenerator:
+    """``da.random.default_rng(seed)`` (``random/``): per-block ``SeedSequence.spawn`` children."""
+
+    def __init__(self, seed=None):
+        self.seed = 0 if seed is None else seed
+
+    def _make(self, dist, size, chunks, dtype, args=()):
+        shape = (size,) if isinstance(size, Integral) else tuple(size)
+        chunks = normalize_chunks(chunks if chunks is not None and chunks != "auto" else shape, shape)
+        return Array(Random(self.seed, dist, shape, chunks, np.dtype(dtype).name, args))
+
+    def random(self, size=None, dtype=np.float64, chunks="auto", **kw):
+        return self._make("random", size, chunks, dtype)
+
+    def standard_normal(self, size=None, dtype=np.float64, chunks="auto", **kw):
+        return self._make("standard_normal", size, chunks, dtype)
+
+    def integers(self, low, high=None, size=None, dtype=np.int64, chunks="auto", **kw):
+        if high is None:
+            low, high = 0, low
+        return self._make("integers", size, chunks, dtype, (int(low), int(high)))
+
+
+class _RandomModule:
+    default_rng = staticmethod(lambda seed=None: _RandomGenerator(seed))
+
+    @staticmethod
+    def random(size=None, chunks="auto", dtype=np.float64, **kw):
+        return _RandomGenerator(None).random(size, dtype=dtype, chunks=chunks)
+
+
+random = _RandomModule()
+
+
+# ----------------------------------------------------------------------------- free functions
+def _ufunc(name):
+    def f(*args, **kwargs):
+        return elemwise(name, *args, **kwargs)
+    f.__name__ = name
+    f.__doc__ = f"Element-wise ``np.{name}`` (``_ufunc.py:284-392``)."
+    return f
+
+
+UFUNC_NAMES = [
+    "add", "subtract", "multiply", "divide", "true_divide", "floor_divide", "negative", "positive", "power",
+    "float_power", "remainder", "mod", "fmod", "exp", "exp2", "log", "log2", "log10", "log1p", "expm1",
+    "logaddexp", "sqrt", "square", "cbrt", "reciprocal", "sin", "cos", "tan", "arcsin", "arccos", "arctan",
+    "arctan2", "hypot", "sinh", "cosh", "tanh", "arcsinh", "arccosh", "arctanh", "deg2rad", "rad2deg",
+    "degrees", "radians", "greater", "greater_equal", "less", "less_equal", "not_equal", "equal",
+    "logical_and", "logical_or", "logical_xor", "logical_not", "maximum", "minimum", "fmax", "fmin",
+    "bitwise_and", "bitwise_or", "bitwise_xor", "bitwise_not", "invert", "left_shift", "right_shift",
+    "isfinite", "isinf", "isnan", "signbit", "copysign", "nextafter", "floor", "ceil", "trunc", "rint",
+    "fabs", "sign", "absolute", "abs", "clip",
+]
+
+
+def where(cond, x, y):
+    return elemwise("where", cond, x, y)
+
+
+def _method(name):
+    def f(a, *args, **kwargs):
+        return getattr(asarray(a), name)(*args, **kwargs)
+    f.__name__ = name
+    return f
+
+
+def transpose(a, axes=None):
+    return asarray(a).transpose(axes) if axes is not None else asarray(a).transpose()
+
+
+def rechunk(a, chunks, **kw):
+    return asarray(a).rechunk(chunks)
+
+
+def matmul(a, b):
+    from ._matmul import matmul as _mm
+
+    return _mm(asarray(a), asarray(b))

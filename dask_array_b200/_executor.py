@@ -1,0 +1,571 @@
+"""Executor: runs an optimised expression tree on the GPU(s).
+
+Takes the place of the scheduler + task graph of the reference (``dask.threaded.get`` chosen by
+``Array.__dask_scheduler__``, ``_collection.py:111``; graph emission in every ``_layer()``):
+instead of one Python task per block there is ONE kernel launch per (expression, device)
+that covers every resident block.
+
+Placement: blocks are dealt block-cyclically,
+``owner(block) = ravel(block id) mod world``; one process per GPU (``torch.distributed``).
+Per-block partials of a tree reduction are tiny, so they are all-gathered and every rank
+folds the tree redundantly (results replicated); a rechunk / transposed read that crosses
+the partition exchanges the needed blocks over NCCL before the local gather.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import _runtime as rt
+from ._blockwise import FusedBlockwise, FusedPlan
+from ._device import DeviceChunk, alloc_bytes
+from ._expr import ArrayExpr, BroadcastTrick, FromArray, Random, Resident
+from ._rechunk import TasksRechunk
+from ._reductions import REDOPS, ArgChunk, ChunkReduce, PartialReduce
+from ._slicing import SliceSlicesIntegers
+
+
+class BlockStore:
+    """Blocks of one expression held by this rank.  ``kind``: array | mean | moment | arg."""
+
+    def __init__(self, expr, kind="array", replicated=False):
+        self.expr = expr
+        self.kind = kind
+        self.replicated = replicated
+        self.blocks = {}          # bid -> DeviceChunk | dict
+        self.keepalive = []       # launch tables / pointer tables the stream may still read
+
+
+class World:
+    """Process group facts.  world == 1 needs no torch.distributed at all."""
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.size = dist.get_rank(), dist.get_world_size()
+        else:
+            self.rank, self.size = 0, 1
+
+    def owner(self, expr, bid) -> int:
+        if self.size == 1:
+            return 0
+        nb = expr.numblocks
+        flat = int(np.ravel_multi_index(bid, nb)) if nb else 0
+        return flat % self.size
+
+
+_PLAN_CACHE: dict = {}
+
+
+class Executor:
+    def __init__(self, world: World | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dask_array_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self.world = world or World()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.results: dict[str, BlockStore] = {}
+
+    # ------------------------------------------------------------------ driver
+    def run(self, expr: ArrayExpr) -> BlockStore:
+        if expr._name in self.results:
+            return self.results[expr._name]
+        for dep in expr.dependencies():
+            self.run(dep)
+        fn = getattr(self, "_run_" + type(expr).__name__, None)
+        if fn is None:
+            raise NotImplementedError(
+                f"{type(expr).__name__} has no B200 execution path (optimise the expression first; "
+                "there is no CPU fallback)")
+        store = fn(expr)
+        self.results[expr._name] = store
+        return store
+
+    def mine(self, expr, bid) -> bool:
+        return self.world.owner(expr, bid) == self.world.rank
+
+    # ------------------------------------------------------------------ leaves
+    def _run_FromArray(self, expr):
+        st = BlockStore(expr)
+        arr = expr.operand("array")
+        for bid in expr.block_ids():
+            if not self.mine(expr, bid):
+                continue
+            start, shape = expr.block_start(bid), expr.block_shape(bid)
+            sl = tuple(slice(s, s + n) for s, n in zip(start, shape))
+            st.blocks[bid] = DeviceChunk.from_numpy(arr[sl], self.device)
+        return st
+
+    def _run_Random(self, expr):
+        st = BlockStore(expr)
+        for bid in expr.block_ids():
+            if self.mine(expr, bid):
+                st.blocks[bid] = DeviceChunk.from_numpy(expr.host_block(bid), self.device)
+        return st
+
+    def _run_Resident(self, expr):
+        return expr.operand("store")
+
+    def _run_BroadcastTrick(self, expr):
+        """A constant leaf that was NOT fused (e.g. evicted by the ``a + a.T`` conflict rule):
+        materialise it with the fill kernel."""
+        st = BlockStore(expr)
+        for bid in expr.block_ids():
+            if self.mine(expr, bid):
+                c = DeviceChunk.empty(expr.block_shape(bid), expr.dtype, self.device)
+                if c.size:
+                    rt.fill(c, expr.operand("value"))
+                st.blocks[bid] = c
+        return st
+
+    # ------------------------------------------------------------------ views
+    def _run_SliceSlicesIntegers(self, expr):
+        src = self.results[expr.operand("array")._name]
+        st = BlockStore(expr)
+        x = expr.operand("array")
+        for bid in expr.block_ids():
+            ibid, idx = expr.source(bid)
+            if self.world.size > 1 and not src.replicated and self.world.owner(x, ibid) != self.world.owner(expr, bid):
+                raise NotImplementedError("slice that moves blocks between GPUs (rechunk first)")
+            if ibid in src.blocks and (src.replicated or self.mine(expr, bid)):
+                st.blocks[bid] = src.blocks[ibid][idx]
+        st.replicated = src.replicated
+        return st
+
+    # ------------------------------------------------------------------ fused blockwise
+    def _fetch_remote(self, needs):
+        """needs: {(dep expr name): set(block ids)} this rank must read but does not own.
+        All ranks call this with their own needs; the schedule is derived symmetrically."""
+        raise NotImplementedError
+
+    def _run_FusedBlockwise(self, expr: FusedBlockwise):
+        key = expr._name
+        plan = _PLAN_CACHE.get(key)
+        if plan is None:
+            plan = _PLAN_CACHE[key] = FusedPlan(expr)
+        red = plan.reduce
+        top = plan.eval_expr
+        kind = red.operand("kind") if red is not None else None
+        store_kind = {"mean": "mean", "var": "moment"}.get(kind, "array")
+        st = BlockStore(expr, store_kind)
+        deps = [self.results[dep._name] for dep, _ in plan.leaves]
+        out_ids = [bid for bid in expr.block_ids() if self.mine(expr, bid)]
+        # ---- blocks of dependencies living on other GPUs (e.g. x.T + x across the partition)
+        extra = self._exchange_for_fused(plan, deps, out_ids) if self.world.size > 1 else {}
+        blocks = []
+        axes = red.operand("axis") if red is not None else ()
+        acc_dtype = None
+        for bid in out_ids:
+            shape = top.block_shape(bid) if red is not None else expr.block_shape(bid)
+            if math.prod(shape) == 0:
+                st.blocks[bid] = self._empty_result(expr, bid, store_kind)
+                continue
+            ins = []
+            for k, (dep, _) in enumerate(plan.leaves):
+                lbid = plan.leaf_block_id(k, bid)
+                src = deps[k].blocks.get(lbid)
+                if src is None:
+                    src = extra.get((dep._name, lbid))
+                if src is None:
+                    raise RuntimeError(f"block {lbid} of {dep._name} is not resident on rank {self.world.rank}")
+                ins.append((src.ptr, plan.leaf_strides(k, src, len(shape))))
+            out_shape = expr.block_shape(bid)
+            if red is None:
+                out = DeviceChunk.empty(out_shape, expr.dtype, self.device)
+                blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
+                st.blocks[bid] = out
+            elif kind == "var":
+                out = DeviceChunk.empty(tuple(out_shape) + (3,), np.float64, self.device)
+                acc_dtype = np.float32 if plan.program.out_dtype == np.float32 else np.float64
+                blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
+                st.blocks[bid] = out
+            elif kind == "mean":
+                out = DeviceChunk.empty(out_shape, red.dtype, self.device)
+                acc_dtype = red.dtype
+                blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
+                n = math.prod(shape[a] for a in axes)
+                st.blocks[bid] = {"total": out, "n": n}
+            else:
+                out = DeviceChunk.empty(out_shape, red.dtype, self.device)
+                acc_dtype = red.dtype
+                blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
+                st.blocks[bid] = out
+        if blocks:
+            launch = rt.FusedLaunch(plan.program, REDOPS[kind] if red is not None else _lib.RED_NONE,
+                                    axes, blocks, acc_dtype=acc_dtype)
+            launch.run()
+            st.keepalive.append(launch)
+            st.keepalive.append(extra)
+        return st
+
+    def _empty_result(self, expr, bid, kind):
+        shape = expr.block_shape(bid)
+        if kind == "moment":
+            c = DeviceChunk.empty(tuple(shape) + (3,), np.float64, self.device)
+            c.buf.zero_()
+            return c
+        c = DeviceChunk.empty(shape, expr.dtype, self.device)
+        c.buf.zero_()
+        return {"total": c, "n": 0} if kind == "mean" else c
+
+    # ------------------------------------------------------------------ arg reductions
+    def _run_ArgChunk(self, expr: ArgChunk):
+        from . import _codegen as cg
+
+        x = expr.operand("array")
+        src = self.results[x._name]
+        kind, axis, ravel = expr.operand("kind"), expr.operand("axis"), expr.operand("ravel")
+        prog = cg.Program()
+        prog.set_output(prog.op("positive", prog.add_input(x.dtype)))
+        st = BlockStore(expr, "arg")
+        blocks = []
+        for bid in x.block_ids():
+            if not self.mine(x, bid):
+                continue
+            c = src.blocks[bid]
+            oshape = expr.block_shape(bid)
+            vals = DeviceChunk.empty(oshape, x.dtype, self.device)
+            arg = DeviceChunk.empty(oshape, np.int64, self.device)
+            start = x.block_start(bid)
+            kw = {}
+            if ravel:
+                kw["arg_ravel"] = (c.shape, start, x.shape)
+            else:
+                kw["arg_offset"] = start[axis[0]]
+            blocks.append(rt.BlockArgs(shape=c.shape, inputs=[(c.ptr, c.strides)], out0=vals.ptr, out1=arg.ptr, **kw))
+            st.blocks[bid] = {"vals": vals, "arg": arg}
+        if blocks:
+            launch = rt.FusedLaunch(prog, REDOPS[kind], axis, blocks)
+            launch.run()
+            st.keepalive.append(launch)
+        return st
+
+    # ------------------------------------------------------------------ tree levels
+    def _gather_partials(self, src: BlockStore, x):
+        """Make every partial block of ``x`` available on this rank (all-gather over NCCL)."""
+        if self.world.size == 1 or src.replicated:
+            return src.blocks
+        return _allgather_blocks(self, src, x)
+
+    def _run_PartialReduce(self, expr: PartialReduce):
+        x = expr.operand("array")
+        src = self.results[x._name]
+        kind, final = expr.operand("kind"), expr.operand("final")
+        parts = self._gather_partials(src, x)
+        redop = REDOPS[kind]
+        st = BlockStore(expr, src.kind if not final else "array", replicated=True)
+        in_dtype = x.dtype if not isinstance(x, (ChunkReduce, ArgChunk)) else None
+        for key, members in expr.groups():
+            blks = [parts[m] for m in members]
+            first = blks[0]
+            if src.kind == "mean":
+                tot0 = first["total"]
+                n = sum(b["n"] for b in blks)
+                out = DeviceChunk.empty(tot0.shape if not final else self._final_shape(expr, tot0.shape),
+                                        expr.dtype if final else tot0.dtype, self.device)
+                tab = rt.combine(_lib.RED_SUM, tot0.dtype, [b["total"].ptr for b in blks], None, tot0.size, out.ptr,
+                                 post=_lib.POST_MEAN if final else _lib.POST_NONE, out_dtype=expr.dtype, count=n)
+                st.blocks[key] = out if final else {"total": out, "n": n}
+            elif src.kind == "moment":
+                nelem = first.size // 3
+                if final:
+                    out = DeviceChunk.empty(self._final_shape(expr, first.shape[:-1]), expr.dtype, self.device)
+                    tab = rt.combine(_lib.RED_MOMENT, np.float64, [b.ptr for b in blks], None, nelem, out.ptr,
+                                     post=_lib.POST_VAR, out_dtype=expr.dtype, ddof=expr.operand("ddof"))
+                else:
+                    out = DeviceChunk.empty(first.shape, np.float64, self.device)
+                    tab = rt.combine(_lib.RED_MOMENT, np.float64, [b.ptr for b in blks], None, nelem, out.ptr)
+                st.blocks[key] = out
+            elif src.kind == "arg":
+                v0 = first["vals"]
+                vals = DeviceChunk.empty(v0.shape, v0.dtype, self.device)
+                arg = DeviceChunk.empty(self._final_shape(expr, v0.shape) if final else v0.shape, np.int64, self.device)
+                tab = rt.combine(redop, v0.dtype, [b["vals"].ptr for b in blks], [b["arg"].ptr for b in blks],
+                                 v0.size, vals.ptr, arg.ptr)
+                st.blocks[key] = arg if final else {"vals": vals, "arg": arg}
+            else:
+                out = DeviceChunk.empty(self._final_shape(expr, first.shape) if final else first.shape,
+                                        first.dtype, self.device)
+                tab = rt.combine(redop, first.dtype, [b.ptr for b in blks], None, first.size, out.ptr)
+                st.blocks[key] = out
+            st.keepalive.append(tab)
+            st.keepalive.append(blks)
+        return st
+
+    @staticmethod
+    def _final_shape(expr: PartialReduce, kd_shape):
+        if expr.operand("keepdims"):
+            return tuple(kd_shape)
+        se = expr.operand("split_every")
+        return tuple(n for d, n in enumerate(kd_shape) if d not in se)
+
+    # ------------------------------------------------------------------ rechunk
+    def _run_TasksRechunk(self, expr: TasksRechunk):
+        x = expr.operand("array")
+        src = self.results[x._name]
+        st = BlockStore(expr)
+        item = expr.dtype.itemsize
+        new_ids = [bid for bid in expr.block_ids() if self.mine(expr, bid)]
+        remote = {}
+        if self.world.size > 1 and not src.replicated:
+            remote = _exchange_for_rechunk(self, expr, src, new_ids)
+        copies = []
+        for nbid in new_ids:
+            out = DeviceChunk.empty(expr.block_shape(nbid), expr.dtype, self.device)
+            st.blocks[nbid] = out
+            for obid, sl, dsl in expr.pieces(nbid):
+                blk = src.blocks.get(obid)
+                if blk is not None:
+                    piece = blk[sl]
+                else:
+                    piece = remote[(obid, nbid)]          # already cut to the piece on the sender
+                copies.extend(_copy_descs(piece, out[dsl], item))
+        launch = rt.GatherLaunch(copies)
+        launch.run()
+        st.keepalive.extend([launch, remote])
+        return st
+
+    # ------------------------------------------------------------------ multi-GPU exchange (fused)
+    def _exchange_for_fused(self, plan, deps, out_ids):
+        return _exchange_for_fused(self, plan, deps, out_ids)
+
+
+def _copy_descs(src: DeviceChunk, dst: DeviceChunk, item: int):
+    """2-D copy rectangles moving ``src`` into ``dst`` (same shape, arbitrary strides with a
+    unit-stride innermost run)."""
+    shape = [n for n in src.shape]
+    if math.prod(shape) == 0:
+        return []
+    dims = [(n, s, d) for n, s, d in zip(shape, src.strides, dst.strides) if n != 1]
+    if not dims:
+        return [(src.ptr, dst.ptr, 1, item, item, item)]
+    merged = []
+    for n, s, d in dims:
+        if merged and merged[-1][1] == s * n and merged[-1][2] == d * n:
+            merged[-1] = (merged[-1][0] * n, s, d)
+        else:
+            merged.append((n, s, d))
+    n_in, s_in, d_in = merged[-1]
+    if s_in != 1 or d_in != 1:
+        raise NotImplementedError("gather needs a unit-stride innermost dimension on both sides")
+    outer = merged[:-1]
+    if not outer:
+        return [(src.ptr, dst.ptr, 1, n_in * item, n_in * item, n_in * item)]
+    rows, s_row, d_row = outer[-1]
+    lead = outer[:-1]
+    out = []
+    for idx in itertools.product(*[range(n) for n, _, _ in lead]):
+        so = sum(i * s for i, (_, s, _) in zip(idx, lead))
+        do = sum(i * d for i, (_, _, d) in zip(idx, lead))
+        out.append((src.ptr + so * item, dst.ptr + do * item, rows, n_in * item, s_row * item, d_row * item))
+    return out
+
+
+# ----------------------------------------------------------------------------- NCCL plumbing
+def _allgather_blocks(ex: Executor, src: BlockStore, x):
+    """All-gather the (tiny) per-block partials of ``x`` so every rank can fold the tree."""
+    import torch.distributed as dist
+
+    W, me = ex.world.size, ex.world.rank
+    ids = list(x.block_ids())
+
+    def fields(b):
+        if isinstance(b, dict):
+            return [(k, v) for k, v in sorted(b.items()) if isinstance(v, DeviceChunk)]
+        return [("", b)]
+
+    # layout is derivable on every rank from shapes alone
+    def proto(bid):
+        kshape = x.block_shape(bid)
+        if src.kind == "moment":
+            return [("", tuple(kshape) + (3,), np.dtype(np.float64))]
+        if src.kind == "mean":
+            return [("total", kshape, x.dtype)]
+        if src.kind == "arg":
+            vdt = x.operand("array").dtype
+            return [("arg", kshape, np.dtype(np.int64)), ("vals", kshape, vdt)]
+        return [("", kshape, x.dtype)]
+
+    def nbytes(bid):
+        return sum(-(-math.prod(s) * d.itemsize // 16) * 16 for _, s, d in proto(bid))
+
+    per_rank = [sum(nbytes(b) for b in ids if ex.world.owner(x, b) == r) for r in range(W)]
+    cap = max(max(per_rank), 16)
+    send = alloc_bytes(cap, ex.device)
+    off = 0
+    copies = []
+    for bid in ids:
+        if ex.world.owner(x, bid) != me:
+            continue
+        blk = src.blocks[bid]
+        for (name, chunk), (_, shp, dt) in zip(fields(blk), proto(bid)):
+            nb = math.prod(shp) * dt.itemsize
+            if nb:
+                copies.append((chunk.ptr, send.data_ptr() + off, 1, nb, nb, nb))
+            off += -(-nb // 16) * 16
+    g = rt.GatherLaunch(copies)
+    g.run()
+    recv = alloc_bytes(cap * W, ex.device)
+    dist.all_gather_into_tensor(recv, send)
+    out = {}
+    offs = [0] * W
+    for bid in ids:
+        r = ex.world.owner(x, bid)
+        parts = {}
+        for name, shp, dt in proto(bid):
+            nb = math.prod(shp) * dt.itemsize
+            parts[name] = DeviceChunk(recv, shp, dt, offset=(r * cap + offs[r]) // dt.itemsize)
+            offs[r] += -(-nb // 16) * 16
+        if src.kind == "mean":
+            axes = x.operand("axis")
+            top = x.operand("array")
+            n = math.prod(top.block_shape(bid)[a] for a in axes)
+            out[bid] = {"total": parts["total"], "n": n}
+        elif src.kind == "arg":
+            out[bid] = parts
+        else:
+            out[bid] = parts[""]
+    src.keepalive.extend([send, recv, g])
+    return out
+
+
+def _p2p_exchange(ex: Executor, sends, recvs):
+    """sends: [(peer, tensor)], recvs: [(peer, tensor)] in a globally consistent order."""
+    import torch.distributed as dist
+
+    ops = [dist.P2POp(dist.isend, t, p) for p, t in sends] + [dist.P2POp(dist.irecv, t, p) for p, t in recvs]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def _exchange_for_fused(ex: Executor, plan: FusedPlan, deps, out_ids):
+    """Blocks of dependencies that some rank's output blocks read but another rank owns are
+    packed per peer, exchanged and exposed as DeviceChunks.  Every rank derives the complete
+    schedule from the (replicated) expression metadata, so no negotiation is needed."""
+    W, me = ex.world.size, ex.world.rank
+    expr = plan.fused
+    # (reader rank, dep index k, leaf block id) for every non-local read, in canonical order
+    wanted = {}
+    for bid in expr.block_ids():
+        r = ex.world.owner(expr, bid)
+        for k, (dep, _) in enumerate(plan.leaves):
+            if deps[k].replicated:
+                continue
+            lbid = plan.leaf_block_id(k, bid)
+            o = ex.world.owner(dep, lbid)
+            if o != r:
+                wanted[(r, dep._name, lbid)] = (o, k)
+    if not wanted:
+        return {}
+    keys = sorted(wanted)
+    send_items = {p: [] for p in range(W)}
+    recv_items = {p: [] for p in range(W)}
+    for (r, name, lbid) in keys:
+        o, k = wanted[(r, name, lbid)]
+        dep = plan.leaves[k][0]
+        nb = math.prod(dep.block_shape(lbid)) * dep.dtype.itemsize
+        if o == me:
+            send_items[r].append((k, lbid, nb))
+        if r == me:
+            recv_items[o].append((k, lbid, nb, name))
+    pad = lambda n: -(-n // 256) * 256
+    sends, recvs, keep, out = [], [], [], {}
+    for p in range(W):
+        if send_items[p]:
+            buf = alloc_bytes(sum(pad(nb) for _, _, nb in send_items[p]), ex.device)
+            off, copies = 0, []
+            for k, lbid, nb in send_items[p]:
+                blk = deps[k].blocks[lbid]
+                flat = DeviceChunk(buf, blk.shape, blk.dtype, offset=off // blk.itemsize)
+                copies.extend(_copy_descs(blk, flat, blk.itemsize))
+                off += pad(nb)
+            g = rt.GatherLaunch(copies)
+            g.run()
+            keep.append(g)
+            sends.append((p, buf))
+        if recv_items[p]:
+            buf = alloc_bytes(sum(pad(nb) for _, _, nb, _ in recv_items[p]), ex.device)
+            off = 0
+            for k, lbid, nb, name in recv_items[p]:
+                dep = plan.leaves[k][0]
+                out[(name, lbid)] = DeviceChunk(buf, dep.block_shape(lbid), dep.dtype, offset=off // dep.dtype.itemsize)
+                off += pad(nb)
+            recvs.append((p, buf))
+    _p2p_exchange(ex, sends, recvs)
+    out["__keep__"] = (keep, sends, recvs)
+    return out
+
+
+def _exchange_for_rechunk(ex: Executor, expr: TasksRechunk, src: BlockStore, new_ids):
+    """All-to-all of the rectangles a rechunk moves across the partition: pack (gather kernel)
+    -> NCCL send/recv -> the local gather reads the received pieces in place."""
+    W, me = ex.world.size, ex.world.rank
+    x = expr.operand("array")
+    item = expr.dtype.itemsize
+    pad = lambda n: -(-n // 256) * 256
+    send_items = {p: [] for p in range(W)}
+    recv_items = {p: [] for p in range(W)}
+    for nbid in expr.block_ids():
+        r = ex.world.owner(expr, nbid)
+        for obid, sl, dsl in expr.pieces(nbid):
+            o = ex.world.owner(x, obid)
+            if o == r:
+                continue
+            shape = tuple(s.stop - s.start for s in sl)
+            nb = math.prod(shape) * item
+            if o == me:
+                send_items[r].append((obid, nbid, sl, shape, nb))
+            if r == me:
+                recv_items[o].append((obid, nbid, shape, nb))
+    sends, recvs, keep, out = [], [], [], {}
+    for p in range(W):
+        if send_items[p]:
+            buf = alloc_bytes(sum(pad(nb) for *_, nb in send_items[p]), ex.device)
+            off, copies = 0, []
+            for obid, nbid, sl, shape, nb in send_items[p]:
+                piece = src.blocks[obid][sl]
+                flat = DeviceChunk(buf, shape, expr.dtype, offset=off // item)
+                copies.extend(_copy_descs(piece, flat, item))
+                off += pad(nb)
+            g = rt.GatherLaunch(copies)
+            g.run()
+            keep.append(g)
+            sends.append((p, buf))
+        if recv_items[p]:
+            buf = alloc_bytes(sum(pad(nb) for *_, nb in recv_items[p]), ex.device)
+            off = 0
+            for obid, nbid, shape, nb in recv_items[p]:
+                out[(obid, nbid)] = DeviceChunk(buf, shape, expr.dtype, offset=off // item)
+                off += pad(nb)
+            recvs.append((p, buf))
+    _p2p_exchange(ex, sends, recvs)
+    out["__keep__"] = (keep, sends, recvs)
+    return out
+
+
+# ----------------------------------------------------------------------------- results to host
+def gather_to_host(ex: Executor, expr: ArrayExpr, store: BlockStore) -> np.ndarray:
+    """finalize -> concatenate3 (``_core_utils.py:1426-1448``): assemble the blocks on the host.
+    With several ranks every rank returns the full array (blocks travel as host objects)."""
+    torch.cuda.synchronize()
+    local = {bid: blk.to_numpy() for bid, blk in store.blocks.items()}
+    if ex.world.size > 1 and not store.replicated:
+        import torch.distributed as dist
+
+        allb = [None] * ex.world.size
+        dist.all_gather_object(allb, local)
+        local = {k: v for d in allb for k, v in d.items()}
+    if expr.ndim == 0:
+        return local[()].reshape(())[()]
+    out = np.empty(expr.shape, dtype=expr.dtype)
+    for bid in expr.block_ids():
+        start, shape = expr.block_start(bid), expr.block_shape(bid)
+        if math.prod(shape) == 0:
+            continue
+        out[tuple(slice(s, s + n) for s, n in zip(start, shape))] = local[bid]
+    return out

@@ -1,0 +1,169 @@
+"""API-level parity on the GPU: ``import dask_array_b200 as da`` against the oracle (the NumPy
+restatement of the reference's threaded compute) on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): slicing, rechunk, integer ops, min/max and arg
+reductions bit-exact; fp32 reductions rtol 1e-5; fp64 reductions rtol 1e-12."""
+import numpy as np
+import pytest
+
+from oracle import reference as ref
+
+pytestmark = pytest.mark.gpu
+
+RTOL32, RTOL64 = 1e-5, 1e-12
+
+
+@pytest.fixture(scope="module")
+def da():
+    import dask_array_b200 as da
+    return da
+
+
+def test_readme_example(da):
+    x = da.ones((1000, 1000), chunks=(100, 100))
+    y = (x + x.T)[:100, :100]
+    out = y.compute()
+    assert out.shape == (100, 100) and out.dtype == np.float64
+    assert np.array_equal(out, np.full((100, 100), 2.0))
+    s = (x + x.T).sum().compute()
+    assert s == 2_000_000.0 and s.dtype == np.float64
+
+
+@pytest.mark.parametrize("shape,chunks", [((1024, 768), (256, 256)), ((1000, 700), (300, 256)), ((513, 129), (128, 64))])
+def test_fused_chain_mean_std(da, shape, chunks):
+    xh = np.random.default_rng(0).random(shape, dtype=np.float32)
+    x = da.from_array(xh, chunks=chunks)
+    y = da.sin(x) * 2 + x**2
+    want_mean, want_std = ref.fused_chain_mean_std(xh, chunks)
+    got_mean, got_std = y.mean(axis=0).compute(), y.std().compute()
+    assert got_mean.dtype == want_mean.dtype == np.float32 and got_mean.shape == want_mean.shape
+    np.testing.assert_allclose(got_mean, want_mean, rtol=RTOL32)
+    np.testing.assert_allclose(got_std, want_std, rtol=RTOL32)
+    # against an fp64 ground truth as well
+    y64 = np.sin(xh.astype(np.float64)) * 2 + xh.astype(np.float64) ** 2
+    np.testing.assert_allclose(got_mean, y64.mean(axis=0), rtol=RTOL32)
+    np.testing.assert_allclose(got_std, y64.std(), rtol=RTOL32)
+    # the element-wise chain itself: +,-,* exact, sin within 2 ulp of NumPy's
+    got = y.compute()
+    np.testing.assert_allclose(got, np.sin(xh) * 2 + xh**2, rtol=3e-7)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32", "int32", "int64"])
+def test_reductions_2d(da, dtype):
+    rng = np.random.default_rng(1)
+    xh = (rng.random((300, 420)) * 200 - 100).astype(dtype)
+    chunks = (128, 100)
+    x = da.from_array(xh, chunks=chunks)
+    b = ref.Blocked.from_array(xh, chunks)
+    rtol = RTOL64 if dtype != "float32" else RTOL32
+    for axis in (None, 0, 1, (0, 1)):
+        for kd in (False, True):
+            got = x.sum(axis=axis, keepdims=kd).compute()
+            want = ref.da_sum(b, axis=axis, keepdims=kd)
+            assert got.dtype == want.dtype and got.shape == np.shape(want)
+            if np.dtype(dtype).kind == "i":
+                assert np.array_equal(got, want)
+            else:
+                np.testing.assert_allclose(got, want, rtol=rtol * 10, atol=1e-9 if dtype == "float64" else 1e-2)
+            got, want = x.mean(axis=axis, keepdims=kd).compute(), ref.da_mean(b, axis=axis, keepdims=kd)
+            assert got.dtype == want.dtype
+            np.testing.assert_allclose(got, want, rtol=rtol * 10, atol=1e-9 if dtype != "float32" else 1e-4)
+            for ddof in (0, 1):
+                got = x.var(axis=axis, keepdims=kd, ddof=ddof).compute()
+                want = ref.da_var(b, axis=axis, keepdims=kd, ddof=ddof)
+                assert got.dtype == want.dtype
+                np.testing.assert_allclose(got, want, rtol=max(rtol, 1e-11))
+            np.testing.assert_allclose(x.std(axis=axis, keepdims=kd).compute(), ref.da_std(b, axis=axis, keepdims=kd),
+                                       rtol=max(rtol, 1e-11))
+            assert np.array_equal(x.min(axis=axis, keepdims=kd).compute(), ref.da_min(b, axis=axis, keepdims=kd))
+            assert np.array_equal(x.max(axis=axis, keepdims=kd).compute(), ref.da_max(b, axis=axis, keepdims=kd))
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32", "int16"])
+@pytest.mark.parametrize("split_every", [None, 2])
+def test_arg_reductions_bit_exact(da, dtype, split_every):
+    rng = np.random.default_rng(2)
+    xh = np.floor(rng.random((260, 330)) * 40).astype(dtype)     # many ties
+    if np.dtype(dtype).kind == "f":
+        xh[5, 7] = np.nan; xh[5, 200] = np.nan; xh[9, 3] = np.inf; xh[11, 300] = -np.inf; xh[200, :] = 3.0
+    chunks = (100, 64)
+    x = da.from_array(xh, chunks=chunks)
+    b = ref.Blocked.from_array(xh, chunks)
+    for axis in (None, 0, 1):
+        for fn, rfn in (("argmax", ref.da_argmax), ("argmin", ref.da_argmin)):
+            got = getattr(x, fn)(axis=axis, split_every=split_every).compute()
+            want = rfn(b, axis=axis, split_every=split_every)
+            assert got.dtype == np.int64
+            assert np.array_equal(got, want), (fn, axis)
+            assert np.array_equal(got, getattr(np, fn)(xh, axis=axis))
+    assert np.array_equal(x.max(axis=1).compute(), xh.max(axis=1), equal_nan=True)
+    assert np.array_equal(x.min(axis=0).compute(), xh.min(axis=0), equal_nan=True)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "int32", "float64", "uint8"])
+def test_rechunk_and_transpose_bit_exact(da, dtype):
+    n = 512
+    xh = np.arange(n * n).reshape(n, n).astype(dtype)
+    x = da.from_array(xh, chunks=(n, 16))
+    r = x.rechunk((16, n))
+    assert r.chunks == ((16,) * 32, (n,))
+    assert np.array_equal(r.compute(), xh)
+    want = ref.rechunk(ref.Blocked.from_array(xh, (n, 16)), (16, n))
+    assert np.array_equal(r.compute(), want.to_array())
+    # ragged both ways
+    xr = da.from_array(xh[:500, :300], chunks=(130, 70))
+    assert np.array_equal(xr.rechunk((64, 300)).compute(), xh[:500, :300])
+    assert np.array_equal(xr.rechunk({0: 499}).compute(), xh[:500, :300])
+    # x.T + x (square chunks: fused transpose) and non-square chunks (rechunk inserted)
+    sq = da.from_array(xh, chunks=(128, 128))
+    assert np.array_equal((sq.T + sq).compute(), xh.T + xh)
+    assert np.array_equal((x.T + x).compute(), xh.T + xh)
+    assert np.array_equal(sq.T.compute(), xh.T)
+
+
+def test_integer_ops_bit_exact(da):
+    rng = np.random.default_rng(3)
+    ah = rng.integers(-1000, 1000, (200, 300)).astype(np.int32)
+    bh = rng.integers(1, 50, (200, 300)).astype(np.int64)
+    a, b = da.from_array(ah, chunks=(64, 128)), da.from_array(bh, chunks=(64, 128))
+    cases = {
+        "floordiv": (a // b, ah // bh), "mod": (a % b, ah % bh), "pow": (a ** 2, ah ** 2),
+        "mix": ((a * 3 - b) // 7, (ah * 3 - bh) // 7), "truediv": (a / b, ah / bh),
+        "cmp": ((a > 5) & (b < 30), (ah > 5) & (bh < 30)), "neg": (-a, -ah), "abs": (abs(a), abs(ah)),
+        "shift": ((a << 3) >> 1, (ah << 3) >> 1), "where": (da.where(a > 0, a, b), np.where(ah > 0, ah, bh)),
+        "astype": (a.astype("float32"), ah.astype("float32")), "xor": (a ^ 12345, ah ^ 12345),
+        "bcast": (a + b[0:1, :], ah + bh[0:1, :]),
+    }
+    for name, (got, want) in cases.items():
+        g = got.compute()
+        assert g.dtype == want.dtype, (name, g.dtype, want.dtype)
+        assert np.array_equal(g, want), name
+
+
+def test_slicing_bit_exact(da):
+    xh = np.arange(300 * 200, dtype=np.float64).reshape(300, 200)
+    x = da.from_array(xh, chunks=(64, 64))
+    for idx in [(slice(10, 250), slice(5, 199)), (slice(0, 64), slice(64, 128)), (7, slice(None)), (slice(100, 101), 3)]:
+        assert np.array_equal(x[idx].compute(), xh[idx])
+    y = (x + 1)[10:100, 20:30]
+    assert np.array_equal(y.compute(), (xh + 1)[10:100, 20:30])
+    assert np.array_equal((x + x)[:5].sum(axis=0).compute(), (xh + xh)[:5].sum(axis=0))
+
+
+def test_persist_keeps_blocks_resident(da):
+    from dask_array_b200 import _lib
+    xh = np.random.default_rng(4).random((256, 256), dtype=np.float32)
+    x = da.from_array(xh, chunks=(64, 64)).persist()
+    before = _lib.launch_count()
+    m1 = (x * 2).sum().compute()
+    assert _lib.launch_count() > before
+    np.testing.assert_allclose(m1, (xh * 2).sum(dtype=np.float32), rtol=RTOL32)
+    np.testing.assert_allclose(x.mean().compute(), xh.mean(), rtol=RTOL32)
+
+
+def test_unsupported_fails_loudly(da):
+    x = da.from_array(np.zeros((8, 8)), chunks=(4, 4))
+    with pytest.raises(NotImplementedError):
+        x[::2]
+    with pytest.raises(NotImplementedError):
+        da.elemwise("frexp", x).compute()
