@@ -195,10 +195,10 @@ class Executor:
                 blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
                 st.blocks[bid] = out
         if blocks:
-            launch = rt.FusedLaunch(plan.program, REDOPS[kind] if red is not None else _lib.RED_NONE,
-                                    axes, blocks, acc_dtype=acc_dtype)
-            launch.run()
-            st.keepalive.append(launch)
+            for launch in rt.fused_launches(plan.program, REDOPS[kind] if red is not None else _lib.RED_NONE,
+                                            axes, blocks, acc_dtype=acc_dtype):
+                launch.run()
+                st.keepalive.append(launch)
             st.keepalive.append(extra)
         return st
 
@@ -239,9 +239,9 @@ class Executor:
             blocks.append(rt.BlockArgs(shape=c.shape, inputs=[(c.ptr, c.strides)], out0=vals.ptr, out1=arg.ptr, **kw))
             st.blocks[bid] = {"vals": vals, "arg": arg}
         if blocks:
-            launch = rt.FusedLaunch(prog, REDOPS[kind], axis, blocks)
-            launch.run()
-            st.keepalive.append(launch)
+            for launch in rt.fused_launches(prog, REDOPS[kind], axis, blocks):
+                launch.run()
+                st.keepalive.append(launch)
         return st
 
     # ------------------------------------------------------------------ tree levels

@@ -183,6 +183,12 @@ class FusedLaunch:
             layouts.append(cls.pop() if len(cls) == 1 else "G")
         sizes = [d.itemsize for d in program.inputs] + ([out_dt.itemsize] if self.mode == _lib.MODE_EW else [])
         vmax = max(1, 16 // max(sizes or [out_dt.itemsize]))
+        if self.mode == _lib.MODE_R:
+            # the row-lane fold stages 256 x V partials in (static) shared memory: keep <= 32 KiB
+            probe = cg.KernelSpec("", (), self.mode, redop, 1, 1, 1, 1, 1, acc_dtype.name)
+            pb = max(1, cg.packed_bytes(probe, out_dt))
+            while vmax > 1 and 256 * vmax * pb > 32768:
+                vmax //= 2
 
         def vec_fits(v):
             for b, c in zip(blocks, canons):
@@ -255,6 +261,16 @@ class FusedLaunch:
         st = current_stream_ptr() if stream is None else stream
         _lib.check(_lib.lib.b2_fused_launch(self.kernel, self.table.data_ptr(), self.nblocks,
                                             self.total_tiles, C.byref(self.scalars), st))
+
+
+def fused_launches(program, redop, reduce_axes, blocks, acc_dtype=None):
+    """One FusedLaunch per canonical mode present among ``blocks`` (ragged edge blocks whose
+    extent-1 dims collapse can need a different kernel shape than the interior blocks)."""
+    groups = {}
+    for b in blocks:
+        c = canonicalize(b.shape, [st for _, st in b.inputs], reduce_axes)
+        groups.setdefault(c.mode, []).append(b)
+    return [FusedLaunch(program, redop, reduce_axes, g, acc_dtype=acc_dtype) for g in groups.values()]
 
 
 # ----------------------------------------------------------------------------- AOT helpers

@@ -276,15 +276,18 @@ b2_combine_kernel(const void* const* __restrict__ parts, const void* const* __re
         for (int g = 1; g < fanin; ++g) { unsigned char v = ((const unsigned char*)parts[g])[e]; acc = (OP == B2R_ALL) ? (acc & v) : (acc | v); }
         ((unsigned char*)out0)[e] = acc;
     } else if constexpr (OP == B2R_ARGMIN || OP == B2R_ARGMAX) {
-        B2AccArg<T, OP == B2R_ARGMAX> acc;
-        acc.v = ((const T*)parts[0])[e]; acc.i = ((const i64*)parts1[0])[e];
+        // _arg_combine (_common.py:675-701) re-applies np.argmax/np.argmin to the concatenated
+        // per-block `vals`: the EARLIEST partial in nesting order wins a tie (and the first NaN
+        // wins outright) -- for axis=None that is block order, not global index order.
+        T bv = ((const T*)parts[0])[e];
+        i64 bi = ((const i64*)parts1[0])[e];
         for (int g = 1; g < fanin; ++g) {
-            B2AccArg<T, OP == B2R_ARGMAX> o;
-            o.v = ((const T*)parts[g])[e]; o.i = ((const i64*)parts1[g])[e];
-            acc.merge(o);
+            T v = ((const T*)parts[g])[e];
+            bool take = !b2_isnan(bv) && (b2_isnan(v) || ((OP == B2R_ARGMAX) ? (v > bv) : (v < bv)));
+            if (take) { bv = v; bi = ((const i64*)parts1[g])[e]; }
         }
-        ((T*)out0)[e] = acc.v;
-        ((i64*)out1)[e] = acc.i;
+        ((T*)out0)[e] = bv;
+        ((i64*)out1)[e] = bi;
     } else {   // MOMENT: packed (n, mean, M2) fp64 triples
         B2AccMoment<double, double> acc; acc.init();
         for (int g = 0; g < fanin; ++g) {

@@ -95,7 +95,11 @@ def test_arg_reductions_bit_exact(da, dtype, split_every):
             want = rfn(b, axis=axis, split_every=split_every)
             assert got.dtype == np.int64
             assert np.array_equal(got, want), (fn, axis)
-            assert np.array_equal(got, getattr(np, fn)(xh, axis=axis))
+            if axis is not None:
+                # (for axis=None the reference breaks cross-block ties by BLOCK order --
+                # _arg_combine re-runs argmax over the concatenated block maxima -- so it can
+                # differ from np.argmax on tied data; the oracle reproduces the reference)
+                assert np.array_equal(got, getattr(np, fn)(xh, axis=axis))
     assert np.array_equal(x.max(axis=1).compute(), xh.max(axis=1), equal_nan=True)
     assert np.array_equal(x.min(axis=0).compute(), xh.min(axis=0), equal_nan=True)
 
