@@ -8,7 +8,8 @@ matmul.  Every result is computed by hand-written sm_100a CUDA kernels behind th
 """
 from . import _lib  # noqa: F401  (fails loudly when libb200da.so is missing)
 from ._collection import (  # noqa: F401
-    UFUNC_NAMES, Array, _method, _ufunc, asarray, elemwise, from_array, full, matmul, ones, random,
+    UFUNC_NAMES, Array, Compiled, _method, _ufunc, asarray, compile, compute, elemwise, from_array,
+    from_host_blocks, full, matmul, ones, random,
     rechunk, transpose, where, zeros,
 )
 

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _codegen as cg
 from ._blockwise import Elemwise, Transpose
-from ._expr import ArrayExpr, BroadcastTrick, FromArray, Random, Resident, normalize_chunks
+from ._expr import ArrayExpr, BroadcastTrick, FromArray, HostBlocks, Random, Resident, normalize_chunks
 from ._reductions import Reduction, validate_axis
 
 
@@ -81,6 +81,12 @@ class Array:
 
         ex, opt, store = self._execute()
         return gather_to_host(ex, opt, store)
+
+    def compile(self):
+        """Optimise, run once and keep the launch tape: ``Compiled.run()`` replays the same
+        kernels on the same buffers (what a steady-state ``compute()`` of a persisted graph does),
+        without re-planning."""
+        return Compiled(self)
 
     def persist(self, **kwargs):
         """Blocks stay on the GPU(s); the returned Array reads them in place."""
@@ -221,10 +227,59 @@ class Array:
         return self._reduce("argmax", axis, keepdims, None, split_every)
 
 
+class Compiled:
+    """Computed expression(s) plus the replayable launch tape.  Several arrays compiled
+    together share one executor, hence common sub-expressions (uploads, rechunks)."""
+
+    def __init__(self, *arrays: "Array"):
+        from ._executor import Executor
+
+        self.executor = Executor()
+        self.exprs = [a.expr.optimize() for a in arrays]
+        self.stores = [self.executor.run(e) for e in self.exprs]
+        self.tape = list(self.executor.tape)
+
+    def run(self):
+        for fn in self.tape:
+            fn()
+
+    def results(self):
+        from ._executor import gather_to_host
+
+        return [gather_to_host(self.executor, e, s) for e, s in zip(self.exprs, self.stores)]
+
+    def result(self):
+        return self.results()[0]
+
+    def fused_launches(self):
+        from ._runtime import FusedLaunch
+
+        out = []
+        for st in self.executor.results.values():
+            out.extend(k for k in st.keepalive if isinstance(k, FusedLaunch))
+        return out
+
+
 def _freeze(split_every):
     if isinstance(split_every, dict):
         return dict(split_every)
     return split_every
+
+
+def compile(*arrays):   # noqa: A001  (mirrors dask.compute's variadic form)
+    return Compiled(*arrays)
+
+
+def compute(*arrays):
+    """``dask.compute(a, b, ...)``: shared sub-expressions are evaluated once."""
+    return tuple(Compiled(*arrays).results())
+
+
+def from_host_blocks(get_block, shape, chunks, dtype, token=None):
+    """Array whose blocks come from ``get_block(block id) -> host ndarray``."""
+    chunks = normalize_chunks(chunks, tuple(shape))
+    token = token if token is not None else f"{id(get_block):x}"
+    return Array(HostBlocks(get_block, chunks, np.dtype(dtype).name, token))
 
 
 # ----------------------------------------------------------------------------- creation

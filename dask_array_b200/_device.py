@@ -66,14 +66,36 @@ class DeviceChunk:
         return cls(alloc_bytes(math.prod(shape) * dtype.itemsize, device), shape, dtype)
 
     @classmethod
-    def from_numpy(cls, arr, device=None, pinned_stage: torch.Tensor | None = None) -> "DeviceChunk":
-        arr = np.ascontiguousarray(arr)
+    def from_numpy(cls, arr, device=None, out: "DeviceChunk | None" = None) -> "DeviceChunk":
+        """Upload a host block.  A block that is a strided slice of a bigger C-ordered host
+        array (from_array of a whole NumPy array) goes up with one pitched copy per 2-D plane,
+        without a host-side gather; ``out`` re-uses an existing device block."""
+        from . import _lib
+
+        arr = np.asarray(arr)
         device = device or current_device()
-        out = cls.empty(arr.shape, arr.dtype, device)
-        if arr.size:
-            src = torch.from_numpy(arr.reshape(-1).view(np.uint8))
-            out.buf[: arr.nbytes].copy_(src, non_blocking=False)
-        return out
+        dst = out if out is not None else cls.empty(arr.shape, arr.dtype, device)
+        if arr.size == 0:
+            return dst
+        item = arr.dtype.itemsize
+        if arr.ndim >= 1 and arr.strides[-1] != item:
+            arr = np.ascontiguousarray(arr)
+        a2 = arr if arr.ndim >= 2 else arr.reshape(1, -1)
+        # merge trailing dims that are contiguous, treat the next one as the pitched dim
+        inner = a2.shape[-1] * item
+        lead_shape = a2.shape[:-2]
+        st = current_stream_ptr()
+        rows, pitch = a2.shape[-2], a2.strides[-2]
+        if pitch < inner and rows > 1:
+            a2 = np.ascontiguousarray(a2)
+            pitch = a2.strides[-2]
+        base = a2.__array_interface__["data"][0]
+        plane = rows * inner
+        for n, idx in enumerate(np.ndindex(*lead_shape) if lead_shape else [()]):
+            off = sum(i * s for i, s in zip(idx, a2.strides[:-2]))
+            _lib.check(_lib.lib.b2_memcpy2d(dst.ptr + n * plane, inner, base + off, pitch, inner, rows, 0, st))
+        dst._host_keepalive = a2
+        return dst
 
     # ---- basic properties
     @property

@@ -23,7 +23,7 @@ from . import _lib
 from . import _runtime as rt
 from ._blockwise import FusedBlockwise, FusedPlan
 from ._device import DeviceChunk, alloc_bytes
-from ._expr import ArrayExpr, BroadcastTrick, FromArray, Random, Resident
+from ._expr import ArrayExpr, BroadcastTrick, FromArray, HostBlocks, Random, Resident
 from ._rechunk import TasksRechunk
 from ._reductions import REDOPS, ArgChunk, ChunkReduce, PartialReduce
 from ._slicing import SliceSlicesIntegers
@@ -69,6 +69,11 @@ class Executor:
         self.world = world or World()
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.results: dict[str, BlockStore] = {}
+        self.tape = []            # every device action in issue order: replaying it repeats the step
+
+    def _do(self, fn):
+        fn()
+        self.tape.append(fn)
 
     # ------------------------------------------------------------------ driver
     def run(self, expr: ArrayExpr) -> BlockStore:
@@ -97,7 +102,25 @@ class Executor:
                 continue
             start, shape = expr.block_start(bid), expr.block_shape(bid)
             sl = tuple(slice(s, s + n) for s, n in zip(start, shape))
-            st.blocks[bid] = DeviceChunk.from_numpy(arr[sl], self.device)
+            host = arr[sl]
+            chunk = DeviceChunk.empty(host.shape, host.dtype, self.device)
+            self._do(lambda h=host, c=chunk: DeviceChunk.from_numpy(h, self.device, out=c))
+            st.blocks[bid] = chunk
+        return st
+
+    def _run_HostBlocks(self, expr):
+        st = BlockStore(expr)
+        get = expr.operand("get_block")
+        for bid in expr.block_ids():
+            if not self.mine(expr, bid):
+                continue
+            host = get(bid)
+            if host.shape != expr.block_shape(bid) or host.dtype != expr.dtype:
+                raise ValueError(f"host block {bid} is {host.shape}/{host.dtype}, expected "
+                                 f"{expr.block_shape(bid)}/{expr.dtype}")
+            chunk = DeviceChunk.empty(host.shape, host.dtype, self.device)
+            self._do(lambda h=host, c=chunk: DeviceChunk.from_numpy(h, self.device, out=c))
+            st.blocks[bid] = chunk
         return st
 
     def _run_Random(self, expr):
@@ -118,7 +141,7 @@ class Executor:
             if self.mine(expr, bid):
                 c = DeviceChunk.empty(expr.block_shape(bid), expr.dtype, self.device)
                 if c.size:
-                    rt.fill(c, expr.operand("value"))
+                    self._do(lambda c=c, v=expr.operand("value"): rt.fill(c, v))
                 st.blocks[bid] = c
         return st
 
@@ -197,7 +220,7 @@ class Executor:
         if blocks:
             for launch in rt.fused_launches(plan.program, REDOPS[kind] if red is not None else _lib.RED_NONE,
                                             axes, blocks, acc_dtype=acc_dtype):
-                launch.run()
+                self._do(launch.run)
                 st.keepalive.append(launch)
             st.keepalive.append(extra)
         return st
@@ -240,7 +263,7 @@ class Executor:
             st.blocks[bid] = {"vals": vals, "arg": arg}
         if blocks:
             for launch in rt.fused_launches(prog, REDOPS[kind], axis, blocks):
-                launch.run()
+                self._do(launch.run)
                 st.keepalive.append(launch)
         return st
 
@@ -267,31 +290,32 @@ class Executor:
                 n = sum(b["n"] for b in blks)
                 out = DeviceChunk.empty(tot0.shape if not final else self._final_shape(expr, tot0.shape),
                                         expr.dtype if final else tot0.dtype, self.device)
-                tab = rt.combine(_lib.RED_SUM, tot0.dtype, [b["total"].ptr for b in blks], None, tot0.size, out.ptr,
+                tab = rt.CombineLaunch(_lib.RED_SUM, tot0.dtype, [b["total"].ptr for b in blks], None, tot0.size, out.ptr,
                                  post=_lib.POST_MEAN if final else _lib.POST_NONE, out_dtype=expr.dtype, count=n)
                 st.blocks[key] = out if final else {"total": out, "n": n}
             elif src.kind == "moment":
                 nelem = first.size // 3
                 if final:
                     out = DeviceChunk.empty(self._final_shape(expr, first.shape[:-1]), expr.dtype, self.device)
-                    tab = rt.combine(_lib.RED_MOMENT, np.float64, [b.ptr for b in blks], None, nelem, out.ptr,
+                    tab = rt.CombineLaunch(_lib.RED_MOMENT, np.float64, [b.ptr for b in blks], None, nelem, out.ptr,
                                      post=_lib.POST_VAR, out_dtype=expr.dtype, ddof=expr.operand("ddof"))
                 else:
                     out = DeviceChunk.empty(first.shape, np.float64, self.device)
-                    tab = rt.combine(_lib.RED_MOMENT, np.float64, [b.ptr for b in blks], None, nelem, out.ptr)
+                    tab = rt.CombineLaunch(_lib.RED_MOMENT, np.float64, [b.ptr for b in blks], None, nelem, out.ptr)
                 st.blocks[key] = out
             elif src.kind == "arg":
                 v0 = first["vals"]
                 vals = DeviceChunk.empty(v0.shape, v0.dtype, self.device)
                 arg = DeviceChunk.empty(self._final_shape(expr, v0.shape) if final else v0.shape, np.int64, self.device)
-                tab = rt.combine(redop, v0.dtype, [b["vals"].ptr for b in blks], [b["arg"].ptr for b in blks],
+                tab = rt.CombineLaunch(redop, v0.dtype, [b["vals"].ptr for b in blks], [b["arg"].ptr for b in blks],
                                  v0.size, vals.ptr, arg.ptr)
                 st.blocks[key] = arg if final else {"vals": vals, "arg": arg}
             else:
                 out = DeviceChunk.empty(self._final_shape(expr, first.shape) if final else first.shape,
                                         first.dtype, self.device)
-                tab = rt.combine(redop, first.dtype, [b.ptr for b in blks], None, first.size, out.ptr)
+                tab = rt.CombineLaunch(redop, first.dtype, [b.ptr for b in blks], None, first.size, out.ptr)
                 st.blocks[key] = out
+            self._do(tab.run)
             st.keepalive.append(tab)
             st.keepalive.append(blks)
         return st
@@ -325,7 +349,7 @@ class Executor:
                     piece = remote[(obid, nbid)]          # already cut to the piece on the sender
                 copies.extend(_copy_descs(piece, out[dsl], item))
         launch = rt.GatherLaunch(copies)
-        launch.run()
+        self._do(launch.run)
         st.keepalive.extend([launch, remote])
         return st
 
@@ -408,9 +432,9 @@ def _allgather_blocks(ex: Executor, src: BlockStore, x):
                 copies.append((chunk.ptr, send.data_ptr() + off, 1, nb, nb, nb))
             off += -(-nb // 16) * 16
     g = rt.GatherLaunch(copies)
-    g.run()
+    ex._do(g.run)
     recv = alloc_bytes(cap * W, ex.device)
-    dist.all_gather_into_tensor(recv, send)
+    ex._do(lambda: dist.all_gather_into_tensor(recv, send))
     out = {}
     offs = [0] * W
     for bid in ids:
@@ -485,7 +509,7 @@ def _exchange_for_fused(ex: Executor, plan: FusedPlan, deps, out_ids):
                 copies.extend(_copy_descs(blk, flat, blk.itemsize))
                 off += pad(nb)
             g = rt.GatherLaunch(copies)
-            g.run()
+            ex._do(g.run)
             keep.append(g)
             sends.append((p, buf))
         if recv_items[p]:
@@ -496,7 +520,7 @@ def _exchange_for_fused(ex: Executor, plan: FusedPlan, deps, out_ids):
                 out[(name, lbid)] = DeviceChunk(buf, dep.block_shape(lbid), dep.dtype, offset=off // dep.dtype.itemsize)
                 off += pad(nb)
             recvs.append((p, buf))
-    _p2p_exchange(ex, sends, recvs)
+    ex._do(lambda: _p2p_exchange(ex, sends, recvs))
     out["__keep__"] = (keep, sends, recvs)
     return out
 
@@ -533,7 +557,7 @@ def _exchange_for_rechunk(ex: Executor, expr: TasksRechunk, src: BlockStore, new
                 copies.extend(_copy_descs(piece, flat, item))
                 off += pad(nb)
             g = rt.GatherLaunch(copies)
-            g.run()
+            ex._do(g.run)
             keep.append(g)
             sends.append((p, buf))
         if recv_items[p]:
@@ -543,7 +567,7 @@ def _exchange_for_rechunk(ex: Executor, expr: TasksRechunk, src: BlockStore, new
                 out[(obid, nbid)] = DeviceChunk(buf, shape, expr.dtype, offset=off // item)
                 off += pad(nb)
             recvs.append((p, buf))
-    _p2p_exchange(ex, sends, recvs)
+    ex._do(lambda: _p2p_exchange(ex, sends, recvs))
     out["__keep__"] = (keep, sends, recvs)
     return out
 

@@ -230,6 +230,29 @@ class FromArray(ArrayExpr):
         return f"FromArray{self.shape}"
 
 
+class HostBlocks(ArrayExpr):
+    """Per-block host arrays (``get_block(block id) -> ndarray``), e.g. the output of a host
+    RNG or loader -- the role of ``from_map`` / ``from_delayed`` leaves (``io/``).  Only the
+    blocks this rank owns are ever requested."""
+
+    _parameters = ["get_block", "chunks_", "dtype_", "token"]
+
+    @property
+    def chunks(self):
+        return self.operand("chunks_")
+
+    @property
+    def dtype(self):
+        return np.dtype(self.operand("dtype_"))
+
+    @property
+    def _name(self):
+        return f"hostblocks-{self.operand('token')}"
+
+    def _tree_label(self):
+        return f"HostBlocks{self.shape}"
+
+
 class Resident(ArrayExpr):
     """Blocks already on the device(s) under their original keys -- what ``persist()``
     leaves behind (``_collection.py:285-300`` -> ``FromGraph`` ``io/_from_graph.py:12``)."""

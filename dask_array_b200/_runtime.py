@@ -257,10 +257,18 @@ class FusedLaunch:
         self.table = torch.from_numpy(raw.copy()).to(torch.device("cuda", torch.cuda.current_device()))
         self.scalars = _lib.Scalars()
 
+    profile = False       # set on an instance: record a CUDA-event pair around every launch
+
     def run(self, stream: int | None = None) -> None:
         st = current_stream_ptr() if stream is None else stream
+        if self.profile:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(_lib.lib.b2_fused_launch(self.kernel, self.table.data_ptr(), self.nblocks,
                                             self.total_tiles, C.byref(self.scalars), st))
+        if self.profile:
+            e1.record()
+            self.__dict__.setdefault("events", []).append((e0, e1))
 
 
 def fused_launches(program, redop, reduce_axes, blocks, acc_dtype=None):
@@ -274,19 +282,30 @@ def fused_launches(program, redop, reduce_axes, blocks, acc_dtype=None):
 
 
 # ----------------------------------------------------------------------------- AOT helpers
-def combine(redop: int, dtype, parts: list[int], parts1: list[int] | None, nelem: int,
-            out0: int, out1: int = 0, post: int = _lib.POST_NONE, out_dtype=None,
-            count: float = 0.0, ddof: float = 0.0, table: torch.Tensor | None = None) -> torch.Tensor:
-    """One PartialReduce level (reductions/_reduction.py:968-983) on the device."""
-    fanin = len(parts)
-    ptrs = list(parts) + (list(parts1) if parts1 else [0] * fanin)
-    host = torch.tensor(ptrs, dtype=torch.int64)
-    tab = host.to(torch.device("cuda", torch.cuda.current_device())) if table is None else table
-    base = tab.data_ptr()
-    _lib.check(_lib.lib.b2_combine(redop, _lib.dtype_code(dtype), base, base + 8 * fanin, fanin, nelem,
-                                   out0, out1, post, _lib.dtype_code(out_dtype if out_dtype is not None else dtype),
-                                   float(count), float(ddof), current_stream_ptr()))
-    return tab   # caller keeps the table alive until the stream has consumed it
+class CombineLaunch:
+    """One PartialReduce output block (reductions/_reduction.py:968-983) as a replayable launch."""
+
+    def __init__(self, redop: int, dtype, parts: list, parts1, nelem: int, out0: int, out1: int = 0,
+                 post: int = _lib.POST_NONE, out_dtype=None, count: float = 0.0, ddof: float = 0.0):
+        self.fanin = len(parts)
+        ptrs = list(parts) + (list(parts1) if parts1 else [0] * self.fanin)
+        self.table = torch.tensor(ptrs, dtype=torch.int64).to(torch.device("cuda", torch.cuda.current_device()))
+        self.args = (redop, _lib.dtype_code(dtype), nelem, out0, out1, post,
+                     _lib.dtype_code(out_dtype if out_dtype is not None else dtype), float(count), float(ddof))
+
+    def run(self, stream: int | None = None) -> None:
+        redop, dcode, nelem, out0, out1, post, ocode, count, ddof = self.args
+        base = self.table.data_ptr()
+        st = current_stream_ptr() if stream is None else stream
+        _lib.check(_lib.lib.b2_combine(redop, dcode, base, base + 8 * self.fanin, self.fanin, nelem,
+                                       out0, out1, post, ocode, count, ddof, st))
+
+
+def combine(redop, dtype, parts, parts1, nelem, out0, out1=0, post=_lib.POST_NONE, out_dtype=None,
+            count=0.0, ddof=0.0):
+    c = CombineLaunch(redop, dtype, parts, parts1, nelem, out0, out1, post, out_dtype, count, ddof)
+    c.run()
+    return c
 
 
 class GatherLaunch:

@@ -437,6 +437,19 @@ extern "C" int b2_gather_launch(const b2_copy* d_copies, int n, int64_t total_ti
     return B2_OK;
 }
 
+extern "C" int b2_memcpy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                           int64_t row_bytes, int64_t rows, int kind, void* stream) {
+    if (!dst || !src || row_bytes < 0 || rows < 0) return fail(B2_ERR_INVALID, "bad argument");
+    if (row_bytes == 0 || rows == 0) return B2_OK;
+    cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (rows == 1 || (dst_pitch == row_bytes && src_pitch == row_bytes))
+        CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)(row_bytes * rows), k, (cudaStream_t)stream));
+    else
+        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)row_bytes,
+                                   (size_t)rows, k, (cudaStream_t)stream));
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------ fill (AOT)
 template <typename W>
 __global__ void __launch_bounds__(256) b2_fill_kernel(W* dst, i64 n, W value) {

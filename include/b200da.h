@@ -202,6 +202,12 @@ typedef struct b2_copy {
 int b2_gather_plan(b2_copy* copies, int n, int64_t* total_tiles);
 int b2_gather_launch(const b2_copy* d_copies, int n, int64_t total_tiles, void* stream);
 
+/* Strided host<->device block transfer: from_array's per-block getitem of a host array
+ * (io/_from_array.py:60-160) and finalize's concatenate3 into the host result
+ * (_core_utils.py:1426-1448), as one cudaMemcpy2DAsync per block. kind: 0 = H2D, 1 = D2H. */
+int b2_memcpy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                int64_t row_bytes, int64_t rows, int kind, void* stream);
+
 /* fill a contiguous buffer with one element (Ones/Zeros/Full materialisation,
  * creation/_ones_zeros.py:17-137) */
 int b2_fill(void* dst, int64_t nelem, int itemsize, const void* value, void* stream);
