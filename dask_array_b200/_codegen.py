@@ -25,6 +25,8 @@ import numpy as np
 
 from . import _lib
 
+CODEGEN_VERSION = "4"     # part of every kernel's cache key: bump when generated code changes
+
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
     "uint16": "unsigned short", "int32": "int", "uint32": "unsigned int", "int64": "long long",
@@ -202,13 +204,24 @@ class Program:
         parts.append("out:" + _ref_key(self.output))
         return "|".join(parts)
 
-    def body(self) -> list[str]:
-        """C++ statements computing ``o[v]`` from ``g.a<k>[v]``."""
+    def uses_fast_sincos(self) -> bool:
+        return any(name in ("sin", "cos") and out == np.float32 for name, _, out, _ in self.ops)
+
+    def body(self, fast: bool = False, slow_calls: bool = False) -> list[str]:
+        """C++ statements computing ``o[v]`` from ``g.a<k>[v]``.  ``fast``: fp32 sin/cos use
+        b2_sinf_fast/b2_cosf_fast and track max|arg| in ``big`` (the caller redoes the vector
+        with libdevice when an argument leaves the Cody-Waite range)."""
         lines = []
         for k, dt in enumerate(self.inputs):
             lines.append(f"const {ctype(dt)} x{k} = g.a{k}[v];")
         for j, (name, args, out, kw) in enumerate(self.ops):
-            lines.append(f"const {ctype(out)} t{j} = {_emit(name, list(args), out, dict(kw))};")
+            if fast and name in ("sin", "cos") and out == np.float32:
+                expr = f"b2_{name}f_fast({_typed_expr(args[0], out)}, big)"
+            elif slow_calls and name in ("sin", "cos") and out == np.float32:
+                expr = f"b2_{name}f_slow({_typed_expr(args[0], out)})"
+            else:
+                expr = _emit(name, list(args), out, dict(kw))
+            lines.append(f"const {ctype(out)} t{j} = {expr};")
         lines.append(f"o[v] = {_typed_expr(self.output, self.out_dtype)};")
         return lines
 
@@ -381,7 +394,7 @@ class KernelSpec:
     acc_dtype: str       # accumulator / output dtype name of SUM/PROD; working type of MOMENT
 
     def digest(self) -> str:
-        return hashlib.sha1(repr(self).encode()).hexdigest()[:20]
+        return hashlib.sha1((CODEGEN_VERSION + repr(self)).encode()).hexdigest()[:20]
 
 
 def packed_bytes(spec: KernelSpec, out_dtype) -> int:
@@ -405,34 +418,64 @@ def render(program: Program, spec: KernelSpec) -> str:
     """Full translation unit of one fused kernel (entry point ``b2_fused``)."""
     T = ctype(program.out_dtype)
     regs = [f"{ctype(dt)} a{k}[B2_V];" for k, dt in enumerate(program.inputs)] or ["char _unused;"]
-    loads = []
+    ptrs, setup_r, setup_c, loads, adv = [], [], [], [], []
     for k, (dt, lay) in enumerate(zip(program.inputs, spec.layouts)):
         ct = ctype(dt)
-        base = f"(const {ct}*)blk.in[{k}] + b * blk.in_sb[{k}] + r * blk.in_sr[{k}]"
+        ptrs.append(f"const {ct}* p{k}; i64 s{k};" + (f" i64 c{k};" if lay == "G" else ""))
+        colmul = {"V": "c", "S": "0", "G": f"c * blk.in_sc[{k}]"}[lay]
+        base = f"(const {ct}*)blk.in[{k}] + b * blk.in_sb[{k}] + r * blk.in_sr[{k}] + {colmul}"
+        extra = f" P.c{k} = blk.in_sc[{k}];" if lay == "G" else ""
+        setup_r.append(f"P.p{k} = {base}; P.s{k} = rstep * blk.in_sr[{k}];{extra}")
+        cstep = {"V": "cstep", "S": "0", "G": f"cstep * blk.in_sc[{k}]"}[lay]
+        setup_c.append(f"P.p{k} = {base}; P.s{k} = {cstep};{extra}")
         if lay == "V":
-            loads.append(f"b2_load_vec<{ct}, B2_V>({base} + c, g.a{k});")
+            loads.append(f"b2_load_vec<{ct}, B2_V>(P.p{k} + k * P.s{k}, g.a{k});")
         elif lay == "S":
-            loads.append(f"b2_load_bcast<{ct}, B2_V>({base}, g.a{k});")
+            loads.append(f"b2_load_bcast<{ct}, B2_V>(P.p{k} + k * P.s{k}, g.a{k});")
         else:
-            loads.append(f"b2_load_strided<{ct}, B2_V>({base} + c * blk.in_sc[{k}], blk.in_sc[{k}], g.a{k});")
+            loads.append(f"b2_load_strided<{ct}, B2_V>(P.p{k} + k * P.s{k}, P.c{k}, g.a{k});")
+        adv.append(f"P.p{k} += n * P.s{k};")
+    if not ptrs:
+        ptrs = ["char _unused;"]
     acc = ctype(spec.acc_dtype)
     nl = "\n            "
-    return f"""// generated by dask_array_b200/_codegen.py -- one FusedBlockwise expression
+    fast = program.uses_fast_sincos()
+    header = "// b2-options: fmad\n" if spec.mode != _lib.MODE_EW else ""
+    compute = f"""    static constexpr bool HAS_SLOW = {'true' if fast else 'false'};
+    // exact chain (libdevice transcendental functions, full argument range)
+    __device__ __forceinline__ static void compute_slow(const Regs& g, const B2Scalars& sc, out_t (&o)[B2_V]) {{
+#pragma unroll
+        for (int v = 0; v < B2_V; ++v) {{
+            {nl.join(program.body(slow_calls=fast))}
+        }}
+    }}
+    __device__ __forceinline__ static void compute(const Regs& g, const B2Scalars& sc, out_t (&o)[B2_V], float& big) {{
+#pragma unroll
+        for (int v = 0; v < B2_V; ++v) {{
+            {nl.join(program.body(fast=fast))}
+        }}
+    }}"""
+    return f"""{header}// generated by dask_array_b200/_codegen.py -- one FusedBlockwise expression
 // program: {program.key()}
 #include "b2_device.cuh"
 #define B2_V {spec.vec}
 struct Chain {{
     typedef {T} out_t;
     struct Regs {{ {' '.join(regs)} }};
-    __device__ __forceinline__ static void load(const B2Block& blk, i64 b, i64 r, i64 c, Regs& g) {{
+    struct Ptrs {{ {' '.join(ptrs)} }};
+    __device__ __forceinline__ static void setup_rows(const B2Block& blk, i64 b, i64 r, i64 c, i64 rstep, Ptrs& P) {{
+        {(nl[:-4]).join(setup_r)}
+    }}
+    __device__ __forceinline__ static void setup_cols(const B2Block& blk, i64 b, i64 r, i64 c, i64 cstep, Ptrs& P) {{
+        {(nl[:-4]).join(setup_c)}
+    }}
+    __device__ __forceinline__ static void load(const Ptrs& P, int k, Regs& g) {{
         {(nl[:-4]).join(loads)}
     }}
-    __device__ __forceinline__ static void compute(const Regs& g, const B2Scalars& sc, out_t (&o)[B2_V]) {{
-#pragma unroll
-        for (int v = 0; v < B2_V; ++v) {{
-            {nl.join(program.body())}
-        }}
+    __device__ __forceinline__ static void advance(Ptrs& P, int n) {{
+        {(nl[:-4]).join(adv)}
     }}
+{compute}
 }};
 extern "C" __global__ void __launch_bounds__({spec.tx * spec.ty})
 b2_fused(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars sc) {{

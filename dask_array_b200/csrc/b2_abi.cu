@@ -128,8 +128,12 @@ extern "C" int b2_jit_compile(const char* source, const char* name, void** cubin
     if (r != NVRTC_SUCCESS) return fail(B2_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
     // --fmad=false: a*b+c stays two roundings, as in NumPy's separate ufunc loops, so float
     // chains are bit-identical to the reference; the kernels call fma() where they want one.
+    // Element-wise kernels keep two roundings for a*b+c (as NumPy's separate ufunc loops) so that
+    // float chains are bit-identical to the reference; a kernel whose chain is only observable
+    // through a reduction (rtol contract) opts in with a first line "// b2-options: fmad".
+    const bool fmad = strncmp(source, "// b2-options: fmad", 19) == 0;
     const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--restrict",
-                          "-default-device", "--fmad=false"};
+                          "-default-device", fmad ? "--fmad=true" : "--fmad=false"};
     r = nvrtcCompileProgram(prog, (int)(sizeof opts / sizeof *opts), opts);
     if (r != NVRTC_SUCCESS) {
         size_t n = 0;

@@ -227,6 +227,49 @@ template <typename T> __device__ __forceinline__ T b2_sign(T a) {
     else return (T)((a > 0) - (a < 0));
 }
 
+// ------------------------------------------------------------------ fp32 sin / cos
+// The chain `sin(x)*2 + x**2` costs ~32 issue slots per element with libdevice's sinf
+// (F2I range reduction, a branch and an inlined Payne-Hanek path PER ELEMENT), which caps a
+// streaming kernel at ~50 % of HBM.  These versions keep libdevice's algorithm class --
+// 3-term Cody-Waite reduction + minimax polynomial, no MUFU approximation -- in 13 slots:
+//   * quotient by magic-number rounding (no F2I/I2F), reduction by pi so that ONE odd
+//     polynomial on [-pi/2, pi/2] serves every quadrant and the sign is an XOR;
+//   * arguments beyond the Cody-Waite range (|x| > 105615, inf) are detected once per
+//     vector by the caller (max of |x|) and that vector is redone with libdevice's sinf/cosf.
+// Max error 1.64 ulp vs the correctly rounded result on the fast path (tests/test_gpu_kernels.py
+// checks it exhaustively against fp64); NumPy's own float32 sin is specified to < 1.5 ulp.
+#define B2_SINCOS_BIG 105615.0f
+__device__ __forceinline__ float b2_sin_poly(float r) {          // |r| <= pi/2
+    const float s = r * r;
+    float p = 2.605750751172309e-06f;
+    p = fmaf(p, s, -0.00019809573132079095f);
+    p = fmaf(p, s, 0.00833306647837162f);
+    p = fmaf(p, s, -0.16666659712791443f);
+    return fmaf(r * s, p, r);
+}
+__device__ __forceinline__ float b2_sinf_fast(float x, float& big) {
+    big = fmaxf(big, fabsf(x));
+    const float jm = fmaf(x, 0.318309886183790672f, 12582912.0f);   // 1.5 * 2^23: low bits = round(x/pi)
+    const float j = jm - 12582912.0f;
+    float r = fmaf(j, -3.1415925025939941406f, x);
+    r = fmaf(j, -1.5099578831723192707e-07f, r);
+    r = fmaf(j, -1.0780605906948476785e-14f, r);
+    return __int_as_float(__float_as_int(b2_sin_poly(r)) ^ (__float_as_int(jm) << 31));
+}
+__device__ __forceinline__ float b2_cosf_fast(float x, float& big) {
+    big = fmaxf(big, fabsf(x));
+    // x = (m + 1/2) pi + r,  m = round(x/pi - 1/2):  cos(x) = (-1)^(m+1) sin(r)
+    const float jm = fmaf(x, 0.318309886183790672f, 12582911.5f);
+    const float j = (jm - 12582912.0f) + 0.5f;
+    float r = fmaf(j, -3.1415925025939941406f, x);
+    r = fmaf(j, -1.5099578831723192707e-07f, r);
+    r = fmaf(j, -1.0780605906948476785e-14f, r);
+    return __int_as_float(__float_as_int(b2_sin_poly(r)) ^ ((~__float_as_int(jm)) << 31));
+}
+
+__device__ __noinline__ float b2_sinf_slow(float x) { return sinf(x); }   // libdevice, full range
+__device__ __noinline__ float b2_cosf_slow(float x) { return cosf(x); }
+
 // ------------------------------------------------------------------ accumulators
 // An accumulator `A` offers: init(), add(value, index), merge(other) [other comes LATER
 // in index order unless the op is commutative], and Packed <-> A for the two-stage
@@ -348,9 +391,10 @@ struct B2AccMoment {
     double n, mean, m2;          // merged phase
     __device__ __forceinline__ void init() { K = (W)0; s1 = (W)0; s2 = (W)0; cnt = 0; n = 0.0; mean = 0.0; m2 = 0.0; }
     __device__ __forceinline__ void prime(T v) { K = (W)v; }
-    __device__ __forceinline__ void add(T v, i64) { W d = (W)v - K; s1 += d; s2 = fma(d, d, s2); ++cnt; }
-    // fold the thread-local sums into (n, mean, M2)
-    __device__ __forceinline__ void finish_local() {
+    __device__ __forceinline__ void add(T v, i64) { W d = (W)v - K; s1 += d; s2 = fma(d, d, s2); }
+    // fold the thread-local sums (over `count` elements, known from the loop bounds) into (n, mean, M2)
+    __device__ __forceinline__ void finish_local(i64 count) {
+        cnt = (int)count;
         if (cnt > 0) {
             double dn = (double)cnt, a = (double)s1, b = (double)s2;
             Packed p; p.n = dn; p.mean = (double)K + a / dn; p.m2 = b - a * a / dn;
@@ -440,7 +484,34 @@ template <typename P> __device__ __forceinline__ P b2_load_cg(const P* p) {
     return u.v;
 }
 
-// Chain supplies:  out_t;  Regs;  load(blk, b, r, c, Regs&);  compute(Regs, scalars, out_t(&)[V]).
+// Evaluate the chain on N loaded vectors.  Chains with fp32 sin/cos run the fast versions and
+// track max|arg|; if any argument of the WHOLE batch left the Cody-Waite range (rare) the batch
+// is re-loaded (P has already advanced past it) and redone with libdevice -- one predictable
+// branch per N*V elements instead of one per element.
+template <typename Chain, int V, int N>
+__device__ __forceinline__ void b2_compute_batch(const typename Chain::Ptrs& P, const typename Chain::Regs (&g)[N],
+                                                 const B2Scalars& sc, typename Chain::out_t (&o)[N][V]) {
+    float big = 0.0f;
+#pragma unroll
+    for (int u = 0; u < N; ++u) Chain::compute(g[u], sc, o[u], big);
+    if constexpr (Chain::HAS_SLOW) {
+        if (big > B2_SINCOS_BIG) {
+#pragma unroll
+            for (int u = 0; u < N; ++u) {
+                typename Chain::Regs gs;
+                Chain::load(P, u - N, gs);
+                Chain::compute_slow(gs, sc, o[u]);
+            }
+        }
+    }
+}
+
+// Chain supplies:
+//   out_t; Regs; Ptrs (one typed pointer + element step per input);
+//   setup_rows(blk, b, r, c, rstep, Ptrs&)  -- point at (b, r, c), one step = rstep rows down;
+//   setup_cols(blk, b, r, c, cstep, Ptrs&)  -- point at (b, r, c), one step = cstep columns right;
+//   load(Ptrs, k, Regs&)   -- the V-wide load k steps ahead;   advance(Ptrs&, n);
+//   compute(Regs, scalars, out_t(&)[V]).
 template <typename Chain, int MODE, int REDOP, int V, int TX, int TY, int RPT, int U, typename ACC>
 __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars& sc) {
     typedef typename Chain::out_t T;
@@ -469,75 +540,94 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
 
     if constexpr (MODE == B2M_EW) {
         const i64 c = (tc * TX + tx) * V;
-        if (c < C) {
-            T* outp = (T*)blk.out0 + b * R * C;
-            for (i64 rb = r0 + ty; rb < rend; rb += (i64)TY * U) {
+        const i64 first = r0 + ty;
+        if (c < C && first < rend) {
+            const int nrows = (int)((rend - first + TY - 1) / TY);
+            T* outp = (T*)blk.out0 + (b * R + first) * C + c;
+            const i64 ostep = (i64)TY * C;
+            typename Chain::Ptrs P;
+            Chain::setup_rows(blk, b, first, c, TY, P);
+            int it = 0;
+            for (; it + U <= nrows; it += U) {
                 typename Chain::Regs g[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) { i64 r = rb + (i64)u * TY; if (r < rend) Chain::load(blk, b, r, c, g[u]); }
+                for (int u = 0; u < U; ++u) Chain::load(P, u, g[u]);
+                Chain::advance(P, U);
+                T o[U][V];
+                b2_compute_batch<Chain, V, U>(P, g, sc, o);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    i64 r = rb + (i64)u * TY;
-                    if (r < rend) { T o[V]; Chain::compute(g[u], sc, o); b2_store_vec<T, V>(outp + r * C + c, o); }
-                }
+                for (int u = 0; u < U; ++u) b2_store_vec<T, V>(outp + u * ostep, o[u]);
+                outp += U * ostep;
+            }
+            for (; it < nrows; ++it) {
+                typename Chain::Regs g[1]; T o[1][V];
+                Chain::load(P, 0, g[0]); Chain::advance(P, 1);
+                b2_compute_batch<Chain, V, 1>(P, g, sc, o);
+                b2_store_vec<T, V>(outp, o[0]); outp += ostep;
             }
         }
         return;
     } else {
         typedef typename B2AccSel<REDOP, T, ACC>::type A;
-        typedef typename A::Packed P;
+        typedef typename A::Packed P_t;
         __shared__ bool last;
+        constexpr bool WANT_IDX = (REDOP == B2R_ARGMIN || REDOP == B2R_ARGMAX);
 
         if constexpr (MODE == B2M_R || MODE == B2M_RC) {
             // ---- accumulate this thread's rows of the tile
             const i64 c = (tc * TX + tx) * V;
+            const i64 first = r0 + ty;
             A acc[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) acc[v].init();
-            if (c < C) {
+            const int nrows = (c < C && first < rend) ? (int)((rend - first + TY - 1) / TY) : 0;
+            if (nrows > 0) {
+                typename Chain::Ptrs P;
+                Chain::setup_rows(blk, b, first, c, TY, P);
                 if constexpr (REDOP == B2R_MOMENT) {
-                    // pivot: the first element this thread (mode R) / this tile (mode RC) sees
+                    // pivot: the first element this thread sees
                     typename Chain::Regs g0; T o0[V];
-                    if constexpr (MODE == B2M_R) {
-                        i64 rp = (r0 + ty < rend) ? (r0 + ty) : r0;
-                        Chain::load(blk, b, rp, c, g0);
-                        Chain::compute(g0, sc, o0);
+                    Chain::load(P, 0, g0);
+                    Chain::compute_slow(g0, sc, o0);
 #pragma unroll
-                        for (int v = 0; v < V; ++v) acc[v].prime(o0[v]);
-                    } else {
-                        Chain::load(blk, b, r0, tc * TX * V, g0);
-                        Chain::compute(g0, sc, o0);
-#pragma unroll
-                        for (int v = 0; v < V; ++v) acc[v].prime(o0[0]);
-                    }
+                    for (int v = 0; v < V; ++v) acc[v].prime(MODE == B2M_R ? o0[v] : o0[0]);
                 }
-                for (i64 rb = r0 + ty; rb < rend; rb += (i64)TY * U) {
+                i64 idx = (MODE == B2M_R) ? first : (first * C + c);       // arg reductions only
+                const i64 istep = (MODE == B2M_R) ? (i64)TY : (i64)TY * C;
+                int it = 0;
+                for (; it + U <= nrows; it += U) {
                     typename Chain::Regs g[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) { i64 r = rb + (i64)u * TY; if (r < rend) Chain::load(blk, b, r, c, g[u]); }
+                    for (int u = 0; u < U; ++u) Chain::load(P, u, g[u]);
+                    Chain::advance(P, U);
+                    T o[U][V];
+                    b2_compute_batch<Chain, V, U>(P, g, sc, o);
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        i64 r = rb + (i64)u * TY;
-                        if (r < rend) {
-                            T o[V]; Chain::compute(g[u], sc, o);
 #pragma unroll
-                            for (int v = 0; v < V; ++v) {
-                                i64 idx = (MODE == B2M_R) ? r : (r * C + c + v);
-                                acc[v].add(o[v], idx);
-                            }
-                        }
+                        for (int v = 0; v < V; ++v)
+                            acc[v].add(o[u][v], WANT_IDX ? (idx + u * istep + (MODE == B2M_R ? 0 : v)) : 0);
                     }
+                    if constexpr (WANT_IDX) idx += U * istep;
+                }
+                for (; it < nrows; ++it) {
+                    typename Chain::Regs g[1]; T o[1][V];
+                    Chain::load(P, 0, g[0]); Chain::advance(P, 1);
+                    b2_compute_batch<Chain, V, 1>(P, g, sc, o);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc[v].add(o[0][v], WANT_IDX ? (idx + (MODE == B2M_R ? 0 : v)) : 0);
+                    if constexpr (WANT_IDX) idx += istep;
                 }
             }
             if constexpr (REDOP == B2R_MOMENT) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) acc[v].finish_local();
+                for (int v = 0; v < V; ++v) acc[v].finish_local(nrows);
             }
 
             if constexpr (MODE == B2M_R) {
                 // ---- fold the TY row-lanes of each column (fixed order), then tiles_r partials
                 if constexpr (TY > 1) {
-                    __shared__ P sm[NT * V];
+                    __shared__ P_t sm[NT * V];
 #pragma unroll
                     for (int v = 0; v < V; ++v) sm[(ty * TX + tx) * V + v] = acc[v].pack();
                     __syncthreads();
@@ -558,7 +648,7 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                     }
                     return;
                 }
-                P* work = (P*)blk.work;
+                P_t* work = (P_t*)blk.work;
                 if (ty == 0 && c < C) {
 #pragma unroll
                     for (int v = 0; v < V; ++v) work[(b * tiles_r + tr) * Cpad + c + v] = acc[v].pack();
@@ -607,14 +697,12 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                 i64 fix = 0;
                 if (ntile == 1) {
                     if (tid == 0) {
-                        if constexpr (REDOP == B2R_ARGMIN || REDOP == B2R_ARGMAX) {
-                            fix = (blk.arg_ndim > 0) ? (b2_ravel_fix(blk, a.i) - a.i) : blk.arg_offset;
-                        }
+                        if constexpr (WANT_IDX) fix = (blk.arg_ndim > 0) ? (b2_ravel_fix(blk, a.i) - a.i) : blk.arg_offset;
                         b2_store_result<REDOP, T, ACC>(blk, b, a, fix);
                     }
                     return;
                 }
-                P* work = (P*)blk.work;
+                P_t* work = (P_t*)blk.work;
                 if (tid == 0) {
                     work[b * ntile + tslot] = a.pack();
                     __threadfence();
@@ -644,9 +732,7 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                     if (tid == 0) { for (int w = 1; w < NW; ++w) tot.merge(smw[w]); }
                 }
                 if (tid == 0) {
-                    if constexpr (REDOP == B2R_ARGMIN || REDOP == B2R_ARGMAX) {
-                        fix = (blk.arg_ndim > 0) ? (b2_ravel_fix(blk, tot.i) - tot.i) : blk.arg_offset;
-                    }
+                    if constexpr (WANT_IDX) fix = (blk.arg_ndim > 0) ? (b2_ravel_fix(blk, tot.i) - tot.i) : blk.arg_offset;
                     b2_store_result<REDOP, T, ACC>(blk, b, tot, fix);
                 }
                 return;
@@ -657,30 +743,44 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
             constexpr int WPR = (TX + 31) / 32;     // warps per row
             constexpr int SW = TX < 32 ? TX : 32;   // shuffle width
             __shared__ A smc[TY * WPR];
+            const i64 c0 = (i64)tx * V;
+            const int ncol = (c0 < C) ? (int)((C - c0 + (i64)TX * V - 1) / ((i64)TX * V)) : 0;   // steps of this lane
             for (i64 rr = r0; rr < rend; rr += TY) {       // uniform trip count (barriers inside)
                 const i64 r = rr + ty;
-                const bool rok = r < rend;
+                const bool rok = (r < rend) && ncol > 0;
                 A acc; acc.init();
                 if (rok) {
+                    typename Chain::Ptrs P;
+                    Chain::setup_cols(blk, b, r, c0, (i64)TX * V, P);
                     if constexpr (REDOP == B2R_MOMENT) {
                         typename Chain::Regs g0; T o0[V];
-                        Chain::load(blk, b, r, 0, g0); Chain::compute(g0, sc, o0); acc.prime(o0[0]);
+                        Chain::load(P, 0, g0); Chain::compute_slow(g0, sc, o0); acc.prime(o0[0]);
                     }
-                    for (i64 cb = (i64)tx * V; cb < C; cb += (i64)TX * V * U) {
+                    i64 idx = c0;
+                    int it = 0;
+                    for (; it + U <= ncol; it += U) {
                         typename Chain::Regs g[U];
 #pragma unroll
-                        for (int u = 0; u < U; ++u) { i64 c = cb + (i64)u * TX * V; if (c < C) Chain::load(blk, b, r, c, g[u]); }
+                        for (int u = 0; u < U; ++u) Chain::load(P, u, g[u]);
+                        Chain::advance(P, U);
+                        T o[U][V];
+                        b2_compute_batch<Chain, V, U>(P, g, sc, o);
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
-                            i64 c = cb + (i64)u * TX * V;
-                            if (c < C) {
-                                T o[V]; Chain::compute(g[u], sc, o);
 #pragma unroll
-                                for (int v = 0; v < V; ++v) acc.add(o[v], c + v);
-                            }
+                            for (int v = 0; v < V; ++v) acc.add(o[u][v], WANT_IDX ? (idx + (i64)u * TX * V + v) : 0);
                         }
+                        if constexpr (WANT_IDX) idx += (i64)U * TX * V;
                     }
-                    if constexpr (REDOP == B2R_MOMENT) acc.finish_local();
+                    for (; it < ncol; ++it) {
+                        typename Chain::Regs g[1]; T o[1][V];
+                        Chain::load(P, 0, g[0]); Chain::advance(P, 1);
+                        b2_compute_batch<Chain, V, 1>(P, g, sc, o);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc.add(o[0][v], WANT_IDX ? (idx + v) : 0);
+                        if constexpr (WANT_IDX) idx += (i64)TX * V;
+                    }
+                    if constexpr (REDOP == B2R_MOMENT) acc.finish_local((i64)ncol * V);
                 }
 #pragma unroll
                 for (int off = SW / 2; off > 0; off >>= 1) acc.shfl(off, SW);
@@ -691,7 +791,7 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                     __syncthreads();
                     if (tx == 0) { for (int k = 1; k < WPR; ++k) acc.merge(smc[ty * WPR + k]); }
                 }
-                if (tx == 0 && rok) b2_store_result<REDOP, T, ACC>(blk, b * R + r, acc, blk.arg_offset);
+                if (tx == 0 && r < rend) b2_store_result<REDOP, T, ACC>(blk, b * R + r, acc, blk.arg_offset);
             }
             return;
         }

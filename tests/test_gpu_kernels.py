@@ -149,3 +149,39 @@ def test_combine_and_gather():
     torch.cuda.synchronize()
     np.testing.assert_array_equal(dst.to_numpy(), src)
     del keep
+
+
+def test_fast_sin_cos_accuracy_and_slow_path():
+    """b2_sinf_fast / b2_cosf_fast (csrc/b2_device.cuh): <= 2 ulp of the correctly rounded value
+    on the Cody-Waite range, libdevice beyond it (per-batch slow path), NaN/inf semantics."""
+    import torch
+    from dask_array_b200 import _codegen as cg, _lib, _runtime as rt
+    from dask_array_b200._device import DeviceChunk
+    rng = np.random.default_rng(11)
+    parts = [
+        rng.random(1 << 20, dtype=np.float32) * 2 - 1,
+        (rng.random(1 << 20, dtype=np.float32) - 0.5) * 200,
+        (rng.random(1 << 20, dtype=np.float32) - 0.5) * 2e5,               # straddles 105615
+        (rng.random(1 << 18, dtype=np.float32) - 0.5) * 1e9,               # far beyond: libdevice path
+        np.float32(np.pi / 2) * rng.integers(-40000, 40000, 1 << 18).astype(np.float32),   # near zeros/extrema
+        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-30, -1e-30, 105615.0, 105616.0, 3.4e38], np.float32),
+    ]
+    x = np.concatenate(parts)
+    x = np.concatenate([x, np.zeros((-len(x)) % 4096, np.float32)]).reshape(-1, 4096)
+    for fn, npf in (("sin", np.sin), ("cos", np.cos)):
+        p = cg.Program()
+        p.set_output(p.op(fn, p.add_input("float32")))
+        c = DeviceChunk.from_numpy(x)
+        out = DeviceChunk.empty(x.shape, np.float32)
+        rt.FusedLaunch(p, _lib.RED_NONE, (), [rt.BlockArgs(shape=x.shape, inputs=[(c.ptr, c.strides)], out0=out.ptr)]).run()
+        torch.cuda.synchronize()
+        got = out.to_numpy()
+        with np.errstate(invalid="ignore"):
+            want64 = npf(x.astype(np.float64))
+            want32 = want64.astype(np.float32)
+            ulp = np.spacing(np.abs(want32))
+        fin = np.isfinite(want64)
+        assert np.array_equal(np.isnan(got), ~fin)
+        err = np.abs(got[fin].astype(np.float64) - want64[fin]) / ulp[fin]
+        assert err.max() <= 2.0, (fn, err.max())
+        assert got.ravel()[np.flatnonzero(x.ravel() == 0)[1]] == npf(np.float32(-0.0))
