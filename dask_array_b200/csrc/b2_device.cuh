@@ -258,15 +258,14 @@ __device__ __forceinline__ float b2_sinf_fast(float x, float& big) {
 }
 __device__ __forceinline__ float b2_cosf_fast(float x, float& big) {
     big = fmaxf(big, fabsf(x));
-    // x = (m + 1/2) pi + r,  m = round(x/pi - 1/2):  cos(x) = (-1)^(m+1) sin(r)
-    const float jm = fmaf(x, 0.318309886183790672f, 12582911.5f);
-    const float j = (jm - 12582912.0f) + 0.5f;
+    // cos(x) = sin(x + pi/2):  j = round(x/pi + 1/2),  r = x - (j - 1/2) pi,  cos(x) = (-1)^j sin(r)
+    const float jm = fmaf(x, 0.318309886183790672f, 0.5f) + 12582912.0f;
+    const float j = (jm - 12582912.0f) - 0.5f;
     float r = fmaf(j, -3.1415925025939941406f, x);
     r = fmaf(j, -1.5099578831723192707e-07f, r);
     r = fmaf(j, -1.0780605906948476785e-14f, r);
-    return __int_as_float(__float_as_int(b2_sin_poly(r)) ^ ((~__float_as_int(jm)) << 31));
+    return __int_as_float(__float_as_int(b2_sin_poly(r)) ^ (__float_as_int(jm) << 31));
 }
-
 __device__ __noinline__ float b2_sinf_slow(float x) { return sinf(x); }   // libdevice, full range
 __device__ __noinline__ float b2_cosf_slow(float x) { return cosf(x); }
 
