@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-CODEGEN_VERSION = "5"     # part of every kernel's cache key: bump when generated code changes
+CODEGEN_VERSION = "7"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
@@ -477,7 +477,7 @@ struct Chain {{
     }}
 {compute}
 }};
-extern "C" __global__ void __launch_bounds__({spec.tx * spec.ty})
+extern "C" __global__ void __launch_bounds__({spec.tx * spec.ty}, {3 if spec.tx * spec.ty <= 256 else 1})
 b2_fused(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars sc) {{
     b2_run<Chain, {_MODE_NAME[spec.mode]}, {_RED_NAME[spec.redop]}, B2_V, {spec.tx}, {spec.ty}, {spec.rpt}, {spec.unroll}, {acc}>(blocks, nblocks, sc);
 }}

@@ -483,34 +483,69 @@ template <typename P> __device__ __forceinline__ P b2_load_cg(const P* p) {
     return u.v;
 }
 
-// Evaluate the chain on N loaded vectors.  Chains with fp32 sin/cos run the fast versions and
-// track max|arg|; if any argument of the WHOLE batch left the Cody-Waite range (rare) the batch
-// is re-loaded (P has already advanced past it) and redone with libdevice -- one predictable
-// branch per N*V elements instead of one per element.
-template <typename Chain, int V, int N>
-__device__ __forceinline__ void b2_compute_batch(const typename Chain::Ptrs& P, const typename Chain::Regs (&g)[N],
-                                                 const B2Scalars& sc, typename Chain::out_t (&o)[N][V]) {
-    float big = 0.0f;
+// Streaming loop shared by every mode: walk `n` V-wide vectors reachable through `P`
+// (one step = one vector), evaluate the chain and hand each result to `consume(state, k, o)`.
+//  * Rolling prefetch: a thread keeps U vector loads in flight at all times -- the registers
+//    of vector u are refilled with the NEXT batch's vector u right after the chain consumed
+//    them -- so HBM latency is covered by this thread's own compute, not only by other warps.
+//  * Chains with fp32 sin/cos run the fast versions and track max|arg|.  If an argument of
+//    the batch left the Cody-Waite range (rare) the state is rolled back to the checkpoint
+//    taken at the start of the batch and the batch is redone from memory with libdevice:
+//    one predictable branch per U*V elements instead of one per element.
+template <typename Chain, int V, int U, typename S, typename F>
+__device__ __forceinline__ void b2_stream(typename Chain::Ptrs& P, const int n, const B2Scalars& sc, S& st, F consume) {
+    typedef typename Chain::out_t T;
+    int it = 0;
+    if (n >= U) {
+        typename Chain::Regs g[U];
 #pragma unroll
-    for (int u = 0; u < N; ++u) Chain::compute(g[u], sc, o[u], big);
-    if constexpr (Chain::HAS_SLOW) {
-        if (big > B2_SINCOS_BIG) {
+        for (int u = 0; u < U; ++u) Chain::load(P, u, g[u]);
+        Chain::advance(P, U);
+        for (; it + U <= n; it += U) {
+            const bool more = it + 2 * U <= n;
+            S saved;
+            if constexpr (Chain::HAS_SLOW) saved = st;
+            float big = 0.0f;
 #pragma unroll
-            for (int u = 0; u < N; ++u) {
-                typename Chain::Regs gs;
-                Chain::load(P, u - N, gs);
-                Chain::compute_slow(gs, sc, o[u]);
+            for (int u = 0; u < U; ++u) {
+                T o[V];
+                Chain::compute(g[u], sc, o, big);
+                if (more) Chain::load(P, u, g[u]);
+                consume(st, it + u, o);
+            }
+            if (more) Chain::advance(P, U);
+            if constexpr (Chain::HAS_SLOW) {
+                if (big > B2_SINCOS_BIG) {
+                    st = saved;
+                    const int back = more ? 2 * U : U;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        typename Chain::Regs gs; T o[V];
+                        Chain::load(P, u - back, gs);
+                        Chain::compute_slow(gs, sc, o);
+                        consume(st, it + u, o);
+                    }
+                }
             }
         }
     }
+    for (; it < n; ++it) {       // tail (< U vectors): exact chain, nothing speculative
+        typename Chain::Regs gs; T o[V];
+        Chain::load(P, 0, gs); Chain::advance(P, 1);
+        Chain::compute_slow(gs, sc, o);
+        consume(st, it, o);
+    }
 }
 
+struct B2NoState {};
+template <typename A, int V> struct B2AccState { A acc[V]; };
+
 // Chain supplies:
-//   out_t; Regs; Ptrs (one typed pointer + element step per input);
+//   out_t; Regs; Ptrs (one typed pointer + element step per input); HAS_SLOW;
 //   setup_rows(blk, b, r, c, rstep, Ptrs&)  -- point at (b, r, c), one step = rstep rows down;
 //   setup_cols(blk, b, r, c, cstep, Ptrs&)  -- point at (b, r, c), one step = cstep columns right;
 //   load(Ptrs, k, Regs&)   -- the V-wide load k steps ahead;   advance(Ptrs&, n);
-//   compute(Regs, scalars, out_t(&)[V]).
+//   compute(Regs, scalars, out_t(&)[V], float& big) [fast], compute_slow(Regs, scalars, out_t(&)[V]).
 template <typename Chain, int MODE, int REDOP, int V, int TX, int TY, int RPT, int U, typename ACC>
 __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars& sc) {
     typedef typename Chain::out_t T;
@@ -542,28 +577,13 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
         const i64 first = r0 + ty;
         if (c < C && first < rend) {
             const int nrows = (int)((rend - first + TY - 1) / TY);
-            T* outp = (T*)blk.out0 + (b * R + first) * C + c;
+            T* const outp = (T*)blk.out0 + (b * R + first) * C + c;
             const i64 ostep = (i64)TY * C;
             typename Chain::Ptrs P;
             Chain::setup_rows(blk, b, first, c, TY, P);
-            int it = 0;
-            for (; it + U <= nrows; it += U) {
-                typename Chain::Regs g[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) Chain::load(P, u, g[u]);
-                Chain::advance(P, U);
-                T o[U][V];
-                b2_compute_batch<Chain, V, U>(P, g, sc, o);
-#pragma unroll
-                for (int u = 0; u < U; ++u) b2_store_vec<T, V>(outp + u * ostep, o[u]);
-                outp += U * ostep;
-            }
-            for (; it < nrows; ++it) {
-                typename Chain::Regs g[1]; T o[1][V];
-                Chain::load(P, 0, g[0]); Chain::advance(P, 1);
-                b2_compute_batch<Chain, V, 1>(P, g, sc, o);
-                b2_store_vec<T, V>(outp, o[0]); outp += ostep;
-            }
+            B2NoState none;
+            b2_stream<Chain, V, U>(P, nrows, sc, none,
+                [&](B2NoState&, int k, const T (&o)[V]) { b2_store_vec<T, V>(outp + k * ostep, o); });
         }
         return;
     } else {
@@ -576,7 +596,8 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
             // ---- accumulate this thread's rows of the tile
             const i64 c = (tc * TX + tx) * V;
             const i64 first = r0 + ty;
-            A acc[V];
+            B2AccState<A, V> st;
+            A (&acc)[V] = st.acc;
 #pragma unroll
             for (int v = 0; v < V; ++v) acc[v].init();
             const int nrows = (c < C && first < rend) ? (int)((rend - first + TY - 1) / TY) : 0;
@@ -591,32 +612,14 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
 #pragma unroll
                     for (int v = 0; v < V; ++v) acc[v].prime(MODE == B2M_R ? o0[v] : o0[0]);
                 }
-                i64 idx = (MODE == B2M_R) ? first : (first * C + c);       // arg reductions only
+                const i64 idx0 = (MODE == B2M_R) ? first : (first * C + c);       // arg reductions only
                 const i64 istep = (MODE == B2M_R) ? (i64)TY : (i64)TY * C;
-                int it = 0;
-                for (; it + U <= nrows; it += U) {
-                    typename Chain::Regs g[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) Chain::load(P, u, g[u]);
-                    Chain::advance(P, U);
-                    T o[U][V];
-                    b2_compute_batch<Chain, V, U>(P, g, sc, o);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
+                b2_stream<Chain, V, U>(P, nrows, sc, st,
+                    [&](B2AccState<A, V>& s_, int k, const T (&o)[V]) {
 #pragma unroll
                         for (int v = 0; v < V; ++v)
-                            acc[v].add(o[u][v], WANT_IDX ? (idx + u * istep + (MODE == B2M_R ? 0 : v)) : 0);
-                    }
-                    if constexpr (WANT_IDX) idx += U * istep;
-                }
-                for (; it < nrows; ++it) {
-                    typename Chain::Regs g[1]; T o[1][V];
-                    Chain::load(P, 0, g[0]); Chain::advance(P, 1);
-                    b2_compute_batch<Chain, V, 1>(P, g, sc, o);
-#pragma unroll
-                    for (int v = 0; v < V; ++v) acc[v].add(o[0][v], WANT_IDX ? (idx + (MODE == B2M_R ? 0 : v)) : 0);
-                    if constexpr (WANT_IDX) idx += istep;
-                }
+                            s_.acc[v].add(o[v], WANT_IDX ? (idx0 + k * istep + (MODE == B2M_R ? 0 : v)) : 0);
+                    });
             }
             if constexpr (REDOP == B2R_MOMENT) {
 #pragma unroll
@@ -747,7 +750,9 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
             for (i64 rr = r0; rr < rend; rr += TY) {       // uniform trip count (barriers inside)
                 const i64 r = rr + ty;
                 const bool rok = (r < rend) && ncol > 0;
-                A acc; acc.init();
+                B2AccState<A, 1> st;
+                A& acc = st.acc[0];
+                acc.init();
                 if (rok) {
                     typename Chain::Ptrs P;
                     Chain::setup_cols(blk, b, r, c0, (i64)TX * V, P);
@@ -755,30 +760,11 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                         typename Chain::Regs g0; T o0[V];
                         Chain::load(P, 0, g0); Chain::compute_slow(g0, sc, o0); acc.prime(o0[0]);
                     }
-                    i64 idx = c0;
-                    int it = 0;
-                    for (; it + U <= ncol; it += U) {
-                        typename Chain::Regs g[U];
+                    b2_stream<Chain, V, U>(P, ncol, sc, st,
+                        [&](B2AccState<A, 1>& s_, int k, const T (&o)[V]) {
 #pragma unroll
-                        for (int u = 0; u < U; ++u) Chain::load(P, u, g[u]);
-                        Chain::advance(P, U);
-                        T o[U][V];
-                        b2_compute_batch<Chain, V, U>(P, g, sc, o);
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-#pragma unroll
-                            for (int v = 0; v < V; ++v) acc.add(o[u][v], WANT_IDX ? (idx + (i64)u * TX * V + v) : 0);
-                        }
-                        if constexpr (WANT_IDX) idx += (i64)U * TX * V;
-                    }
-                    for (; it < ncol; ++it) {
-                        typename Chain::Regs g[1]; T o[1][V];
-                        Chain::load(P, 0, g[0]); Chain::advance(P, 1);
-                        b2_compute_batch<Chain, V, 1>(P, g, sc, o);
-#pragma unroll
-                        for (int v = 0; v < V; ++v) acc.add(o[0][v], WANT_IDX ? (idx + v) : 0);
-                        if constexpr (WANT_IDX) idx += (i64)TX * V;
-                    }
+                            for (int v = 0; v < V; ++v) s_.acc[0].add(o[v], WANT_IDX ? (c0 + (i64)k * TX * V + v) : 0);
+                        });
                     if constexpr (REDOP == B2R_MOMENT) acc.finish_local((i64)ncol * V);
                 }
 #pragma unroll
