@@ -302,6 +302,9 @@ struct B2AccSum {   // np.sum(x, dtype=ACC)  (_chunk.py:172; ints widen to 64 bi
     __device__ __forceinline__ void add(T v, i64) { s += (ACC)v; }
     __device__ __forceinline__ void merge(const B2AccSum& o) { s += o.s; }
     __device__ __forceinline__ void shfl(int off, int width) { B2AccSum o; o.s = b2_shfl_down(s, off, width); merge(o); }
+    __device__ __forceinline__ void lane_merge(const B2AccSum& o) { merge(o); }
+    __device__ __forceinline__ void lane_shfl(int off, int width) { shfl(off, width); }
+    __device__ __forceinline__ void lane_finish() {}
     __device__ __forceinline__ Packed pack() const { return s; }
     __device__ __forceinline__ void unpack(const Packed& p) { s = p; }
 };
@@ -314,6 +317,9 @@ struct B2AccProd {
     __device__ __forceinline__ void add(T v, i64) { s *= (ACC)v; }
     __device__ __forceinline__ void merge(const B2AccProd& o) { s *= o.s; }
     __device__ __forceinline__ void shfl(int off, int width) { B2AccProd o; o.s = b2_shfl_down(s, off, width); merge(o); }
+    __device__ __forceinline__ void lane_merge(const B2AccProd& o) { merge(o); }
+    __device__ __forceinline__ void lane_shfl(int off, int width) { shfl(off, width); }
+    __device__ __forceinline__ void lane_finish() {}
     __device__ __forceinline__ Packed pack() const { return s; }
     __device__ __forceinline__ void unpack(const Packed& p) { s = p; }
 };
@@ -326,6 +332,9 @@ struct B2AccAnyAll {   // np.any / np.all -> bool
     __device__ __forceinline__ void add(T v, i64) { bool t = (v != (T)0); s = ALL ? (s & (unsigned char)t) : (s | (unsigned char)t); }
     __device__ __forceinline__ void merge(const B2AccAnyAll& o) { s = ALL ? (s & o.s) : (s | o.s); }
     __device__ __forceinline__ void shfl(int off, int width) { B2AccAnyAll o; o.s = b2_shfl_down(s, off, width); merge(o); }
+    __device__ __forceinline__ void lane_merge(const B2AccAnyAll& o) { merge(o); }
+    __device__ __forceinline__ void lane_shfl(int off, int width) { shfl(off, width); }
+    __device__ __forceinline__ void lane_finish() {}
     __device__ __forceinline__ Packed pack() const { return s; }
     __device__ __forceinline__ void unpack(const Packed& p) { s = p; }
 };
@@ -347,6 +356,9 @@ struct B2AccMinMax {   // np.min / np.max: NaN propagates (chunk_min/chunk_max _
     __device__ __forceinline__ void shfl(int off, int width) {
         B2AccMinMax o; o.m = b2_shfl_down(m, off, width); o.has = b2_shfl_down(has, off, width); merge(o);
     }
+    __device__ __forceinline__ void lane_merge(const B2AccMinMax& o) { merge(o); }
+    __device__ __forceinline__ void lane_shfl(int off, int width) { shfl(off, width); }
+    __device__ __forceinline__ void lane_finish() {}
     __device__ __forceinline__ Packed pack() const { Packed p; p.m = m; p.has = has ? 1 : 0; return p; }
     __device__ __forceinline__ void unpack(const Packed& p) { m = p.m; has = (p.has != 0); }
 };
@@ -375,6 +387,9 @@ struct B2AccArg {
     __device__ __forceinline__ void shfl(int off, int width) {
         B2AccArg o; o.v = b2_shfl_down(v, off, width); o.i = b2_shfl_down(i, off, width); merge(o);
     }
+    __device__ __forceinline__ void lane_merge(const B2AccArg& o) { merge(o); }
+    __device__ __forceinline__ void lane_shfl(int off, int width) { shfl(off, width); }
+    __device__ __forceinline__ void lane_finish() {}
     __device__ __forceinline__ Packed pack() const { Packed p; p.v = v; p.i = i; return p; }
     __device__ __forceinline__ void unpack(const Packed& p) { v = p.v; i = p.i; }
 };
@@ -411,6 +426,22 @@ struct B2AccMoment {
         n = tot;
     }
     __device__ __forceinline__ void merge(const B2AccMoment& o) { chan(o.n, o.mean, o.m2); }
+    // Lanes that share ONE pivot K (a whole tile in mode RC, a whole row in mode C) reduce the raw
+    // shifted sums -- plain adds, no divisions -- and convert once: (n, mean, m2) temporarily hold
+    // (count, sum(x-K), sum((x-K)^2)).
+    __device__ __forceinline__ void to_raw(i64 count) { n = (double)count; mean = (double)s1; m2 = (double)s2; }
+    __device__ __forceinline__ void lane_merge(const B2AccMoment& o) { n += o.n; mean += o.mean; m2 += o.m2; }
+    __device__ __forceinline__ void lane_shfl(int off, int width) {
+        n += b2_shfl_down(n, off, width); mean += b2_shfl_down(mean, off, width); m2 += b2_shfl_down(m2, off, width);
+    }
+    __device__ __forceinline__ void lane_finish() {
+        if (n > 0.0) {
+            const double a = mean, bsum = m2;
+            mean = (double)K + a / n;
+            m2 = bsum - a * a / n;
+            if (m2 < 0.0) m2 = 0.0;
+        } else { mean = 0.0; m2 = 0.0; }
+    }
     __device__ __forceinline__ void shfl(int off, int width) {
         double on = b2_shfl_down(n, off, width), om = b2_shfl_down(mean, off, width), o2 = b2_shfl_down(m2, off, width);
         chan(on, om, o2);
@@ -605,9 +636,16 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                 typename Chain::Ptrs P;
                 Chain::setup_rows(blk, b, first, c, TY, P);
                 if constexpr (REDOP == B2R_MOMENT) {
-                    // pivot: the first element this thread sees
+                    // pivot: mode R -- the first element of each column lane; mode RC -- ONE pivot
+                    // for the whole tile (its first element), so the CTA reduces plain sums
                     typename Chain::Regs g0; T o0[V];
-                    Chain::load(P, 0, g0);
+                    if constexpr (MODE == B2M_R) {
+                        Chain::load(P, 0, g0);
+                    } else {
+                        typename Chain::Ptrs P0;
+                        Chain::setup_rows(blk, b, r0, tc * TX * V, TY, P0);
+                        Chain::load(P0, 0, g0);
+                    }
                     Chain::compute_slow(g0, sc, o0);
 #pragma unroll
                     for (int v = 0; v < V; ++v) acc[v].prime(MODE == B2M_R ? o0[v] : o0[0]);
@@ -623,7 +661,7 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
             }
             if constexpr (REDOP == B2R_MOMENT) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) acc[v].finish_local(nrows);
+                for (int v = 0; v < V; ++v) { if constexpr (MODE == B2M_R) acc[v].finish_local(nrows); else acc[v].to_raw(nrows); }
             }
 
             if constexpr (MODE == B2M_R) {
@@ -682,18 +720,19 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                 // ---- MODE RC: one value per tile, then all tiles of (block, b) in order
                 A a = acc[0];
 #pragma unroll
-                for (int v = 1; v < V; ++v) a.merge(acc[v]);
+                for (int v = 1; v < V; ++v) a.lane_merge(acc[v]);
                 // warp reduce (lower lane = earlier), then across warps in order
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) a.shfl(off, 32);
+                for (int off = 16; off > 0; off >>= 1) a.lane_shfl(off, 32);
                 constexpr int NW = (NT + 31) / 32;
                 __shared__ A smw[NW];
                 const int lane = tid & 31, wid = tid >> 5;
                 if constexpr (NW > 1) {
                     if (lane == 0) smw[wid] = a;
                     __syncthreads();
-                    if (tid == 0) { for (int w = 1; w < NW; ++w) a.merge(smw[w]); }
+                    if (tid == 0) { for (int w = 1; w < NW; ++w) a.lane_merge(smw[w]); }
                 }
+                if (tid == 0) a.lane_finish();
                 const i64 ntile = blk.tiles_r * blk.tiles_c;
                 const i64 tslot = tr * blk.tiles_c + tc;
                 i64 fix = 0;
@@ -758,24 +797,31 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                     Chain::setup_cols(blk, b, r, c0, (i64)TX * V, P);
                     if constexpr (REDOP == B2R_MOMENT) {
                         typename Chain::Regs g0; T o0[V];
-                        Chain::load(P, 0, g0); Chain::compute_slow(g0, sc, o0); acc.prime(o0[0]);
+                        typename Chain::Ptrs P0;                       // ONE pivot per row: its first element
+                        Chain::setup_cols(blk, b, r, 0, (i64)TX * V, P0);
+                        Chain::load(P0, 0, g0); Chain::compute_slow(g0, sc, o0); acc.prime(o0[0]);
                     }
                     b2_stream<Chain, V, U>(P, ncol, sc, st,
                         [&](B2AccState<A, 1>& s_, int k, const T (&o)[V]) {
 #pragma unroll
                             for (int v = 0; v < V; ++v) s_.acc[0].add(o[v], WANT_IDX ? (c0 + (i64)k * TX * V + v) : 0);
                         });
-                    if constexpr (REDOP == B2R_MOMENT) acc.finish_local((i64)ncol * V);
+                    if constexpr (REDOP == B2R_MOMENT) acc.to_raw((i64)ncol * V);
+                }
+                if constexpr (REDOP == B2R_MOMENT) {
+                    // lanes without work must still agree on the row's pivot: take lane 0's
+                    acc.K = __shfl_sync(0xffffffffu, acc.K, (tid & 31) & ~(SW - 1), 32);
                 }
 #pragma unroll
-                for (int off = SW / 2; off > 0; off >>= 1) acc.shfl(off, SW);
+                for (int off = SW / 2; off > 0; off >>= 1) acc.lane_shfl(off, SW);
                 if constexpr (WPR > 1) {
                     const int lane = tid & 31, w = tx >> 5;
                     __syncthreads();
                     if (lane == 0) smc[ty * WPR + w] = acc;
                     __syncthreads();
-                    if (tx == 0) { for (int k = 1; k < WPR; ++k) acc.merge(smc[ty * WPR + k]); }
+                    if (tx == 0) { for (int k = 1; k < WPR; ++k) acc.lane_merge(smc[ty * WPR + k]); }
                 }
+                if (tx == 0) acc.lane_finish();
                 if (tx == 0 && r < rend) b2_store_result<REDOP, T, ACC>(blk, b * R + r, acc, blk.arg_offset);
             }
             return;
