@@ -52,11 +52,7 @@ class World:
             self.rank, self.size = 0, 1
 
     def owner(self, expr, bid) -> int:
-        if self.size == 1:
-            return 0
-        nb = expr.numblocks
-        flat = int(np.ravel_multi_index(bid, nb)) if nb else 0
-        return flat % self.size
+        return owner_of(expr, bid, self.size)
 
 
 _PLAN_CACHE: dict = {}
@@ -467,36 +463,72 @@ def _p2p_exchange(ex: Executor, sends, recvs):
             w.wait()
 
 
-def _exchange_for_fused(ex: Executor, plan: FusedPlan, deps, out_ids):
-    """Blocks of dependencies that some rank's output blocks read but another rank owns are
-    packed per peer, exchanged and exposed as DeviceChunks.  Every rank derives the complete
-    schedule from the (replicated) expression metadata, so no negotiation is needed."""
-    W, me = ex.world.size, ex.world.rank
+def owner_of(expr, bid, world_size: int) -> int:
+    """Block-cyclic placement: ``ravel(block id) mod world``."""
+    if world_size == 1:
+        return 0
+    nb = expr.numblocks
+    return (int(np.ravel_multi_index(bid, nb)) if nb else 0) % world_size
+
+
+def plan_fused_exchange(plan: FusedPlan, replicated, W: int, me: int):
+    """Pure (no device) schedule of the blocks a fused expression reads across the partition.
+    Returns (send_items, recv_items): per peer, lists in one global canonical order --
+    every rank derives the same order from the expression metadata, so sends and receives
+    pair up without negotiation.  Items: (leaf index k, leaf block id, nbytes)."""
     expr = plan.fused
-    # (reader rank, dep index k, leaf block id) for every non-local read, in canonical order
     wanted = {}
     for bid in expr.block_ids():
-        r = ex.world.owner(expr, bid)
+        r = owner_of(expr, bid, W)
         for k, (dep, _) in enumerate(plan.leaves):
-            if deps[k].replicated:
+            if replicated[k]:
                 continue
             lbid = plan.leaf_block_id(k, bid)
-            o = ex.world.owner(dep, lbid)
+            o = owner_of(dep, lbid, W)
             if o != r:
                 wanted[(r, dep._name, lbid)] = (o, k)
-    if not wanted:
-        return {}
-    keys = sorted(wanted)
     send_items = {p: [] for p in range(W)}
     recv_items = {p: [] for p in range(W)}
-    for (r, name, lbid) in keys:
+    for (r, name, lbid) in sorted(wanted):
         o, k = wanted[(r, name, lbid)]
         dep = plan.leaves[k][0]
         nb = math.prod(dep.block_shape(lbid)) * dep.dtype.itemsize
         if o == me:
             send_items[r].append((k, lbid, nb))
         if r == me:
-            recv_items[o].append((k, lbid, nb, name))
+            recv_items[o].append((k, lbid, nb))
+    return send_items, recv_items
+
+
+def plan_rechunk_exchange(expr: TasksRechunk, W: int, me: int):
+    """Pure schedule of the rectangles a rechunk moves across the partition (the all-to-all of
+    SURVEY.md 8e).  Items: (old block id, new block id, source slices, piece shape, nbytes)."""
+    x = expr.operand("array")
+    item = expr.dtype.itemsize
+    send_items = {p: [] for p in range(W)}
+    recv_items = {p: [] for p in range(W)}
+    for nbid in expr.block_ids():
+        r = owner_of(expr, nbid, W)
+        for obid, sl, dsl in expr.pieces(nbid):
+            o = owner_of(x, obid, W)
+            if o == r:
+                continue
+            shape = tuple(s.stop - s.start for s in sl)
+            nb = math.prod(shape) * item
+            if o == me:
+                send_items[r].append((obid, nbid, sl, shape, nb))
+            if r == me:
+                recv_items[o].append((obid, nbid, sl, shape, nb))
+    return send_items, recv_items
+
+
+def _exchange_for_fused(ex: Executor, plan: FusedPlan, deps, out_ids):
+    """Blocks of dependencies that some rank's output blocks read but another rank owns are
+    packed per peer, exchanged over NCCL and exposed as DeviceChunks."""
+    W, me = ex.world.size, ex.world.rank
+    send_items, recv_items = plan_fused_exchange(plan, [d.replicated for d in deps], W, me)
+    if not any(send_items.values()) and not any(recv_items.values()):
+        return {}
     pad = lambda n: -(-n // 256) * 256
     sends, recvs, keep, out = [], [], [], {}
     for p in range(W):
@@ -513,11 +545,11 @@ def _exchange_for_fused(ex: Executor, plan: FusedPlan, deps, out_ids):
             keep.append(g)
             sends.append((p, buf))
         if recv_items[p]:
-            buf = alloc_bytes(sum(pad(nb) for _, _, nb, _ in recv_items[p]), ex.device)
+            buf = alloc_bytes(sum(pad(nb) for _, _, nb in recv_items[p]), ex.device)
             off = 0
-            for k, lbid, nb, name in recv_items[p]:
+            for k, lbid, nb in recv_items[p]:
                 dep = plan.leaves[k][0]
-                out[(name, lbid)] = DeviceChunk(buf, dep.block_shape(lbid), dep.dtype, offset=off // dep.dtype.itemsize)
+                out[(dep._name, lbid)] = DeviceChunk(buf, dep.block_shape(lbid), dep.dtype, offset=off // dep.dtype.itemsize)
                 off += pad(nb)
             recvs.append((p, buf))
     ex._do(lambda: _p2p_exchange(ex, sends, recvs))
@@ -529,27 +561,13 @@ def _exchange_for_rechunk(ex: Executor, expr: TasksRechunk, src: BlockStore, new
     """All-to-all of the rectangles a rechunk moves across the partition: pack (gather kernel)
     -> NCCL send/recv -> the local gather reads the received pieces in place."""
     W, me = ex.world.size, ex.world.rank
-    x = expr.operand("array")
     item = expr.dtype.itemsize
     pad = lambda n: -(-n // 256) * 256
-    send_items = {p: [] for p in range(W)}
-    recv_items = {p: [] for p in range(W)}
-    for nbid in expr.block_ids():
-        r = ex.world.owner(expr, nbid)
-        for obid, sl, dsl in expr.pieces(nbid):
-            o = ex.world.owner(x, obid)
-            if o == r:
-                continue
-            shape = tuple(s.stop - s.start for s in sl)
-            nb = math.prod(shape) * item
-            if o == me:
-                send_items[r].append((obid, nbid, sl, shape, nb))
-            if r == me:
-                recv_items[o].append((obid, nbid, shape, nb))
+    send_items, recv_items = plan_rechunk_exchange(expr, W, me)
     sends, recvs, keep, out = [], [], [], {}
     for p in range(W):
         if send_items[p]:
-            buf = alloc_bytes(sum(pad(nb) for *_, nb in send_items[p]), ex.device)
+            buf = alloc_bytes(sum(pad(it[-1]) for it in send_items[p]), ex.device)
             off, copies = 0, []
             for obid, nbid, sl, shape, nb in send_items[p]:
                 piece = src.blocks[obid][sl]
@@ -561,9 +579,9 @@ def _exchange_for_rechunk(ex: Executor, expr: TasksRechunk, src: BlockStore, new
             keep.append(g)
             sends.append((p, buf))
         if recv_items[p]:
-            buf = alloc_bytes(sum(pad(nb) for *_, nb in recv_items[p]), ex.device)
+            buf = alloc_bytes(sum(pad(it[-1]) for it in recv_items[p]), ex.device)
             off = 0
-            for obid, nbid, shape, nb in recv_items[p]:
+            for obid, nbid, sl, shape, nb in recv_items[p]:
                 out[(obid, nbid)] = DeviceChunk(buf, shape, expr.dtype, offset=off // item)
                 off += pad(nb)
             recvs.append((p, buf))

@@ -74,7 +74,16 @@ __device__ __forceinline__ u32 b2_ldg4(const void* p) {
     return w;
 }
 
-template <int BYTES> struct B2Raw { u32 w[(BYTES + 3) / 4]; };
+// scalar read-only load of any element type (bool / 8-bit types go through unsigned char)
+template <typename T> __device__ __forceinline__ T b2_ld(const T* p) {
+    if constexpr (sizeof(T) == 1) {
+        union { unsigned char c; T t; } u;
+        u.c = __ldg(reinterpret_cast<const unsigned char*>(p));
+        return u.t;
+    } else {
+        return __ldg(p);
+    }
+}
 
 // V consecutive elements of T starting at p (p is V*sizeof(T)-aligned by host contract)
 template <typename T, int V>
@@ -106,13 +115,13 @@ __device__ __forceinline__ void b2_load_vec(const T* p, T (&dst)[V]) {
         for (int v = 0; v < V; ++v) dst[v] = u.t[v];
     } else {
 #pragma unroll
-        for (int v = 0; v < V; ++v) dst[v] = __ldg(p + v);
+        for (int v = 0; v < V; ++v) dst[v] = b2_ld(p + v);
     }
 }
 // one element broadcast to the V lanes (column stride 0)
 template <typename T, int V>
 __device__ __forceinline__ void b2_load_bcast(const T* p, T (&dst)[V]) {
-    T x = __ldg(p);
+    T x = b2_ld(p);
 #pragma unroll
     for (int v = 0; v < V; ++v) dst[v] = x;
 }
@@ -120,7 +129,7 @@ __device__ __forceinline__ void b2_load_bcast(const T* p, T (&dst)[V]) {
 template <typename T, int V>
 __device__ __forceinline__ void b2_load_strided(const T* p, i64 sc, T (&dst)[V]) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) dst[v] = __ldg(p + v * sc);
+    for (int v = 0; v < V; ++v) dst[v] = b2_ld(p + v * sc);
 }
 
 template <typename T, int V>

@@ -1,0 +1,96 @@
+"""Structure of optimised expression trees (CPU): the fusion groups, tree depths and rewrite
+rules the reference documents (README.md:52-57, tests/test_collection.py:996-1135,
+tests/test_reductions.py:646-681), reproduced by the host-side front-end."""
+import numpy as np
+import pytest
+
+import dask_array_b200 as da
+from dask_array_b200._blockwise import FusedBlockwise, FusedPlan
+from dask_array_b200._rechunk import TasksRechunk, old_to_new
+from dask_array_b200._reductions import PartialReduce, normalize_split_every
+from oracle import reference as ref
+
+
+def labels(expr):
+    out = [expr._tree_label()]
+    for d in expr.dependencies():
+        out += labels(d)
+    return out
+
+
+def test_readme_example_tree():
+    x = da.ones((1000, 1000), chunks=(100, 100))
+    opt = (x + x.T)[:100, :100].optimize().expr
+    # README: FusedBlockwise(add, transpose) <- Ones(100, 100); `x` is evicted from the group by
+    # the a + a.T conflict rule (_blockwise.py:1342-1402) and the slice reached the leaf.
+    assert isinstance(opt, FusedBlockwise)
+    assert [e._tree_label() for e in opt.exprs] == ["Elemwise(add)", "Transpose(1, 0)"]
+    (dep,) = opt.dependencies()
+    assert dep.shape == (100, 100) and "Ones" in dep._tree_label()
+
+
+def test_chunk_step_fuses_with_chain_and_tree_depth():
+    x = da.random.default_rng(0).random((32768, 32768), dtype=np.float32, chunks=(4096, 4096))
+    y = da.sin(x) * 2 + x**2
+    m = y.mean(axis=0).optimize().expr
+    assert isinstance(m, PartialReduce) and m.operand("final") and m.operand("split_every") == {0: 16}
+    (f,) = m.dependencies()
+    assert isinstance(f, FusedBlockwise) and len(f.exprs) == 5 and f.exprs[0]._tree_label().startswith("mean_chunk")
+    s = y.std().optimize().expr                      # sqrt <- aggregate <- partial <- fused chunk step
+    agg = s.dependencies()[0]
+    part = agg.dependencies()[0]
+    assert agg.operand("split_every") == {0: 4, 1: 4} and not part.operand("final")
+    assert part.chunks == ((1, 1), (1, 1))
+    plan = FusedPlan(part.dependencies()[0])
+    assert len(plan.program.inputs) == 1 and "sin" in plan.program.key()
+
+
+def test_partial_reduce_groups_match_oracle_nesting():
+    x = da.from_array(np.zeros((50, 30)), chunks=(10, 10))
+    e = x.sum().optimize().expr
+    while not (isinstance(e, PartialReduce) and not e.operand("final")):
+        e = e.dependencies()[0]
+    got = {k: m for k, m in e.groups()}
+    blocks = {bid: bid for bid in np.ndindex(5, 3)}
+    want = ref.partial_reduce(ref.Blocked(blocks, ((1,) * 5, (1,) * 3)), lambda lst: lst, {0: 4, 1: 4}, True)
+
+    def flat(v):
+        return [t for i in v for t in flat(i)] if isinstance(v, list) else [v]
+    assert {k: flat(v) for k, v in want.blocks.items()} == got
+    assert normalize_split_every(None, (0, 1, 2)) == ref.normalize_split_every(None, (0, 1, 2))
+
+
+def test_transpose_conflict_and_same_mapping():
+    a = da.from_array(np.zeros((8, 8)), chunks=4)
+    opt = (a + a.T).optimize().expr                   # leaf read through two mappings -> two kernel inputs
+    plan = FusedPlan(opt)
+    assert len(plan.leaves) == 2 and {m for _, m in plan.leaves} == {(0, 1), (1, 0)}
+    plan2 = FusedPlan((a + a * 2).optimize().expr)    # same mapping twice -> one input
+    assert len(plan2.leaves) == 1
+    assert (a.T.T).optimize().expr._name == a.optimize().expr._name
+
+
+def test_rechunk_rules_and_pieces():
+    x = da.from_array(np.zeros((16, 16)), chunks=(16, 2))
+    assert x.rechunk((16, 2)).optimize().expr._name == x.optimize().expr._name      # no-op removed
+    r = x.rechunk((4, 8)).rechunk((2, 16)).optimize().expr                            # double rechunk collapses
+    assert isinstance(r, TasksRechunk) and r.chunks == ((2,) * 8, (16,))
+    assert not isinstance(r.operand("array"), TasksRechunk)
+    assert len(r.pieces((0, 0))) == 8
+    o2n = old_to_new(((4, 4, 3), (2, 2, 2)), ((2, 6, 3), (6,)))
+    assert o2n[0][1] == [(0, slice(2, 4)), (1, slice(0, 4))]
+
+
+def test_elemwise_dtypes_follow_numpy_nep50():
+    i4 = da.from_array(np.zeros((4,), np.int32), chunks=2)
+    f4 = da.from_array(np.zeros((4,), np.float32), chunks=2)
+    assert (f4 * 2).dtype == np.float32 and (i4 / i4).dtype == np.float64 and (i4**2).dtype == np.int32
+    assert (i4 < 3).dtype == np.bool_ and (f4 + i4).dtype == np.float64 and (f4 * 2.5).dtype == np.float32
+    assert i4.sum().dtype == np.int64 and i4.mean().dtype == np.float64 and f4.var().dtype == np.float32
+    assert i4.argmax().dtype == np.int64
+
+
+def test_unaligned_chunks_get_rechunked():
+    a = da.from_array(np.zeros((12, 12)), chunks=(4, 12))
+    b = da.from_array(np.zeros((12, 12)), chunks=(6, 12))
+    assert any("Rechunk" in l for l in labels((a + b).optimize().expr))
