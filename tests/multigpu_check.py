@@ -1,0 +1,63 @@
+"""Multi-GPU parity check, launched with torchrun (one rank per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multigpu_check.py
+
+Every rank builds the same expressions, owns its block-cyclic share and must end up with the
+oracle's result (reductions are replicated; array results are assembled on every rank)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import dask_array_b200 as da
+    from oracle import reference as ref
+
+    rng = np.random.default_rng(0)
+    xh = rng.random((1024, 1536), dtype=np.float32)
+    chunks = (256, 256)
+    x = da.from_array(xh, chunks=chunks)
+    y = da.sin(x) * 2 + x**2
+    want_mean, want_std = ref.fused_chain_mean_std(xh, chunks)
+    got_mean, got_std = da.compute(y.mean(axis=0), y.std())
+    np.testing.assert_allclose(got_mean, want_mean, rtol=1e-5)
+    np.testing.assert_allclose(got_std, want_std, rtol=1e-5)
+
+    b = ref.Blocked.from_array(xh, chunks)
+    t = np.floor(xh * 50)
+    tb, td = ref.Blocked.from_array(t, chunks), da.from_array(t, chunks=chunks)
+    for axis in (None, 0, 1):
+        assert np.array_equal(td.argmax(axis=axis).compute(), ref.da_argmax(tb, axis=axis)), axis
+        assert np.array_equal(td.argmin(axis=axis).compute(), ref.da_argmin(tb, axis=axis)), axis
+        assert np.array_equal(x.max(axis=axis).compute(), ref.da_max(b, axis=axis))
+        np.testing.assert_allclose(x.sum(axis=axis).compute(), ref.da_sum(b, axis=axis), rtol=1e-5)
+
+    ih = np.arange(512 * 512, dtype=np.int32).reshape(512, 512)
+    xi = da.from_array(ih, chunks=(512, 32))
+    assert np.array_equal(xi.rechunk((32, 512)).compute(), ih)                 # all-to-all over NCCL
+    sq = da.from_array(ih, chunks=(128, 128))
+    assert np.array_equal((sq.T + sq).compute(), ih.T + ih)                     # remote transposed blocks
+    assert np.array_equal((xi.T + xi).compute(), ih.T + ih)                     # rechunk + fused transpose
+    p = (sq * 2).persist()
+    assert np.array_equal((p + 1).compute(), ih * 2 + 1)
+    ones = da.ones((1000, 1000), chunks=(100, 100))
+    assert (ones + ones.T).sum().compute() == 2_000_000.0
+    dist.barrier()
+    if rank == 0:
+        print(f"multigpu_check ok on {world} GPUs")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
