@@ -441,8 +441,9 @@ def _allgather_blocks(ex: Executor, src: BlockStore, x):
             parts[name] = DeviceChunk(recv, shp, dt, offset=(r * cap + offs[r]) // dt.itemsize)
             offs[r] += -(-nb // 16) * 16
         if src.kind == "mean":
-            axes = x.operand("axis")
-            top = x.operand("array")
+            red = x.root if isinstance(x, FusedBlockwise) else x        # the ChunkReduce
+            axes = red.operand("axis")
+            top = red.operand("array")
             n = math.prod(top.block_shape(bid)[a] for a in axes)
             out[bid] = {"total": parts["total"], "n": n}
         elif src.kind == "arg":
