@@ -192,6 +192,72 @@ def run_reference(args):
     }))
 
 
+# ----------------------------------------------------------------------------- configs 3 and 4
+def run_other(args):
+    """Secondary configs (single GPU, resident data): c3 = fp64 argmax/argmin/min/max(axis=1) on
+    (65536,16384) chunks (8192,16384); c4 = rechunk (16384,16384) (16384,256)->(256,16384) and x.T + x."""
+    import torch
+    import dask_array_b200 as da
+    from dask_array_b200 import _lib
+
+    torch.cuda.set_device(0)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    def timed(step, nbytes, label, extra=None):
+        for _ in range(max(args.warmup, 3)):
+            step.run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for _ in range(args.steps):
+            step.run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out = {"metric": METRIC, "config": {"workload": label}, "value": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
+               "ms_per_step": ms, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "frac_of_measured_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": nbytes,
+               "gpu_launches": _lib.launch_count() - n0, "data": "synthetic", "higher_is_better": True}
+        out.update(extra or {})
+        print(json.dumps(out))
+
+    if args.config == "c3":
+        R, Cc, RB = 65536, 16384, 8192
+        rng = np.random.default_rng(0)
+
+        def blk(bid):
+            return np.random.default_rng(bid[0]).random((RB, Cc))
+        x = da.from_host_blocks(blk, (R, Cc), (RB, Cc), np.float64, token="c3").persist()
+        nbytes = R * Cc * 8
+        for name in ("argmax", "argmin", "max", "min"):
+            step = da.compile(getattr(x, name)(axis=1))
+            timed(step, nbytes, f"c3: fp64 (65536,16384) chunks (8192,16384) {name}(axis=1)", {"dtype": "f64"})
+        step = da.compile(x.argmax(axis=1), x.argmin(axis=1), x.max(axis=1), x.min(axis=1))
+        timed(step, 4 * nbytes, "c3: all four reductions, four passes", {"dtype": "f64"})
+    else:
+        n = 16384
+        for dt in (np.float32, np.float64):
+            item = np.dtype(dt).itemsize
+            host = np.arange(n * n, dtype=np.int64).reshape(n, n).astype(dt) if dt == np.float64 else \
+                np.arange(n * n, dtype=np.int32).reshape(n, n).view(np.float32)
+            x = da.from_array(host, chunks=(n, 256)).persist()
+            step = da.compile(x.rechunk((256, n)))
+            timed(step, 2 * n * n * item, f"c4: rechunk (16384,16384) {np.dtype(dt).name} (16384,256)->(256,16384)",
+                  {"dtype": np.dtype(dt).name})
+            sq = da.from_array(host, chunks=(2048, 2048)).persist()
+            step = da.compile(sq.T + sq)
+            timed(step, 2 * n * n * item, f"c4: x.T + x (16384,16384) {np.dtype(dt).name} chunks 2048^2 "
+                  "(2N bytes: the symmetric minimum; the kernel moves 3N)", {"dtype": np.dtype(dt).name})
+            del x, sq, step
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -201,9 +267,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 = headline (default). c3 / c4 = the other BASELINE configs (extra lines for DESIGN.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != "c2":
+        return run_other(args)
     args.warmup = max(args.warmup, 3)
 
     import torch
