@@ -19,6 +19,7 @@ _TORCH_DTYPES = {
     "bool": torch.bool, "int8": torch.int8, "uint8": torch.uint8, "int16": torch.int16,
     "int32": torch.int32, "int64": torch.int64, "float32": torch.float32, "float64": torch.float64,
     "float16": torch.float16, "uint16": torch.uint16, "uint32": torch.uint32, "uint64": torch.uint64,
+    "bfloat16": torch.bfloat16,
 }
 
 
@@ -249,7 +250,7 @@ class DeviceChunk:
         if self.size == 0:
             return np.empty(self.shape, self.dtype)
         t = self.as_torch()
-        if self.dtype.name in ("uint16", "uint32", "uint64"):
+        if self.dtype.name in ("uint16", "uint32", "uint64", "bfloat16"):
             host = t.contiguous().view(torch.uint8).cpu().numpy().view(self.dtype)
             return host.reshape(self.shape)
         return t.cpu().numpy()

@@ -349,6 +349,59 @@ class Executor:
         st.keepalive.extend([launch, remote])
         return st
 
+    # ------------------------------------------------------------------ blocked matmul
+    def _run_BlockGEMM(self, expr):
+        """One tcgen05 launch per output block; the k blocks (and, for fp32 operands, the six
+        bf16 x 3 split products) are accumulated in TMEM (``b2_gemm_tn_pairs``)."""
+        import ctypes as C
+
+        a, bt = expr.operand("a"), expr.operand("bt")
+        sa, sb = self.results[a._name], self.results[bt._name]
+        if self.world.size > 1:
+            raise NotImplementedError("blocked matmul across GPUs (operand panel exchange) is not implemented yet")
+        st = BlockStore(expr)
+        fp32 = a.dtype == np.float32
+        bf16 = np.dtype("uint16")          # raw 16-bit planes
+
+        def planes(store, x):
+            out = {}
+            for bid, blk in store.blocks.items():
+                if not blk.is_contiguous:
+                    raise NotImplementedError("matmul operand blocks must be contiguous (persist / rechunk first)")
+                if not fp32:
+                    out[bid] = (blk,)
+                    continue
+                hi, mid, lo = (DeviceChunk.empty(blk.shape, bf16, self.device) for _ in range(3))
+                self._do(lambda b=blk, h=hi, m=mid, l=lo: _lib.check(_lib.lib.b2_split3_bf16(
+                    b.ptr, h.ptr, m.ptr, l.ptr, b.size, rt.current_stream_ptr())))
+                out[bid] = (hi, mid, lo)
+            return out
+
+        pa, pb = planes(sa, a), planes(sb, bt)
+        # products kept for fp32: hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi  (error ~2^-24)
+        combos = [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0)] if fp32 else [(0, 0)]
+        nk = a.numblocks[1]
+        for (i, j) in expr.block_ids():
+            M, N = expr.block_shape((i, j))
+            out = DeviceChunk.empty((M, N), np.float32, self.device)
+            st.blocks[(i, j)] = out
+            A, B = [], []
+            K = None
+            for k in range(nk):
+                K = a.block_shape((i, k))[1]
+                for ca, cb in combos:
+                    A.append(pa[(i, k)][ca].ptr)
+                    B.append(pb[(j, k)][cb].ptr)
+            if len({a.block_shape((i, k))[1] for k in range(nk)}) != 1:
+                raise NotImplementedError("matmul with ragged contraction chunks")
+            arrA = (C.c_void_p * len(A))(*A)
+            arrB = (C.c_void_p * len(B))(*B)
+            self._do(lambda arrA=arrA, arrB=arrB, n=len(A), M=M, N=N, K=K, o=out: _lib.check(
+                _lib.lib.b2_gemm_tn_pairs(_lib.dtype_code("bfloat16"), arrA, arrB, n, K, K, o.ptr, N, M, N, K, 0,
+                                          rt.current_stream_ptr())))
+        st.keepalive.extend([pa, pb])
+        return st
+
     # ------------------------------------------------------------------ multi-GPU exchange (fused)
     def _exchange_for_fused(self, plan, deps, out_ids):
         return _exchange_for_fused(self, plan, deps, out_ids)

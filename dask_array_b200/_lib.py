@@ -29,7 +29,7 @@ _DTYPE_CODES = {
 
 
 def dtype_code(dt) -> int:
-    name = np.dtype(dt).name if not isinstance(dt, str) or dt not in _DTYPE_CODES else dt
+    name = dt if isinstance(dt, str) and dt in _DTYPE_CODES else np.dtype(dt).name
     try:
         return _DTYPE_CODES[name]
     except KeyError:
@@ -89,7 +89,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_launch_count", "b2_device_sm_count",
     "b2_jit_compile", "b2_free", "b2_device_header", "b2_kernel_load", "b2_kernel_free",
     "b2_fused_plan", "b2_fused_launch", "b2_combine", "b2_gather_plan", "b2_gather_launch",
-    "b2_fill", "b2_gemm_tn", "b2_memcpy2d",
+    "b2_fill", "b2_gemm_tn", "b2_memcpy2d", "b2_gemm_tn_pairs", "b2_split3_bf16",
 ]
 
 
@@ -119,6 +119,8 @@ def _load():
     lib.b2_fill.argtypes = [vp, i64, i32, vp, vp]
     lib.b2_memcpy2d.argtypes = [vp, i64, vp, i64, i64, i64, i32, vp]
     lib.b2_gemm_tn.argtypes = [i32, vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, vp]
+    lib.b2_gemm_tn_pairs.argtypes = [i32, vp, vp, i32, i64, i64, vp, i64, i64, i64, i64, i32, vp]
+    lib.b2_split3_bf16.argtypes = [vp, vp, vp, vp, i64, vp]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError here = header and library out of sync
     return lib

@@ -1,14 +1,312 @@
-// gemm_tcgen05.cu -- blocked contraction C (+)= A @ B^T on the 5th-gen tensor cores.
-// (placeholder entry point: filled in by the tcgen05/TMA kernel; fails loudly until then.)
+// gemm_tcgen05.cu -- blocked contraction on the 5th-generation tensor cores (sm_100a).
+//
+//     C[M,N] (fp32)  (+)=  sum_p  A_p[M,K] . B_p[N,K]^T          (all operands K-major, bf16)
+//
+// Replaces, for one output block (i, j), the reference's loop
+//     reduce(np.add, [np.matmul(a[i,k], b[k,j])[..., None, :] for k in ...])
+// (`_matmul` linalg/_tensordot.py:194-213 + `_sum_wo_cat` :216-249): the pair list p runs over
+// the contracted block index k, so the (M,1,N) partials the reference materialises (32 GiB at
+// BASELINE config 5) never exist -- the k-accumulation stays in TMEM.  The same pair list
+// carries the bf16 x 3 splitting used for fp32 operands (6 products per k block).
+//
+// Kernel: one CTA per 128 x 128 output tile, warp-specialised:
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d (128B-swizzled 128x64 bf16 boxes) -> 6-stage smem ring
+//   warp 1      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16);
+//                              accumulator = 128 lanes x 128 fp32 columns of TMEM; tcgen05.commit frees stages
+//   warps 2..5  epilogue       tcgen05.ld 32x32b -> registers -> (+= C) -> global
+// SASS evidence: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld).
 #include "../../include/b200da.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
 
 extern "C" int b2_set_error_(int code, const char* msg);
+extern "C" void b2_count_launch_(void);
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int MAX_PAIRS = 12;             // 24 tensor maps = 3 KiB of kernel parameters
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+struct GemmMaps {
+    CUtensorMap a[MAX_PAIRS];
+    CUtensorMap b[MAX_PAIRS];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "B2_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra B2_DONE_%=;\n\t"
+        "bra B2_WAIT_%=;\n\t"
+        "B2_DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// K-major operand tile, 128-byte swizzle (what the TMA box writes): rows are 128 B apart inside an
+// 8-row swizzle atom, atoms 1024 B apart (stride byte offset); descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                    // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset
+    d |= (uint64_t)1 << 46;                    // descriptor version
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3, M >> 4
+__device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+b2_gemm_tn_kernel(const __grid_constant__ GemmMaps maps, int npairs, float* __restrict__ C, long long ldc,
+                  int M, int N, int K, int accumulate) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B: 1024 B aligned
+    uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int k_iters = (K + BK - 1) / BK;
+    const int total_iters = npairs * k_iters;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {      // one warp allocates the accumulator: 128 TMEM columns (128 lanes x 128 fp32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < total_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                const int p = it / k_iters, kk = it % k_iters;
+                uint8_t* sa = smem + s * STAGE_BYTES;
+                tma_load_2d(sa, &maps.a[p], kk * BK, m0, &full_bar[s]);
+                tma_load_2d(sa + A_BYTES, &maps.b[p], kk * BK, n0, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            for (int it = 0; it < total_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+                    umma_bf16(tmem_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);          // frees the stage when these MMAs retire
+            }
+            umma_commit(tmem_full_bar);              // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5: a warp may only touch TMEM lanes [32*(warp%4), +32)
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        float* crow = C + (long long)row * ldc + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            if (row < M) {
+                if (n0 + c + 32 <= N && (ldc % 4 == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        float4* dst = reinterpret_cast<float4*>(crow + c + j);
+                        if (accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                        *dst = v;
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j) {
+                        if (n0 + c + j < N) {
+                            float v = __uint_as_float(r[j]);
+                            if (accumulate) v += crow[c + j];
+                            crow[c + j] = v;
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN));
+    }
+}
+
+// fp32 -> three bf16 planes with hi + mid + lo == x to ~2^-24 (x - hi and the next residual are exact)
+__global__ void __launch_bounds__(256) b2_split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                        __nv_bfloat16* __restrict__ mid, __nv_bfloat16* __restrict__ lo,
+                                                        long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(h);
+        const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+        const float r2 = r1 - __bfloat162float(m);
+        hi[i] = h; mid[i] = m; lo[i] = __float2bfloat16_rn(r2);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (h) fn = (EncodeTiledFn)dlsym(h, "cuTensorMapEncodeTiled");
+    });
+    return fn;
+}
+
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return b2_set_error_(B2_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no NVIDIA driver): no CPU fallback");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r,
+                 (long long)rows, (long long)K, (long long)ld);
+        return b2_set_error_(B2_ERR_CUDA, msg);
+    }
+    return B2_OK;
+}
+
+}  // namespace
+
+extern "C" int b2_gemm_tn_pairs(int dtype, const void* const* A, const void* const* B, int npairs,
+                                int64_t lda, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                                int accumulate, void* stream) {
+    if (dtype != B2_BF16) return b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_pairs: operands must be bf16 planes (split fp32 with b2_split3_bf16)");
+    if (!A || !B || !C || npairs <= 0 || M <= 0 || N <= 0 || K <= 0) return b2_set_error_(B2_ERR_INVALID, "b2_gemm_tn_pairs: bad argument");
+    if (lda % 8 || ldb % 8) return b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_pairs: lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(b2_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    });
+    if (attr_err != cudaSuccess) return b2_set_error_(B2_ERR_CUDA, cudaGetErrorString(attr_err));
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
+    for (int p0 = 0; p0 < npairs; p0 += MAX_PAIRS) {
+        const int np = (npairs - p0 < MAX_PAIRS) ? npairs - p0 : MAX_PAIRS;
+        GemmMaps maps;
+        memset(&maps, 0, sizeof maps);
+        for (int p = 0; p < np; ++p) {
+            if (((uintptr_t)A[p0 + p] | (uintptr_t)B[p0 + p]) % 16) return b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_pairs: operand not 16-byte aligned");
+            int rc = make_map(&maps.a[p], A[p0 + p], M, K, lda, BM);
+            if (rc) return rc;
+            rc = make_map(&maps.b[p], B[p0 + p], N, K, ldb, BN);
+            if (rc) return rc;
+        }
+        b2_gemm_tn_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+            maps, np, C, (long long)ldc, (int)M, (int)N, (int)K, (accumulate || p0 > 0) ? 1 : 0);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return b2_set_error_(B2_ERR_CUDA, cudaGetErrorString(e));
+        b2_count_launch_();
+    }
+    return B2_OK;
+}
 
 extern "C" int b2_gemm_tn(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb,
                           float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                           int accumulate, void* stream) {
-    (void)dtype; (void)A; (void)lda; (void)B; (void)ldb; (void)C; (void)ldc; (void)M; (void)N; (void)K;
-    (void)accumulate; (void)stream;
-    return b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn: tcgen05 kernel not built yet");
+    const void* a[1] = {A};
+    const void* b[1] = {B};
+    return b2_gemm_tn_pairs(dtype, a, b, 1, lda, ldb, C, ldc, M, N, K, accumulate, stream);
+}
+
+extern "C" int b2_split3_bf16(const float* src, void* hi, void* mid, void* lo, int64_t n, void* stream) {
+    if (!src || !hi || !mid || !lo || n < 0) return b2_set_error_(B2_ERR_INVALID, "b2_split3_bf16: bad argument");
+    if (n == 0) return B2_OK;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    b2_split3_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)mid,
+                                                                  (__nv_bfloat16*)lo, (long long)n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return b2_set_error_(B2_ERR_CUDA, cudaGetErrorString(e));
+    b2_count_launch_();
+    return B2_OK;
 }

@@ -220,6 +220,16 @@ int b2_fill(void* dst, int64_t nelem, int itemsize, const void* value, void* str
 int b2_gemm_tn(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb,
                float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                int accumulate, void* stream);
+/* C (+)= sum_p A[p] @ B[p]^T in ONE accumulation (TMEM): the pair list runs over the contracted
+ * block index k of `_sum_wo_cat` (linalg/_tensordot.py:216-249) -- the (M,1,N) partials of
+ * `_matmul` (:194-213) are never materialised -- and over the bf16 x 3 split products when the
+ * operands were fp32.  A[p], B[p]: HOST arrays of device pointers to bf16 planes. */
+int b2_gemm_tn_pairs(int dtype, const void* const* A, const void* const* B, int npairs,
+                     int64_t lda, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                     int accumulate, void* stream);
+/* fp32 -> bf16 hi/mid/lo planes with hi + mid + lo == x to ~2^-24 (operand preparation of the
+ * fp32 matmul; tensor cores have no IEEE fp32 mode) */
+int b2_split3_bf16(const float* src, void* hi, void* mid, void* lo, int64_t nelem, void* stream);
 
 #ifdef __cplusplus
 }
