@@ -228,6 +228,37 @@ def run_other(args):
         out.update(extra or {})
         print(json.dumps(out))
 
+    if args.config == "c5":
+        import ml_dtypes
+        n, cb = 32768, 4096
+        rng = np.random.default_rng(0)
+        base32 = (rng.random((cb, cb), dtype=np.float32) - 0.5)
+        tflops_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        for dt, label in ((ml_dtypes.bfloat16, "bf16"), (np.float32, "fp32 (bf16x3 split, 6 products)")):
+            base = base32.astype(dt)
+            x = da.from_host_blocks(lambda bid: base, (n, n), (cb, cb), dt, token=f"c5x{label}").persist()
+            y = da.from_host_blocks(lambda bid: base, (n, n), (cb, cb), dt, token=f"c5y{label}").persist()
+            step = da.compile((x @ y.T).sum())
+            for _ in range(2):
+                step.run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(1, min(args.steps, 3))
+            e0.record()
+            for _ in range(reps):
+                step.run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            flop = 2.0 * n * n * n
+            mma_flop = flop * (6 if dt == np.float32 else 1)
+            print(json.dumps({"metric": "blocked matmul TFLOP/s", "config": {"workload": f"c5: (x @ y.T).sum() 32768^2 {label} chunks 4096^2"},
+                              "value": flop / (ms * 1e-3) / 1e12, "unit": "TFLOP/s (algorithmic 2N^3)", "ms_per_step": ms,
+                              "tensor_pipe_TFLOPs": mma_flop / (ms * 1e-3) / 1e12,
+                              "frac_of_measured_bf16_sustained": mma_flop / (ms * 1e-3) / 1e12 / tflops_peak,
+                              "n_gpus": 1, "steps": reps, "data": "synthetic (one random 4096^2 block tiled)"}))
+            del x, y, step
+        return
     if args.config == "c3":
         R, Cc, RB = 65536, 16384, 8192
         rng = np.random.default_rng(0)
@@ -267,7 +298,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4"],
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 = headline (default). c3 / c4 = the other BASELINE configs (extra lines for DESIGN.md)")
     args = ap.parse_args()
     if args.impl == "reference":
