@@ -7,6 +7,8 @@ matmul.  Every result is computed by hand-written sm_100a CUDA kernels behind th
 ``include/b200da.h``; there is no CPU fallback (importing without the built library fails).
 """
 from . import _lib  # noqa: F401  (fails loudly when libb200da.so is missing)
+from . import _eager  # noqa: F401  (NEP-13 / NEP-18 on DeviceChunk)
+from ._device import DeviceChunk  # noqa: F401
 from ._collection import (  # noqa: F401
     UFUNC_NAMES, Array, Compiled, _method, _ufunc, asarray, compile, compute, elemwise, from_array,
     from_host_blocks, full, matmul, ones, random,
