@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-CODEGEN_VERSION = "8"     # part of every kernel's cache key: bump when generated code changes
+CODEGEN_VERSION = "10"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
@@ -419,8 +419,26 @@ def render(program: Program, spec: KernelSpec) -> str:
     T = ctype(program.out_dtype)
     regs = [f"{ctype(dt)} a{k}[B2_V];" for k, dt in enumerate(program.inputs)] or ["char _unused;"]
     ptrs, setup_r, setup_c, loads, adv = [], [], [], [], []
+    stage, loads_t, toff = [], [], 0
+    ewt = "T" in spec.layouts
     for k, (dt, lay) in enumerate(zip(program.inputs, spec.layouts)):
         ct = ctype(dt)
+        if lay == "T":
+            # staged through shared memory by b2_run_ewt (no pointer walking)
+            ptrs.append(f"const {ct}* p{k}; i64 s{k};")
+            setup_r.append(f"P.p{k} = nullptr; P.s{k} = 0;")
+            setup_c.append(f"P.p{k} = nullptr; P.s{k} = 0;")
+            loads.append(f"/* input {k} is staged */")
+            adv.append("")
+            stage.append(
+                f"{{ const {ct}* src = (const {ct}*)blk.in[{k}] + b * blk.in_sb[{k}]; {ct}* sm = ({ct}*)(smem + {toff});\n"
+                f"              const i64 sr = blk.in_sr[{k}], scs = blk.in_sc[{k}];\n"
+                f"              for (int idx = tid; idx < B2_TT * B2_TT; idx += nthreads) {{ const int ii = idx / B2_TT, jj = idx % B2_TT;\n"
+                f"                  const i64 r = r0 + jj, c = c0 + ii; if (r < blk.R && c < blk.C) sm[jj * B2_TP + ii] = b2_ld(src + r * sr + c * scs); }} }}")
+            loads_t.append(f"{{ const {ct}* sm = (const {ct}*)(smem + {toff}) + lr * B2_TP + lc;\n"
+                           f"              _Pragma(\"unroll\") for (int v = 0; v < B2_V; ++v) g.a{k}[v] = sm[v]; }}")
+            toff += -(-64 * 65 * dt.itemsize // 16) * 16
+            continue
         ptrs.append(f"const {ct}* p{k}; i64 s{k};" + (f" i64 c{k};" if lay == "G" else ""))
         colmul = {"V": "c", "S": "0", "G": f"c * blk.in_sc[{k}]"}[lay]
         base = f"(const {ct}*)blk.in[{k}] + b * blk.in_sb[{k}] + r * blk.in_sr[{k}] + {colmul}"
@@ -435,8 +453,11 @@ def render(program: Program, spec: KernelSpec) -> str:
         else:
             loads.append(f"b2_load_strided<{ct}, B2_V>(P.p{k} + k * P.s{k}, P.c{k}, g.a{k});")
         adv.append(f"P.p{k} += n * P.s{k};")
+        loads_t.append(loads[-1].replace("P.p%d + k * P.s%d" % (k, k), "P.p%d + (i64)lr * P.s%d" % (k, k)))
     if not ptrs:
         ptrs = ["char _unused;"]
+    if ewt and toff > 40 * 1024:
+        raise NotImplementedError("too many transposed operands for the shared-memory staged kernel")
     acc = ctype(spec.acc_dtype)
     nl = "\n            "
     fast = program.uses_fast_sincos()
@@ -455,6 +476,11 @@ def render(program: Program, spec: KernelSpec) -> str:
             {nl.join(program.body(fast=fast))}
         }}
     }}"""
+    if ewt:
+        run = f"b2_run_ewt<Chain, B2_V, {spec.tx}, {spec.ty}>(blocks, nblocks, sc);"
+    else:
+        run = (f"b2_run<Chain, {_MODE_NAME[spec.mode]}, {_RED_NAME[spec.redop]}, B2_V, {spec.tx}, {spec.ty}, "
+               f"{spec.rpt}, {spec.unroll}, {acc}>(blocks, nblocks, sc);")
     return f"""{header}// generated by dask_array_b200/_codegen.py -- one FusedBlockwise expression
 // program: {program.key()}
 #include "b2_device.cuh"
@@ -475,11 +501,18 @@ struct Chain {{
     __device__ __forceinline__ static void advance(Ptrs& P, int n) {{
         {(nl[:-4]).join(adv)}
     }}
+    static constexpr int TBYTES = {max(toff, 16)};
+    __device__ __forceinline__ static void stage(const B2Block& blk, i64 b, i64 r0, i64 c0, unsigned char* smem, int tid, int nthreads) {{
+        {(nl[:-4]).join(stage)}
+    }}
+    __device__ __forceinline__ static void load_t(const Ptrs& P, const unsigned char* smem, int lr, int lc, Regs& g) {{
+        {(nl[:-4]).join(loads_t)}
+    }}
 {compute}
 }};
 extern "C" __global__ void __launch_bounds__({spec.tx * spec.ty}, {3 if spec.tx * spec.ty <= 256 else 1})
 b2_fused(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars sc) {{
-    b2_run<Chain, {_MODE_NAME[spec.mode]}, {_RED_NAME[spec.redop]}, B2_V, {spec.tx}, {spec.ty}, {spec.rpt}, {spec.unroll}, {acc}>(blocks, nblocks, sc);
+    {run}
 }}
 """
 

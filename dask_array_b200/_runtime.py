@@ -181,6 +181,17 @@ class FusedLaunch:
             cls = {("S" if c.in_strides[k][2] == 0 else "V" if c.in_strides[k][2] == 1 else "G")
                    for c in canons if c.C > 1} or {"V"}
             layouts.append(cls.pop() if len(cls) == 1 else "G")
+        # transposed operands of an element-wise launch (contiguous along the OUTPUT's rows, e.g. the
+        # x.T of x.T + x): staged through shared memory by b2_run_ewt instead of strided loads
+        ewt, staged = False, 0
+        if self.mode == _lib.MODE_EW:
+            for k in range(nin):
+                tile_bytes = -(-64 * 65 * program.inputs[k].itemsize // 16) * 16
+                if layouts[k] == "G" and all(c.in_strides[k][1] == 1 for c in canons if c.R > 1) \
+                        and all(c.R >= 32 and c.C >= 32 for c in canons) and staged + tile_bytes <= 40 * 1024:
+                    layouts[k] = "T"
+                    staged += tile_bytes
+                    ewt = True
         sizes = [d.itemsize for d in program.inputs] + ([out_dt.itemsize] if self.mode == _lib.MODE_EW else [])
         vmax = max(1, 16 // max(sizes or [out_dt.itemsize]))
         if self.mode == _lib.MODE_R:
@@ -196,6 +207,8 @@ class FusedLaunch:
                     return False
                 for k, (ptr, _) in enumerate(b.inputs):
                     sb, sr, sc = c.in_strides[k]
+                    if layouts[k] == "T":
+                        continue
                     if layouts[k] == "V":
                         it = program.inputs[k].itemsize
                         if ptr % (v * it) or (c.B > 1 and sb % v) or (c.R > 1 and sr % v):
@@ -210,10 +223,14 @@ class FusedLaunch:
         v = vmax
         while v > 1 and not vec_fits(v):
             v //= 2
+        if ewt:
+            v = min(v, 4)
         if v == 1:
-            layouts = ["S" if l == "S" else "G" for l in layouts]
+            layouts = [l if l in ("S", "T") else "G" for l in layouts]
         shapes = [(c.B, c.R, c.C) for c in canons]
         geo = cg.choose_geometry(program, self.mode, shapes, v)
+        if ewt:      # 64 x 64 output tiles, 256 threads
+            geo = dict(vec=v, tx=64 // v, ty=256 // (64 // v), rpt=64, unroll=1)
         self.spec = cg.KernelSpec(program.key(), tuple(layouts), self.mode, redop,
                                   acc_dtype=acc_dtype.name, **geo)
         self.kernel = load_kernel(program, self.spec)

@@ -308,7 +308,7 @@ struct B2AccSum {   // np.sum(x, dtype=ACC)  (_chunk.py:172; ints widen to 64 bi
     ACC s;
     __device__ __forceinline__ void init() { s = (ACC)0; }
     __device__ __forceinline__ void prime(T) {}
-    __device__ __forceinline__ void add(T v, i64) { s += (ACC)v; }
+    __device__ __forceinline__ void add(T v, int, int) { s += (ACC)v; }
     __device__ __forceinline__ void merge(const B2AccSum& o) { s += o.s; }
     __device__ __forceinline__ void shfl(int off, int width) { B2AccSum o; o.s = b2_shfl_down(s, off, width); merge(o); }
     __device__ __forceinline__ void lane_merge(const B2AccSum& o) { merge(o); }
@@ -323,7 +323,7 @@ struct B2AccProd {
     ACC s;
     __device__ __forceinline__ void init() { s = (ACC)1; }
     __device__ __forceinline__ void prime(T) {}
-    __device__ __forceinline__ void add(T v, i64) { s *= (ACC)v; }
+    __device__ __forceinline__ void add(T v, int, int) { s *= (ACC)v; }
     __device__ __forceinline__ void merge(const B2AccProd& o) { s *= o.s; }
     __device__ __forceinline__ void shfl(int off, int width) { B2AccProd o; o.s = b2_shfl_down(s, off, width); merge(o); }
     __device__ __forceinline__ void lane_merge(const B2AccProd& o) { merge(o); }
@@ -338,7 +338,7 @@ struct B2AccAnyAll {   // np.any / np.all -> bool
     unsigned char s;
     __device__ __forceinline__ void init() { s = ALL ? 1 : 0; }
     __device__ __forceinline__ void prime(T) {}
-    __device__ __forceinline__ void add(T v, i64) { bool t = (v != (T)0); s = ALL ? (s & (unsigned char)t) : (s | (unsigned char)t); }
+    __device__ __forceinline__ void add(T v, int, int) { bool t = (v != (T)0); s = ALL ? (s & (unsigned char)t) : (s | (unsigned char)t); }
     __device__ __forceinline__ void merge(const B2AccAnyAll& o) { s = ALL ? (s & o.s) : (s | o.s); }
     __device__ __forceinline__ void shfl(int off, int width) { B2AccAnyAll o; o.s = b2_shfl_down(s, off, width); merge(o); }
     __device__ __forceinline__ void lane_merge(const B2AccAnyAll& o) { merge(o); }
@@ -353,7 +353,7 @@ struct B2AccMinMax {   // np.min / np.max: NaN propagates (chunk_min/chunk_max _
     T m; bool has;
     __device__ __forceinline__ void init() { has = false; m = (T)0; }
     __device__ __forceinline__ void prime(T) {}
-    __device__ __forceinline__ void add(T v, i64) {
+    __device__ __forceinline__ void add(T v, int, int) {
         if (!has) { m = v; has = true; return; }
         m = ISMAX ? b2_np_max(m, v) : b2_np_min(m, v);
     }
@@ -371,23 +371,57 @@ struct B2AccMinMax {   // np.min / np.max: NaN propagates (chunk_min/chunk_max _
     __device__ __forceinline__ Packed pack() const { Packed p; p.m = m; p.has = has ? 1 : 0; return p; }
     __device__ __forceinline__ void unpack(const Packed& p) { m = p.m; has = (p.has != 0); }
 };
+// identities for min / max style folds
+template <typename T> struct b2_limits;
+template <> struct b2_limits<float> { __device__ static float lowest() { return __int_as_float(0xff800000); } __device__ static float highest() { return __int_as_float(0x7f800000); } };
+template <> struct b2_limits<double> { __device__ static double lowest() { return __longlong_as_double(0xfff0000000000000LL); } __device__ static double highest() { return __longlong_as_double(0x7ff0000000000000LL); } };
+template <> struct b2_limits<bool> { __device__ static bool lowest() { return false; } __device__ static bool highest() { return true; } };
+template <> struct b2_limits<signed char> { __device__ static signed char lowest() { return -128; } __device__ static signed char highest() { return 127; } };
+template <> struct b2_limits<unsigned char> { __device__ static unsigned char lowest() { return 0; } __device__ static unsigned char highest() { return 255; } };
+template <> struct b2_limits<short> { __device__ static short lowest() { return -32768; } __device__ static short highest() { return 32767; } };
+template <> struct b2_limits<unsigned short> { __device__ static unsigned short lowest() { return 0; } __device__ static unsigned short highest() { return 65535; } };
+template <> struct b2_limits<int> { __device__ static int lowest() { return -2147483647 - 1; } __device__ static int highest() { return 2147483647; } };
+template <> struct b2_limits<unsigned int> { __device__ static unsigned int lowest() { return 0u; } __device__ static unsigned int highest() { return 4294967295u; } };
+template <> struct b2_limits<long long> { __device__ static long long lowest() { return -9223372036854775807LL - 1; } __device__ static long long highest() { return 9223372036854775807LL; } };
+template <> struct b2_limits<unsigned long long> { __device__ static unsigned long long lowest() { return 0ULL; } __device__ static unsigned long long highest() { return 18446744073709551615ULL; } };
+
 // index-carrying argmin/argmax with np.argmax semantics: first occurrence wins ties,
 // the first NaN wins outright (arg_chunk _common.py:704-732; keepdims_wrapper _chunk.py:137).
+// Thread-local phase: a thread visits its elements in increasing index order, so "first
+// occurrence" is simply "replace only when strictly better" -- branch-free selects on a 32-bit
+// step counter; the 64-bit index is rebuilt once in finish_arg().  Merged phase: (v, i) with
+// lexicographic (value, index) merges.
 template <typename T, bool ISMAX>
 struct B2AccArg {
     struct Packed { T v; i64 i; };
-    T v; i64 i;    // i < 0: empty
-    __device__ __forceinline__ void init() { v = (T)0; i = -1; }
+    T v; i64 i;                 // merged phase; i < 0: empty
+    int bk, bl; bool bnan;      // thread-local phase: step / lane of the best element, best-is-NaN flag
+    __device__ __forceinline__ void init() {
+        v = ISMAX ? b2_limits<T>::lowest() : b2_limits<T>::highest();
+        i = -1; bk = -1; bl = 0; bnan = false;
+    }
     __device__ __forceinline__ void prime(T) {}
+    __device__ __forceinline__ void add(T x, int k, int lane) {
+        bool better = ISMAX ? (x > v) : (x < v);
+        bool xnan = false;
+        if constexpr (b2_is_float<T>::value) { xnan = (x != x); better = better || xnan; }
+        const bool take = better && !bnan;
+        v = take ? x : v;
+        bk = take ? k : bk;
+        bl = take ? lane : bl;
+        if constexpr (b2_is_float<T>::value) bnan = bnan || xnan;
+    }
+    // any: the thread saw at least one element; element (k, lane) has index idx0 + k * istep + lane
+    __device__ __forceinline__ void finish_arg(bool any, i64 idx0, i64 istep) {
+        // bk < 0 with elements seen: every element equalled the identity -> the first one wins
+        i = any ? (bk < 0 ? idx0 : idx0 + (i64)bk * istep + bl) : -1;
+    }
     // `a` strictly better than `b` (both valid)?
     __device__ __forceinline__ static bool better(T av, i64 ai, T bv, i64 bi) {
         bool an = b2_isnan(av), bn = b2_isnan(bv);
         if (an || bn) { if (an && bn) return ai < bi; return an; }
         if (av == bv) return ai < bi;
         return ISMAX ? (av > bv) : (av < bv);
-    }
-    __device__ __forceinline__ void add(T x, i64 idx) {
-        if (i < 0 || better(x, idx, v, i)) { v = x; i = idx; }
     }
     __device__ __forceinline__ void merge(const B2AccArg& o) {
         if (o.i < 0) return;
@@ -400,7 +434,7 @@ struct B2AccArg {
     __device__ __forceinline__ void lane_shfl(int off, int width) { shfl(off, width); }
     __device__ __forceinline__ void lane_finish() {}
     __device__ __forceinline__ Packed pack() const { Packed p; p.v = v; p.i = i; return p; }
-    __device__ __forceinline__ void unpack(const Packed& p) { v = p.v; i = p.i; }
+    __device__ __forceinline__ void unpack(const Packed& p) { v = p.v; i = p.i; bk = -1; bl = 0; bnan = false; }
 };
 // Single-pass second moment.  Per thread: sums of (x-K) and (x-K)^2 around a pivot K
 // taken from the data (kills the catastrophic cancellation of the naive sum of squares);
@@ -414,7 +448,7 @@ struct B2AccMoment {
     double n, mean, m2;          // merged phase
     __device__ __forceinline__ void init() { K = (W)0; s1 = (W)0; s2 = (W)0; cnt = 0; n = 0.0; mean = 0.0; m2 = 0.0; }
     __device__ __forceinline__ void prime(T v) { K = (W)v; }
-    __device__ __forceinline__ void add(T v, i64) { W d = (W)v - K; s1 += d; s2 = fma(d, d, s2); }
+    __device__ __forceinline__ void add(T v, int, int) { W d = (W)v - K; s1 += d; s2 = fma(d, d, s2); }
     // fold the thread-local sums (over `count` elements, known from the loop bounds) into (n, mean, M2)
     __device__ __forceinline__ void finish_local(i64 count) {
         cnt = (int)count;
@@ -659,14 +693,18 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
 #pragma unroll
                     for (int v = 0; v < V; ++v) acc[v].prime(MODE == B2M_R ? o0[v] : o0[0]);
                 }
-                const i64 idx0 = (MODE == B2M_R) ? first : (first * C + c);       // arg reductions only
-                const i64 istep = (MODE == B2M_R) ? (i64)TY : (i64)TY * C;
                 b2_stream<Chain, V, U>(P, nrows, sc, st,
                     [&](B2AccState<A, V>& s_, int k, const T (&o)[V]) {
 #pragma unroll
-                        for (int v = 0; v < V; ++v)
-                            s_.acc[v].add(o[v], WANT_IDX ? (idx0 + k * istep + (MODE == B2M_R ? 0 : v)) : 0);
+                        for (int v = 0; v < V; ++v) s_.acc[v].add(o[v], k, 0);
                     });
+            }
+            if constexpr (WANT_IDX) {
+                // element k of accumulator v: row first + k*TY (mode R) / flat (first + k*TY)*C + c + v (mode RC)
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    acc[v].finish_arg(nrows > 0, (MODE == B2M_R) ? first : (first * C + c + v),
+                                      (MODE == B2M_R) ? (i64)TY : (i64)TY * C);
             }
             if constexpr (REDOP == B2R_MOMENT) {
 #pragma unroll
@@ -813,8 +851,9 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                     b2_stream<Chain, V, U>(P, ncol, sc, st,
                         [&](B2AccState<A, 1>& s_, int k, const T (&o)[V]) {
 #pragma unroll
-                            for (int v = 0; v < V; ++v) s_.acc[0].add(o[v], WANT_IDX ? (c0 + (i64)k * TX * V + v) : 0);
+                            for (int v = 0; v < V; ++v) s_.acc[0].add(o[v], k, v);
                         });
+                    if constexpr (WANT_IDX) acc.finish_arg(true, c0, (i64)TX * V);
                     if constexpr (REDOP == B2R_MOMENT) acc.to_raw((i64)ncol * V);
                 }
                 if constexpr (REDOP == B2R_MOMENT) {
@@ -835,5 +874,59 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
             }
             return;
         }
+    }
+}
+
+// ------------------------------------------------------------------ element-wise with transposed operands
+// `x.T + x` style chains (manipulation/_transpose.py:14-75 feeding an Elemwise): an operand whose
+// contiguous dimension is the OUTPUT's row dimension would be read with a stride by b2_run.
+// Here a CTA owns a 64 x 64 output tile; every transposed operand is first staged through a
+// padded shared-memory tile -- read along ITS contiguous dimension (coalesced 256 B runs), written
+// transposed with a 65-element pitch (bank-conflict free) -- and the chain then reads it like any
+// other operand.  Chain supplies, besides the b2_run interface:
+//   TBYTES (shared bytes of all staged tiles), stage(blk, b, r0, c0, smem, tid, nthreads),
+//   load_t(blk, Ptrs, smem, lr, lc, Regs&)  -- normal operands through Ptrs, staged ones from smem.
+#define B2_TT 64           // tile edge
+#define B2_TP 65           // padded pitch (elements)
+template <typename Chain, int V, int TX, int TY>
+__device__ __forceinline__ void b2_run_ewt(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars& sc) {
+    typedef typename Chain::out_t T;
+    constexpr int NT = TX * TY;
+    static_assert(TX * V == B2_TT, "tile width");
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    __shared__ B2Block sblk;
+    __shared__ __align__(16) unsigned char tiles[Chain::TBYTES];
+    {
+        const i64 tile = blockIdx.x;
+        const int bi = b2_find_block(blocks, nblocks, tile);
+        const int nw = (int)(sizeof(B2Block) / 4);
+        const u32* src = reinterpret_cast<const u32*>(blocks + bi);
+        u32* dst = reinterpret_cast<u32*>(&sblk);
+        for (int i = tid; i < nw; i += NT) dst[i] = src[i];
+        __syncthreads();
+    }
+    const B2Block& blk = sblk;
+    i64 t = (i64)blockIdx.x - blk.tile_begin;
+    const i64 tc = t % blk.tiles_c; t /= blk.tiles_c;
+    const i64 tr = t % blk.tiles_r; t /= blk.tiles_r;
+    const i64 b = t;
+    const i64 R = blk.R, C = blk.C;
+    const i64 r0 = tr * B2_TT, c0 = tc * B2_TT;
+    Chain::stage(blk, b, r0, c0, tiles, tid, NT);
+    __syncthreads();
+    const int lc = tx * V;
+    const i64 c = c0 + lc;
+    if (c >= C) return;
+    T* outp = (T*)blk.out0 + (b * R + r0) * C + c;
+    typename Chain::Ptrs P;
+    Chain::setup_rows(blk, b, r0, c, 1, P);
+#pragma unroll 4
+    for (int lr = ty; lr < B2_TT; lr += TY) {
+        if (r0 + lr >= R) break;
+        typename Chain::Regs g; T o[V];
+        Chain::load_t(P, tiles, lr, lc, g);
+        Chain::compute_slow(g, sc, o);
+        b2_store_vec<T, V>(outp + (i64)lr * C, o);
     }
 }
