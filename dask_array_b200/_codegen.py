@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-CODEGEN_VERSION = "10"     # part of every kernel's cache key: bump when generated code changes
+CODEGEN_VERSION = "11"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
@@ -419,7 +419,7 @@ def render(program: Program, spec: KernelSpec) -> str:
     T = ctype(program.out_dtype)
     regs = [f"{ctype(dt)} a{k}[B2_V];" for k, dt in enumerate(program.inputs)] or ["char _unused;"]
     ptrs, setup_r, setup_c, loads, adv = [], [], [], [], []
-    stage, loads_t, toff = [], [], 0
+    stage, loads_n, loads_s, toff = [], [], [], 0
     ewt = "T" in spec.layouts
     for k, (dt, lay) in enumerate(zip(program.inputs, spec.layouts)):
         ct = ctype(dt)
@@ -432,10 +432,12 @@ def render(program: Program, spec: KernelSpec) -> str:
             adv.append("")
             stage.append(
                 f"{{ const {ct}* src = (const {ct}*)blk.in[{k}] + b * blk.in_sb[{k}]; {ct}* sm = ({ct}*)(smem + {toff});\n"
-                f"              const i64 sr = blk.in_sr[{k}], scs = blk.in_sc[{k}];\n"
-                f"              for (int idx = tid; idx < B2_TT * B2_TT; idx += nthreads) {{ const int ii = idx / B2_TT, jj = idx % B2_TT;\n"
-                f"                  const i64 r = r0 + jj, c = c0 + ii; if (r < blk.R && c < blk.C) sm[jj * B2_TP + ii] = b2_ld(src + r * sr + c * scs); }} }}")
-            loads_t.append(f"{{ const {ct}* sm = (const {ct}*)(smem + {toff}) + lr * B2_TP + lc;\n"
+                f"              const i64 sr = blk.in_sr[{k}], scs = blk.in_sc[{k}]; {ct} tmp[B2_TT * B2_TT / NTHR];\n"
+                f"              _Pragma(\"unroll\") for (int m = 0; m < B2_TT * B2_TT / NTHR; ++m) {{ const int idx = tid + m * NTHR, ii = idx / B2_TT, jj = idx % B2_TT;\n"
+                f"                  const i64 r = r0 + jj, c = c0 + ii; if (r < blk.R && c < blk.C) tmp[m] = b2_ld(src + r * sr + c * scs); }}\n"
+                f"              _Pragma(\"unroll\") for (int m = 0; m < B2_TT * B2_TT / NTHR; ++m) {{ const int idx = tid + m * NTHR, ii = idx / B2_TT, jj = idx % B2_TT;\n"
+                f"                  sm[jj * B2_TP + ii] = tmp[m]; }} }}")
+            loads_s.append(f"{{ const {ct}* sm = (const {ct}*)(smem + {toff}) + lr * B2_TP + lc;\n"
                            f"              _Pragma(\"unroll\") for (int v = 0; v < B2_V; ++v) g.a{k}[v] = sm[v]; }}")
             toff += -(-64 * 65 * dt.itemsize // 16) * 16
             continue
@@ -453,7 +455,7 @@ def render(program: Program, spec: KernelSpec) -> str:
         else:
             loads.append(f"b2_load_strided<{ct}, B2_V>(P.p{k} + k * P.s{k}, P.c{k}, g.a{k});")
         adv.append(f"P.p{k} += n * P.s{k};")
-        loads_t.append(loads[-1].replace("P.p%d + k * P.s%d" % (k, k), "P.p%d + (i64)lr * P.s%d" % (k, k)))
+        loads_n.append(loads[-1].replace("P.p%d + k * P.s%d" % (k, k), "P.p%d + (i64)lr * P.s%d" % (k, k)))
     if not ptrs:
         ptrs = ["char _unused;"]
     if ewt and toff > 40 * 1024:
@@ -502,11 +504,15 @@ struct Chain {{
         {(nl[:-4]).join(adv)}
     }}
     static constexpr int TBYTES = {max(toff, 16)};
-    __device__ __forceinline__ static void stage(const B2Block& blk, i64 b, i64 r0, i64 c0, unsigned char* smem, int tid, int nthreads) {{
+    template <int NTHR>
+    __device__ __forceinline__ static void stage(const B2Block& blk, i64 b, i64 r0, i64 c0, unsigned char* smem, int tid) {{
         {(nl[:-4]).join(stage)}
     }}
-    __device__ __forceinline__ static void load_t(const Ptrs& P, const unsigned char* smem, int lr, int lc, Regs& g) {{
-        {(nl[:-4]).join(loads_t)}
+    __device__ __forceinline__ static void load_n(const Ptrs& P, int lr, Regs& g) {{
+        {(nl[:-4]).join(loads_n)}
+    }}
+    __device__ __forceinline__ static void load_s(const unsigned char* smem, int lr, int lc, Regs& g) {{
+        {(nl[:-4]).join(loads_s)}
     }}
 {compute}
 }};

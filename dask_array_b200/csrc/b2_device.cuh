@@ -913,20 +913,30 @@ __device__ __forceinline__ void b2_run_ewt(const B2Block* __restrict__ blocks, i
     const i64 b = t;
     const i64 R = blk.R, C = blk.C;
     const i64 r0 = tr * B2_TT, c0 = tc * B2_TT;
-    Chain::stage(blk, b, r0, c0, tiles, tid, NT);
-    __syncthreads();
     const int lc = tx * V;
     const i64 c = c0 + lc;
+    constexpr int ITER = B2_TT / TY;
+    typename Chain::Ptrs P;
+    typename Chain::Regs g[ITER];
+    Chain::setup_rows(blk, b, r0, (c < C) ? c : 0, 1, P);
+    // 1. staged operands: all loads of the tile in flight, then the transposed smem writes
+    Chain::template stage<NT>(blk, b, r0, c0, tiles, tid);
+    // 2. the other operands' loads are issued before the barrier so they overlap the staging
+    if (c < C) {
+#pragma unroll
+        for (int m = 0; m < ITER; ++m) { const int lr = ty + m * TY; if (r0 + lr < R) Chain::load_n(P, lr, g[m]); }
+    }
+    __syncthreads();
     if (c >= C) return;
     T* outp = (T*)blk.out0 + (b * R + r0) * C + c;
-    typename Chain::Ptrs P;
-    Chain::setup_rows(blk, b, r0, c, 1, P);
-#pragma unroll 4
-    for (int lr = ty; lr < B2_TT; lr += TY) {
-        if (r0 + lr >= R) break;
-        typename Chain::Regs g; T o[V];
-        Chain::load_t(P, tiles, lr, lc, g);
-        Chain::compute_slow(g, sc, o);
-        b2_store_vec<T, V>(outp + (i64)lr * C, o);
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+        const int lr = ty + m * TY;
+        if (r0 + lr < R) {
+            T o[V];
+            Chain::load_s(tiles, lr, lc, g[m]);
+            Chain::compute_slow(g[m], sc, o);
+            b2_store_vec<T, V>(outp + (i64)lr * C, o);
+        }
     }
 }
