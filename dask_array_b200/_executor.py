@@ -277,7 +277,7 @@ class Executor:
         parts = self._gather_partials(src, x)
         redop = REDOPS[kind]
         st = BlockStore(expr, src.kind if not final else "array", replicated=True)
-        in_dtype = x.dtype if not isinstance(x, (ChunkReduce, ArgChunk)) else None
+        groups, in_dt, out_dt, op = [], None, None, redop
         for key, members in expr.groups():
             blks = [parts[m] for m in members]
             first = blks[0]
@@ -286,34 +286,40 @@ class Executor:
                 n = sum(b["n"] for b in blks)
                 out = DeviceChunk.empty(tot0.shape if not final else self._final_shape(expr, tot0.shape),
                                         expr.dtype if final else tot0.dtype, self.device)
-                tab = rt.CombineLaunch(_lib.RED_SUM, tot0.dtype, [b["total"].ptr for b in blks], None, tot0.size, out.ptr,
-                                 post=_lib.POST_MEAN if final else _lib.POST_NONE, out_dtype=expr.dtype, count=n)
+                groups.append(dict(parts=[b["total"].ptr for b in blks], nelem=tot0.size, out0=out.ptr,
+                                   post=_lib.POST_MEAN if final else _lib.POST_NONE, count=n))
+                in_dt, out_dt, op = tot0.dtype, (expr.dtype if final else tot0.dtype), _lib.RED_SUM
                 st.blocks[key] = out if final else {"total": out, "n": n}
             elif src.kind == "moment":
                 nelem = first.size // 3
                 if final:
                     out = DeviceChunk.empty(self._final_shape(expr, first.shape[:-1]), expr.dtype, self.device)
-                    tab = rt.CombineLaunch(_lib.RED_MOMENT, np.float64, [b.ptr for b in blks], None, nelem, out.ptr,
-                                     post=_lib.POST_VAR, out_dtype=expr.dtype, ddof=expr.operand("ddof"))
+                    groups.append(dict(parts=[b.ptr for b in blks], nelem=nelem, out0=out.ptr, post=_lib.POST_VAR,
+                                       ddof=expr.operand("ddof")))
                 else:
                     out = DeviceChunk.empty(first.shape, np.float64, self.device)
-                    tab = rt.CombineLaunch(_lib.RED_MOMENT, np.float64, [b.ptr for b in blks], None, nelem, out.ptr)
+                    groups.append(dict(parts=[b.ptr for b in blks], nelem=nelem, out0=out.ptr))
+                in_dt, out_dt, op = np.dtype(np.float64), (expr.dtype if final else np.dtype(np.float64)), _lib.RED_MOMENT
                 st.blocks[key] = out
             elif src.kind == "arg":
                 v0 = first["vals"]
                 vals = DeviceChunk.empty(v0.shape, v0.dtype, self.device)
                 arg = DeviceChunk.empty(self._final_shape(expr, v0.shape) if final else v0.shape, np.int64, self.device)
-                tab = rt.CombineLaunch(redop, v0.dtype, [b["vals"].ptr for b in blks], [b["arg"].ptr for b in blks],
-                                 v0.size, vals.ptr, arg.ptr)
+                groups.append(dict(parts=[b["vals"].ptr for b in blks], parts1=[b["arg"].ptr for b in blks],
+                                   nelem=v0.size, out0=vals.ptr, out1=arg.ptr))
+                in_dt = out_dt = v0.dtype
                 st.blocks[key] = arg if final else {"vals": vals, "arg": arg}
+                st.keepalive.append(vals)
             else:
                 out = DeviceChunk.empty(self._final_shape(expr, first.shape) if final else first.shape,
                                         first.dtype, self.device)
-                tab = rt.CombineLaunch(redop, first.dtype, [b.ptr for b in blks], None, first.size, out.ptr)
+                groups.append(dict(parts=[b.ptr for b in blks], nelem=first.size, out0=out.ptr))
+                in_dt = out_dt = first.dtype
                 st.blocks[key] = out
-            self._do(tab.run)
-            st.keepalive.append(tab)
             st.keepalive.append(blks)
+        launch = rt.CombineGroupsLaunch(op, in_dt, out_dt, groups)       # ONE launch for the whole level
+        self._do(launch.run)
+        st.keepalive.append(launch)
         return st
 
     @staticmethod

@@ -76,6 +76,14 @@ class Geom(C.Structure):
     ]
 
 
+class Group(C.Structure):
+    _fields_ = [
+        ("parts", C.c_void_p), ("parts1", C.c_void_p), ("out0", C.c_void_p), ("out1", C.c_void_p),
+        ("nelem", C.c_int64), ("elem_begin", C.c_int64), ("fanin", C.c_int32), ("post", C.c_int32),
+        ("count", C.c_double), ("ddof", C.c_double),
+    ]
+
+
 class Copy(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int64), ("row_bytes", C.c_int64),
@@ -89,7 +97,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_launch_count", "b2_device_sm_count",
     "b2_jit_compile", "b2_free", "b2_device_header", "b2_kernel_load", "b2_kernel_free",
     "b2_fused_plan", "b2_fused_launch", "b2_combine", "b2_gather_plan", "b2_gather_launch",
-    "b2_fill", "b2_gemm_tn", "b2_memcpy2d", "b2_gemm_tn_pairs", "b2_split3_bf16",
+    "b2_fill", "b2_gemm_tn", "b2_memcpy2d", "b2_gemm_tn_pairs", "b2_split3_bf16", "b2_combine_groups",
 ]
 
 
@@ -114,6 +122,7 @@ def _load():
     lib.b2_fused_plan.argtypes = [vp, C.POINTER(Block), i32, vp, sz, C.POINTER(sz), C.POINTER(i64)]
     lib.b2_fused_launch.argtypes = [vp, vp, i32, i64, C.POINTER(Scalars), vp]
     lib.b2_combine.argtypes = [i32, i32, vp, vp, i32, i64, vp, vp, i32, i32, C.c_double, C.c_double, vp]
+    lib.b2_combine_groups.argtypes = [i32, i32, i32, vp, i32, i64, vp]
     lib.b2_gather_plan.argtypes = [C.POINTER(Copy), i32, C.POINTER(i64)]
     lib.b2_gather_launch.argtypes = [vp, i32, i64, vp]
     lib.b2_fill.argtypes = [vp, i64, i32, vp, vp]

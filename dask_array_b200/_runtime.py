@@ -318,6 +318,41 @@ class CombineLaunch:
                                        out0, out1, post, ocode, count, ddof, st))
 
 
+class CombineGroupsLaunch:
+    """All output blocks of one PartialReduce level (reductions/_reduction.py:968-983) in ONE launch."""
+
+    def __init__(self, redop: int, dtype, out_dtype, groups: list):
+        """groups: dicts with parts, parts1 (or None), nelem, out0, out1, post, count, ddof."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ptrs, offs = [], []
+        for g in groups:
+            offs.append(len(ptrs))
+            ptrs.extend(g["parts"])
+            ptrs.extend(g["parts1"] if g.get("parts1") else [0] * len(g["parts"]))
+        self.ptr_table = torch.tensor(ptrs or [0], dtype=torch.int64).to(dev)
+        base = self.ptr_table.data_ptr()
+        arr = (_lib.Group * len(groups))()
+        total = 0
+        for a, g, off in zip(arr, groups, offs):
+            fan = len(g["parts"])
+            a.parts = base + 8 * off
+            a.parts1 = base + 8 * (off + fan)
+            a.out0, a.out1 = g["out0"], g.get("out1", 0)
+            a.nelem, a.elem_begin, a.fanin = g["nelem"], total, fan
+            a.post, a.count, a.ddof = g.get("post", _lib.POST_NONE), float(g.get("count", 0.0)), float(g.get("ddof", 0.0))
+            total += g["nelem"]
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8)
+        self.table = torch.from_numpy(raw.copy()).to(dev)
+        self.n, self.total = len(groups), total
+        self.codes = (redop, _lib.dtype_code(dtype), _lib.dtype_code(out_dtype if out_dtype is not None else dtype))
+
+    def run(self, stream: int | None = None) -> None:
+        if not self.total:
+            return
+        st = current_stream_ptr() if stream is None else stream
+        _lib.check(_lib.lib.b2_combine_groups(*self.codes, self.table.data_ptr(), self.n, self.total, st))
+
+
 def combine(redop, dtype, parts, parts1, nelem, out0, out1=0, post=_lib.POST_NONE, out_dtype=None,
             count=0.0, ddof=0.0):
     c = CombineLaunch(redop, dtype, parts, parts1, nelem, out0, out1, post, out_dtype, count, ddof)

@@ -262,11 +262,8 @@ __device__ __forceinline__ void b2_post_store(void* out0, i64 e, T total, int po
 }
 
 template <typename T, int OP, typename OUT>
-__global__ void __launch_bounds__(256)
-b2_combine_kernel(const void* const* __restrict__ parts, const void* const* __restrict__ parts1, int fanin,
-                  i64 nelem, void* out0, void* out1, int post, double count, double ddof) {
-    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nelem) return;
+__device__ __forceinline__ void b2_combine_one(const void* const* __restrict__ parts, const void* const* __restrict__ parts1,
+                                               int fanin, i64 e, void* out0, void* out1, int post, double count, double ddof) {
     if constexpr (OP == B2R_SUM || OP == B2R_PROD) {
         T acc = ((const T*)parts[0])[e];
         for (int g = 1; g < fanin; ++g) { T v = ((const T*)parts[g])[e]; acc = (OP == B2R_SUM) ? (T)(acc + v) : (T)(acc * v); }
@@ -308,6 +305,45 @@ b2_combine_kernel(const void* const* __restrict__ parts, const void* const* __re
             ((OUT*)out0)[e] = (OUT)var;
         }
     }
+}
+
+template <typename T, int OP, typename OUT>
+__global__ void __launch_bounds__(256)
+b2_combine_kernel(const void* const* __restrict__ parts, const void* const* __restrict__ parts1, int fanin,
+                  i64 nelem, void* out0, void* out1, int post, double count, double ddof) {
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nelem) return;
+    b2_combine_one<T, OP, OUT>(parts, parts1, fanin, e, out0, out1, post, count, ddof);
+}
+
+template <typename T, int OP, typename OUT>
+__global__ void __launch_bounds__(256)
+b2_combine_groups_kernel(const b2_group* __restrict__ groups, int ngroups, i64 total) {
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    int lo = 0, hi = ngroups - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (groups[mid].elem_begin <= e) lo = mid; else hi = mid - 1;
+    }
+    const b2_group g = groups[lo];
+    b2_combine_one<T, OP, OUT>(g.parts, g.parts1, g.fanin, e - g.elem_begin, g.out0, g.out1, g.post, g.count, g.ddof);
+}
+
+template <typename T, typename OUT>
+static int launch_groups_t(int redop, const b2_group* g, int ng, int64_t total, cudaStream_t st) {
+    const unsigned grid = (unsigned)cdiv(total, 256);
+#define B2_CASE(OPC)                                                                     \
+    case OPC:                                                                            \
+        b2_combine_groups_kernel<T, OPC, OUT><<<grid, 256, 0, st>>>(g, ng, total);       \
+        break;
+    switch (redop) {
+        B2_CASE(B2R_SUM) B2_CASE(B2R_PROD) B2_CASE(B2R_MIN) B2_CASE(B2R_MAX)
+        B2_CASE(B2R_ARGMIN) B2_CASE(B2R_ARGMAX) B2_CASE(B2R_ANY) B2_CASE(B2R_ALL)
+        default: return fail(B2_ERR_UNSUPPORTED, "combine: redop %d", redop);
+    }
+#undef B2_CASE
+    return B2_OK;
 }
 
 template <typename T, typename OUT>
@@ -364,15 +400,68 @@ extern "C" int b2_combine(int redop, int dtype, const void* const* d_parts, cons
     return B2_OK;
 }
 
+extern "C" int b2_combine_groups(int redop, int dtype, int out_dtype, const b2_group* d_groups, int ngroups,
+                                 int64_t total_elems, void* stream) {
+    if (!d_groups || ngroups <= 0 || total_elems < 0) return fail(B2_ERR_INVALID, "bad argument");
+    if (total_elems == 0) return B2_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = B2_OK;
+    const unsigned grid = (unsigned)cdiv(total_elems, 256);
+    if (redop == B2R_MOMENT) {
+        if (out_dtype == B2_F32)
+            b2_combine_groups_kernel<double, B2R_MOMENT, float><<<grid, 256, 0, st>>>(d_groups, ngroups, total_elems);
+        else
+            b2_combine_groups_kernel<double, B2R_MOMENT, double><<<grid, 256, 0, st>>>(d_groups, ngroups, total_elems);
+    } else {
+        const bool f32out = (out_dtype == B2_F32);
+#define B2_T(DT, T)                                                                                     \
+    case DT:                                                                                            \
+        rc = f32out ? launch_groups_t<T, float>(redop, d_groups, ngroups, total_elems, st)              \
+                    : launch_groups_t<T, double>(redop, d_groups, ngroups, total_elems, st);            \
+        break;
+        switch (dtype) {
+            B2_T(B2_BOOL, unsigned char) B2_T(B2_I8, signed char) B2_T(B2_U8, unsigned char)
+            B2_T(B2_I16, short) B2_T(B2_U16, unsigned short) B2_T(B2_I32, int) B2_T(B2_U32, unsigned)
+            B2_T(B2_I64, long long) B2_T(B2_U64, unsigned long long) B2_T(B2_F32, float) B2_T(B2_F64, double)
+            default: return fail(B2_ERR_UNSUPPORTED, "combine: dtype %d", dtype);
+        }
+#undef B2_T
+    }
+    if (rc != B2_OK) return rc;
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------ tiled gather (AOT)
 // One CTA copies one tile = tile_rows x (<= B2_GATHER_COL_BYTES) of one rectangle; a warp
 // takes a row, lanes move the widest aligned word.
-template <typename W>
-__device__ __forceinline__ void b2_copy_row(const char* s, char* d, i64 nbytes, int lane) {
-    const i64 n = nbytes / (i64)sizeof(W);
-    const W* sw = reinterpret_cast<const W*>(s);
-    W* dw = reinterpret_cast<W*>(d);
-    for (i64 i = lane; i < n; i += 32) dw[i] = sw[i];
+// A warp moves GR rows at a time: every lane first issues the loads of up to GR x GC words
+// (GR * GC independent requests in flight per lane), then the stores -- a copy is pure latency
+// hiding, there is no compute to overlap.
+template <typename W, int GR, int GC>
+__device__ __forceinline__ void b2_copy_rows(const char* __restrict__ s, char* __restrict__ d, i64 src_pitch, i64 dst_pitch,
+                                             i64 nrows, i64 nbytes, int lane) {
+    const i64 n = nbytes / (i64)sizeof(W);           // words per row
+    for (i64 w0 = 0; w0 < n; w0 += 32 * GC) {
+        W v[GR][GC];
+#pragma unroll
+        for (int r = 0; r < GR; ++r) {
+#pragma unroll
+            for (int c = 0; c < GC; ++c) {
+                const i64 w = w0 + lane + 32 * c;
+                if (r < nrows && w < n) v[r][c] = reinterpret_cast<const W*>(s + r * src_pitch)[w];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < GR; ++r) {
+#pragma unroll
+            for (int c = 0; c < GC; ++c) {
+                const i64 w = w0 + lane + 32 * c;
+                if (r < nrows && w < n) reinterpret_cast<W*>(d + r * dst_pitch)[w] = v[r][c];
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) b2_gather_kernel(const b2_copy* __restrict__ copies, int n) {
@@ -396,15 +485,17 @@ __global__ void __launch_bounds__(256) b2_gather_kernel(const b2_copy* __restric
     const i64 c0 = tc * B2_GATHER_COL_BYTES;
     const i64 cb = (c0 + B2_GATHER_COL_BYTES < cp.row_bytes) ? B2_GATHER_COL_BYTES : cp.row_bytes - c0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (i64 r = r0 + warp; r < r1; r += nwarp) {
+    constexpr int GR = 4;
+    for (i64 r = r0 + (i64)warp * GR; r < r1; r += (i64)nwarp * GR) {
         const char* s = (const char*)cp.src + r * cp.src_pitch + c0;
         char* d = (char*)cp.dst + r * cp.dst_pitch + c0;
+        const i64 nr = r1 - r;
         switch (cp.vec_bytes) {
-            case 16: b2_copy_row<uint4>(s, d, cb, lane); break;
-            case 8: b2_copy_row<uint2>(s, d, cb, lane); break;
-            case 4: b2_copy_row<unsigned>(s, d, cb, lane); break;
-            case 2: b2_copy_row<unsigned short>(s, d, cb, lane); break;
-            default: b2_copy_row<unsigned char>(s, d, cb, lane); break;
+            case 16: b2_copy_rows<uint4, GR, 2>(s, d, cp.src_pitch, cp.dst_pitch, nr, cb, lane); break;
+            case 8: b2_copy_rows<uint2, GR, 2>(s, d, cp.src_pitch, cp.dst_pitch, nr, cb, lane); break;
+            case 4: b2_copy_rows<unsigned, GR, 4>(s, d, cp.src_pitch, cp.dst_pitch, nr, cb, lane); break;
+            case 2: b2_copy_rows<unsigned short, GR, 4>(s, d, cp.src_pitch, cp.dst_pitch, nr, cb, lane); break;
+            default: b2_copy_rows<unsigned char, GR, 4>(s, d, cp.src_pitch, cp.dst_pitch, nr, cb, lane); break;
         }
     }
 }

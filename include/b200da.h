@@ -179,6 +179,24 @@ int b2_combine(int redop, int dtype, const void* const* d_parts, const void* con
                int fanin, int64_t nelem, void* out0, void* out1,
                int post, int out_dtype, double count, double ddof, void* stream);
 
+/* All output blocks of ONE PartialReduce level in a single launch: `ngroups` groups, group g
+ * folding `fanin` partials of `nelem` elements each (same semantics as b2_combine).  The group
+ * table lives in DEVICE memory; parts / parts1 point into a device pointer table. */
+typedef struct b2_group {
+    const void* const* parts;
+    const void* const* parts1;
+    void* out0;
+    void* out1;
+    int64_t nelem;
+    int64_t elem_begin;   /* exclusive prefix sum of nelem over the groups */
+    int32_t fanin;
+    int32_t post;         /* b2_post */
+    double count;
+    double ddof;
+} b2_group;
+int b2_combine_groups(int redop, int dtype, int out_dtype, const b2_group* d_groups, int ngroups,
+                      int64_t total_elems, void* stream);
+
 /* ------------------------------------------------------------------ data movement
  * Rechunk / slicing / concatenation (_rechunk.py:1252-1323 split+merge tasks,
  * _chunk.py:285-317 getitem, _core_utils.py:1182-1248 concatenate3) as ONE tiled
