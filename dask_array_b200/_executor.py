@@ -428,9 +428,9 @@ def _copy_descs(src: DeviceChunk, dst: DeviceChunk, item: int):
             merged[-1] = (merged[-1][0] * n, s, d)
         else:
             merged.append((n, s, d))
+    if merged[-1][1] != 1 or merged[-1][2] != 1:
+        merged.append((1, 1, 1))        # e.g. a single column: rows of one element each
     n_in, s_in, d_in = merged[-1]
-    if s_in != 1 or d_in != 1:
-        raise NotImplementedError("gather needs a unit-stride innermost dimension on both sides")
     outer = merged[:-1]
     if not outer:
         return [(src.ptr, dst.ptr, 1, n_in * item, n_in * item, n_in * item)]

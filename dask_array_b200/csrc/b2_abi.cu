@@ -436,32 +436,12 @@ extern "C" int b2_combine_groups(int redop, int dtype, int out_dtype, const b2_g
 // ------------------------------------------------------------------ tiled gather (AOT)
 // One CTA copies one tile = tile_rows x (<= B2_GATHER_COL_BYTES) of one rectangle; a warp
 // takes a row, lanes move the widest aligned word.
-// A warp moves GR rows at a time: every lane first issues the loads of up to GR x GC words
-// (GR * GC independent requests in flight per lane), then the stores -- a copy is pure latency
-// hiding, there is no compute to overlap.
-template <typename W, int GR, int GC>
-__device__ __forceinline__ void b2_copy_rows(const char* __restrict__ s, char* __restrict__ d, i64 src_pitch, i64 dst_pitch,
-                                             i64 nrows, i64 nbytes, int lane) {
-    const i64 n = nbytes / (i64)sizeof(W);           // words per row
-    for (i64 w0 = 0; w0 < n; w0 += 32 * GC) {
-        W v[GR][GC];
-#pragma unroll
-        for (int r = 0; r < GR; ++r) {
-#pragma unroll
-            for (int c = 0; c < GC; ++c) {
-                const i64 w = w0 + lane + 32 * c;
-                if (r < nrows && w < n) v[r][c] = reinterpret_cast<const W*>(s + r * src_pitch)[w];
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < GR; ++r) {
-#pragma unroll
-            for (int c = 0; c < GC; ++c) {
-                const i64 w = w0 + lane + 32 * c;
-                if (r < nrows && w < n) reinterpret_cast<W*>(d + r * dst_pitch)[w] = v[r][c];
-            }
-        }
-    }
+template <typename W>
+__device__ __forceinline__ void b2_copy_row(const char* s, char* d, i64 nbytes, int lane) {
+    const i64 n = nbytes / (i64)sizeof(W);
+    const W* sw = reinterpret_cast<const W*>(s);
+    W* dw = reinterpret_cast<W*>(d);
+    for (i64 i = lane; i < n; i += 32) dw[i] = sw[i];
 }
 
 __global__ void __launch_bounds__(256) b2_gather_kernel(const b2_copy* __restrict__ copies, int n) {
@@ -485,17 +465,15 @@ __global__ void __launch_bounds__(256) b2_gather_kernel(const b2_copy* __restric
     const i64 c0 = tc * B2_GATHER_COL_BYTES;
     const i64 cb = (c0 + B2_GATHER_COL_BYTES < cp.row_bytes) ? B2_GATHER_COL_BYTES : cp.row_bytes - c0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    constexpr int GR = 4;
-    for (i64 r = r0 + (i64)warp * GR; r < r1; r += (i64)nwarp * GR) {
+    for (i64 r = r0 + warp; r < r1; r += nwarp) {
         const char* s = (const char*)cp.src + r * cp.src_pitch + c0;
         char* d = (char*)cp.dst + r * cp.dst_pitch + c0;
-        const i64 nr = r1 - r;
         switch (cp.vec_bytes) {
-            case 16: b2_copy_rows<uint4, GR, 2>(s, d, cp.src_pitch, cp.dst_pitch, nr, cb, lane); break;
-            case 8: b2_copy_rows<uint2, GR, 2>(s, d, cp.src_pitch, cp.dst_pitch, nr, cb, lane); break;
-            case 4: b2_copy_rows<unsigned, GR, 4>(s, d, cp.src_pitch, cp.dst_pitch, nr, cb, lane); break;
-            case 2: b2_copy_rows<unsigned short, GR, 4>(s, d, cp.src_pitch, cp.dst_pitch, nr, cb, lane); break;
-            default: b2_copy_rows<unsigned char, GR, 4>(s, d, cp.src_pitch, cp.dst_pitch, nr, cb, lane); break;
+            case 16: b2_copy_row<uint4>(s, d, cb, lane); break;
+            case 8: b2_copy_row<uint2>(s, d, cb, lane); break;
+            case 4: b2_copy_row<unsigned>(s, d, cb, lane); break;
+            case 2: b2_copy_row<unsigned short>(s, d, cb, lane); break;
+            default: b2_copy_row<unsigned char>(s, d, cb, lane); break;
         }
     }
 }
