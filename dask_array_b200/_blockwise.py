@@ -312,16 +312,18 @@ def optimize_blockwise_fusion(expr):
             return memo[node._name]
         if node._name in replacements:
             fb = replacements[node._name]
-            inside = {e._name for e in fb.exprs}
+            inside = {e._name: e for e in fb.exprs}
             rebuilt = {}
-            for inner in reversed(fb.exprs):      # leaves of the group first
-                def sub(o, _inside=inside, _rebuilt=rebuilt):
-                    if o._name in _rebuilt:
-                        return _rebuilt[o._name]
-                    if o._name in _inside:
-                        return o
-                    return rebuild(o)
-                rebuilt[inner._name] = _visit_children(inner, sub)
+
+            def rebuild_inner(e, _inside=inside, _rebuilt=rebuilt):
+                # children first (the group is a DAG, e.g. x + x*2 shares x), keyed by the OLD name
+                if e._name not in _rebuilt:
+                    _rebuilt[e._name] = e.map_children(
+                        lambda o: rebuild_inner(o) if o._name in _inside else rebuild(o))
+                return _rebuilt[e._name]
+
+            for inner in fb.exprs:
+                rebuild_inner(inner)
             out = FusedBlockwise(tuple(rebuilt[e._name] for e in fb.exprs))
         else:
             out = _visit_children(node, rebuild)

@@ -94,3 +94,17 @@ def test_unaligned_chunks_get_rechunked():
     a = da.from_array(np.zeros((12, 12)), chunks=(4, 12))
     b = da.from_array(np.zeros((12, 12)), chunks=(6, 12))
     assert any("Rechunk" in l for l in labels((a + b).optimize().expr))
+
+
+def test_diamond_group_is_rebuilt_consistently():
+    """x + x*2 with x = abs(T(rechunk(...))): the fused group is a DAG; after substitution no
+    un-fused Elemwise/Transpose may remain anywhere in the tree (found by the fuzz test)."""
+    from dask_array_b200._blockwise import Elemwise, Transpose
+    a = da.from_array(np.zeros((81, 51)), chunks=(20, 17))
+    x = abs((abs(a) * 3).rechunk((48, 15)).T)
+    opt = (x + x * 2).optimize().expr
+
+    def bare(e):
+        return int(isinstance(e, (Elemwise, Transpose))) + sum(bare(d) for d in e.dependencies())
+    assert bare(opt) == 0
+    assert len(FusedPlan(opt).leaves) == 1
