@@ -387,24 +387,35 @@ class Executor:
         # products kept for fp32: hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi  (error ~2^-24)
         combos = [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0)] if fp32 else [(0, 0)]
         nk = a.numblocks[1]
+        probs, keep = [], []
         for (i, j) in expr.block_ids():
             M, N = expr.block_shape((i, j))
             out = DeviceChunk.empty((M, N), np.float32, self.device)
             st.blocks[(i, j)] = out
+            if len({a.block_shape((i, k))[1] for k in range(nk)}) != 1:
+                raise NotImplementedError("matmul with ragged contraction chunks")
+            K = a.block_shape((i, 0))[1]
             A, B = [], []
-            K = None
             for k in range(nk):
-                K = a.block_shape((i, k))[1]
                 for ca, cb in combos:
                     A.append(pa[(i, k)][ca].ptr)
                     B.append(pb[(j, k)][cb].ptr)
-            if len({a.block_shape((i, k))[1] for k in range(nk)}) != 1:
-                raise NotImplementedError("matmul with ragged contraction chunks")
             arrA = (C.c_void_p * len(A))(*A)
             arrB = (C.c_void_p * len(B))(*B)
-            self._do(lambda arrA=arrA, arrB=arrB, n=len(A), M=M, N=N, K=K, o=out: _lib.check(
-                _lib.lib.b2_gemm_tn_pairs(_lib.dtype_code("bfloat16"), arrA, arrB, n, K, K, o.ptr, N, M, N, K, 0,
-                                          rt.current_stream_ptr())))
+            keep.extend([arrA, arrB])
+            p = _lib.GemmProblem()
+            p.A, p.B = C.cast(arrA, C.c_void_p), C.cast(arrB, C.c_void_p)
+            p.npairs, p.accumulate, p.lda, p.ldb = len(A), 0, K, K
+            p.C, p.ldc, p.M, p.N, p.K = out.ptr, N, M, N, K
+            probs.append(p)
+        arr = (_lib.GemmProblem * len(probs))(*probs)
+        need = C.c_size_t()
+        _lib.check(_lib.lib.b2_gemm_tn_batched(_lib.dtype_code("bfloat16"), arr, len(probs), None, 0, C.byref(need), None))
+        ws = alloc_bytes(need.value + 64, self.device)
+        wptr = (ws.data_ptr() + 63) // 64 * 64
+        self._do(lambda: _lib.check(_lib.lib.b2_gemm_tn_batched(
+            _lib.dtype_code("bfloat16"), arr, len(probs), wptr, need.value, C.byref(need), rt.current_stream_ptr())))
+        st.keepalive.extend([keep, arr, ws])
         st.keepalive.extend([pa, pb])
         return st
 

@@ -84,6 +84,14 @@ class Group(C.Structure):
     ]
 
 
+class GemmProblem(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("B", C.c_void_p), ("npairs", C.c_int32), ("accumulate", C.c_int32),
+        ("lda", C.c_int64), ("ldb", C.c_int64), ("C", C.c_void_p), ("ldc", C.c_int64),
+        ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+    ]
+
+
 class Copy(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int64), ("row_bytes", C.c_int64),
@@ -97,7 +105,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_launch_count", "b2_device_sm_count",
     "b2_jit_compile", "b2_free", "b2_device_header", "b2_kernel_load", "b2_kernel_free",
     "b2_fused_plan", "b2_fused_launch", "b2_combine", "b2_gather_plan", "b2_gather_launch",
-    "b2_fill", "b2_gemm_tn", "b2_memcpy2d", "b2_gemm_tn_pairs", "b2_split3_bf16", "b2_combine_groups",
+    "b2_fill", "b2_gemm_tn", "b2_memcpy2d", "b2_gemm_tn_pairs", "b2_split3_bf16", "b2_combine_groups", "b2_gemm_tn_batched",
 ]
 
 
@@ -130,6 +138,7 @@ def _load():
     lib.b2_gemm_tn.argtypes = [i32, vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, vp]
     lib.b2_gemm_tn_pairs.argtypes = [i32, vp, vp, i32, i64, i64, vp, i64, i64, i64, i64, i32, vp]
     lib.b2_split3_bf16.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.b2_gemm_tn_batched.argtypes = [i32, C.POINTER(GemmProblem), i32, vp, sz, C.POINTER(sz), vp]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError here = header and library out of sync
     return lib

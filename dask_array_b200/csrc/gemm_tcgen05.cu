@@ -9,10 +9,12 @@
 // BASELINE config 5) never exist -- the k-accumulation stays in TMEM.  The same pair list
 // carries the bf16 x 3 splitting used for fp32 operands (6 products per k block).
 //
-// Kernel: one CTA per 128 x 128 output tile, warp-specialised:
-//   warp 0      TMA producer   cp.async.bulk.tensor.2d (128B-swizzled 128x64 bf16 boxes) -> 6-stage smem ring
-//   warp 1      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16);
-//                              accumulator = 128 lanes x 128 fp32 columns of TMEM; tcgen05.commit frees stages
+// Kernel: one CTA per 128 x 256 output tile, warp-specialised:
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d (128B-swizzled 128x64 / 256x64 bf16 boxes) -> 4-stage smem ring
+//   warp 1      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16);
+//                              accumulator = 128 lanes x 256 fp32 columns of TMEM; tcgen05.commit frees stages
+//                              (a 128x128 tile needs 32 KiB of operands per 256 MMA cycles = the whole 128 B/clk
+//                              shared-memory bandwidth -- ncu: tensor pipe 66 % -- 128x256 needs 94 B/clk)
 //   warps 2..5  epilogue       tcgen05.ld 32x32b -> registers -> (+= C) -> global
 // SASS evidence: UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM (tcgen05.ld).
 #include "../../include/b200da.h"
@@ -23,6 +25,7 @@
 #include <dlfcn.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -32,7 +35,7 @@ extern "C" void b2_count_launch_(void);
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6, UMMA_K = 16;
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int MAX_PAIRS = 12;             // 24 tensor maps = 3 KiB of kernel parameters
 constexpr int NUM_THREADS = 192;
@@ -106,9 +109,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-b2_gemm_tn_kernel(const __grid_constant__ GemmMaps maps, int npairs, float* __restrict__ C, long long ldc,
-                  int M, int N, int K, int accumulate) {
+// one output block of a batched launch (device copy of b2_gemm_problem + launch bookkeeping)
+struct GemmProblem {
+    float* C;
+    long long ldc;
+    int M, N, K, npairs;
+    int accumulate, map_begin;      // maps[2 * (map_begin + p)] = A_p, +1 = B_p
+    long long tile_begin;           // exclusive prefix sum of tiles
+    int tiles_n, _pad;
+};
+
+__device__ __forceinline__ void gemm_tile(const CUtensorMap* __restrict__ amaps, const CUtensorMap* __restrict__ bmaps,
+                                          int map_stride, int npairs, float* __restrict__ C, long long ldc,
+                                          int M, int N, int K, int accumulate, int m0, int n0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B: 1024 B aligned
     uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -117,7 +130,6 @@ b2_gemm_tn_kernel(const __grid_constant__ GemmMaps maps, int npairs, float* __re
     uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int k_iters = (K + BK - 1) / BK;
     const int total_iters = npairs * k_iters;
 
@@ -127,7 +139,7 @@ b2_gemm_tn_kernel(const __grid_constant__ GemmMaps maps, int npairs, float* __re
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) {      // one warp allocates the accumulator: 128 TMEM columns (128 lanes x 128 fp32)
+    if (warp == 1) {      // one warp allocates the accumulator: 256 TMEM columns (128 lanes x 256 fp32)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -145,8 +157,8 @@ b2_gemm_tn_kernel(const __grid_constant__ GemmMaps maps, int npairs, float* __re
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 const int p = it / k_iters, kk = it % k_iters;
                 uint8_t* sa = smem + s * STAGE_BYTES;
-                tma_load_2d(sa, &maps.a[p], kk * BK, m0, &full_bar[s]);
-                tma_load_2d(sa + A_BYTES, &maps.b[p], kk * BK, n0, &full_bar[s]);
+                tma_load_2d(sa, amaps + (size_t)p * map_stride, kk * BK, m0, &full_bar[s]);
+                tma_load_2d(sa + A_BYTES, bmaps + (size_t)p * map_stride, kk * BK, n0, &full_bar[s]);
             }
         }
     } else if (warp == 1) {
@@ -207,6 +219,33 @@ b2_gemm_tn_kernel(const __grid_constant__ GemmMaps maps, int npairs, float* __re
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN));
     }
+}
+
+// single problem, tensor maps passed as kernel parameters
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+b2_gemm_tn_kernel(const __grid_constant__ GemmMaps maps, int npairs, float* __restrict__ C, long long ldc,
+                  int M, int N, int K, int accumulate) {
+    gemm_tile(maps.a, maps.b, 1, npairs, C, ldc, M, N, K, accumulate, blockIdx.y * BM, blockIdx.x * BN);
+}
+
+// all output blocks of a blocked matmul in ONE launch: problems + tensor maps live in global memory
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+b2_gemm_tn_batched_kernel(const GemmProblem* __restrict__ probs, int nprobs, const CUtensorMap* __restrict__ maps) {
+    __shared__ GemmProblem pr;
+    if (threadIdx.x == 0) {
+        const long long tile = blockIdx.x;
+        int lo = 0, hi = nprobs - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (probs[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+        }
+        pr = probs[lo];
+    }
+    __syncthreads();
+    const int t = (int)((long long)blockIdx.x - pr.tile_begin);
+    const int mt = t / pr.tiles_n, nt = t % pr.tiles_n;
+    const CUtensorMap* base = maps + 2 * (size_t)pr.map_begin;
+    gemm_tile(base, base + 1, 2, pr.npairs, pr.C, pr.ldc, pr.M, pr.N, pr.K, pr.accumulate, mt * BM, nt * BN);
 }
 
 // fp32 -> three bf16 planes with hi + mid + lo == x to ~2^-24 (x - hi and the next residual are exact)
@@ -287,6 +326,63 @@ extern "C" int b2_gemm_tn_pairs(int dtype, const void* const* A, const void* con
         if (e != cudaSuccess) return b2_set_error_(B2_ERR_CUDA, cudaGetErrorString(e));
         b2_count_launch_();
     }
+    return B2_OK;
+}
+
+extern "C" int b2_gemm_tn_batched(int dtype, const b2_gemm_problem* problems, int nproblems,
+                                  void* workspace, size_t workspace_bytes, size_t* needed, void* stream) {
+    if (dtype != B2_BF16) return b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_batched: operands must be bf16 planes");
+    if (!problems || nproblems <= 0) return b2_set_error_(B2_ERR_INVALID, "b2_gemm_tn_batched: bad argument");
+    size_t npairs_total = 0;
+    for (int i = 0; i < nproblems; ++i) npairs_total += (size_t)problems[i].npairs;
+    const size_t maps_bytes = npairs_total * 2 * sizeof(CUtensorMap);
+    const size_t probs_off = (maps_bytes + 255) / 256 * 256;
+    const size_t need = probs_off + (size_t)nproblems * sizeof(GemmProblem);
+    if (needed) *needed = need;
+    if (!workspace) return B2_OK;                       // size query
+    if (workspace_bytes < need || ((uintptr_t)workspace % 64)) return b2_set_error_(B2_ERR_WORKSPACE, "b2_gemm_tn_batched: workspace too small or not 64-byte aligned");
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(b2_gemm_tn_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    });
+    if (attr_err != cudaSuccess) return b2_set_error_(B2_ERR_CUDA, cudaGetErrorString(attr_err));
+    void* host = nullptr;
+    if (posix_memalign(&host, 64, need)) return b2_set_error_(B2_ERR_INVALID, "out of host memory");
+    memset(host, 0, need);
+    CUtensorMap* hm = (CUtensorMap*)host;
+    GemmProblem* hp = (GemmProblem*)((char*)host + probs_off);
+    long long tiles = 0;
+    int map_begin = 0, rc = B2_OK;
+    for (int i = 0; i < nproblems && rc == B2_OK; ++i) {
+        const b2_gemm_problem& q = problems[i];
+        if (!q.A || !q.B || !q.C || q.npairs <= 0 || q.M <= 0 || q.N <= 0 || q.K <= 0) { rc = b2_set_error_(B2_ERR_INVALID, "b2_gemm_tn_batched: bad problem"); break; }
+        if (q.lda % 8 || q.ldb % 8) { rc = b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_batched: lda/ldb must be multiples of 8 elements"); break; }
+        for (int p = 0; p < q.npairs && rc == B2_OK; ++p) {
+            if (((uintptr_t)q.A[p] | (uintptr_t)q.B[p]) % 16) { rc = b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_batched: operand not 16-byte aligned"); break; }
+            rc = make_map(&hm[2 * (map_begin + p)], q.A[p], q.M, q.K, q.lda, BM);
+            if (rc == B2_OK) rc = make_map(&hm[2 * (map_begin + p) + 1], q.B[p], q.N, q.K, q.ldb, BN);
+        }
+        GemmProblem& g = hp[i];
+        g.C = q.C; g.ldc = q.ldc; g.M = (int)q.M; g.N = (int)q.N; g.K = (int)q.K; g.npairs = q.npairs;
+        g.accumulate = q.accumulate; g.map_begin = map_begin; g.tile_begin = tiles;
+        g.tiles_n = (int)((q.N + BN - 1) / BN);
+        tiles += (long long)((q.M + BM - 1) / BM) * g.tiles_n;
+        map_begin += q.npairs;
+    }
+    if (rc == B2_OK && tiles > 0x7fffffffLL) rc = b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_batched: too many tiles");
+    if (rc == B2_OK) {
+        // pageable source: the copy is staged before the call returns, so `host` can be freed
+        cudaError_t e = cudaMemcpyAsync(workspace, host, need, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+        if (e != cudaSuccess) rc = b2_set_error_(B2_ERR_CUDA, cudaGetErrorString(e));
+    }
+    free(host);
+    if (rc != B2_OK) return rc;
+    b2_gemm_tn_batched_kernel<<<(unsigned)tiles, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const GemmProblem*)((char*)workspace + probs_off), nproblems, (const CUtensorMap*)workspace);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return b2_set_error_(B2_ERR_CUDA, cudaGetErrorString(e));
+    b2_count_launch_();
     return B2_OK;
 }
 

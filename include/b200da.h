@@ -245,6 +245,21 @@ int b2_gemm_tn(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb
 int b2_gemm_tn_pairs(int dtype, const void* const* A, const void* const* B, int npairs,
                      int64_t lda, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                      int accumulate, void* stream);
+/* Every output block of a blocked matmul in ONE launch (no wave quantisation between blocks).
+ * `problems` is a HOST array; the tensor maps and the problem table are written into the
+ * caller's DEVICE workspace (64-byte aligned; call with workspace == NULL to get *needed). */
+typedef struct b2_gemm_problem {
+    const void* const* A;   /* host array of npairs device pointers, each (M, K) bf16, leading dim lda */
+    const void* const* B;   /* host array of npairs device pointers, each (N, K) bf16, leading dim ldb */
+    int32_t npairs;
+    int32_t accumulate;
+    int64_t lda, ldb;
+    float* C;
+    int64_t ldc;
+    int64_t M, N, K;
+} b2_gemm_problem;
+int b2_gemm_tn_batched(int dtype, const b2_gemm_problem* problems, int nproblems,
+                       void* workspace, size_t workspace_bytes, size_t* needed, void* stream);
 /* fp32 -> bf16 hi/mid/lo planes with hi + mid + lo == x to ~2^-24 (operand preparation of the
  * fp32 matmul; tensor cores have no IEEE fp32 mode) */
 int b2_split3_bf16(const float* src, void* hi, void* mid, void* lo, int64_t nelem, void* stream);
