@@ -408,14 +408,41 @@ class Executor:
             p.npairs, p.accumulate, p.lda, p.ldb = len(A), 0, K, K
             p.C, p.ldc, p.M, p.N, p.K = out.ptr, N, M, N, K
             probs.append(p)
-        arr = (_lib.GemmProblem * len(probs))(*probs)
-        need = C.c_size_t()
-        _lib.check(_lib.lib.b2_gemm_tn_batched(_lib.dtype_code("bfloat16"), arr, len(probs), None, 0, C.byref(need), None))
-        ws = alloc_bytes(need.value + 64, self.device)
-        wptr = (ws.data_ptr() + 63) // 64 * 64
-        self._do(lambda: _lib.check(_lib.lib.b2_gemm_tn_batched(
-            _lib.dtype_code("bfloat16"), arr, len(probs), wptr, need.value, C.byref(need), rt.current_stream_ptr())))
-        st.keepalive.extend([keep, arr, ws])
+        import os
+        if os.environ.get("B2_GEMM_BATCHED", "1") == "0":         # diagnostic: one launch per output block
+            for p in probs:
+                self._do(lambda p=p: _lib.check(_lib.lib.b2_gemm_tn_pairs(
+                    _lib.dtype_code("bfloat16"), p.A, p.B, p.npairs, p.lda, p.ldb, p.C, p.ldc, p.M, p.N, p.K, 0,
+                    rt.current_stream_ptr())))
+            st.keepalive.extend([keep, probs, pa, pb])
+            return st
+        # Long pair lists are issued as several batched launches that accumulate into C.  Same-box
+        # A/B (bench --config c5, fp32 split = 48 pairs): 48 pairs/launch 693, 24 -> 763, 12 -> 993,
+        # 6 -> 1058 tensor TFLOP/s: in a long launch the CTAs drift out of lockstep and stop sharing
+        # operand tiles in L2; a kernel boundary re-aligns them.  (Cluster multicast is the real fix.)
+        longest = max(p.npairs for p in probs)
+        CH = int(os.environ.get("B2_GEMM_CHUNK", "12" if longest <= 12 else "6"))
+        nchunks = max(-(-p.npairs // CH) for p in probs)
+        for ci in range(nchunks):
+            sub = []
+            for p in probs:
+                lo, hi = ci * CH, min((ci + 1) * CH, p.npairs)
+                if lo >= hi:
+                    continue
+                q = _lib.GemmProblem()
+                q.A, q.B = p.A + 8 * lo, p.B + 8 * lo
+                q.npairs, q.accumulate, q.lda, q.ldb = hi - lo, 1 if ci > 0 else 0, p.lda, p.ldb
+                q.C, q.ldc, q.M, q.N, q.K = p.C, p.ldc, p.M, p.N, p.K
+                sub.append(q)
+            arr = (_lib.GemmProblem * len(sub))(*sub)
+            need = C.c_size_t()
+            _lib.check(_lib.lib.b2_gemm_tn_batched(_lib.dtype_code("bfloat16"), arr, len(sub), None, 0, C.byref(need), None))
+            ws = alloc_bytes(need.value + 64, self.device)
+            wptr = (ws.data_ptr() + 63) // 64 * 64
+            self._do(lambda arr=arr, n=len(sub), wptr=wptr, nb=need.value: _lib.check(_lib.lib.b2_gemm_tn_batched(
+                _lib.dtype_code("bfloat16"), arr, n, wptr, nb, None, rt.current_stream_ptr())))
+            st.keepalive.extend([arr, ws])
+        st.keepalive.append(keep)
         st.keepalive.extend([pa, pb])
         return st
 

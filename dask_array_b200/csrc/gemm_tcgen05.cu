@@ -65,6 +65,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "B2_DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -150,12 +153,18 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* __restrict__ amaps,
 
     if (warp == 0) {
         if (lane == 0) {
+            tma_prefetch_desc(amaps);
+            tma_prefetch_desc(bmaps);
             for (int it = 0; it < total_iters; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                const int p = it / k_iters, kk = it % k_iters;
+                if (kk == 0 && p + 1 < npairs) {      // descriptors of the NEXT pair: fetched a whole K loop ahead
+                    tma_prefetch_desc(amaps + (size_t)(p + 1) * map_stride);
+                    tma_prefetch_desc(bmaps + (size_t)(p + 1) * map_stride);
+                }
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                const int p = it / k_iters, kk = it % k_iters;
                 uint8_t* sa = smem + s * STAGE_BYTES;
                 tma_load_2d(sa, amaps + (size_t)p * map_stride, kk * BK, m0, &full_bar[s]);
                 tma_load_2d(sa + A_BYTES, bmaps + (size_t)p * map_stride, kk * BK, n0, &full_bar[s]);
