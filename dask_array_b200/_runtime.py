@@ -142,9 +142,31 @@ def canonicalize(shape, in_strides, reduce_axes) -> Canon:
         return pack(merged[0], merged[1], merged[2], _lib.MODE_R)
     if kinds == "KXX":
         return pack(merged[0], merged[1], merged[2], _lib.MODE_RC)
+    if kinds == "KKX":
+        return pack(merged[0], merged[1], merged[2], _lib.MODE_C)
+    # Interleaved patterns (e.g. sum(axis=(0, 2)) of a 3-D block = "XKX"): the kernels only need the
+    # kept dims and the reduced dims grouped, not in memory order -- reorder the VIEW (kept dims
+    # first, stable; no data moves), merge again.  The output is indexed by the kept dims in their
+    # original order, which a stable reorder preserves.
+    def merge(seq):
+        out = []
+        for n, kind, st in seq:
+            if out and out[-1][1] == kind and all(p == q * n for p, q in zip(out[-1][2], st)):
+                out[-1] = [out[-1][0] * n, kind, st]
+            else:
+                out.append([n, kind, list(st)])
+        return out
+
+    ks, xs = merge([d for d in dims if d[1] == "K"]), merge([d for d in dims if d[1] == "X"])
+    if len(ks) <= 2 and len(xs) == 1:
+        while len(ks) < 2:
+            ks.insert(0, one)
+        return pack(ks[0], ks[1], xs[0], _lib.MODE_C)
+    if len(ks) <= 1 and len(xs) == 2:
+        return pack(ks[0] if ks else one, xs[0], xs[1], _lib.MODE_RC)
     raise NotImplementedError(
-        f"reduction pattern {kinds!r} (shape {tuple(shape)}, axes {sorted(red)}) is not supported by the B200 kernels yet"
-    )
+        f"reduction pattern {kinds!r} (shape {tuple(shape)}, axes {sorted(red)}) needs more than three strided "
+        "dimension groups: not supported by the B200 kernels yet")
 
 
 @dataclass
