@@ -158,12 +158,17 @@ def canonicalize(shape, in_strides, reduce_axes) -> Canon:
         return out
 
     ks, xs = merge([d for d in dims if d[1] == "K"]), merge([d for d in dims if d[1] == "X"])
-    if len(ks) <= 2 and len(xs) == 1:
-        while len(ks) < 2:
-            ks.insert(0, one)
-        return pack(ks[0], ks[1], xs[0], _lib.MODE_C)
-    if len(ks) <= 1 and len(xs) == 2:
-        return pack(ks[0] if ks else one, xs[0], xs[1], _lib.MODE_RC)
+    # kept groups beyond what (B, R, C) can hold become host-side "lead" dims: one descriptor per
+    # index, input AND output pointers offset (the output is contiguous over the kept dims)
+    room = 2 if len(xs) == 1 else 1 if len(xs) == 2 else -1
+    if room >= 0:
+        lead = [(m[0], m[2]) for m in ks[:max(0, len(ks) - room)]]
+        ks = ks[max(0, len(ks) - room):]
+        if len(xs) == 1:
+            while len(ks) < 2:
+                ks.insert(0, one)
+            return pack(ks[0], ks[1], xs[0], _lib.MODE_C, lead)
+        return pack(ks[0] if ks else one, xs[0], xs[1], _lib.MODE_RC, lead)
     raise NotImplementedError(
         f"reduction pattern {kinds!r} (shape {tuple(shape)}, axes {sorted(red)}) needs more than three strided "
         "dimension groups: not supported by the B200 kernels yet")
@@ -263,14 +268,24 @@ class FusedLaunch:
             lead_ranges = [range(n) for n, _ in c.lead]
             lead_elems = math.prod(n for n, _ in c.lead) if c.lead else 1
             inner = c.B * c.R * c.C
+            # output elements produced per descriptor and their size (reductions)
+            out_per = {_lib.MODE_EW: inner, _lib.MODE_C: c.B * c.R, _lib.MODE_R: c.B * c.C, _lib.MODE_RC: c.B}[self.mode]
+            if self.mode == _lib.MODE_EW or redop in (_lib.RED_MIN, _lib.RED_MAX, _lib.RED_ARGMIN, _lib.RED_ARGMAX):
+                out_item = out_dt.itemsize
+            elif redop == _lib.RED_MOMENT:
+                out_item = 24
+            elif redop in (_lib.RED_ANY, _lib.RED_ALL):
+                out_item = 1
+            else:
+                out_item = acc_dtype.itemsize
             for li, idx in enumerate(np.ndindex(*[len(r) for r in lead_ranges]) if c.lead else [()]):
                 d = _lib.Block()
                 for k, (ptr, _) in enumerate(b.inputs):
                     off = sum(i * c.lead[j][1][k] for j, i in enumerate(idx))
                     d.in_[k] = ptr + off * program.inputs[k].itemsize
                     d.in_sb[k], d.in_sr[k], d.in_sc[k] = c.in_strides[k]
-                d.out0 = b.out0 + (li * inner * out_dt.itemsize if self.mode == _lib.MODE_EW else 0)
-                d.out1 = b.out1
+                d.out0 = b.out0 + li * out_per * out_item
+                d.out1 = b.out1 + (li * out_per * 8 if b.out1 else 0)
                 d.B, d.R, d.C = c.B, c.R, c.C
                 d.arg_offset = b.arg_offset
                 if b.arg_ravel is not None:
