@@ -11,9 +11,12 @@ from . import _eager  # noqa: F401  (NEP-13 / NEP-18 on DeviceChunk)
 from ._device import DeviceChunk  # noqa: F401
 from ._collection import (  # noqa: F401
     UFUNC_NAMES, Array, Compiled, _method, _ufunc, asarray, compile, compute, elemwise, from_array,
-    from_host_blocks, full, matmul, ones, random,
+    dot, from_host_blocks, full, matmul, nanargmax, nanargmin, nanmax, nanmean, nanmin, nanprod, nanstd, nansum,
+    nanvar, ones, random, tensordot,
     rechunk, transpose, where, zeros,
 )
+
+from ._views import broadcast_to, concatenate, expand_dims, squeeze, stack  # noqa: F401,E402
 
 for _n in UFUNC_NAMES:
     globals()[_n] = _ufunc(_n)

@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-CODEGEN_VERSION = "11"     # part of every kernel's cache key: bump when generated code changes
+CODEGEN_VERSION = "12"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
@@ -376,6 +376,7 @@ _RED_NAME = {
     _lib.RED_NONE: "B2R_NONE", _lib.RED_SUM: "B2R_SUM", _lib.RED_MIN: "B2R_MIN", _lib.RED_MAX: "B2R_MAX",
     _lib.RED_ARGMIN: "B2R_ARGMIN", _lib.RED_ARGMAX: "B2R_ARGMAX", _lib.RED_MOMENT: "B2R_MOMENT",
     _lib.RED_PROD: "B2R_PROD", _lib.RED_ANY: "B2R_ANY", _lib.RED_ALL: "B2R_ALL",
+    _lib.RED_NANMIN: "B2R_NANMIN", _lib.RED_NANMAX: "B2R_NANMAX",
 }
 
 
@@ -403,7 +404,7 @@ def packed_bytes(spec: KernelSpec, out_dtype) -> int:
     r = spec.redop
     if r in (_lib.RED_SUM, _lib.RED_PROD):
         return np.dtype(spec.acc_dtype).itemsize
-    if r in (_lib.RED_MIN, _lib.RED_MAX):
+    if r in (_lib.RED_MIN, _lib.RED_MAX, _lib.RED_NANMIN, _lib.RED_NANMAX):
         return max(it, 4) * 2 if it <= 4 else 16
     if r in (_lib.RED_ARGMIN, _lib.RED_ARGMAX):
         return 16

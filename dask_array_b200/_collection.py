@@ -214,6 +214,14 @@ class Array:
     def max(self, axis=None, keepdims=False, split_every=None):
         return self._reduce("max", axis, keepdims, None, split_every)
 
+    def dot(self, other):
+        return self @ other
+
+    def squeeze(self, axis=None):
+        from ._views import squeeze
+
+        return squeeze(self, axis)
+
     def any(self, axis=None, keepdims=False, split_every=None):
         return self._reduce("any", axis, keepdims, None, split_every)
 
@@ -258,6 +266,102 @@ class Compiled:
         for st in self.executor.results.values():
             out.extend(k for k in st.keepalive if isinstance(k, FusedLaunch))
         return out
+
+
+# ----------------------------------------------------------------------------- NaN-aware reducers
+def _nan_to(x, value):
+    """``where(isnan(x), value, x)`` fused in front of the reduction chunk step (the role of
+    ``chunk.nansum`` / ``np.nanmin`` ... in ``reductions/_common.py:170-266``)."""
+    x = asarray(x)
+    if x.dtype.kind != "f":
+        return x
+    return elemwise("where", elemwise("isnan", x), value, x)
+
+
+def nansum(a, axis=None, dtype=None, keepdims=False, split_every=None):
+    """``_common.py:170-183``."""
+    return _nan_to(a, 0).sum(axis=axis, dtype=dtype, keepdims=keepdims, split_every=split_every)
+
+
+def nanprod(a, axis=None, dtype=None, keepdims=False, split_every=None):
+    return _nan_to(a, 1).prod(axis=axis, dtype=dtype, keepdims=keepdims, split_every=split_every)
+
+
+def _nancount(a, axis, keepdims, split_every):
+    a = asarray(a)
+    if a.dtype.kind != "f":
+        n = 1
+        for ax in validate_axis(axis, a.ndim):
+            n *= a.shape[ax]
+        return n
+    return elemwise("logical_not", elemwise("isnan", a)).sum(axis=axis, keepdims=keepdims, split_every=split_every)
+
+
+def nanmean(a, axis=None, dtype=None, keepdims=False, split_every=None):
+    """``_common.py:346-365``: sum of the non-NaN values over their count (0/0 -> NaN, as NumPy)."""
+    a = asarray(a)
+    dt = np.dtype(dtype) if dtype is not None else np.mean(np.zeros((1,), dtype=a.dtype)).dtype
+    total = nansum(a, axis=axis, dtype=dt, keepdims=keepdims, split_every=split_every)
+    return elemwise("true_divide", total, _nancount(a, axis, keepdims, split_every)).astype(dt)
+
+
+def nanvar(a, axis=None, dtype=None, keepdims=False, ddof=0, split_every=None):
+    """``_common.py:596-622`` by its definition: two more passes (mean, then squared deviations of
+    the non-NaN values); the fused kernels make each pass one read of ``a``."""
+    a = asarray(a)
+    dt = np.dtype(dtype) if dtype is not None else np.var(np.ones((1,), dtype=a.dtype)).dtype
+    mu = nanmean(a, axis=axis, dtype=dt, keepdims=True, split_every=split_every)
+    d = _nan_to(elemwise("subtract", a.astype(dt), mu), 0)
+    ss = elemwise("multiply", d, d).sum(axis=axis, dtype=dt, keepdims=keepdims, split_every=split_every)
+    n = _nancount(a, axis, keepdims, split_every)
+    den = elemwise("subtract", n, ddof) if isinstance(n, Array) else n - ddof
+    if isinstance(den, Array):
+        den = elemwise("where", elemwise("less_equal", den, 0), np.float64(np.nan), den)
+    elif den <= 0:
+        den = np.nan
+    return elemwise("true_divide", ss, den).astype(dt)
+
+
+def nanstd(a, axis=None, dtype=None, keepdims=False, ddof=0, split_every=None):
+    return elemwise("sqrt", nanvar(a, axis, dtype, keepdims, ddof, split_every))
+
+
+def nanmin(a, axis=None, keepdims=False, split_every=None):
+    """``_common.py:196-229``: NaNs skipped by the accumulator itself (``B2AccNanMinMax``)."""
+    return asarray(a)._reduce("nanmin", axis, keepdims, None, split_every)
+
+
+def nanmax(a, axis=None, keepdims=False, split_every=None):
+    return asarray(a)._reduce("nanmax", axis, keepdims, None, split_every)
+
+
+def nanargmin(a, axis=None, keepdims=False, split_every=None):
+    """``_common.py:815-827`` (NaN -> +inf; an all-NaN slice is not diagnosed here)."""
+    return _nan_to(a, np.inf).argmin(axis=axis, keepdims=keepdims, split_every=split_every)
+
+
+def nanargmax(a, axis=None, keepdims=False, split_every=None):
+    return _nan_to(a, -np.inf).argmax(axis=axis, keepdims=keepdims, split_every=split_every)
+
+
+def tensordot(a, b, axes=2):
+    """``linalg/_tensordot.py:45-136`` for the 2-D contractions the block GEMM covers."""
+    a, b = asarray(a), asarray(b)
+    if isinstance(axes, int):
+        la, lb = tuple(range(a.ndim - axes, a.ndim)), tuple(range(axes))
+    else:
+        la, lb = axes
+        la = (la,) if isinstance(la, int) else tuple(la)
+        lb = (lb,) if isinstance(lb, int) else tuple(lb)
+    if a.ndim != 2 or b.ndim != 2 or len(la) != 1 or len(lb) != 1:
+        raise NotImplementedError("B200 tensordot covers 2-D operands contracted over one axis (use @ for matmul)")
+    aa = a if la[0] % 2 == 1 else a.T
+    bb = b if lb[0] % 2 == 0 else b.T
+    return aa @ bb
+
+
+def dot(a, b):
+    return asarray(a) @ asarray(b)
 
 
 def _freeze(split_every):

@@ -155,6 +155,45 @@ class Executor:
         st.replicated = src.replicated
         return st
 
+    def _view_store(self, expr, src_of, view_of):
+        """Zero-copy structural expressions: each output block is a view of one input block."""
+        st = BlockStore(expr)
+        rep = None
+        for bid in expr.block_ids():
+            store, x, ibid = src_of(bid)
+            rep = store.replicated if rep is None else (rep and store.replicated)
+            if self.world.size > 1 and not store.replicated and self.world.owner(x, ibid) != self.world.owner(expr, bid):
+                raise NotImplementedError(f"{type(expr).__name__} that moves blocks between GPUs (rechunk first)")
+            blk = store.blocks.get(ibid)
+            if blk is not None and (store.replicated or self.mine(expr, bid)):
+                st.blocks[bid] = view_of(blk, bid)
+        st.replicated = bool(rep)
+        return st
+
+    def _run_ExpandDims(self, expr):
+        x = expr.operand("array")
+        src = self.results[x._name]
+        return self._view_store(expr, lambda bid: (src, x, expr.source(bid)), lambda blk, bid: expr.view(blk))
+
+    def _run_Squeeze(self, expr):
+        x = expr.operand("array")
+        src = self.results[x._name]
+        return self._view_store(expr, lambda bid: (src, x, expr.source(bid)), lambda blk, bid: expr.view(blk))
+
+    def _run_BroadcastTo(self, expr):
+        x = expr.operand("array")
+        src = self.results[x._name]
+        return self._view_store(expr, lambda bid: (src, x, expr.source(bid)), lambda blk, bid: expr.view(blk, bid))
+
+    def _run_Concatenate(self, expr):
+        arrs = expr.operand("arrays")
+        stores = [self.results[a._name] for a in arrs]
+
+        def src_of(bid):
+            k, ibid = expr.source(bid)
+            return stores[k], arrs[k], ibid
+        return self._view_store(expr, src_of, lambda blk, bid: blk)
+
     # ------------------------------------------------------------------ fused blockwise
     def _fetch_remote(self, needs):
         """needs: {(dep expr name): set(block ids)} this rank must read but does not own.

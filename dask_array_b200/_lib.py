@@ -20,6 +20,7 @@ B2_MAX_ND = 4
 # enums (include/b200da.h)
 MODE_EW, MODE_R, MODE_C, MODE_RC = 0, 1, 2, 3
 RED_NONE, RED_SUM, RED_MIN, RED_MAX, RED_ARGMIN, RED_ARGMAX, RED_MOMENT, RED_PROD, RED_ANY, RED_ALL = range(10)
+RED_NANMIN, RED_NANMAX = 10, 11
 POST_NONE, POST_MEAN, POST_VAR, POST_STD = range(4)
 
 _DTYPE_CODES = {

@@ -26,7 +26,7 @@ from ._expr import ArrayExpr
 REDOPS = {
     "sum": _lib.RED_SUM, "prod": _lib.RED_PROD, "min": _lib.RED_MIN, "max": _lib.RED_MAX,
     "any": _lib.RED_ANY, "all": _lib.RED_ALL, "mean": _lib.RED_SUM, "var": _lib.RED_MOMENT,
-    "argmin": _lib.RED_ARGMIN, "argmax": _lib.RED_ARGMAX,
+    "argmin": _lib.RED_ARGMIN, "argmax": _lib.RED_ARGMAX, "nanmin": _lib.RED_NANMIN, "nanmax": _lib.RED_NANMAX,
 }
 
 
@@ -67,7 +67,7 @@ def result_dtype(kind, in_dtype, dtype=None) -> np.dtype:
         return np.dtype(dtype) if dtype is not None else np.mean(np.zeros((1,), dtype=in_dtype)).dtype
     if kind == "var":
         return np.dtype(dtype) if dtype is not None else np.var(np.ones((1,), dtype=in_dtype)).dtype
-    if kind in ("min", "max"):
+    if kind in ("min", "max", "nanmin", "nanmax"):
         return in_dtype
     if kind in ("any", "all"):
         return np.dtype(bool)

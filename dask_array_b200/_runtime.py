@@ -270,7 +270,7 @@ class FusedLaunch:
             inner = c.B * c.R * c.C
             # output elements produced per descriptor and their size (reductions)
             out_per = {_lib.MODE_EW: inner, _lib.MODE_C: c.B * c.R, _lib.MODE_R: c.B * c.C, _lib.MODE_RC: c.B}[self.mode]
-            if self.mode == _lib.MODE_EW or redop in (_lib.RED_MIN, _lib.RED_MAX, _lib.RED_ARGMIN, _lib.RED_ARGMAX):
+            if self.mode == _lib.MODE_EW or redop in (_lib.RED_MIN, _lib.RED_MAX, _lib.RED_NANMIN, _lib.RED_NANMAX, _lib.RED_ARGMIN, _lib.RED_ARGMAX):
                 out_item = out_dt.itemsize
             elif redop == _lib.RED_MOMENT:
                 out_item = 24

@@ -272,6 +272,10 @@ __device__ __forceinline__ void b2_combine_one(const void* const* __restrict__ p
         T acc = ((const T*)parts[0])[e];
         for (int g = 1; g < fanin; ++g) { T v = ((const T*)parts[g])[e]; acc = (OP == B2R_MAX) ? b2_np_max(acc, v) : b2_np_min(acc, v); }
         ((T*)out0)[e] = acc;
+    } else if constexpr (OP == B2R_NANMIN || OP == B2R_NANMAX) {
+        T acc = ((const T*)parts[0])[e];
+        for (int g = 1; g < fanin; ++g) { T v = ((const T*)parts[g])[e]; acc = (OP == B2R_NANMAX) ? b2_nan_max(acc, v) : b2_nan_min(acc, v); }
+        ((T*)out0)[e] = acc;
     } else if constexpr (OP == B2R_ANY || OP == B2R_ALL) {
         unsigned char acc = ((const unsigned char*)parts[0])[e];
         for (int g = 1; g < fanin; ++g) { unsigned char v = ((const unsigned char*)parts[g])[e]; acc = (OP == B2R_ALL) ? (acc & v) : (acc | v); }
@@ -340,6 +344,7 @@ static int launch_groups_t(int redop, const b2_group* g, int ng, int64_t total, 
     switch (redop) {
         B2_CASE(B2R_SUM) B2_CASE(B2R_PROD) B2_CASE(B2R_MIN) B2_CASE(B2R_MAX)
         B2_CASE(B2R_ARGMIN) B2_CASE(B2R_ARGMAX) B2_CASE(B2R_ANY) B2_CASE(B2R_ALL)
+        B2_CASE(B2R_NANMIN) B2_CASE(B2R_NANMAX)
         default: return fail(B2_ERR_UNSUPPORTED, "combine: redop %d", redop);
     }
 #undef B2_CASE
@@ -357,6 +362,7 @@ static int launch_combine_t(int redop, const void* const* p0, const void* const*
     switch (redop) {
         B2_CASE(B2R_SUM) B2_CASE(B2R_PROD) B2_CASE(B2R_MIN) B2_CASE(B2R_MAX)
         B2_CASE(B2R_ARGMIN) B2_CASE(B2R_ARGMAX) B2_CASE(B2R_ANY) B2_CASE(B2R_ALL)
+        B2_CASE(B2R_NANMIN) B2_CASE(B2R_NANMAX)
         default: return fail(B2_ERR_UNSUPPORTED, "combine: redop %d", redop);
     }
 #undef B2_CASE

@@ -55,7 +55,7 @@ struct B2Scalars {
 
 enum { B2M_EW = 0, B2M_R = 1, B2M_C = 2, B2M_RC = 3 };
 enum { B2R_NONE = 0, B2R_SUM = 1, B2R_MIN = 2, B2R_MAX = 3, B2R_ARGMIN = 4, B2R_ARGMAX = 5,
-       B2R_MOMENT = 6, B2R_PROD = 7, B2R_ANY = 8, B2R_ALL = 9 };
+       B2R_MOMENT = 6, B2R_PROD = 7, B2R_ANY = 8, B2R_ALL = 9, B2R_NANMIN = 10, B2R_NANMAX = 11 };
 
 // ------------------------------------------------------------------ loads / stores
 // 128-bit (or narrower) read-only streaming loads: every input byte is touched once,
@@ -347,6 +347,39 @@ struct B2AccAnyAll {   // np.any / np.all -> bool
     __device__ __forceinline__ Packed pack() const { return s; }
     __device__ __forceinline__ void unpack(const Packed& p) { s = p; }
 };
+// np.nanmin / np.nanmax (_chunk.py:189-190): NaNs are skipped, an all-NaN slice gives NaN
+template <typename T> __device__ __forceinline__ T b2_nan_max(T a, T b) {
+    if constexpr (b2_is_float<T>::value) return (a != a) ? b : ((b != b) ? a : (a >= b ? a : b));
+    else return a >= b ? a : b;
+}
+template <typename T> __device__ __forceinline__ T b2_nan_min(T a, T b) {
+    if constexpr (b2_is_float<T>::value) return (a != a) ? b : ((b != b) ? a : (a <= b ? a : b));
+    else return a <= b ? a : b;
+}
+template <typename T, bool ISMAX>
+struct B2AccNanMinMax {
+    struct Packed { T m; int has; };
+    T m; bool has;
+    __device__ __forceinline__ void init() { has = false; m = (T)0; }
+    __device__ __forceinline__ void prime(T) {}
+    __device__ __forceinline__ void add(T v, int, int) {
+        if (!has) { m = v; has = true; return; }
+        m = ISMAX ? b2_nan_max(m, v) : b2_nan_min(m, v);
+    }
+    __device__ __forceinline__ void merge(const B2AccNanMinMax& o) {
+        if (!o.has) return;
+        if (!has) { m = o.m; has = true; return; }
+        m = ISMAX ? b2_nan_max(m, o.m) : b2_nan_min(m, o.m);
+    }
+    __device__ __forceinline__ void shfl(int off, int width) {
+        B2AccNanMinMax o; o.m = b2_shfl_down(m, off, width); o.has = b2_shfl_down(has, off, width); merge(o);
+    }
+    __device__ __forceinline__ void lane_merge(const B2AccNanMinMax& o) { merge(o); }
+    __device__ __forceinline__ void lane_shfl(int off, int width) { shfl(off, width); }
+    __device__ __forceinline__ void lane_finish() {}
+    __device__ __forceinline__ Packed pack() const { Packed p; p.m = m; p.has = has ? 1 : 0; return p; }
+    __device__ __forceinline__ void unpack(const Packed& p) { m = p.m; has = (p.has != 0); }
+};
 template <typename T, bool ISMAX>
 struct B2AccMinMax {   // np.min / np.max: NaN propagates (chunk_min/chunk_max _common.py:92-105)
     struct Packed { T m; int has; };
@@ -498,6 +531,8 @@ template <typename T, typename ACC> struct B2AccSel<B2R_SUM, T, ACC> { typedef B
 template <typename T, typename ACC> struct B2AccSel<B2R_PROD, T, ACC> { typedef B2AccProd<T, ACC> type; };
 template <typename T, typename ACC> struct B2AccSel<B2R_MIN, T, ACC> { typedef B2AccMinMax<T, false> type; };
 template <typename T, typename ACC> struct B2AccSel<B2R_MAX, T, ACC> { typedef B2AccMinMax<T, true> type; };
+template <typename T, typename ACC> struct B2AccSel<B2R_NANMIN, T, ACC> { typedef B2AccNanMinMax<T, false> type; };
+template <typename T, typename ACC> struct B2AccSel<B2R_NANMAX, T, ACC> { typedef B2AccNanMinMax<T, true> type; };
 template <typename T, typename ACC> struct B2AccSel<B2R_ARGMIN, T, ACC> { typedef B2AccArg<T, false> type; };
 template <typename T, typename ACC> struct B2AccSel<B2R_ARGMAX, T, ACC> { typedef B2AccArg<T, true> type; };
 template <typename T, typename ACC> struct B2AccSel<B2R_MOMENT, T, ACC> { typedef B2AccMoment<T, ACC> type; };
@@ -509,7 +544,7 @@ template <int REDOP, typename T, typename ACC, typename A>
 __device__ __forceinline__ void b2_store_result(const B2Block& blk, i64 o, A& a, i64 idx_fix) {
     if constexpr (REDOP == B2R_SUM || REDOP == B2R_PROD) {
         ((ACC*)blk.out0)[o] = a.s;
-    } else if constexpr (REDOP == B2R_MIN || REDOP == B2R_MAX) {
+    } else if constexpr (REDOP == B2R_MIN || REDOP == B2R_MAX || REDOP == B2R_NANMIN || REDOP == B2R_NANMAX) {
         ((T*)blk.out0)[o] = a.m;
     } else if constexpr (REDOP == B2R_ARGMIN || REDOP == B2R_ARGMAX) {
         ((T*)blk.out0)[o] = a.v;

@@ -57,7 +57,8 @@ typedef enum b2_dtype {
 typedef enum b2_redop {
     B2_RED_NONE = 0, B2_RED_SUM = 1, B2_RED_MIN = 2, B2_RED_MAX = 3,
     B2_RED_ARGMIN = 4, B2_RED_ARGMAX = 5, B2_RED_MOMENT = 6,
-    B2_RED_PROD = 7, B2_RED_ANY = 8, B2_RED_ALL = 9
+    B2_RED_PROD = 7, B2_RED_ANY = 8, B2_RED_ALL = 9,
+    B2_RED_NANMIN = 10, B2_RED_NANMAX = 11   /* np.nanmin / np.nanmax: NaN only if every element is NaN */
 } b2_redop;
 
 /* which canonical axes of a (B, R, C) block are reduced */

@@ -1,0 +1,62 @@
+"""SURVEY 8(f) widening: structural views (expand_dims / squeeze / broadcast_to / concatenate /
+stack) and the NaN-aware reducers, against NumPy."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def da():
+    import dask_array_b200 as da
+    return da
+
+
+def test_structural_views(da):
+    rng = np.random.default_rng(0)
+    ah = rng.integers(0, 100, (12, 10)).astype(np.int64)
+    bh = rng.integers(0, 100, (7, 10)).astype(np.int64)
+    a, b = da.from_array(ah, chunks=(5, 4)), da.from_array(bh, chunks=(3, 4))
+    assert np.array_equal(da.concatenate([a, b], axis=0).compute(), np.concatenate([ah, bh], axis=0))
+    assert np.array_equal((da.concatenate([a, a * 2], axis=1) + 1).sum(axis=0).compute(),
+                          (np.concatenate([ah, ah * 2], axis=1) + 1).sum(axis=0))
+    assert np.array_equal(da.stack([a, a + 1], axis=0).compute(), np.stack([ah, ah + 1], axis=0))
+    assert np.array_equal(da.stack([a, a + 1], axis=2).max(axis=2).compute(), np.stack([ah, ah + 1], axis=2).max(axis=2))
+    e = da.expand_dims(a, 1)
+    assert e.shape == (12, 1, 10) and np.array_equal(e.compute(), ah[:, None, :])
+    assert np.array_equal((e * da.expand_dims(b, 0)[:, :7, :]).compute(), ah[:, None, :] * bh[None, :, :])
+    assert np.array_equal(da.squeeze(e, 1).compute(), ah) and np.array_equal(e.squeeze().compute(), ah)
+    assert np.array_equal(a.sum(axis=0, keepdims=True).squeeze().compute(), ah.sum(axis=0))
+    bt = da.broadcast_to(da.from_array(ah[:1], chunks=(1, 4)), (6, 10))
+    assert np.array_equal((bt + 0).compute(), np.broadcast_to(ah[:1], (6, 10)))
+    assert np.array_equal(da.broadcast_to(a, (3, 12, 10)).sum(axis=0).compute(), 3 * ah)
+    mm = da.tensordot(a.astype("float32"), da.from_array(bh.astype(np.float32), chunks=(3, 4)), axes=((1,), (1,)))
+    np.testing.assert_allclose(mm.compute(), ah.astype(np.float64) @ bh.T.astype(np.float64), rtol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_nan_reducers(da, dtype):
+    rng = np.random.default_rng(1)
+    xh = rng.random((90, 70)).astype(dtype) * 10 - 5
+    xh[rng.random(xh.shape) < 0.1] = np.nan
+    xh[5, :] = np.nan                              # an all-NaN row
+    x = da.from_array(xh, chunks=(32, 25))
+    rtol = 1e-5 if dtype == "float32" else 1e-12
+    with np.errstate(all="ignore"):
+        import warnings
+        warnings.simplefilter("ignore")
+        for axis in (None, 0, 1):
+            np.testing.assert_allclose(da.nansum(x, axis=axis).compute(), np.nansum(xh, axis=axis), rtol=rtol * 10)
+            np.testing.assert_allclose(da.nanmean(x, axis=axis).compute(), np.nanmean(xh, axis=axis), rtol=rtol * 10, equal_nan=True)
+            np.testing.assert_allclose(da.nanvar(x, axis=axis, ddof=1).compute(), np.nanvar(xh, axis=axis, ddof=1), rtol=rtol * 100, equal_nan=True)
+            np.testing.assert_allclose(da.nanstd(x, axis=axis).compute(), np.nanstd(xh, axis=axis), rtol=rtol * 100, equal_nan=True)
+            assert np.array_equal(da.nanmin(x, axis=axis).compute(), np.nanmin(xh, axis=axis), equal_nan=True)
+            assert np.array_equal(da.nanmax(x, axis=axis).compute(), np.nanmax(xh, axis=axis), equal_nan=True)
+        ok = ~np.all(np.isnan(xh), axis=1)
+        assert np.array_equal(da.nanargmax(x, axis=1).compute()[ok], np.nanargmax(xh[ok], axis=1))
+        assert np.array_equal(da.nanargmin(x, axis=0).compute(), np.nanargmin(xh, axis=0))
+    ih = rng.integers(-9, 9, (40, 30)).astype(np.int32)
+    i = da.from_array(ih, chunks=(16, 16))
+    assert da.nansum(i).compute() == ih.sum() and np.array_equal(da.nanmax(i, axis=0).compute(), ih.max(axis=0))
+    assert np.array_equal(i.prod(axis=1).compute(), ih.prod(axis=1)) and i.any().compute() == ih.any()
+    assert np.array_equal((i > 0).all(axis=0).compute(), (ih > 0).all(axis=0))
