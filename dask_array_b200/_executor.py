@@ -431,24 +431,29 @@ class Executor:
             M, N = expr.block_shape((i, j))
             out = DeviceChunk.empty((M, N), np.float32, self.device)
             st.blocks[(i, j)] = out
-            if len({a.block_shape((i, k))[1] for k in range(nk)}) != 1:
-                raise NotImplementedError("matmul with ragged contraction chunks")
-            K = a.block_shape((i, 0))[1]
-            A, B = [], []
+            ks = [a.block_shape((i, k))[1] for k in range(nk)]
+            if any(kk % 8 for kk in ks):
+                raise NotImplementedError(
+                    f"matmul contraction chunks {tuple(ks)} must be multiples of 8 elements (16-byte TMA row strides): rechunk the contracted axis")
+            K = max(ks)
+            A, B, Kp = [], [], []
             for k in range(nk):
                 for ca, cb in combos:
                     A.append(pa[(i, k)][ca].ptr)
                     B.append(pb[(j, k)][cb].ptr)
+                    Kp.append(ks[k])
             arrA = (C.c_void_p * len(A))(*A)
             arrB = (C.c_void_p * len(B))(*B)
-            keep.extend([arrA, arrB])
+            arrK = (C.c_int64 * len(Kp))(*Kp)
+            keep.extend([arrA, arrB, arrK])
             p = _lib.GemmProblem()
             p.A, p.B = C.cast(arrA, C.c_void_p), C.cast(arrB, C.c_void_p)
+            p.Kpair = C.cast(arrK, C.c_void_p).value if len(set(ks)) > 1 else None
             p.npairs, p.accumulate, p.lda, p.ldb = len(A), 0, K, K
             p.C, p.ldc, p.M, p.N, p.K = out.ptr, N, M, N, K
             probs.append(p)
         import os
-        if os.environ.get("B2_GEMM_BATCHED", "1") == "0":         # diagnostic: one launch per output block
+        if os.environ.get("B2_GEMM_BATCHED", "1") == "0" and all(not p.Kpair for p in probs):   # diagnostic: one launch per output block
             for p in probs:
                 self._do(lambda p=p: _lib.check(_lib.lib.b2_gemm_tn_pairs(
                     _lib.dtype_code("bfloat16"), p.A, p.B, p.npairs, p.lda, p.ldb, p.C, p.ldc, p.M, p.N, p.K, 0,
@@ -472,6 +477,7 @@ class Executor:
                 q.A, q.B = p.A + 8 * lo, p.B + 8 * lo
                 q.npairs, q.accumulate, q.lda, q.ldb = hi - lo, 1 if ci > 0 else 0, p.lda, p.ldb
                 q.C, q.ldc, q.M, q.N, q.K = p.C, p.ldc, p.M, p.N, p.K
+                q.Kpair = (p.Kpair + 8 * lo) if p.Kpair else None
                 sub.append(q)
             arr = (_lib.GemmProblem * len(sub))(*sub)
             need = C.c_size_t()

@@ -89,7 +89,7 @@ class GemmProblem(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("B", C.c_void_p), ("npairs", C.c_int32), ("accumulate", C.c_int32),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("C", C.c_void_p), ("ldc", C.c_int64),
-        ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+        ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("Kpair", C.c_void_p),
     ]
 
 

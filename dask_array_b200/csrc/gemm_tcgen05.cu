@@ -369,8 +369,11 @@ extern "C" int b2_gemm_tn_batched(int dtype, const b2_gemm_problem* problems, in
         if (q.lda % 8 || q.ldb % 8) { rc = b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_batched: lda/ldb must be multiples of 8 elements"); break; }
         for (int p = 0; p < q.npairs && rc == B2_OK; ++p) {
             if (((uintptr_t)q.A[p] | (uintptr_t)q.B[p]) % 16) { rc = b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_batched: operand not 16-byte aligned"); break; }
-            rc = make_map(&hm[2 * (map_begin + p)], q.A[p], q.M, q.K, q.lda, BM);
-            if (rc == B2_OK) rc = make_map(&hm[2 * (map_begin + p) + 1], q.B[p], q.N, q.K, q.ldb, BN);
+            const int64_t kp = q.Kpair ? q.Kpair[p] : q.K;
+            const int64_t la = q.Kpair ? kp : q.lda, lb = q.Kpair ? kp : q.ldb;
+            if (kp <= 0 || kp > q.K || la % 8 || lb % 8) { rc = b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_batched: per-pair K must be in (0, K] and a multiple of 8"); break; }
+            rc = make_map(&hm[2 * (map_begin + p)], q.A[p], q.M, kp, la, BM);
+            if (rc == B2_OK) rc = make_map(&hm[2 * (map_begin + p) + 1], q.B[p], q.N, kp, lb, BN);
         }
         GemmProblem& g = hp[i];
         g.C = q.C; g.ldc = q.ldc; g.M = (int)q.M; g.N = (int)q.N; g.K = (int)q.K; g.npairs = q.npairs;

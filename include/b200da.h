@@ -258,6 +258,9 @@ typedef struct b2_gemm_problem {
     float* C;
     int64_t ldc;
     int64_t M, N, K;
+    /* optional (may be NULL): ragged contraction blocks.  Pair p then has contraction length
+     * Kpair[p] <= K and dense operands (leading dimensions Kpair[p]); the tail is zero-filled. */
+    const int64_t* Kpair;
 } b2_gemm_problem;
 int b2_gemm_tn_batched(int dtype, const b2_gemm_problem* problems, int nproblems,
                        void* workspace, size_t workspace_bytes, size_t* needed, void* stream);

@@ -30,8 +30,12 @@ def test_structural_views(da):
     bt = da.broadcast_to(da.from_array(ah[:1], chunks=(1, 4)), (6, 10))
     assert np.array_equal((bt + 0).compute(), np.broadcast_to(ah[:1], (6, 10)))
     assert np.array_equal(da.broadcast_to(a, (3, 12, 10)).sum(axis=0).compute(), 3 * ah)
-    mm = da.tensordot(a.astype("float32"), da.from_array(bh.astype(np.float32), chunks=(3, 4)), axes=((1,), (1,)))
-    np.testing.assert_allclose(mm.compute(), ah.astype(np.float64) @ bh.T.astype(np.float64), rtol=1e-5)
+    th, uh = rng.random((12, 40)).astype(np.float32), rng.random((7, 40)).astype(np.float32)
+    t, u = da.from_array(th, chunks=(5, 16)), da.from_array(uh, chunks=(3, 16))      # ragged k blocks: 16, 16, 8
+    mm = da.tensordot(t, u, axes=((1,), (1,)))
+    np.testing.assert_allclose(mm.compute(), th.astype(np.float64) @ uh.T.astype(np.float64), rtol=1e-5)
+    with pytest.raises(NotImplementedError, match="multiples of 8"):
+        (da.from_array(th[:, :10], chunks=(5, 4)) @ da.from_array(uh[:, :10], chunks=(3, 4)).T).compute()
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
