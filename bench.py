@@ -228,6 +228,27 @@ def run_other(args):
         out.update(extra or {})
         print(json.dumps(out))
 
+    if args.config == "c1":
+        # README example: latency only (80 kB blocks are not a roofline config)
+        x = da.ones((1000, 1000), chunks=(100, 100))
+        for label, arr in (("(x + x.T)[:100, :100]", (x + x.T)[:100, :100]), ("(x + x.T).sum()", (x + x.T).sum())):
+            t0 = time.perf_counter(); first = arr.compute(); cold = time.perf_counter() - t0
+            step = da.compile(arr)
+            for _ in range(5):
+                step.run()
+            torch.cuda.synchronize()
+            n0 = _lib.launch_count()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step.run()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / args.steps
+            t0 = time.perf_counter(); val = arr.compute(); full = time.perf_counter() - t0
+            print(json.dumps({"metric": "latency", "config": {"workload": "c1: README example " + label},
+                              "replay_us": dt * 1e6, "compute_call_ms": full * 1e3, "first_call_ms": cold * 1e3,
+                              "launches_per_replay": (_lib.launch_count() - n0) / args.steps,
+                              "result": float(np.asarray(val).ravel()[0]), "n_gpus": 1}))
+        return
     if args.config == "c5":
         import ml_dtypes
         n, cb = 32768, 4096
@@ -298,7 +319,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="c2 = headline (default). c3 / c4 = the other BASELINE configs (extra lines for DESIGN.md)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -131,14 +131,20 @@ class Executor:
 
     def _run_BroadcastTrick(self, expr):
         """A constant leaf that was NOT fused (e.g. evicted by the ``a + a.T`` conflict rule):
-        materialise it with the fill kernel."""
+        ONE allocation and ONE fill launch for all resident blocks, carved into per-block views."""
         st = BlockStore(expr)
-        for bid in expr.block_ids():
-            if self.mine(expr, bid):
-                c = DeviceChunk.empty(expr.block_shape(bid), expr.dtype, self.device)
-                if c.size:
-                    self._do(lambda c=c, v=expr.operand("value"): rt.fill(c, v))
-                st.blocks[bid] = c
+        ids = [bid for bid in expr.block_ids() if self.mine(expr, bid)]
+        item = expr.dtype.itemsize
+        sizes = [-(-math.prod(expr.block_shape(bid)) * item // 256) * 256 for bid in ids]
+        total = sum(sizes)
+        buf = alloc_bytes(total, self.device)
+        off = 0
+        for bid, nb in zip(ids, sizes):
+            st.blocks[bid] = DeviceChunk(buf, expr.block_shape(bid), expr.dtype, offset=off // item)
+            off += nb
+        if total:
+            whole = DeviceChunk(buf, (total // item,), expr.dtype)
+            self._do(lambda c=whole, v=expr.operand("value"): rt.fill(c, v))
         return st
 
     # ------------------------------------------------------------------ views
