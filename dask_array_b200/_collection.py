@@ -189,8 +189,27 @@ class Array:
         if kind in ("argmin", "argmax") and axis is not None and not isinstance(axis, Integral):
             raise TypeError(f"axis must be either `None` or int, got '{axis}'")
         ax = validate_axis(axis, self.ndim)
+        if ax == () and self.ndim > 0:
+            # axis=(): nothing is reduced (NumPy semantics) -- an element-wise identity / cast
+            from ._reductions import result_dtype
+
+            dt = result_dtype(kind, self.dtype, dtype)
+            if kind in ("sum", "prod", "mean"):
+                return self.astype(dt)
+            if kind == "var":
+                return (self - self).astype(dt)
+            if kind in ("any", "all"):
+                return self != 0
+            if kind in ("min", "max", "nanmin", "nanmax"):
+                return self
+            raise TypeError(f"axis=() is not valid for {kind}")
+        from ._reductions import normalize_split_every
+
+        # canonical {axis: n} form at construction, so equivalent spellings share a name
+        # (reductions/_reduction.py:715-725)
+        se = normalize_split_every(split_every, ax)
         return Array(Reduction(self.expr, kind, ax, bool(keepdims), None if dtype is None else np.dtype(dtype).name,
-                               _freeze(split_every), ddof))
+                               se, ddof))
 
     def sum(self, axis=None, dtype=None, keepdims=False, split_every=None):
         return self._reduce("sum", axis, keepdims, dtype, split_every)
