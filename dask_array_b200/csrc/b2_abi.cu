@@ -257,8 +257,12 @@ extern "C" int b2_fused_launch(const b2_kernel* k, const b2_block* d_blocks, int
 // ------------------------------------------------------------------ tree-level combine (AOT)
 template <typename T, typename OUT>
 __device__ __forceinline__ void b2_post_store(void* out0, i64 e, T total, int post, double count) {
-    if (post == B2_POST_MEAN) ((OUT*)out0)[e] = (OUT)total / (OUT)count;   // divide(total, n, dtype)
-    else ((T*)out0)[e] = total;
+    if (post == B2_POST_MEAN) {      // divide(total, n, dtype): in the output type (integer dtype= truncates like NumPy's cast)
+        if constexpr (b2_is_float<OUT>::value) ((OUT*)out0)[e] = (OUT)total / (OUT)count;
+        else ((OUT*)out0)[e] = (OUT)((double)total / count);
+    } else {
+        ((T*)out0)[e] = total;
+    }
 }
 
 template <typename T, int OP, typename OUT>
@@ -385,7 +389,7 @@ extern "C" int b2_combine(int redop, int dtype, const void* const* d_parts, cons
     } else {
         const bool mean = (post == B2_POST_MEAN);
         if (mean && redop != B2R_SUM) return fail(B2_ERR_INVALID, "POST_MEAN needs SUM");
-        if (mean && out_dtype != B2_F32 && out_dtype != B2_F64) return fail(B2_ERR_INVALID, "mean output must be f32/f64");
+        if (mean && out_dtype != B2_F32 && out_dtype != B2_F64) return fail(B2_ERR_UNSUPPORTED, "b2_combine: mean output must be f32/f64 (use b2_combine_groups)");
 #define B2_T(DT, T)                                                                                                   \
     case DT:                                                                                                          \
         rc = (mean && out_dtype == B2_F32)                                                                            \
@@ -416,13 +420,16 @@ extern "C" int b2_combine_groups(int redop, int dtype, int out_dtype, const b2_g
     if (redop == B2R_MOMENT) {
         if (out_dtype == B2_F32)
             b2_combine_groups_kernel<double, B2R_MOMENT, float><<<grid, 256, 0, st>>>(d_groups, ngroups, total_elems);
+        else if (out_dtype == B2_I64)
+            b2_combine_groups_kernel<double, B2R_MOMENT, long long><<<grid, 256, 0, st>>>(d_groups, ngroups, total_elems);
         else
             b2_combine_groups_kernel<double, B2R_MOMENT, double><<<grid, 256, 0, st>>>(d_groups, ngroups, total_elems);
     } else {
-        const bool f32out = (out_dtype == B2_F32);
+        const bool f32out = (out_dtype == B2_F32), i64out = (out_dtype == B2_I64);
 #define B2_T(DT, T)                                                                                     \
     case DT:                                                                                            \
         rc = f32out ? launch_groups_t<T, float>(redop, d_groups, ngroups, total_elems, st)              \
+           : i64out ? launch_groups_t<T, long long>(redop, d_groups, ngroups, total_elems, st)          \
                     : launch_groups_t<T, double>(redop, d_groups, ngroups, total_elems, st);            \
         break;
         switch (dtype) {
