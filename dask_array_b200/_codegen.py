@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-CODEGEN_VERSION = "12"     # part of every kernel's cache key: bump when generated code changes
+CODEGEN_VERSION = "13"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
@@ -269,6 +269,9 @@ def _emit(name, args, out, kw) -> str:
     fidx = 0 if out == np.float32 else 1
 
     if name == "astype":
+        src = args[0]
+        if out == np.int64 and not src.weak and src.kind != "const" and np.dtype(src.dtype).kind == "f":
+            return f"b2_cast<long long>({_ref_expr(src)})"      # x86 NumPy semantics for non-finite values
         return a(0)
     if name in _ARITH:
         if out == np.bool_ and name == "subtract":

@@ -225,7 +225,10 @@ class Array:
 
     def std(self, axis=None, dtype=None, keepdims=False, ddof=0, split_every=None):
         """``std = sqrt(var)`` as an Elemwise on the aggregate (``_common.py:625-653``)."""
-        return elemwise("sqrt", self.var(axis, dtype, keepdims, ddof, split_every))
+        result = elemwise("sqrt", self.var(axis, dtype, keepdims, ddof, split_every))
+        if dtype is not None and np.dtype(dtype) != result.dtype:
+            result = result.astype(dtype)          # _common.py:650-652
+        return result
 
     def min(self, axis=None, keepdims=False, split_every=None):
         return self._reduce("min", axis, keepdims, None, split_every)
@@ -342,7 +345,10 @@ def nanvar(a, axis=None, dtype=None, keepdims=False, ddof=0, split_every=None):
 
 
 def nanstd(a, axis=None, dtype=None, keepdims=False, ddof=0, split_every=None):
-    return elemwise("sqrt", nanvar(a, axis, dtype, keepdims, ddof, split_every))
+    result = elemwise("sqrt", nanvar(a, axis, dtype, keepdims, ddof, split_every))
+    if dtype is not None and np.dtype(dtype) != result.dtype:
+        result = result.astype(dtype)
+    return result
 
 
 def nanmin(a, axis=None, keepdims=False, split_every=None):

@@ -171,6 +171,16 @@ template <typename T> __device__ __forceinline__ bool b2_isnan(T v) {
     if constexpr (b2_is_float<T>::value) return v != v; else return false;
 }
 
+// Value conversion as the reference's NumPy performs it on x86-64: float -> int64 of a NaN or
+// out-of-range value yields INT64_MIN (cvttsd2si "integer indefinite"), where CUDA's cvt saturates.
+template <typename TO, typename FROM> __device__ __forceinline__ TO b2_cast(FROM v) {
+    if constexpr (b2_is_float<FROM>::value && sizeof(TO) == 8 && !b2_is_float<TO>::value && (TO)(-1) < (TO)0) {
+        return (v >= (FROM)-9223372036854775808.0 && v < (FROM)9223372036854775808.0) ? (TO)v : (TO)(-9223372036854775807LL - 1);
+    } else {
+        return (TO)v;
+    }
+}
+
 // Python/NumPy floor division and modulo (sign follows the divisor; x // 0 == 0 for ints)
 template <typename T> __device__ __forceinline__ T b2_floordiv_int(T a, T b) {
     if (b == 0) return 0;
@@ -308,7 +318,7 @@ struct B2AccSum {   // np.sum(x, dtype=ACC)  (_chunk.py:172; ints widen to 64 bi
     ACC s;
     __device__ __forceinline__ void init() { s = (ACC)0; }
     __device__ __forceinline__ void prime(T) {}
-    __device__ __forceinline__ void add(T v, int, int) { s += (ACC)v; }
+    __device__ __forceinline__ void add(T v, int, int) { s += b2_cast<ACC>(v); }
     __device__ __forceinline__ void merge(const B2AccSum& o) { s += o.s; }
     __device__ __forceinline__ void shfl(int off, int width) { B2AccSum o; o.s = b2_shfl_down(s, off, width); merge(o); }
     __device__ __forceinline__ void lane_merge(const B2AccSum& o) { merge(o); }
@@ -323,7 +333,7 @@ struct B2AccProd {
     ACC s;
     __device__ __forceinline__ void init() { s = (ACC)1; }
     __device__ __forceinline__ void prime(T) {}
-    __device__ __forceinline__ void add(T v, int, int) { s *= (ACC)v; }
+    __device__ __forceinline__ void add(T v, int, int) { s *= b2_cast<ACC>(v); }
     __device__ __forceinline__ void merge(const B2AccProd& o) { s *= o.s; }
     __device__ __forceinline__ void shfl(int off, int width) { B2AccProd o; o.s = b2_shfl_down(s, off, width); merge(o); }
     __device__ __forceinline__ void lane_merge(const B2AccProd& o) { merge(o); }
@@ -766,7 +776,11 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                 if (tiles_r == 1) {
                     if (ty == 0 && c < C) {
 #pragma unroll
-                        for (int v = 0; v < V; ++v) b2_store_result<REDOP, T, ACC>(blk, b * C + c + v, acc[v], blk.arg_offset);
+                        for (int v = 0; v < V; ++v) {
+                            i64 fx = blk.arg_offset;
+                            if constexpr (WANT_IDX) { if (blk.arg_ndim > 0) fx = b2_ravel_fix(blk, acc[v].i) - acc[v].i; }
+                            b2_store_result<REDOP, T, ACC>(blk, b * C + c + v, acc[v], fx);
+                        }
                     }
                     return;
                 }
@@ -905,7 +919,11 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                     if (tx == 0) { for (int k = 1; k < WPR; ++k) acc.lane_merge(smc[ty * WPR + k]); }
                 }
                 if (tx == 0) acc.lane_finish();
-                if (tx == 0 && r < rend) b2_store_result<REDOP, T, ACC>(blk, b * R + r, acc, blk.arg_offset);
+                if (tx == 0 && r < rend) {
+                    i64 fx = blk.arg_offset;      // a ravelled arg reduction over a block whose other dims are 1
+                    if constexpr (WANT_IDX) { if (blk.arg_ndim > 0) fx = b2_ravel_fix(blk, acc.i) - acc.i; }
+                    b2_store_result<REDOP, T, ACC>(blk, b * R + r, acc, fx);
+                }
             }
             return;
         }
