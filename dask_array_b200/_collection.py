@@ -333,7 +333,9 @@ def nanvar(a, axis=None, dtype=None, keepdims=False, ddof=0, split_every=None):
     a = asarray(a)
     dt = np.dtype(dtype) if dtype is not None else np.var(np.ones((1,), dtype=a.dtype)).dtype
     mu = nanmean(a, axis=axis, dtype=dt, keepdims=True, split_every=split_every)
-    d = _nan_to(elemwise("subtract", a.astype(dt), mu), 0)
+    d = elemwise("subtract", a.astype(dt), mu)
+    if a.dtype.kind == "f":          # drop the entries that were NaN in the INPUT (inf - inf stays NaN, as np.nanvar)
+        d = elemwise("where", elemwise("isnan", a), 0, d)
     ss = elemwise("multiply", d, d).sum(axis=axis, dtype=dt, keepdims=keepdims, split_every=split_every)
     n = _nancount(a, axis, keepdims, split_every)
     den = elemwise("subtract", n, ddof) if isinstance(n, Array) else n - ddof
