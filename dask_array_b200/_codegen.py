@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-CODEGEN_VERSION = "13"     # part of every kernel's cache key: bump when generated code changes
+CODEGEN_VERSION = "14"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
@@ -398,7 +398,10 @@ class KernelSpec:
     acc_dtype: str       # accumulator / output dtype name of SUM/PROD; working type of MOMENT
 
     def digest(self) -> str:
-        return hashlib.sha1((CODEGEN_VERSION + repr(self)).encode()).hexdigest()[:20]
+        import os
+
+        tune = os.environ.get("B2_MINB", "")
+        return hashlib.sha1((CODEGEN_VERSION + tune + repr(self)).encode()).hexdigest()[:20]
 
 
 def packed_bytes(spec: KernelSpec, out_dtype) -> int:
@@ -520,11 +523,23 @@ struct Chain {{
     }}
 {compute}
 }};
-extern "C" __global__ void __launch_bounds__({spec.tx * spec.ty}, {3 if spec.tx * spec.ty <= 256 else 1})
+extern "C" __global__ void __launch_bounds__({spec.tx * spec.ty}, {_min_blocks(spec)})
 b2_fused(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars sc) {{
     {run}
 }}
 """
+
+
+def _min_blocks(spec) -> int:
+    import os
+
+    if os.environ.get("B2_MINB"):
+        return int(os.environ["B2_MINB"])
+    if spec.tx * spec.ty > 256:
+        return 1
+    light = spec.mode in (_lib.MODE_R, _lib.MODE_RC) and spec.redop in (
+        _lib.RED_SUM, _lib.RED_PROD, _lib.RED_MIN, _lib.RED_MAX, _lib.RED_ANY, _lib.RED_ALL, _lib.RED_NANMIN, _lib.RED_NANMAX)
+    return 4 if light else 3
 
 
 def _pow2_ceil(n: int) -> int:
@@ -553,7 +568,18 @@ def choose_geometry(program: Program, mode: int, shapes, vec: int) -> dict:
     U = 8 if nin == 1 else (4 if nin <= 3 else 2)
     row_bytes = sum(sizes) * (tx * V if mode != _lib.MODE_C else Cmax)
     target = 512 * 1024 if mode != _lib.MODE_EW else 256 * 1024
+    if mode in (_lib.MODE_R, _lib.MODE_RC):
+        # same-box sweep on B200 (c2 chain, 4 GiB): U=4 / 1 MiB tiles beat U=8 / 512 KiB by 6-16 %:
+        # 4 loads in flight per thread x 4 (3 for the moment accumulator) CTAs/SM keeps HBM as busy with
+        # fewer live registers (profiles/README.md)
+        U = min(U, 4)
+        target = 1024 * 1024
     rpt = max(1, min(Rmax, target // max(1, row_bytes)))
     step = ty * U if mode != _lib.MODE_C else ty
     rpt = -(-rpt // step) * step
+    import os                                   # tuning overrides (sweeps only)
+    if os.environ.get("B2_U"):
+        U = int(os.environ["B2_U"])
+    if os.environ.get("B2_RPT") and mode != _lib.MODE_C:
+        rpt = int(os.environ["B2_RPT"])
     return dict(vec=V, tx=tx, ty=ty, rpt=int(rpt), unroll=U)
