@@ -408,9 +408,30 @@ class Executor:
 
         a, bt = expr.operand("a"), expr.operand("bt")
         sa, sb = self.results[a._name], self.results[bt._name]
-        if self.world.size > 1:
-            raise NotImplementedError("blocked matmul across GPUs (operand panel exchange) is not implemented yet")
         st = BlockStore(expr)
+        nk_ = a.numblocks[1]
+        mine = [bid for bid in expr.block_ids() if self.mine(expr, bid)]
+        if self.world.size > 1:
+            # the owner of output block (i, j) gathers row-panel i of a and row-panel j of bt;
+            # the k-accumulation then stays local (TMEM)
+            wanted = []
+            for bid in expr.block_ids():
+                r = self.world.owner(expr, bid)
+                for k in range(nk_):
+                    if not sa.replicated:
+                        wanted.append((r, a, (bid[0], k)))
+                    if not sb.replicated:
+                        wanted.append((r, bt, (bid[1], k)))
+            got = _fetch_blocks(self, wanted, {a._name: sa, bt._name: sb})
+            va, vb = BlockStore(a), BlockStore(bt)
+            for (i, j) in mine:
+                for k in range(nk_):
+                    blk = sa.blocks.get((i, k))
+                    va.blocks[(i, k)] = blk if blk is not None else got[(a._name, (i, k))]
+                    blk = sb.blocks.get((j, k))
+                    vb.blocks[(j, k)] = blk if blk is not None else got[(bt._name, (j, k))]
+            sa, sb = va, vb
+            st.keepalive.append(got)
         fp32 = a.dtype == np.float32
         bf16 = np.dtype("uint16")          # raw 16-bit planes
 
@@ -433,7 +454,9 @@ class Executor:
         combos = [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0)] if fp32 else [(0, 0)]
         nk = a.numblocks[1]
         probs, keep = [], []
-        for (i, j) in expr.block_ids():
+        if not mine:
+            return st
+        for (i, j) in mine:
             M, N = expr.block_shape((i, j))
             out = DeviceChunk.empty((M, N), np.float32, self.device)
             st.blocks[(i, j)] = out
@@ -647,6 +670,60 @@ def plan_fused_exchange(plan: FusedPlan, replicated, W: int, me: int):
         if r == me:
             recv_items[o].append((k, lbid, nb))
     return send_items, recv_items
+
+
+def plan_block_fetch(wanted, W: int, me: int):
+    """Pure schedule for whole-block reads across the partition.  ``wanted``: iterable of
+    (reader rank, dep expr, block id) over ALL ranks (every rank computes the same list).
+    Returns (send_items, recv_items) per peer: (dep expr, block id, nbytes), canonical order."""
+    uniq = {}
+    for r, dep, bid in wanted:
+        o = owner_of(dep, bid, W)
+        if o != r:
+            uniq[(r, dep._name, bid)] = (o, dep)
+    send_items = {p: [] for p in range(W)}
+    recv_items = {p: [] for p in range(W)}
+    for (r, name, bid) in sorted(uniq):
+        o, dep = uniq[(r, name, bid)]
+        nb = math.prod(dep.block_shape(bid)) * dep.dtype.itemsize
+        if o == me:
+            send_items[r].append((dep, bid, nb))
+        if r == me:
+            recv_items[o].append((dep, bid, nb))
+    return send_items, recv_items
+
+
+def _fetch_blocks(ex: Executor, wanted, stores):
+    """Execute a ``plan_block_fetch`` schedule over NCCL; ``stores``: {dep name: BlockStore}.
+    Returns {(dep name, block id): DeviceChunk} for the blocks this rank received."""
+    W, me = ex.world.size, ex.world.rank
+    send_items, recv_items = plan_block_fetch(wanted, W, me)
+    pad = lambda n: -(-n // 256) * 256
+    sends, recvs, keep, out = [], [], [], {}
+    for p in range(W):
+        if send_items[p]:
+            buf = alloc_bytes(sum(pad(nb) for *_, nb in send_items[p]), ex.device)
+            off, copies = 0, []
+            for dep, bid, nb in send_items[p]:
+                blk = stores[dep._name].blocks[bid]
+                flat = DeviceChunk(buf, blk.shape, blk.dtype, offset=off // blk.itemsize)
+                copies.extend(_copy_descs(blk, flat, blk.itemsize))
+                off += pad(nb)
+            g = rt.GatherLaunch(copies)
+            ex._do(g.run)
+            keep.append(g)
+            sends.append((p, buf))
+        if recv_items[p]:
+            buf = alloc_bytes(sum(pad(nb) for *_, nb in recv_items[p]), ex.device)
+            off = 0
+            for dep, bid, nb in recv_items[p]:
+                out[(dep._name, bid)] = DeviceChunk(buf, dep.block_shape(bid), dep.dtype, offset=off // dep.dtype.itemsize)
+                off += pad(nb)
+            recvs.append((p, buf))
+    if sends or recvs:
+        ex._do(lambda: _p2p_exchange(ex, sends, recvs))
+    out["__keep__"] = (keep, sends, recvs)
+    return out
 
 
 def plan_rechunk_exchange(expr: TasksRechunk, W: int, me: int):

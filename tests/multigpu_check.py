@@ -51,6 +51,14 @@ def main():
     assert np.array_equal((xi.T + xi).compute(), ih.T + ih)                     # rechunk + fused transpose
     p = (sq * 2).persist()
     assert np.array_equal((p + 1).compute(), ih * 2 + 1)
+    # blocked matmul across the partition: operand blocks are fetched over NCCL, k-accumulation local
+    ah = (rng.random((512, 384)) - 0.5).astype(np.float32)
+    bh = (rng.random((384, 256)) - 0.5).astype(np.float32)
+    am, bm = da.from_array(ah, chunks=(128, 128)), da.from_array(bh, chunks=(128, 128))
+    got = (am @ bm).compute()
+    a64, b64 = ah.astype(np.float64), bh.astype(np.float64)
+    assert np.all(np.abs(got - a64 @ b64) <= 1e-5 * (np.abs(a64) @ np.abs(b64)))
+    np.testing.assert_allclose((am @ bm).sum().compute(), (a64 @ b64).sum(), rtol=1e-4, atol=1e-2)
     ones = da.ones((1000, 1000), chunks=(100, 100))
     assert (ones + ones.T).sum().compute() == 2_000_000.0
     dist.barrier()
