@@ -192,6 +192,11 @@ class FusedLaunch:
                  acc_dtype=None, out_is_contiguous: bool = True):
         if not blocks:
             raise ValueError("FusedLaunch needs at least one block")
+        if len(program.inputs) >= 2 and len(blocks) > 2:
+            # blocks that read the same input blocks (x.T + x: output (i, j) and (j, i)) become
+            # neighbours in the launch, so the second read of a tile can hit the 126 MB L2
+            order = sorted(range(len(blocks)), key=lambda i: (tuple(sorted(p for p, _ in blocks[i].inputs)), i))
+            blocks = [blocks[i] for i in order]
         self.program = program
         self.redop = redop
         nin = len(program.inputs)
