@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-CODEGEN_VERSION = "14"     # part of every kernel's cache key: bump when generated code changes
+CODEGEN_VERSION = "15"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
@@ -203,6 +203,96 @@ class Program:
             parts.append(f"{name}({a})->{out.name}{kw if kw else ''}")
         parts.append("out:" + _ref_key(self.output))
         return "|".join(parts)
+
+    _PACKED_OPS = {"sin", "cos", "add", "subtract", "multiply", "negative", "positive", "absolute", "square"}
+
+    def packable(self) -> bool:
+        """fp32-only chain whose operators all have a packed f32x2 form (FFMA2 family)."""
+        f4 = np.dtype(np.float32)
+        if not self.ops or any(d != f4 for d in self.inputs) or self.out_dtype != f4:
+            return False
+        for name, args, out, kw in self.ops:
+            if out != f4:
+                return False
+            if name == "power":
+                if not (args[1].kind == "const" and args[1].value == 2):
+                    return False
+            elif name not in self._PACKED_OPS:
+                return False
+            for r in args:
+                if r.kind != "const" and np.dtype(r.dtype) != f4:
+                    return False
+        return True
+
+    def body_packed(self, contract: bool) -> list[str]:
+        """Statements computing the pair (o[v], o[v+1]) with packed f32x2 arithmetic.  ``contract``:
+        fold a single-use multiply / square into the add that consumes it (FFMA2) -- only for kernels
+        whose chain is observed through a reduction; element-wise kernels keep NumPy's two roundings."""
+        f4 = np.float32
+        uses = {}
+        for name, args, out, kw in self.ops:
+            for r in args:
+                if r.kind == "tmp":
+                    uses[r.index] = uses.get(r.index, 0) + 1
+        if self.output.kind == "tmp":
+            uses[self.output.index] = uses.get(self.output.index, 0) + 1
+
+        def ex(r):
+            if r.kind == "in":
+                return f"x{r.index}"
+            if r.kind == "tmp":
+                return f"t{r.index}"
+            return f"b2_bc({literal(r.value, f4)})"
+
+        def as_product(r):
+            """(a, b) if r is a single-use multiply / square / power-2 that may be contracted."""
+            if not contract or r.kind != "tmp" or uses.get(r.index, 0) != 1:
+                return None
+            name, args, out, kw = self.ops[r.index]
+            if name == "multiply":
+                return ex(args[0]), ex(args[1])
+            if name == "square" or name == "power":
+                return ex(args[0]), ex(args[0])
+            return None
+
+        lines, skipped = [], set()
+        for k in range(len(self.inputs)):
+            lines.append(f"const b2f2 x{k} = b2_pk(g.a{k}[v], g.a{k}[v + 1]);")
+        # decide contractions first so that the folded products are not emitted
+        folded = {}
+        for j, (name, args, out, kw) in enumerate(self.ops):
+            if name in ("add", "subtract"):
+                for pos in ((1, 0) if name == "add" else (1,)):     # a + (b*c), (b*c) + a, a - ... only a*b - c handled below
+                    pr = as_product(args[pos]) if args[pos].kind == "tmp" and args[pos].index not in skipped else None
+                    if pr and name == "add":
+                        folded[j] = (pr, args[1 - pos])
+                        skipped.add(args[pos].index)
+                        break
+        for j, (name, args, out, kw) in enumerate(self.ops):
+            if j in skipped:
+                continue
+            if j in folded:
+                (pa, pb), other = folded[j]
+                expr = f"b2_fma2({pa}, {pb}, {ex(other)})"
+            elif name in ("sin", "cos"):
+                expr = f"b2_{name}f_fast2({ex(args[0])}, big)"
+            elif name == "add":
+                expr = f"b2_add2({ex(args[0])}, {ex(args[1])})"
+            elif name == "subtract":
+                expr = f"b2_sub2({ex(args[0])}, {ex(args[1])})"
+            elif name == "multiply":
+                expr = f"b2_mul2({ex(args[0])}, {ex(args[1])})"
+            elif name in ("square", "power"):
+                expr = f"b2_mul2({ex(args[0])}, {ex(args[0])})"
+            elif name == "negative":
+                expr = f"b2_neg2({ex(args[0])})"
+            elif name == "absolute":
+                expr = f"b2_abs2({ex(args[0])})"
+            else:   # positive
+                expr = ex(args[0])
+            lines.append(f"const b2f2 t{j} = {expr};")
+        lines.append(f"b2_upk({ex(self.output)}, o[v], o[v + 1]);")
+        return lines
 
     def uses_fast_sincos(self) -> bool:
         return any(name in ("sin", "cos") and out == np.float32 for name, _, out, _ in self.ops)
@@ -471,6 +561,12 @@ def render(program: Program, spec: KernelSpec) -> str:
     nl = "\n            "
     fast = program.uses_fast_sincos()
     header = "// b2-options: fmad\n" if spec.mode != _lib.MODE_EW else ""
+    packed = program.packable() and spec.vec % 2 == 0
+    if packed:
+        fast_body = nl.join(program.body_packed(contract=spec.mode != _lib.MODE_EW))
+        fast_loop = f"for (int v = 0; v < B2_V; v += 2) {{{nl}{fast_body}\n        }}"
+    else:
+        fast_loop = f"for (int v = 0; v < B2_V; ++v) {{{nl}{nl.join(program.body(fast=fast))}\n        }}"
     compute = f"""    static constexpr bool HAS_SLOW = {'true' if fast else 'false'};
     // exact chain (libdevice transcendental functions, full argument range)
     __device__ __forceinline__ static void compute_slow(const Regs& g, const B2Scalars& sc, out_t (&o)[B2_V]) {{
@@ -481,9 +577,7 @@ def render(program: Program, spec: KernelSpec) -> str:
     }}
     __device__ __forceinline__ static void compute(const Regs& g, const B2Scalars& sc, out_t (&o)[B2_V], float& big) {{
 #pragma unroll
-        for (int v = 0; v < B2_V; ++v) {{
-            {nl.join(program.body(fast=fast))}
-        }}
+        {fast_loop}
     }}"""
     if ewt:
         run = f"b2_run_ewt<Chain, B2_V, {spec.tx}, {spec.ty}>(blocks, nblocks, sc);"

@@ -285,6 +285,46 @@ __device__ __forceinline__ float b2_cosf_fast(float x, float& big) {
     r = fmaf(j, -1.0780605906948476785e-14f, r);
     return __int_as_float(__float_as_int(b2_sin_poly(r)) ^ (__float_as_int(jm) << 31));
 }
+// ---- packed fp32 x 2 (Blackwell FFMA2 / FADD2 / FMUL2): one issue slot for two lanes.  The chain
+// kernels are issue-bound (ncu: issue-active ~80 %), so halving the slots of the polynomial and
+// of the +,-,* operators moves them back under the HBM roofline.  Values are (lo, hi) pairs in one
+// 64-bit register; consecutive elements of a 128-bit load are already such pairs.
+typedef unsigned long long b2f2;
+__device__ __forceinline__ b2f2 b2_pk(float a, float b) { b2f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void b2_upk(b2f2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ b2f2 b2_bc(float c) { return b2_pk(c, c); }
+__device__ __forceinline__ b2f2 b2_fma2(b2f2 a, b2f2 b, b2f2 c) { b2f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ b2f2 b2_add2(b2f2 a, b2f2 b) { b2f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ b2f2 b2_sub2(b2f2 a, b2f2 b) { b2f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ b2f2 b2_mul2(b2f2 a, b2f2 b) { b2f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ b2f2 b2_neg2(b2f2 a) { return a ^ 0x8000000080000000ULL; }
+__device__ __forceinline__ b2f2 b2_abs2(b2f2 a) { return a & 0x7fffffff7fffffffULL; }
+__device__ __forceinline__ float b2_maxabs2(b2f2 v) { float a, b; b2_upk(v, a, b); return fmaxf(fabsf(a), fabsf(b)); }
+__device__ __forceinline__ b2f2 b2_sin_poly2(b2f2 r) {
+    const b2f2 s = b2_mul2(r, r);
+    b2f2 p = b2_fma2(b2_bc(2.605750751172309e-06f), s, b2_bc(-0.00019809573132079095f));
+    p = b2_fma2(p, s, b2_bc(0.00833306647837162f));
+    p = b2_fma2(p, s, b2_bc(-0.16666659712791443f));
+    return b2_fma2(b2_mul2(r, s), p, r);
+}
+__device__ __forceinline__ b2f2 b2_sinf_fast2(b2f2 x, float& big) {
+    big = fmaxf(big, b2_maxabs2(x));
+    const b2f2 jm = b2_fma2(x, b2_bc(0.318309886183790672f), b2_bc(12582912.0f));
+    const b2f2 j = b2_add2(jm, b2_bc(-12582912.0f));
+    b2f2 r = b2_fma2(j, b2_bc(-3.1415925025939941406f), x);
+    r = b2_fma2(j, b2_bc(-1.5099578831723192707e-07f), r);
+    r = b2_fma2(j, b2_bc(-1.0780605906948476785e-14f), r);
+    return b2_sin_poly2(r) ^ ((jm << 31) & 0x8000000080000000ULL);       // (-1)^j per lane
+}
+__device__ __forceinline__ b2f2 b2_cosf_fast2(b2f2 x, float& big) {
+    big = fmaxf(big, b2_maxabs2(x));
+    const b2f2 jm = b2_add2(b2_fma2(x, b2_bc(0.318309886183790672f), b2_bc(0.5f)), b2_bc(12582912.0f));
+    const b2f2 j = b2_add2(b2_add2(jm, b2_bc(-12582912.0f)), b2_bc(-0.5f));
+    b2f2 r = b2_fma2(j, b2_bc(-3.1415925025939941406f), x);
+    r = b2_fma2(j, b2_bc(-1.5099578831723192707e-07f), r);
+    r = b2_fma2(j, b2_bc(-1.0780605906948476785e-14f), r);
+    return b2_sin_poly2(r) ^ ((jm << 31) & 0x8000000080000000ULL);
+}
 __device__ __noinline__ float b2_sinf_slow(float x) { return sinf(x); }   // libdevice, full range
 __device__ __noinline__ float b2_cosf_slow(float x) { return cosf(x); }
 
