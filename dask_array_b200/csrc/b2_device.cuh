@@ -698,6 +698,8 @@ __device__ __forceinline__ void b2_stream(typename Chain::Ptrs& P, const int n, 
 
 struct B2NoState {};
 template <typename A, int V> struct B2AccState { A acc[V]; };
+// packed thread-local state of the fp32 moment accumulators: lanes (v, v+1) share one register pair
+template <int V> struct B2MomState2 { b2f2 K[V / 2], s1[V / 2], s2[V / 2]; };
 
 // Chain supplies:
 //   out_t; Regs; Ptrs (one typed pointer + element step per input); HAS_SLOW;
@@ -778,11 +780,35 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
 #pragma unroll
                     for (int v = 0; v < V; ++v) acc[v].prime(MODE == B2M_R ? o0[v] : o0[0]);
                 }
-                b2_stream<Chain, V, U>(P, nrows, sc, st,
-                    [&](B2AccState<A, V>& s_, int k, const T (&o)[V]) {
+                if constexpr (REDOP == B2R_MOMENT && sizeof(T) == 4 && sizeof(ACC) == 4 && b2_is_float<T>::value && V % 2 == 0) {
+                    // fp32 moments: d = v - K, s1 += d, s2 += d*d as FADD2 / FADD2 / FFMA2 on lane pairs
+                    B2MomState2<V> ms;
 #pragma unroll
-                        for (int v = 0; v < V; ++v) s_.acc[v].add(o[v], k, 0);
-                    });
+                    for (int h = 0; h < V / 2; ++h) {
+                        ms.K[h] = b2_pk(acc[2 * h].K, acc[2 * h + 1].K);
+                        ms.s1[h] = 0ULL; ms.s2[h] = 0ULL;
+                    }
+                    b2_stream<Chain, V, U>(P, nrows, sc, ms,
+                        [&](B2MomState2<V>& s_, int, const T (&o)[V]) {
+#pragma unroll
+                            for (int h = 0; h < V / 2; ++h) {
+                                const b2f2 d = b2_sub2(b2_pk(o[2 * h], o[2 * h + 1]), s_.K[h]);
+                                s_.s1[h] = b2_add2(s_.s1[h], d);
+                                s_.s2[h] = b2_fma2(d, d, s_.s2[h]);
+                            }
+                        });
+#pragma unroll
+                    for (int h = 0; h < V / 2; ++h) {
+                        b2_upk(ms.s1[h], acc[2 * h].s1, acc[2 * h + 1].s1);
+                        b2_upk(ms.s2[h], acc[2 * h].s2, acc[2 * h + 1].s2);
+                    }
+                } else {
+                    b2_stream<Chain, V, U>(P, nrows, sc, st,
+                        [&](B2AccState<A, V>& s_, int k, const T (&o)[V]) {
+#pragma unroll
+                            for (int v = 0; v < V; ++v) s_.acc[v].add(o[v], k, 0);
+                        });
+                }
             }
             if constexpr (WANT_IDX) {
                 // element k of accumulator v: row first + k*TY (mode R) / flat (first + k*TY)*C + c + v (mode RC)
