@@ -106,7 +106,7 @@ SYMBOLS = [
     "b2_abi_version", "b2_last_error", "b2_launch_count", "b2_device_sm_count",
     "b2_jit_compile", "b2_free", "b2_device_header", "b2_kernel_load", "b2_kernel_free",
     "b2_fused_plan", "b2_fused_launch", "b2_combine", "b2_gather_plan", "b2_gather_launch",
-    "b2_fill", "b2_gemm_tn", "b2_memcpy2d", "b2_gemm_tn_pairs", "b2_split3_bf16", "b2_combine_groups", "b2_gemm_tn_batched",
+    "b2_fill", "b2_gemm_tn", "b2_memcpy2d", "b2_gemm_tn_pairs", "b2_split3_bf16", "b2_combine_groups", "b2_gemm_tn_batched", "b2_gather_launch_bulk",
 ]
 
 
@@ -134,6 +134,7 @@ def _load():
     lib.b2_combine_groups.argtypes = [i32, i32, i32, vp, i32, i64, vp]
     lib.b2_gather_plan.argtypes = [C.POINTER(Copy), i32, C.POINTER(i64)]
     lib.b2_gather_launch.argtypes = [vp, i32, i64, vp]
+    lib.b2_gather_launch_bulk.argtypes = [vp, i32, i64, vp]
     lib.b2_fill.argtypes = [vp, i64, i32, vp, vp]
     lib.b2_memcpy2d.argtypes = [vp, i64, vp, i64, i64, i64, i32, vp]
     lib.b2_gemm_tn.argtypes = [i32, vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, vp]

@@ -417,6 +417,10 @@ class GatherLaunch:
         tiles = C.c_int64()
         _lib.check(_lib.lib.b2_gather_plan(arr, self.n, C.byref(tiles)))
         self.total_tiles = tiles.value
+        # TMA bulk path when every rectangle is 16-byte aligned and big enough to matter
+        self.bulk = (os.environ.get("B2_GATHER_BULK", "1") == "1" and all(c.vec_bytes == 16 for c in arr)
+                     and sum(c.rows * c.row_bytes for c in arr) >= (1 << 20)
+                     and all(c.tile_rows * min(c.row_bytes, 4096) <= 65536 for c in arr))
         raw = np.frombuffer(bytes(arr), dtype=np.uint8)
         self.table = torch.from_numpy(raw.copy()).to(torch.device("cuda", torch.cuda.current_device()))
 
@@ -424,7 +428,8 @@ class GatherLaunch:
         if not self.n:
             return
         st = current_stream_ptr() if stream is None else stream
-        _lib.check(_lib.lib.b2_gather_launch(self.table.data_ptr(), self.n, self.total_tiles, st))
+        fn = _lib.lib.b2_gather_launch_bulk if self.bulk else _lib.lib.b2_gather_launch
+        _lib.check(fn(self.table.data_ptr(), self.n, self.total_tiles, st))
 
 
 def fill(chunk: DeviceChunk, value) -> None:

@@ -491,6 +491,61 @@ __global__ void __launch_bounds__(256) b2_gather_kernel(const b2_copy* __restric
     }
 }
 
+// Bulk-async variant (TMA, cp.async.bulk): one elected thread issues a global->shared bulk copy per
+// row segment of the tile (all tracked by one mbarrier), then a shared->global bulk store per row.
+// No register staging, ~64 KiB in flight per CTA.  Used when every address / pitch / length is a
+// multiple of 16 bytes (vec_bytes == 16 for all rectangles).
+__device__ __forceinline__ unsigned b2_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(128) b2_gather_bulk_kernel(const b2_copy* __restrict__ copies, int n) {
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    __shared__ b2_copy cp;
+    __shared__ __align__(8) unsigned long long mbar;
+    {
+        const i64 tile = blockIdx.x;
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (copies[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+        }
+        const unsigned* src = reinterpret_cast<const unsigned*>(copies + lo);
+        unsigned* dst = reinterpret_cast<unsigned*>(&cp);
+        for (int i = threadIdx.x; i < (int)(sizeof(b2_copy) / 4); i += blockDim.x) dst[i] = src[i];
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b2_smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    const i64 t = (i64)blockIdx.x - cp.tile_begin;
+    const i64 tc = t % cp.tiles_c, tr = t / cp.tiles_c;
+    const i64 r0 = tr * cp.tile_rows;
+    const int nr = (int)((r0 + cp.tile_rows < cp.rows) ? cp.tile_rows : cp.rows - r0);
+    const i64 c0 = tc * B2_GATHER_COL_BYTES;
+    const unsigned cb = (unsigned)((c0 + B2_GATHER_COL_BYTES < cp.row_bytes) ? B2_GATHER_COL_BYTES : cp.row_bytes - c0);
+    const char* s = (const char*)cp.src + r0 * cp.src_pitch + c0;
+    char* d = (char*)cp.dst + r0 * cp.dst_pitch + c0;
+    const unsigned bar = b2_smem_u32(&mbar);
+    if (threadIdx.x == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cb * (unsigned)nr) : "memory");
+    __syncthreads();
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(b2_smem_u32(bulk_smem + (size_t)r * cb)), "l"(s + (i64)r * cp.src_pitch), "r"(cb), "r"(bar) : "memory");
+    }
+    // everyone waits for the tile to land (phase 0)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tB2G_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra B2G_DONE_%=;\n\tbra B2G_WAIT_%=;\n\tB2G_DONE_%=:\n\t}" ::"r"(bar) : "memory");
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(d + (i64)r * cp.dst_pitch), "r"(b2_smem_u32(bulk_smem + (size_t)r * cb)), "r"(cb) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // smem may be released once read
+}
+
 extern "C" int b2_gather_plan(b2_copy* copies, int n, int64_t* total_tiles) {
     if (!copies || n <= 0 || !total_tiles) return fail(B2_ERR_INVALID, "bad argument");
     int64_t tiles = 0;
@@ -512,6 +567,20 @@ extern "C" int b2_gather_plan(b2_copy* copies, int n, int64_t* total_tiles) {
     }
     if (tiles > 0x7fffffffLL) return fail(B2_ERR_UNSUPPORTED, "gather needs %lld tiles", (long long)tiles);
     *total_tiles = tiles;
+    return B2_OK;
+}
+
+extern "C" int b2_gather_launch_bulk(const b2_copy* d_copies, int n, int64_t total_tiles, void* stream) {
+    if (!d_copies || n <= 0 || total_tiles <= 0) return fail(B2_ERR_INVALID, "bad argument");
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(b2_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    });
+    if (attr_err != cudaSuccess) return fail(B2_ERR_CUDA, "%s", cudaGetErrorString(attr_err));
+    b2_gather_bulk_kernel<<<(unsigned)total_tiles, 128, 65536, (cudaStream_t)stream>>>(d_copies, n);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
     return B2_OK;
 }
 

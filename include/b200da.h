@@ -220,6 +220,10 @@ typedef struct b2_copy {
 
 int b2_gather_plan(b2_copy* copies, int n, int64_t* total_tiles);
 int b2_gather_launch(const b2_copy* d_copies, int n, int64_t total_tiles, void* stream);
+/* same plan, moved with TMA bulk copies (cp.async.bulk global->shared->global, no register staging).
+ * Requires vec_bytes == 16 for EVERY rectangle (all addresses, pitches and row lengths 16-byte
+ * multiples) and tile_rows * min(row_bytes, B2_GATHER_COL_BYTES) <= 64 KiB (what b2_gather_plan makes). */
+int b2_gather_launch_bulk(const b2_copy* d_copies, int n, int64_t total_tiles, void* stream);
 
 /* Strided host<->device block transfer: from_array's per-block getitem of a host array
  * (io/_from_array.py:60-160) and finalize's concatenate3 into the host result
