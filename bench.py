@@ -306,7 +306,7 @@ def run_other(args):
             sq = da.from_array(host, chunks=(2048, 2048)).persist()
             step = da.compile(sq.T + sq)
             timed(step, 2 * n * n * item, f"c4: x.T + x (16384,16384) {np.dtype(dt).name} chunks 2048^2 "
-                  "(2N bytes: the symmetric minimum; the kernel moves 3N)", {"dtype": np.dtype(dt).name})
+                  "(2N bytes: mirror-pair kernel, every tile read once)", {"dtype": np.dtype(dt).name})
             del x, sq, step
 
 

@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-CODEGEN_VERSION = "17"     # part of every kernel's cache key: bump when generated code changes
+CODEGEN_VERSION = "19"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
@@ -486,6 +486,7 @@ class KernelSpec:
     rpt: int
     unroll: int
     acc_dtype: str       # accumulator / output dtype name of SUM/PROD; working type of MOMENT
+    variant: str = ""    # "sym": mirror-pair kernel for f(x, x.T) chains (b2_run_ewt_sym)
 
     def digest(self) -> str:
         import os
@@ -579,7 +580,18 @@ def render(program: Program, spec: KernelSpec) -> str:
 #pragma unroll
         {fast_loop}
     }}"""
-    if ewt:
+    sym = ""
+    if spec.variant == "sym":
+        kn, kt = spec.layouts.index("V"), spec.layouts.index("T")
+        ct = ctype(program.inputs[kn])
+        sym = f"""    typedef {ct} sym_t;
+    __device__ __forceinline__ static void sym_put(sym_t* tile, int off, const Regs& g) {{ b2_store_vec<{ct}, B2_V>(tile + off, g.a{kn}); }}
+    __device__ __forceinline__ static void sym_get(const sym_t* tile, int base, Regs& g) {{
+#pragma unroll
+        for (int v = 0; v < B2_V; ++v) g.a{kt}[v] = tile[base + v * {spec.rpt}];
+    }}"""
+        run = f"b2_run_ewt_sym<Chain, B2_V, {spec.rpt}>(blocks, nblocks, sc);"
+    elif ewt:
         run = f"b2_run_ewt<Chain, B2_V, {spec.tx}, {spec.ty}>(blocks, nblocks, sc);"
     else:
         run = (f"b2_run<Chain, {_MODE_NAME[spec.mode]}, {_RED_NAME[spec.redop]}, B2_V, {spec.tx}, {spec.ty}, "
@@ -616,6 +628,7 @@ struct Chain {{
         {(nl[:-4]).join(loads_s)}
     }}
 {compute}
+{sym}
 }};
 extern "C" __global__ void __launch_bounds__({spec.tx * spec.ty}, {_min_blocks(spec, packed)})
 b2_fused(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars sc) {{
@@ -631,6 +644,8 @@ def _min_blocks(spec, packed: bool = False) -> int:
         return int(os.environ["B2_MINB"])
     if spec.tx * spec.ty > 256:
         return 1
+    if spec.variant == "sym":
+        return 5 if spec.vec == 4 else 4      # B200 sweep (c4): 5 CTAs/SM (51 regs) f4 5943 GB/s; 6 spills
     if packed:
         return 3
     light = spec.mode in (_lib.MODE_R, _lib.MODE_RC) and spec.redop in (

@@ -59,7 +59,7 @@ class Block(C.Structure):
         ("counter", C.c_void_p),
         ("arg_offset", C.c_int64),
         ("arg_ndim", C.c_int32),
-        ("_pad", C.c_int32),
+        ("mirror", C.c_int32),
         ("arg_shape", C.c_int64 * B2_MAX_ND),
         ("arg_start", C.c_int64 * B2_MAX_ND),
         ("arg_total", C.c_int64 * B2_MAX_ND),

@@ -263,8 +263,18 @@ class FusedLaunch:
         geo = cg.choose_geometry(program, self.mode, shapes, v)
         if ewt:      # 64 x 64 output tiles, 256 threads
             geo = dict(vec=v, tx=64 // v, ty=256 // (64 // v), rpt=64, unroll=1)
+        variant, mirror, n_primary = "", None, len(blocks)
+        if ewt:
+            pairing = _mirror_pairs(program, layouts, blocks, canons, v)
+            if pairing is not None:
+                order, mirror, n_primary = pairing
+                blocks = [blocks[i] for i in order]
+                canons = [canons[i] for i in order]
+                tt = 16 * v                       # a tile row is 16 chunks of 16 bytes (64 f4 / 32 f8)
+                geo = dict(vec=v, tx=16, ty=16, rpt=tt, unroll=1)
+                variant = "sym"
         self.spec = cg.KernelSpec(program.key(), tuple(layouts), self.mode, redop,
-                                  acc_dtype=acc_dtype.name, **geo)
+                                  acc_dtype=acc_dtype.name, variant=variant, **geo)
         self.kernel = load_kernel(program, self.spec)
 
         # ---- descriptor table (leading EW dims expanded into extra descriptors)
@@ -302,8 +312,14 @@ class FusedLaunch:
                         d.arg_shape[j], d.arg_start[j], d.arg_total[j] = bshape[j], bstart[j], total[j]
                 descs.append(d)
             assert lead_elems >= 1
-        self.nblocks = len(descs)
-        arr = (_lib.Block * self.nblocks)(*descs)
+        if mirror is not None:
+            assert len(descs) == len(mirror)
+            for d, m in zip(descs, mirror):
+                d.mirror = m
+        # mirror-pair launches tile the primary block of each pair only; the partners sit behind
+        # them in the table and are reached through `mirror`
+        self.nblocks = n_primary if mirror is not None else len(descs)
+        arr = (_lib.Block * len(descs))(*descs)
         need = C.c_size_t()
         tiles = C.c_int64()
         _lib.check(_lib.lib.b2_fused_plan(self.kernel, arr, self.nblocks, None, 0, C.byref(need), C.byref(tiles)))
@@ -328,6 +344,50 @@ class FusedLaunch:
         if self.profile:
             e1.record()
             self.__dict__.setdefault("events", []).append((e0, e1))
+
+
+def _mirror_pairs(program, layouts, blocks, canons, v):
+    """Pair the blocks of an ``f(x, x.T)`` launch (``a + a.T``, tests/test_collection.py): block d reads
+    ``(N=p, T=q)``, its mirror d' reads ``(N=q, T=p)`` with the transposed shape.  Returns
+    ``(order, mirror index per table slot, number of primaries)`` or None when the launch is not of
+    that form (the generic staged kernel b2_run_ewt then runs it)."""
+    if sorted(layouts) != ["T", "V"]:
+        return None
+    kn, kt = layouts.index("V"), layouts.index("T")
+    dn, dt_ = program.inputs[kn], program.inputs[kt]
+    if dn != dt_ or dn.itemsize not in (4, 8) or v * dn.itemsize != 16:
+        return None
+    sig = {}
+    for i, (b, c) in enumerate(zip(blocks, canons)):
+        if c.B != 1 or c.lead or c.R % v or c.C % v:
+            return None
+        if c.in_strides[kn][2] != 1 or c.in_strides[kt][1] != 1:
+            return None
+        if b.inputs[kt][0] % 16 or b.out0 % 16:
+            return None
+        key = (b.inputs[kn][0], b.inputs[kt][0])
+        if key in sig:
+            return None
+        sig[key] = i
+    mirror_of = {}
+    for (pn, pt), i in sig.items():
+        j = sig.get((pt, pn))
+        if j is None:
+            return None
+        ci, cj = canons[i], canons[j]
+        if (cj.R, cj.C) != (ci.C, ci.R):
+            return None
+        # the partner reads the SAME memory: its row pitch is this block's transposed column pitch
+        if cj.in_strides[kn][1] != ci.in_strides[kt][2] or cj.in_strides[kt][2] != ci.in_strides[kn][1]:
+            return None
+        if ci.in_strides[kt][2] % v:
+            return None
+        mirror_of[i] = j
+    primaries = [i for i in range(len(blocks)) if i <= mirror_of[i]]
+    secondaries = [i for i in range(len(blocks)) if i > mirror_of[i]]
+    order = primaries + secondaries
+    slot = {i: s for s, i in enumerate(order)}
+    return order, [slot[mirror_of[i]] for i in order], len(primaries)
 
 
 def fused_launches(program, redop, reduce_axes, blocks, acc_dtype=None):

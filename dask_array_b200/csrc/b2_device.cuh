@@ -42,7 +42,7 @@ struct B2Block {
     u32* counter;
     i64 arg_offset;
     int arg_ndim;
-    int _pad;
+    int mirror;              // b2_run_ewt_sym: table index of the transposed partner block
     i64 arg_shape[B2_MAX_ND];
     i64 arg_start[B2_MAX_ND];
     i64 arg_total[B2_MAX_ND];
@@ -620,6 +620,16 @@ __device__ __forceinline__ i64 b2_ravel_fix(const B2Block& blk, i64 local) {
 
 // ------------------------------------------------------------------ tile lookup
 __device__ __forceinline__ int b2_find_block(const B2Block* __restrict__ blocks, int nblocks, i64 tile) {
+    if (nblocks == 1) return 0;
+    {   // uniform launches (all blocks tiled alike -- the common case): one division finds the block,
+        // two independent loads confirm it, instead of log2(nblocks) dependent L2 round trips
+        const i64 per = blocks[1].tile_begin;
+        i64 g = tile / per;
+        if (g > nblocks - 1) g = nblocks - 1;
+        const i64 lo_t = blocks[g].tile_begin;
+        const i64 hi_t = (g + 1 < nblocks) ? blocks[g + 1].tile_begin : tile + 1;
+        if (lo_t <= tile && tile < hi_t) return (int)g;
+    }
     int lo = 0, hi = nblocks - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
@@ -1056,6 +1066,108 @@ __device__ __forceinline__ void b2_run_ewt(const B2Block* __restrict__ blocks, i
             Chain::load_s(tiles, lr, lc, g[m]);
             Chain::compute_slow(g[m], sc, o);
             b2_store_vec<T, V>(outp + (i64)lr * C, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ mirror-pair element-wise kernel
+// `x.T + x` (and every chain f(x, x.T) over ONE array, tests/test_collection.py `a + a.T`):
+// output block (i, j) reads x[i, j] and x[j, i].T, output block (j, i) reads x[j, i] and x[i, j].T --
+// the same two input blocks.  b2_run_ewt moves 3 N bytes for that (every element is read twice);
+// here a CTA owns a PAIR of tiles, A = tile (tr, tc) of block d and B = tile (tc, tr) of its mirror
+// block d', loads each once with 128-bit loads, parks both in swizzled shared memory and produces
+//   out [d ] tile (tr, tc) = f(A, B^T)     and     out[d'] tile (tc, tr) = f(B, A^T),
+// so the launch moves the algorithmic minimum of 2 N bytes.  The host lists the primary
+// block of every pair first (only those are tiled) and the partners behind them; `mirror` is the
+// table index of the partner (== own index for diagonal blocks, whose tiles below the diagonal exit).
+//
+// Shared layout of a TT x TT tile (rows of 256 B = 16 chunks of 16 B): element (r, c) lives at
+//   r * TT + ((c / V) ^ ((r / V) & 7)) * V + c % V
+// -- row-wise 16 B stores are conflict free, the transposed scalar reads are 2-way conflicted (no
+// 16 B-preserving swizzle does better for 16 chunk columns over 32 banks); shared bandwidth is not
+// the limit, issue slots are: 1 LDG.128 + 1 STS.128 + 4 LDS + chain + 1 STG.128 per 4 elements.
+// Chain supplies: sym_t, sym_put(tile, off, Regs) [the normal operand's V lanes -> 16 B store],
+// sym_get(tile, base, Regs) [V lanes of the transposed operand, TT apart].
+template <typename Chain, int V, int TT>
+__device__ __forceinline__ void b2_run_ewt_sym(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars& sc) {
+    typedef typename Chain::out_t T;
+    typedef typename Chain::sym_t E;
+    constexpr int NT = 256, TX = TT / V, TY = NT / TX, ITER = TT / TY;
+    static_assert(TX == 16, "a tile row is 16 chunks of 16 bytes");
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    __shared__ B2Block sblk[2];
+    __shared__ __align__(16) E tiles[2][TT * TT];
+    {
+        const int bi = b2_find_block(blocks, nblocks, (i64)blockIdx.x);
+        const int mi = blocks[bi].mirror;
+        constexpr int nw = (int)(sizeof(B2Block) / 4);
+        const u32* s0 = reinterpret_cast<const u32*>(blocks + bi);
+        const u32* s1 = reinterpret_cast<const u32*>(blocks + mi);
+        u32* dst = reinterpret_cast<u32*>(&sblk[0]);
+        for (int i = tid; i < 2 * nw; i += NT) dst[i] = (i < nw) ? s0[i] : s1[i - nw];
+        __syncthreads();
+    }
+    const B2Block& blk = sblk[0];
+    const B2Block& blk2 = sblk[1];
+    const int t = (int)((i64)blockIdx.x - blk.tile_begin);
+    const int tc = t % (int)blk.tiles_c, tr = t / (int)blk.tiles_c;
+    const bool diag = (blk.out0 == blk2.out0);
+    if (diag && tr > tc) return;
+    const bool self = diag && tr == tc;
+    const int R = (int)blk.R, C = (int)blk.C;             // partner block: C rows x R columns
+    const int r0 = tr * TT, c0 = tc * TT;
+    const int lc = tx * V;
+    const bool colA = (c0 + lc < C), colB = (r0 + lc < R);
+    typename Chain::Ptrs PA, PB;
+    typename Chain::Regs gA[ITER], gB[ITER];
+    Chain::setup_rows(blk, 0, r0, colA ? c0 + lc : 0, 1, PA);
+    Chain::setup_rows(blk2, 0, c0, colB ? r0 + lc : 0, 1, PB);
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+        const int lr = ty + m * TY;
+        if (colA && r0 + lr < R) Chain::load_n(PA, lr, gA[m]);
+    }
+    if (!self) {
+#pragma unroll
+        for (int m = 0; m < ITER; ++m) {
+            const int lr = ty + m * TY;
+            if (colB && c0 + lr < C) Chain::load_n(PB, lr, gB[m]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < ITER; ++m) {
+        const int lr = ty + m * TY;
+        const int off = lr * TT + ((tx ^ ((lr / V) & 7)) * V);
+        if (colA && r0 + lr < R) Chain::sym_put(tiles[0], off, gA[m]);
+        if (!self && colB && c0 + lr < C) Chain::sym_put(tiles[1], off, gB[m]);
+    }
+    __syncthreads();
+    const E* const tB = self ? tiles[0] : tiles[1];
+    if (colA) {
+        T* outp = (T*)blk.out0 + (i64)r0 * C + c0 + lc;
+#pragma unroll
+        for (int m = 0; m < ITER; ++m) {
+            const int lr = ty + m * TY;
+            if (r0 + lr < R) {
+                T o[V];
+                Chain::sym_get(tB, lc * TT + (((lr / V) ^ (tx & 7)) * V) + lr % V, gA[m]);
+                Chain::compute_slow(gA[m], sc, o);
+                b2_store_vec<T, V>(outp + (i64)lr * C, o);
+            }
+        }
+    }
+    if (!self && colB) {
+        T* outp = (T*)blk2.out0 + (i64)c0 * R + r0 + lc;
+#pragma unroll
+        for (int m = 0; m < ITER; ++m) {
+            const int lr = ty + m * TY;
+            if (c0 + lr < C) {
+                T o[V];
+                Chain::sym_get(tiles[0], lc * TT + (((lr / V) ^ (tx & 7)) * V) + lr % V, gB[m]);
+                Chain::compute_slow(gB[m], sc, o);
+                b2_store_vec<T, V>(outp + (i64)lr * R, o);
+            }
         }
     }
 }

@@ -100,7 +100,8 @@ typedef struct b2_block {
      * or -- ravel mode -- the block's N-d shape/offset inside the whole array.         */
     int64_t arg_offset;
     int32_t arg_ndim;      /* 0 = plain axis mode; >0 = ravel mode with the fields below */
-    int32_t _pad;
+    int32_t mirror;        /* mirror-pair kernels (f(x, x.T), manipulation/_transpose.py:14-75 feeding an
+                            * Elemwise): table index of the transposed partner block, else 0         */
     int64_t arg_shape[B2_MAX_ND];
     int64_t arg_start[B2_MAX_ND];
     int64_t arg_total[B2_MAX_ND];
