@@ -200,7 +200,18 @@ def run_other(args):
     import dask_array_b200 as da
     from dask_array_b200 import _lib
 
-    torch.cuda.set_device(0)
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        if args.config != "c4":
+            if rank == 0:
+                print(json.dumps({"error": f"--config {args.config} is a single-GPU line; only c2 and c4 shard"}))
+            return
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -209,24 +220,38 @@ def run_other(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     def timed(step, nbytes, label, extra=None):
         for _ in range(max(args.warmup, 3)):
             step.run()
-        torch.cuda.synchronize()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = _lib.launch_count()
         e0.record()
         for _ in range(args.steps):
             step.run()
         e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
         out = {"metric": METRIC, "config": {"workload": label}, "value": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
-               "ms_per_step": ms, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-               "frac_of_measured_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": nbytes,
+               "ms_per_step": ms, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "frac_of_measured_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak / world, "algorithmic_bytes_per_step": nbytes,
                "gpu_launches": _lib.launch_count() - n0, "data": "synthetic", "higher_is_better": True}
         out.update(extra or {})
-        print(json.dumps(out))
+        if world > 1:
+            # (G-1)/G of the array crosses the partition; per-GPU egress over NVLink
+            cross = nbytes / 2 * (world - 1) / world
+            out.update({"scaling": "strong", "comm": os.environ.get("B2_COMM", "peer"),
+                        "nvlink_bytes_per_step": cross, "nvlink_GBps_per_gpu_egress": cross / world / (ms * 1e-3) / 1e9})
+        if rank == 0:
+            print(json.dumps(out))
 
     if args.config == "c1":
         # README example: latency only (80 kB blocks are not a roofline config)
@@ -295,19 +320,41 @@ def run_other(args):
         timed(step, 4 * nbytes, "c3: all four reductions, four passes", {"dtype": "f64"})
     else:
         n = 16384
+
+        def gen(dt, r0, nr, c0, nc):
+            """value(i, j) = i * n + j (int32 bit patterns viewed as f4: distinct values)"""
+            v = np.add.outer(np.arange(r0, r0 + nr, dtype=np.int64) * n, np.arange(c0, c0 + nc, dtype=np.int64))
+            return v.astype(np.float64) if dt == np.float64 else v.astype(np.int32).view(np.float32)
+
+        def source(dt, chunks):
+            blk = lambda bid: gen(dt, bid[0] * chunks[0], chunks[0], bid[1] * chunks[1], chunks[1])
+            return da.from_host_blocks(blk, (n, n), chunks, dt, token=f"c4-{np.dtype(dt).name}-{chunks}").persist()
+
         for dt in (np.float32, np.float64):
             item = np.dtype(dt).itemsize
-            host = np.arange(n * n, dtype=np.int64).reshape(n, n).astype(dt) if dt == np.float64 else \
-                np.arange(n * n, dtype=np.int32).reshape(n, n).view(np.float32)
-            x = da.from_array(host, chunks=(n, 256)).persist()
-            step = da.compile(x.rechunk((256, n)))
+            x = source(dt, (n, 256))
+            y = x.rechunk((256, n))
+            step = da.compile(y)
             timed(step, 2 * n * n * item, f"c4: rechunk (16384,16384) {np.dtype(dt).name} (16384,256)->(256,16384)",
                   {"dtype": np.dtype(dt).name})
-            sq = da.from_array(host, chunks=(2048, 2048)).persist()
+            # bit-exact check of one new row panel this rank owns against the generator
+            torch.cuda.synchronize()
+            mine = [b for b in sorted(step.stores[0].blocks)][:1]
+            for b in mine:
+                got = step.stores[0].blocks[b].to_numpy()
+                want = gen(dt, b[0] * 256, 256, 0, n)
+                if not np.array_equal(got.view(np.uint8), want.view(np.uint8)):
+                    raise SystemExit(f"bench c4: rechunked block {b} differs from the source on rank {rank}")
+            del x, y, step
+            sq = source(dt, (2048, 2048))
             step = da.compile(sq.T + sq)
             timed(step, 2 * n * n * item, f"c4: x.T + x (16384,16384) {np.dtype(dt).name} chunks 2048^2 "
-                  "(2N bytes: mirror-pair kernel, every tile read once)", {"dtype": np.dtype(dt).name})
-            del x, sq, step
+                  "(2N bytes: mirror-pair kernel, every tile read once)" if world == 1 else
+                  f"c4: x.T + x (16384,16384) {np.dtype(dt).name} chunks 2048^2 (remote operand read in place over NVLink)",
+                  {"dtype": np.dtype(dt).name})
+            del sq, step
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------- GPU arm

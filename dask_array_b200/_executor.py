@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import _peer
 from . import _runtime as rt
 from ._blockwise import FusedBlockwise, FusedPlan
 from ._device import DeviceChunk, alloc_bytes
@@ -258,12 +259,17 @@ class Executor:
                 acc_dtype = red.dtype
                 blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
                 st.blocks[bid] = out
+        bar = extra.get("__barrier__")
+        if bar is not None:
+            self._do(bar)         # the owners have produced the blocks this rank reads in place
         if blocks:
             for launch in rt.fused_launches(plan.program, REDOPS[kind] if red is not None else _lib.RED_NONE,
                                             axes, blocks, acc_dtype=acc_dtype):
                 self._do(launch.run)
                 st.keepalive.append(launch)
             st.keepalive.append(extra)
+        if bar is not None:
+            self._do(bar)         # ... and every reader is done before an owner may reuse them
         return st
 
     def _empty_result(self, expr, bid, kind):
@@ -380,6 +386,8 @@ class Executor:
         src = self.results[x._name]
         st = BlockStore(expr)
         item = expr.dtype.itemsize
+        if self.world.size > 1 and not src.replicated and _peer.enabled():
+            return _rechunk_push(self, expr, src, st)
         new_ids = [bid for bid in expr.block_ids() if self.mine(expr, bid)]
         remote = {}
         if self.world.size > 1 and not src.replicated:
@@ -748,10 +756,120 @@ def plan_rechunk_exchange(expr: TasksRechunk, W: int, me: int):
     return send_items, recv_items
 
 
+def plan_rechunk_push(expr: TasksRechunk, W: int, me: int):
+    """Pure (no device) plan of a rechunk across the partition as ONE gather per rank that stores
+    straight into the owners' memory.  Every rank lays out the new blocks of every rank the same
+    way (one slab per rank, blocks in block-id order, 512-byte aligned).  Returns
+    ``(layout, totals, pushes)``: ``layout[r] = {new block id: byte offset in rank r's slab}``,
+    ``totals[r]`` = slab bytes, ``pushes`` = [(old block id, source slices, owner rank of the new
+    block, new block id, destination slices)] for every piece whose SOURCE block ``me`` owns --
+    local pieces included: the same launch moves them."""
+    x = expr.operand("array")
+    item = expr.dtype.itemsize
+    layout = [dict() for _ in range(W)]
+    totals = [0] * W
+    pushes = []
+    for nbid in expr.block_ids():
+        r = owner_of(expr, nbid, W)
+        layout[r][nbid] = totals[r]
+        totals[r] += -(-math.prod(expr.block_shape(nbid)) * item // 512) * 512
+        for obid, sl, dsl in expr.pieces(nbid):
+            if owner_of(x, obid, W) == me:
+                pushes.append((obid, sl, r, nbid, dsl))
+    return layout, totals, pushes
+
+
+def _rechunk_push(ex: Executor, expr: TasksRechunk, src: BlockStore, st: BlockStore):
+    """The all-to-all of a rechunk as the rechunk kernel itself: every rank's tiled
+    gather reads its own old blocks and writes the pieces into the new blocks where they live --
+    local HBM or a peer's HBM over NVLink (``_peer``) -- bracketed by two stream-ordered barriers.
+    Bytes per element: one read + one write, wherever the destination is."""
+    W, me = ex.world.size, ex.world.rank
+    item = expr.dtype.itemsize
+    layout, totals, pushes = plan_rechunk_push(expr, W, me)
+    slab = alloc_bytes(totals[me], ex.device)
+    for nbid, off in layout[me].items():
+        st.blocks[nbid] = DeviceChunk(slab, expr.block_shape(nbid), expr.dtype, offset=off // item)
+    bases = [p[0] for p in _peer.exchange_pointers(ex.device, [slab.data_ptr()], [1] * W, me)]
+    windows = [slab if r == me else _peer.PeerBuffer(bases[r], ex.device, totals[r], r) for r in range(W)]
+    copies = []
+    for obid, sl, r, nbid, dsl in pushes:
+        dst = DeviceChunk(windows[r], expr.block_shape(nbid), expr.dtype, offset=layout[r][nbid] // item)
+        copies.extend(_copy_descs(src.blocks[obid][sl], dst[dsl], item))
+    launch = rt.GatherLaunch(copies)
+    bar = _peer.StreamBarrier(ex.device)
+    ex._do(bar)                 # every owner is done with the previous contents of its slab
+    ex._do(launch.run)
+    ex._do(bar)                 # every piece has landed before anyone reads a new block
+    st.keepalive.extend([launch, slab, bar, windows])
+    return st
+
+
+def plan_fused_peer_reads(plan: FusedPlan, replicated, W: int):
+    """Pure plan of the remote block reads of a fused expression: ``exports[o]`` = the (leaf index,
+    leaf block id) pairs rank o owns and some other rank reads, in one canonical order;
+    ``readers[(o, i)]`` = the set of ranks reading export i of rank o."""
+    expr = plan.fused
+    wanted = {}
+    for bid in expr.block_ids():
+        r = owner_of(expr, bid, W)
+        for k, (dep, _) in enumerate(plan.leaves):
+            if replicated[k]:
+                continue
+            lbid = plan.leaf_block_id(k, bid)
+            o = owner_of(dep, lbid, W)
+            if o != r:
+                wanted.setdefault((o, dep._name, lbid), [k, set()])[1].add(r)
+    exports = [[] for _ in range(W)]
+    readers = {}
+    for (o, name, lbid) in sorted(wanted):
+        k, rs = wanted[(o, name, lbid)]
+        readers[(o, len(exports[o]))] = rs
+        exports[o].append((k, lbid))
+    return exports, readers
+
+
+def _peer_reads_for_fused(ex: Executor, plan: FusedPlan, deps):
+    """Remote operands of a fused expression (``x.T + x`` across the partition) are read IN PLACE:
+    the owners export the blocks once, the fused kernel of the reading rank loads them over NVLink
+    while it computes -- no pack, no send/recv, no staging copy.  Returns {(dep name, block id):
+    DeviceChunk over peer memory}; ``__barrier__`` must bracket the launch on the tape."""
+    import struct
+
+    W, me = ex.world.size, ex.world.rank
+    exports, readers = plan_fused_peer_reads(plan, [d.replicated for d in deps], W)
+    if not any(exports):
+        return {}
+    rec = _peer.HANDLE_BYTES + 8 * 9
+    mine = []
+    for k, lbid in exports[me]:
+        blk = deps[k].blocks[lbid]
+        st = list(blk.strides) + [0] * (8 - blk.ndim)
+        mine.append(_peer.export_handle(blk.ptr) + struct.pack("<9q", blk.ndim, *st))
+    recs = _peer.exchange_records(ex.device, mine, [len(e) for e in exports], rec)
+    out = {}
+    for o in range(W):
+        if o == me:
+            continue
+        for i, (k, lbid) in enumerate(exports[o]):
+            if me not in readers[(o, i)]:
+                continue
+            raw = recs[o][i]
+            meta = struct.unpack("<9q", raw[_peer.HANDLE_BYTES:])
+            dep = plan.leaves[k][0]
+            ptr = _peer.open_handle(raw[: _peer.HANDLE_BYTES])
+            out[(dep._name, lbid)] = DeviceChunk(_peer.PeerBuffer(ptr, ex.device, owner=o), dep.block_shape(lbid),
+                                                 dep.dtype, strides=meta[1: 1 + meta[0]])
+    out["__barrier__"] = _peer.StreamBarrier(ex.device)
+    return out
+
+
 def _exchange_for_fused(ex: Executor, plan: FusedPlan, deps, out_ids):
     """Blocks of dependencies that some rank's output blocks read but another rank owns are
     packed per peer, exchanged over NCCL and exposed as DeviceChunks."""
     W, me = ex.world.size, ex.world.rank
+    if _peer.enabled():
+        return _peer_reads_for_fused(ex, plan, deps)
     send_items, recv_items = plan_fused_exchange(plan, [d.replicated for d in deps], W, me)
     if not any(send_items.values()) and not any(recv_items.values()):
         return {}

@@ -107,7 +107,13 @@ SYMBOLS = [
     "b2_jit_compile", "b2_free", "b2_device_header", "b2_kernel_load", "b2_kernel_free",
     "b2_fused_plan", "b2_fused_launch", "b2_combine", "b2_gather_plan", "b2_gather_launch",
     "b2_fill", "b2_gemm_tn", "b2_memcpy2d", "b2_gemm_tn_pairs", "b2_split3_bf16", "b2_combine_groups", "b2_gemm_tn_batched", "b2_gather_launch_bulk",
+    "b2_ipc_export", "b2_ipc_open",
 ]
+
+
+class IpcHandle(C.Structure):
+    _fields_ = [("reserved", C.c_ubyte * 64), ("offset", C.c_int64), ("size", C.c_int64)]
+
 
 
 def _load():
@@ -141,6 +147,8 @@ def _load():
     lib.b2_gemm_tn_pairs.argtypes = [i32, vp, vp, i32, i64, i64, vp, i64, i64, i64, i64, i32, vp]
     lib.b2_split3_bf16.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.b2_gemm_tn_batched.argtypes = [i32, C.POINTER(GemmProblem), i32, vp, sz, C.POINTER(sz), vp]
+    lib.b2_ipc_export.argtypes = [vp, C.POINTER(IpcHandle)]
+    lib.b2_ipc_open.argtypes = [C.POINTER(IpcHandle), C.POINTER(vp)]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError here = header and library out of sync
     return lib

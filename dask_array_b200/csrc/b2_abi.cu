@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -87,6 +88,7 @@ struct DriverApi {
                              unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
     CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*MemGetAddressRange)(CUdeviceptr*, size_t*, CUdeviceptr) = nullptr;
     bool ok = false;
     std::string why;
 };
@@ -105,6 +107,7 @@ static DriverApi& driver() {
         LOAD(LaunchKernel, "cuLaunchKernel");
         LOAD(GetErrorString, "cuGetErrorString");
         LOAD(FuncGetAttribute, "cuFuncGetAttribute");
+        LOAD(MemGetAddressRange, "cuMemGetAddressRange_v2");
 #undef LOAD
         d.ok = true;
     });
@@ -602,6 +605,48 @@ extern "C" int b2_memcpy2d(void* dst, int64_t dst_pitch, const void* src, int64_
     else
         CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)row_bytes,
                                    (size_t)rows, k, (cudaStream_t)stream));
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------ peer memory (CUDA IPC)
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+extern "C" int b2_ipc_export(const void* ptr, b2_ipc_handle* out) {
+    if (!ptr || !out) return fail(B2_ERR_INVALID, "NULL argument");
+    DriverApi& d = driver();
+    if (!d.ok) return fail(B2_ERR_CUDA, "%s", d.why.c_str());
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    CUresult r = d.MemGetAddressRange(&base, &size, (CUdeviceptr)ptr);
+    if (r != CUDA_SUCCESS) return fail(B2_ERR_CUDA, "cuMemGetAddressRange: %s", cu_err(r));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, (void*)base));
+    memcpy(out->reserved, &h, 64);
+    out->offset = (int64_t)((CUdeviceptr)ptr - base);
+    out->size = (int64_t)size;
+    return B2_OK;
+}
+
+extern "C" int b2_ipc_open(const b2_ipc_handle* h, void** ptr) {
+    if (!h || !ptr) return fail(B2_ERR_INVALID, "NULL argument");
+    // an allocation can be opened once per process: cache the mapping per (device, handle)
+    static std::mutex mu;
+    static std::map<std::string, void*> mapped;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::string key((const char*)h->reserved, 64);
+    key.push_back((char)dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = mapped.find(key);
+    void* base = nullptr;
+    if (it != mapped.end()) {
+        base = it->second;
+    } else {
+        cudaIpcMemHandle_t ch;
+        memcpy(&ch, h->reserved, 64);
+        CUDA_TRY(cudaIpcOpenMemHandle(&base, ch, cudaIpcMemLazyEnablePeerAccess));
+        mapped[key] = base;
+    }
+    *ptr = (char*)base + h->offset;
     return B2_OK;
 }
 

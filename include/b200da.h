@@ -226,6 +226,22 @@ int b2_gather_launch(const b2_copy* d_copies, int n, int64_t total_tiles, void* 
  * multiples) and tile_rows * min(row_bytes, B2_GATHER_COL_BYTES) <= 64 KiB (what b2_gather_plan makes). */
 int b2_gather_launch_bulk(const b2_copy* d_copies, int n, int64_t total_tiles, void* stream);
 
+/* ---- peer memory (one process per GPU) ------------------------------------------
+ * The reference moves blocks between workers by pickling them through the scheduler
+ * (rechunk: _rechunk.py:1171-1323 getitem + concatenate3 tasks; transposed reads:
+ * manipulation/_transpose.py:66-75).  Here a rank exports the allocation behind a block once
+ * (CUDA IPC), the other ranks map it, and the SAME gather / fused kernels then store to or load
+ * from the peer's HBM over NVLink: the all-to-all of a rechunk is the rechunk kernel itself.
+ * b2_ipc_export: handle of the allocation containing `ptr` + the offset of `ptr` in it.
+ * b2_ipc_open:   map it in this process (cached per allocation) and return the peer's `ptr`.   */
+typedef struct b2_ipc_handle {
+    unsigned char reserved[64];   /* cudaIpcMemHandle_t */
+    int64_t offset;               /* ptr - allocation base */
+    int64_t size;                 /* allocation size */
+} b2_ipc_handle;
+int b2_ipc_export(const void* ptr, b2_ipc_handle* out);
+int b2_ipc_open(const b2_ipc_handle* h, void** ptr);
+
 /* Strided host<->device block transfer: from_array's per-block getitem of a host array
  * (io/_from_array.py:60-160) and finalize's concatenate3 into the host result
  * (_core_utils.py:1426-1448), as one cudaMemcpy2DAsync per block. kind: 0 = H2D, 1 = D2H. */

@@ -46,6 +46,18 @@ def main():
     ih = np.arange(512 * 512, dtype=np.int32).reshape(512, 512)
     xi = da.from_array(ih, chunks=(512, 32))
     assert np.array_equal(xi.rechunk((32, 512)).compute(), ih)                 # all-to-all over NCCL
+    big = np.arange(2048 * 2048, dtype=np.int32).reshape(2048, 2048).view(np.float32)
+    xb = da.from_array(big, chunks=(2048, 64)).persist()
+    step = da.compile(xb.rechunk((64, 2048)))                                    # TMA bulk stores into peer HBM
+    for _ in range(3):                                                           # replays: barriers order the slabs
+        step.run()
+    assert np.array_equal(step.results()[0].view(np.int32), big.view(np.int32))
+    fh = rng.random((1024, 1024))
+    fs = da.from_array(fh, chunks=(256, 256)).persist()
+    step = da.compile(fs.T - fs)
+    for _ in range(3):
+        step.run()
+    assert np.array_equal(step.results()[0], fh.T - fh)
     sq = da.from_array(ih, chunks=(128, 128))
     assert np.array_equal((sq.T + sq).compute(), ih.T + ih)                     # remote transposed blocks
     assert np.array_equal((xi.T + xi).compute(), ih.T + ih)                     # rechunk + fused transpose
@@ -63,7 +75,7 @@ def main():
     assert (ones + ones.T).sum().compute() == 2_000_000.0
     dist.barrier()
     if rank == 0:
-        print(f"multigpu_check ok on {world} GPUs")
+        print(f"multigpu_check ok on {world} GPUs (B2_COMM={os.environ.get('B2_COMM', 'peer')})")
     dist.destroy_process_group()
 
 

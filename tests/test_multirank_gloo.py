@@ -31,7 +31,16 @@ def _worker(rank, world, port, case, q):
 
         n = 64
         xh = np.arange(n * n, dtype=np.float64).reshape(n, n)
-        if case == "rechunk":
+        if case == "records":
+            # the handle exchange of the peer-memory path: fixed-size records, per-rank counts known to all
+            from dask_array_b200 import _peer
+            counts = [3, 1]
+            mine = [bytes([rank * 16 + i]) * 80 for i in range(counts[rank])]
+            recs = _peer.exchange_records(torch.device("cpu"), mine, counts, 80)
+            ok = [len(r) for r in recs] == counts and all(
+                recs[r][i] == bytes([r * 16 + i]) * 80 for r in range(world) for i in range(counts[r]))
+            q.put((rank, bool(ok), 0))
+        elif case == "rechunk":
             x = da.from_array(xh, chunks=(n, 8))
             expr = x.rechunk((8, n)).optimize().expr
             src = expr.operand("array")
@@ -110,12 +119,12 @@ def _worker(rank, world, port, case, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["rechunk", "fused_transpose"])
+@pytest.mark.parametrize("case", ["rechunk", "fused_transpose", "records"])
 def test_exchange_schedules_pair_up(case):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + (0 if case == "rechunk" else 1)
+    port = 29500 + (os.getpid() % 2000) + ["rechunk", "fused_transpose", "records"].index(case)
     procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -137,3 +146,69 @@ def test_owner_is_block_cyclic():
     assert [owner_of(x, (0, j), 8) for j in range(8)] == list(range(8))
     assert owner_of(x, (3, 5), 8) == 5 and owner_of(x, (3, 5), 1) == 0
     assert owner_of(x, (1, 0), 3) == 8 % 3
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("old,new", [((64, 8), (8, 64)), ((16, 16), (64, 4)), ((20, 7), (9, 64))])
+def test_rechunk_push_plan_covers_every_new_block_once(world, old, new):
+    """Peer-store rechunk: the pushes of all ranks, applied to per-rank slabs laid out as every rank
+    derives them, must write every element of every new block exactly once with the right value."""
+    sys.path.insert(0, ROOT)
+    import dask_array_b200 as da
+    from dask_array_b200._executor import owner_of, plan_rechunk_push
+    n = 64
+    xh = np.arange(n * n, dtype=np.float64).reshape(n, n)
+    expr = da.from_array(xh, chunks=old).rechunk(new).optimize().expr
+    src = expr.operand("array")
+    plans = [plan_rechunk_push(expr, world, me) for me in range(world)]
+    layout, totals, _ = plans[0]
+    assert all(p[0] == layout and p[1] == totals for p in plans)            # same layout on every rank
+    slabs = [np.full(t // 8, np.nan) for t in totals]
+    hits = [np.zeros(t // 8, dtype=np.int64) for t in totals]
+    moved = 0
+    for me, (_, _, pushes) in enumerate(plans):
+        for obid, sl, r, nbid, dsl in pushes:
+            assert owner_of(src, obid, world) == me and owner_of(expr, nbid, world) == r
+            start = src.block_start(obid)
+            piece = xh[tuple(slice(s0 + s.start, s0 + s.stop) for s0, s in zip(start, sl))]
+            shape = expr.block_shape(nbid)
+            off = layout[r][nbid] // 8
+            view = slabs[r][off: off + shape[0] * shape[1]].reshape(shape)
+            view[dsl] = piece
+            hits[r][off: off + shape[0] * shape[1]].reshape(shape)[dsl] += 1
+            moved += piece.size * (me != r)
+    for nbid in expr.block_ids():
+        r = owner_of(expr, nbid, world)
+        shape, start = expr.block_shape(nbid), expr.block_start(nbid)
+        off = layout[r][nbid] // 8
+        got = slabs[r][off: off + shape[0] * shape[1]].reshape(shape)
+        assert np.array_equal(got, xh[start[0]:start[0] + shape[0], start[1]:start[1] + shape[1]])
+        assert (hits[r][off: off + shape[0] * shape[1]] == 1).all()
+    if old == (64, 8) and new == (8, 64) and 8 % world == 0:
+        assert moved == n * n * (world - 1) // world                          # (G-1)/G crosses NVLink
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_peer_read_plan(world):
+    sys.path.insert(0, ROOT)
+    import dask_array_b200 as da
+    from dask_array_b200._blockwise import FusedPlan
+    from dask_array_b200._executor import owner_of, plan_fused_peer_reads
+    x = da.from_array(np.zeros((64, 64)), chunks=(16, 16))
+    fused = (x.T + x).optimize().expr
+    plan = FusedPlan(fused)
+    exports, readers = plan_fused_peer_reads(plan, [False] * len(plan.leaves), world)
+    dep = plan.leaves[0][0]
+    for o, ex in enumerate(exports):
+        assert len(set(ex)) == len(ex)
+        for i, (k, lbid) in enumerate(ex):
+            assert owner_of(dep, lbid, world) == o and o not in readers[(o, i)]
+    # every remote read of every output block is covered by exactly one export of the owner
+    for bid in fused.block_ids():
+        r = owner_of(fused, bid, world)
+        for k in range(len(plan.leaves)):
+            lbid = plan.leaf_block_id(k, bid)
+            o = owner_of(dep, lbid, world)
+            if o != r:
+                i = [j for j, (kk, lb) in enumerate(exports[o]) if lb == lbid]
+                assert len(i) == 1 and r in readers[(o, i[0])]
