@@ -797,7 +797,7 @@ def _rechunk_push(ex: Executor, expr: TasksRechunk, src: BlockStore, st: BlockSt
         dst = DeviceChunk(windows[r], expr.block_shape(nbid), expr.dtype, offset=layout[r][nbid] // item)
         copies.extend(_copy_descs(src.blocks[obid][sl], dst[dsl], item))
     launch = rt.GatherLaunch(copies)
-    bar = _peer.StreamBarrier(ex.device)
+    bar = _peer.StreamBarrier(ex.device, me, W)
     ex._do(bar)                 # every owner is done with the previous contents of its slab
     ex._do(launch.run)
     ex._do(bar)                 # every piece has landed before anyone reads a new block
@@ -860,7 +860,7 @@ def _peer_reads_for_fused(ex: Executor, plan: FusedPlan, deps):
             ptr = _peer.open_handle(raw[: _peer.HANDLE_BYTES])
             out[(dep._name, lbid)] = DeviceChunk(_peer.PeerBuffer(ptr, ex.device, owner=o), dep.block_shape(lbid),
                                                  dep.dtype, strides=meta[1: 1 + meta[0]])
-    out["__barrier__"] = _peer.StreamBarrier(ex.device)
+    out["__barrier__"] = _peer.StreamBarrier(ex.device, me, W)
     return out
 
 

@@ -84,9 +84,8 @@ def exchange_pointers(device, my_ptrs: list[int], counts: list[int], rank: int, 
     return out
 
 
-class StreamBarrier:
-    """Stream-ordered barrier over all ranks (a 4-byte NCCL all-reduce): everything the ranks enqueued
-    before it has completed -- and is visible system-wide -- before anything enqueued after it runs."""
+class NcclBarrier:
+    """Stream-ordered barrier as a 4-byte NCCL all-reduce (``B2_BARRIER=nccl``; ~20 us)."""
 
     def __init__(self, device):
         self.flag = torch.zeros(1, dtype=torch.int32, device=device)
@@ -95,3 +94,35 @@ class StreamBarrier:
         import torch.distributed as dist
 
         dist.all_reduce(self.flag)
+
+
+class PeerBarrier:
+    """Stream-ordered barrier through peer memory (``b2_peer_barrier``): every rank stores an epoch
+    into every peer's signal array over NVLink and waits for its own array to fill.  Everything the
+    ranks enqueued before it has completed -- and is visible system-wide -- before anything enqueued
+    after it runs.  One instance per process; all ranks call it in the same order."""
+
+    def __init__(self, device, rank: int, world: int):
+        self.rank, self.world, self.epoch = rank, world, 0
+        self.sig = torch.zeros(max(world, 2), dtype=torch.int64, device=device)
+        # the all-gather inside is ordered after the zero-fill on every rank: no signal can precede it
+        ptrs = exchange_pointers(device, [self.sig.data_ptr()], [1] * world, rank)
+        self.table = torch.tensor([p[0] for p in ptrs], dtype=torch.int64).to(device)
+
+    def __call__(self):
+        from ._device import current_stream_ptr
+
+        self.epoch += 1
+        _lib.check(_lib.lib.b2_peer_barrier(self.table.data_ptr(), self.rank, self.world, self.epoch,
+                                            current_stream_ptr()))
+
+
+_BARRIER = None
+
+
+def StreamBarrier(device, rank: int = 0, world: int = 1):
+    """The process-wide stream-ordered barrier (created collectively on first use)."""
+    global _BARRIER
+    if _BARRIER is None:
+        _BARRIER = NcclBarrier(device) if os.environ.get("B2_BARRIER", "peer") == "nccl" else PeerBarrier(device, rank, world)
+    return _BARRIER

@@ -650,6 +650,36 @@ extern "C" int b2_ipc_open(const b2_ipc_handle* h, void** ptr) {
     return B2_OK;
 }
 
+__global__ void __launch_bounds__(32) b2_peer_barrier_kernel(unsigned long long* const* __restrict__ sig, int me, int world,
+                                                             unsigned long long epoch, unsigned long long timeout_ns) {
+    for (int p = threadIdx.x; p < world; p += blockDim.x) {
+        __threadfence_system();
+        unsigned long long* remote = sig[p] + me;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
+    }
+    for (int p = threadIdx.x; p < world; p += blockDim.x) {
+        const unsigned long long* mine = sig[me] + p;
+        unsigned long long v, t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if (v >= epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) __trap();
+            __nanosleep(100);
+        }
+    }
+}
+
+extern "C" int b2_peer_barrier(void* const* d_sig_table, int me, int world, uint64_t epoch, void* stream) {
+    if (!d_sig_table || world <= 0 || me < 0 || me >= world) return fail(B2_ERR_INVALID, "bad argument");
+    b2_peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long* const*)d_sig_table, me, world,
+                                                               (unsigned long long)epoch, 120ull * 1000000000ull);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------ fill (AOT)
 template <typename W>
 __global__ void __launch_bounds__(256) b2_fill_kernel(W* dst, i64 n, W value) {

@@ -241,6 +241,13 @@ typedef struct b2_ipc_handle {
 } b2_ipc_handle;
 int b2_ipc_export(const void* ptr, b2_ipc_handle* out);
 int b2_ipc_open(const b2_ipc_handle* h, void** ptr);
+/* Stream-ordered barrier over all ranks through peer memory: rank `me` stores `epoch` into slot `me`
+ * of every rank's signal array (d_sig_table[p] = rank p's array of `world` uint64, mapped here) and
+ * waits until its own slots reach `epoch`.  Everything enqueued before it on any rank has completed,
+ * and is visible, before anything enqueued after it runs.  Epochs must increase by one per call, in
+ * the same order on every rank.  A peer that does not arrive within 120 s traps the kernel (a loud
+ * failure instead of a hung GPU). */
+int b2_peer_barrier(void* const* d_sig_table, int me, int world, uint64_t epoch, void* stream);
 
 /* Strided host<->device block transfer: from_array's per-block getitem of a host array
  * (io/_from_array.py:60-160) and finalize's concatenate3 into the host result
