@@ -221,7 +221,7 @@ class Executor:
         out_ids = [bid for bid in expr.block_ids() if self.mine(expr, bid)]
         # ---- blocks of dependencies living on other GPUs (e.g. x.T + x across the partition)
         extra = self._exchange_for_fused(plan, deps, out_ids) if self.world.size > 1 else {}
-        blocks = []
+        blocks, block_owner = [], []
         axes = red.operand("axis") if red is not None else ()
         acc_dtype = None
         for bid in out_ids:
@@ -230,14 +230,18 @@ class Executor:
                 st.blocks[bid] = self._empty_result(expr, bid, store_kind)
                 continue
             ins = []
+            remote_owner = self.world.rank
             for k, (dep, _) in enumerate(plan.leaves):
                 lbid = plan.leaf_block_id(k, bid)
                 src = deps[k].blocks.get(lbid)
                 if src is None:
                     src = extra.get((dep._name, lbid))
+                    remote_owner = getattr(getattr(src, "buf", None), "owner", remote_owner)
                 if src is None:
                     raise RuntimeError(f"block {lbid} of {dep._name} is not resident on rank {self.world.rank}")
                 ins.append((src.ptr, plan.leaf_strides(k, src, len(shape))))
+            if red is None:
+                block_owner.append(remote_owner)
             out_shape = expr.block_shape(bid)
             if red is None:
                 out = DeviceChunk.empty(out_shape, expr.dtype, self.device)
@@ -260,11 +264,16 @@ class Executor:
                 blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
                 st.blocks[bid] = out
         bar = extra.get("__barrier__")
+        keep_order = False
         if bar is not None:
             self._do(bar)         # the owners have produced the blocks this rank reads in place
+            if red is None:
+                blocks, keep_order = _interleave_remote_reads(
+                    blocks, block_owner, self.world.rank, self.world.size,
+                    [d.itemsize for d in plan.program.inputs], expr.dtype.itemsize), True
         if blocks:
             for launch in rt.fused_launches(plan.program, REDOPS[kind] if red is not None else _lib.RED_NONE,
-                                            axes, blocks, acc_dtype=acc_dtype):
+                                            axes, blocks, acc_dtype=acc_dtype, keep_order=keep_order):
                 self._do(launch.run)
                 st.keepalive.append(launch)
             st.keepalive.append(extra)
@@ -769,13 +778,22 @@ def plan_rechunk_push(expr: TasksRechunk, W: int, me: int):
     layout = [dict() for _ in range(W)]
     totals = [0] * W
     pushes = []
+    per_dest = [[] for _ in range(W)]
     for nbid in expr.block_ids():
         r = owner_of(expr, nbid, W)
         layout[r][nbid] = totals[r]
         totals[r] += -(-math.prod(expr.block_shape(nbid)) * item // 512) * 512
         for obid, sl, dsl in expr.pieces(nbid):
             if owner_of(x, obid, W) == me:
-                pushes.append((obid, sl, r, nbid, dsl))
+                per_dest[r].append((obid, sl, r, nbid, dsl))
+    # All-to-all schedule: consecutive pieces go to DIFFERENT owners, starting with the right-hand
+    # neighbour -- at any moment rank r stores to r+1, r+2, ... and no owner is the target of every
+    # rank at once (in block-id order all ranks would hammer rank 0's NVLink ingress first).
+    rot = [per_dest[(me + 1 + k) % W] for k in range(W)]
+    for i in range(max((len(q) for q in rot), default=0)):
+        for q in rot:
+            if i < len(q):
+                pushes.append(q[i])
     return layout, totals, pushes
 
 
@@ -803,6 +821,31 @@ def _rechunk_push(ex: Executor, expr: TasksRechunk, src: BlockStore, st: BlockSt
     ex._do(bar)                 # every piece has landed before anyone reads a new block
     st.keepalive.extend([launch, slab, bar, windows])
     return st
+
+
+def _interleave_remote_reads(blocks, owners, me: int, W: int, in_items, out_item: int, band_rows: int = 256):
+    """Element-wise blocks whose operands sit in peers' memory are cut into row bands and dealt so
+    that consecutive bands read from DIFFERENT peers, starting with the right-hand neighbour: every
+    NVLink port pair is busy all the time instead of all ranks pulling from rank 0 first."""
+    if len(owners) != len(blocks) or not any(o != me for o in owners):
+        return blocks
+    per_owner = [[] for _ in range(W)]
+    for b, o in zip(blocks, owners):
+        if len(b.shape) != 2 or b.shape[0] <= band_rows or b.out1:
+            per_owner[o].append(b)
+            continue
+        R, Ccols = b.shape
+        for a in range(0, R, band_rows):
+            n = min(band_rows, R - a)
+            ins = [(ptr + a * st[0] * item, st) for (ptr, st), item in zip(b.inputs, in_items)]
+            per_owner[o].append(rt.BlockArgs(shape=(n, Ccols), inputs=ins, out0=b.out0 + a * Ccols * out_item))
+    rot = [per_owner[(me + 1 + k) % W] for k in range(W)]
+    out = []
+    for i in range(max(len(q) for q in rot)):
+        for q in rot:
+            if i < len(q):
+                out.append(q[i])
+    return out
 
 
 def plan_fused_peer_reads(plan: FusedPlan, replicated, W: int):

@@ -189,10 +189,10 @@ class FusedLaunch:
     """Persistent launch table of one fused expression over its resident blocks."""
 
     def __init__(self, program: cg.Program, redop: int, reduce_axes, blocks: list[BlockArgs],
-                 acc_dtype=None, out_is_contiguous: bool = True):
+                 acc_dtype=None, out_is_contiguous: bool = True, keep_order: bool = False):
         if not blocks:
             raise ValueError("FusedLaunch needs at least one block")
-        if len(program.inputs) >= 2 and len(blocks) > 2:
+        if len(program.inputs) >= 2 and len(blocks) > 2 and not keep_order:
             # blocks that read the same input blocks (x.T + x: output (i, j) and (j, i)) become
             # neighbours in the launch, so the second read of a tile can hit the 126 MB L2
             order = sorted(range(len(blocks)), key=lambda i: (tuple(sorted(p for p, _ in blocks[i].inputs)), i))
@@ -390,14 +390,15 @@ def _mirror_pairs(program, layouts, blocks, canons, v):
     return order, [slot[mirror_of[i]] for i in order], len(primaries)
 
 
-def fused_launches(program, redop, reduce_axes, blocks, acc_dtype=None):
+def fused_launches(program, redop, reduce_axes, blocks, acc_dtype=None, keep_order=False):
     """One FusedLaunch per canonical mode present among ``blocks`` (ragged edge blocks whose
     extent-1 dims collapse can need a different kernel shape than the interior blocks)."""
     groups = {}
     for b in blocks:
         c = canonicalize(b.shape, [st for _, st in b.inputs], reduce_axes)
         groups.setdefault(c.mode, []).append(b)
-    return [FusedLaunch(program, redop, reduce_axes, g, acc_dtype=acc_dtype) for g in groups.values()]
+    return [FusedLaunch(program, redop, reduce_axes, g, acc_dtype=acc_dtype, keep_order=keep_order)
+            for g in groups.values()]
 
 
 # ----------------------------------------------------------------------------- AOT helpers
