@@ -23,21 +23,26 @@ def _is_scalar(x) -> bool:
     return isinstance(x, (bool, int, float, np.generic)) or (isinstance(x, np.ndarray) and x.ndim == 0)
 
 
+def unified_chunks(args):
+    """Output chunks of an element-wise op and the chunks every array operand must have for it
+    (``Blockwise.chunks`` -> ``unify_chunks_expr``, ``_blockwise.py:94-98``, ``_expr.py:723-905``).
+    Returns ``(out_chunks, {operand name: target chunks})``; an operand used twice votes once, as in
+    the reference (``seen`` keys, ``_expr.py:783-786``)."""
+    from ._unify import unify
+
+    arrs = {}
+    for a in args:
+        if isinstance(a, ArrayExpr):
+            arrs.setdefault(a._name, a)
+    uniq = list(arrs.values())
+    out, targets = unify([(a.shape, a.chunks, a.dtype.itemsize) for a in uniq])
+    return out, {a._name: t for a, t in zip(uniq, targets)}
+
+
 def broadcast_chunks(args):
-    """Output chunks of an element-wise op over chunk-aligned operands (NumPy right-aligned
-    broadcasting on the block grid; 1-block dims of extent 1 broadcast,
-    ``_blockwise.py:1243 _broadcast_block_id``)."""
-    arrs = [a for a in args if isinstance(a, ArrayExpr)]
-    nd = max(a.ndim for a in arrs)
-    out = []
-    for d in range(nd):
-        cands = [a.chunks[d - (nd - a.ndim)] for a in arrs if d - (nd - a.ndim) >= 0]
-        best = max(cands, key=lambda c: (sum(c), len(c)))
-        for c in cands:
-            if c != best and c != (1,):
-                raise ValueError(f"operands are not chunk-aligned on axis {d}: {c} vs {best}")
-        out.append(best)
-    return tuple(out)
+    """Output chunks of an element-wise op (NumPy right-aligned broadcasting on the block grid; 1-block
+    dims of extent 1 broadcast, ``_blockwise.py:1243 _broadcast_block_id``)."""
+    return unified_chunks(args)[0]
 
 
 class Elemwise(ArrayExpr):
@@ -97,29 +102,10 @@ class Elemwise(ArrayExpr):
         arrs = [a for a in self.args if isinstance(a, ArrayExpr)]
         if len(arrs) < 2:
             return None
-        nd = max(a.ndim for a in arrs)
-        target = []
-        for d in range(nd):
-            cands = [(a, a.chunks[d - (nd - a.ndim)]) for a in arrs
-                     if d - (nd - a.ndim) >= 0 and a.shape[d - (nd - a.ndim)] != 1]
-            if not cands:
-                target.append(None)
-                continue
-            distinct = {c for _, c in cands}
-            if len(distinct) == 1:
-                target.append(None)
-            else:   # policy: follow the operand that moves the most bytes
-                target.append(max(cands, key=lambda ac: ac[0].nbytes)[1])
-        if all(t is None for t in target):
+        _, targets = unified_chunks(self.args)
+        if all(targets[a._name] == a.chunks for a in arrs):
             return None
-
-        def fix(a):
-            off = nd - a.ndim
-            new = tuple(target[d + off] if (target[d + off] is not None and a.shape[d] != 1) else a.chunks[d]
-                        for d in range(a.ndim))
-            return a if new == a.chunks else Rechunk(a, new)
-
-        return self._map_args(fix)
+        return self._map_args(lambda a: a if targets[a._name] == a.chunks else Rechunk(a, targets[a._name]))
 
 
 class Transpose(ArrayExpr):

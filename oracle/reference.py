@@ -607,3 +607,168 @@ def fused_chain_mean_std(xh, chunks, workers=0):
     x = Blocked.from_array(xh, chunks)
     y = elemwise(fused_chain, x, workers=workers)
     return da_mean(y, axis=0, workers=workers), da_std(y, workers=workers)
+
+
+# ----------------------------------------------------------------------------- chunk unification
+# Restatement of ``unify_chunks_expr`` and its helpers (``_expr.py:586-905``,
+# ``_core_utils.py:893-960``) for element-wise operands.  Pinned by tests/golden/unify.json, which
+# tests/golden/generate_unify.py records from the reference's own functions.
+MERGE_COST_RATIO = 4                    # _expr.py:669
+UNIFY_CHUNKS_LIMIT = 512 * 2**20        # dask_array/__init__.py:25 ("512 MiB")
+
+
+def common_blockdim(blockdims):
+    """Finest common refinement of several chunkings of one axis (``_core_utils.py:893-960``)."""
+    blockdims = set(map(tuple, blockdims))
+    if not any(blockdims):
+        return ()
+    multi = {d for d in blockdims if len(d) > 1}
+    if len(multi) == 1:
+        return next(iter(multi))
+    if not multi:
+        return max(blockdims, key=lambda d: d[0])
+    if len({sum(d) for d in multi}) > 1:
+        raise ValueError("Chunks do not add up to same value", blockdims)
+    stacks = [list(d)[::-1] for d in multi]
+    total, done, out = sum(next(iter(multi))), 0, []
+    while done < total:
+        m = min(s[-1] for s in stacks)
+        out.append(m)
+        for s in stacks:
+            s[-1] -= m
+            if s[-1] == 0:
+                s.pop()
+        done += m
+    return tuple(out)
+
+
+def coarse_blockdim(blockdims):
+    """Coarsest chunking when every other one nests inside it, else ``common_blockdim``
+    (``_expr.py:586-660``)."""
+    blockdims = set(map(tuple, blockdims))
+    if not any(blockdims):
+        return ()
+    multi = {d for d in blockdims if len(d) > 1}
+    if not multi:
+        return max(blockdims, key=lambda d: d[0])
+    if len(multi) == 1:
+        return next(iter(multi))
+    if len({sum(d) for d in multi}) > 1:
+        raise ValueError("Chunks do not add up to same value", blockdims)
+    coarsest = min(multi, key=len)
+    edges = set(np.cumsum(coarsest[:-1]).tolist())
+    for d in multi:
+        if d != coarsest and not edges.issubset(set(np.cumsum(d[:-1]).tolist())):
+            return common_blockdim(blockdims)
+    return coarsest
+
+
+def moved_fraction(src, dst):
+    """Fraction of an axis's bytes a rechunk ``src -> dst`` moves when every ``dst`` chunk is
+    assembled where its largest ``src`` piece already lives (``_expr.py:672-720``)."""
+    total = sum(src)
+    if not total or tuple(src) == tuple(dst) or sum(dst) != total:
+        return 0.0
+    moved, i, s0, d0 = 0.0, 0, 0.0, 0.0
+    for t in dst:
+        d1, best = d0 + t, 0.0
+        while True:
+            s1 = s0 + src[i]
+            best = max(best, min(s1, d1) - max(s0, d0))
+            if s1 <= d1 and i + 1 < len(src):
+                i, s0 = i + 1, s1
+            else:
+                break
+        moved += t - best
+        d0 = d1
+    return moved / total
+
+
+def _broadcast_dimensions(pairs, consolidate):
+    """``dask.blockwise.broadcast_dimensions``: per index label the set of operand chunkings, the
+    broadcast sentinel ``(1,)`` dropped when something else is present."""
+    g = {}
+    for chunks, ind in pairs:
+        for j, c in zip(ind, chunks):
+            g.setdefault(j, set()).add(tuple(c))
+    return {j: consolidate(v - {(1,)} if len(v) > 1 else v) for j, v in g.items()}
+
+
+def unify_chunks(operands, policy="auto", limit=UNIFY_CHUNKS_LIMIT):
+    """``unify_chunks_expr`` (``_expr.py:723-905``) for element-wise operands.
+
+    ``operands``: [(shape, chunks, itemsize)], NumPy right-aligned; index labels as
+    ``Elemwise.args`` builds them (``_blockwise.py:985-1001``): axis n of an operand carries label
+    ``ndim - 1 - n``.  Returns ``(chunkss by label, [target chunks per operand], changed)``.
+    """
+    ops = []
+    for shape, chunks, itemsize in operands:
+        nd = len(shape)
+        if nd == 0:
+            ops.append(None)                       # scalars carry no layout (:741)
+            continue
+        ops.append((tuple(shape), tuple(map(tuple, chunks)), tuple(range(nd))[::-1],
+                    float(math.prod(shape) * itemsize), itemsize))
+    live = [o for o in ops if o is not None]
+    inds = [o[2] for o in live]
+    if live and all(i == inds[0] for i in inds) and all(o[1] == live[0][1] for o in live):
+        return dict(zip(inds[0], live[0][1])), [o[1] if o else () for o in ops], False      # :733-734
+    pairs = [(o[1], o[2]) for o in live]
+    consolidate = common_blockdim if policy == "refine" else coarse_blockdim
+    chunkss = _broadcast_dimensions(pairs, consolidate)
+    fine = None
+    if consolidate is coarse_blockdim and policy != "coarse":
+        moved, anchored, layouts, seen = {}, {}, {}, set()
+        for k, o in enumerate(live):
+            shape, chunks, ind, nbytes, _ = o
+            for n, j in enumerate(ind):
+                src, target = chunks[n], chunkss[j]
+                if shape[n] <= 1 or len(src) <= 1:
+                    continue
+                layouts.setdefault(j, []).append((src, nbytes))
+                if src == target:
+                    anchored[j] = anchored.get(j, 0.0) + nbytes
+                elif len(target) < len(src):
+                    moved[j] = moved.get(j, 0.0) + nbytes * moved_fraction(src, target)
+        refused = {j for j, cost in moved.items() if cost > MERGE_COST_RATIO * anchored.get(j, 0.0)}
+        if refused:
+            fine = _broadcast_dimensions(pairs, common_blockdim)
+            chunkss = {j: fine[j] if j in refused else c for j, c in chunkss.items()}
+        for j, lay in layouts.items():                                                         # :815-838
+            if j in anchored and j not in refused:
+                continue
+            target = chunkss[j]
+            if any(src == target for src, _ in lay):
+                continue
+            cands = {}
+            for src, nb in lay:
+                cands[src] = cands.get(src, 0.0) + nb
+            feasible = []
+            for layout, anchor in cands.items():
+                cost = sum(nb * moved_fraction(src, layout) for src, nb in lay if src != layout)
+                if cost <= MERGE_COST_RATIO * anchor:
+                    feasible.append((len(layout), cost, -anchor, layout))
+            if feasible:
+                chunkss[j] = min(feasible)[3]
+    if limit and consolidate is coarse_blockdim:                                               # :840-872
+        worst = 0
+        for shape, chunks, ind, _, itemsize in live:
+            target = itemsize * math.prod(max(chunkss[j]) for n, j in enumerate(ind) if shape[n] > 1)
+            current = itemsize * math.prod(max(c) for n, c in enumerate(chunks) if shape[n] > 1)
+            if target > current:
+                worst = max(worst, target)
+        if worst > limit:
+            if fine is None:
+                fine = _broadcast_dimensions(pairs, common_blockdim)
+            coarsened = {j for j, c in chunkss.items() if len(fine[j]) > len(c)}
+            chunkss = {j: fine[j] if j in coarsened else c for j, c in chunkss.items()}
+    out, changed = [], False
+    for o in ops:
+        if o is None:
+            out.append(())
+            continue
+        shape, chunks, ind, _, _ = o
+        tgt = tuple(chunkss[j] if (shape[n] > 1 or shape[n] == 0) else (shape[n],) for n, j in enumerate(ind))
+        changed |= tgt != chunks
+        out.append(tgt)
+    return chunkss, out, changed

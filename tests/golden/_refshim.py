@@ -151,7 +151,42 @@ def merge(*dicts, **kw):
     return out
 
 
+def partition(n, seq):
+    it = iter(seq)
+    return zip(*([it] * n))
+
+
+def groupby(key, seq):
+    fn = key if callable(key) else (lambda x, _k=key: x[_k])
+    out = {}
+    for x in seq:
+        out.setdefault(fn(x), []).append(x)
+    return out
+
+
+def valmap(func, d):
+    return {k: func(v) for k, v in d.items()}
+
+
+def broadcast_dimensions(argpairs, numblocks, sentinels=(1, (1,)), consolidate=None):
+    """dask.blockwise.broadcast_dimensions (dask 2025.12): per index label, the set of block
+    dimensions of every operand carrying it, minus the broadcast sentinels, then consolidated."""
+    pairs = [(a, ind) for a, ind in argpairs if ind is not None]
+    g = {}
+    for name, inds in pairs:
+        if name in numblocks:
+            for i, d in zip(inds, numblocks[name]):
+                g.setdefault(i, set()).add(d)
+    g2 = {k: (v - set(sentinels) if len(v) > 1 else v) for k, v in g.items()}
+    if consolidate:
+        return valmap(consolidate, g2)
+    if g2 and not set(map(len, g2.values())) == {1}:
+        raise ValueError(f"Shapes do not align {g}")
+    return valmap(first, g2)
+
+
 _TOOLZ = dict(
+    partition=partition, groupby=groupby, valmap=valmap,
     partition_all=partition_all, compose=compose, get=get, accumulate=accumulate,
     pluck=pluck, first=first, concat=concat, frequencies=frequencies, curry=curry,
     unique=unique, merge=merge, identity=lambda x: x,
@@ -299,6 +334,8 @@ class _Config:
         "array.rechunk.method": "tasks",
         "array.slicing.split-large-chunks": None,
         "array.optimize-graph": True,
+        "array.unify-chunks-policy": "auto",      # dask_array/__init__.py:14-29
+        "array.unify-chunks-limit": "512 MiB",
     }
 
     def get(self, key, default="__no__default__"):
@@ -385,7 +422,7 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         elif name == "dask.core":
             attrs = {"flatten": flatten}
         elif name == "dask.blockwise":
-            attrs = {"lol_tuples": lol_tuples}
+            attrs = {"lol_tuples": lol_tuples, "broadcast_dimensions": broadcast_dimensions}
         elif name == "dask.base":
             attrs = {"is_dask_collection": lambda x: False, "tokenize": lambda *a, **k: "token"}
         elif name == "dask.tokenize":

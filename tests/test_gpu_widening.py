@@ -64,3 +64,23 @@ def test_nan_reducers(da, dtype):
     assert da.nansum(i).compute() == ih.sum() and np.array_equal(da.nanmax(i, axis=0).compute(), ih.max(axis=0))
     assert np.array_equal(i.prod(axis=1).compute(), ih.prod(axis=1)) and i.any().compute() == ih.any()
     assert np.array_equal((i > 0).all(axis=0).compute(), (ih > 0).all(axis=0))
+
+
+def test_elementwise_over_mismatched_chunks_unifies_like_the_reference():
+    """operands on different block grids are rechunked to the reference's unified
+    layout (tests/golden/unify.json) and fused; values bit-exact."""
+    import dask_array_b200 as da
+    rng = np.random.default_rng(11)
+    ah, bh, vh = rng.random((1000, 700)), rng.random((1000, 700)), rng.random(700)
+    a = da.from_array(ah, chunks=((300, 300, 300, 100), (256, 256, 188)))
+    b = da.from_array(bh, chunks=((600, 400), (700,)))
+    v = da.from_array(vh, chunks=100)
+    y = a * 2 + b - v
+    assert y.chunks[0] == (600, 400)                       # golden case "ragged_nested"
+    assert np.array_equal(y.compute(), ah * 2 + bh - vh)
+    xh = rng.integers(0, 100, size=400).astype(np.int64)
+    x = da.from_array(xh, chunks=100)
+    shifted = da.concatenate([x[350:], x[:350]])            # the roll pattern: (50, 100, 100, 100, 50)
+    z = x + shifted
+    assert z.chunks == ((100,) * 4,)                        # golden case "roll_shift"
+    assert np.array_equal(z.compute(), xh + np.roll(xh, 50))

@@ -192,3 +192,30 @@ def test_oracle_end_to_end_matches_numpy():
     y = ref.elemwise(np.add, ones, ref.transpose(ones))
     assert ref.da_sum(y) == 2_000_000.0
     assert np.array_equal(ref.getitem_slices(y, (slice(0, 100), slice(0, 100))).to_array(), np.full((100, 100), 2.0))
+
+
+# ----------------------------------------------------------------------------- chunk unification
+def _unify_golden():
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "unify.json")) as f:
+        return json.load(f)
+
+
+def test_blockdim_helpers_match_reference():
+    g = _unify_golden()
+    for sets, want in g["coarse_blockdim"]:
+        assert list(ref.coarse_blockdim([tuple(s) for s in sets])) == want, sets
+    for sets, want in g["common_blockdim"]:
+        assert list(ref.common_blockdim([tuple(s) for s in sets])) == want, sets
+    for src, dst, want in g["moved_fraction"]:
+        assert ref.moved_fraction(tuple(src), tuple(dst)) == want, (src, dst)
+
+
+@pytest.mark.parametrize("case", sorted(_unify_golden()["unify"]))
+def test_unify_chunks_matches_reference(case):
+    rec = _unify_golden()["unify"][case]
+    operands = [(tuple(s), tuple(map(tuple, ch)), np.dtype(d).itemsize) for s, ch, d in rec["operands"]]
+    chunkss, targets, changed = ref.unify_chunks(operands)
+    assert {str(k): list(v) for k, v in chunkss.items()} == rec["chunkss"]
+    assert [[list(c) for c in t] for t in targets] == rec["result_chunks"]
+    assert changed == rec["changed"]
