@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 
-CODEGEN_VERSION = "19"     # part of every kernel's cache key: bump when generated code changes
+CODEGEN_VERSION = "20"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
@@ -464,7 +464,8 @@ def _emit(name, args, out, kw) -> str:
 
 
 # ----------------------------------------------------------------------------- kernels
-_MODE_NAME = {_lib.MODE_EW: "B2M_EW", _lib.MODE_R: "B2M_R", _lib.MODE_C: "B2M_C", _lib.MODE_RC: "B2M_RC"}
+_MODE_NAME = {_lib.MODE_EW: "B2M_EW", _lib.MODE_R: "B2M_R", _lib.MODE_C: "B2M_C", _lib.MODE_RC: "B2M_RC",
+              _lib.MODE_SR: "B2M_SR", _lib.MODE_SC: "B2M_SC"}
 _RED_NAME = {
     _lib.RED_NONE: "B2R_NONE", _lib.RED_SUM: "B2R_SUM", _lib.RED_MIN: "B2R_MIN", _lib.RED_MAX: "B2R_MAX",
     _lib.RED_ARGMIN: "B2R_ARGMIN", _lib.RED_ARGMAX: "B2R_ARGMAX", _lib.RED_MOMENT: "B2R_MOMENT",
@@ -593,6 +594,11 @@ def render(program: Program, spec: KernelSpec) -> str:
         run = f"b2_run_ewt_sym<Chain, B2_V, {spec.rpt}>(blocks, nblocks, sc);"
     elif ewt:
         run = f"b2_run_ewt<Chain, B2_V, {spec.tx}, {spec.ty}>(blocks, nblocks, sc);"
+    elif spec.mode in (_lib.MODE_SR, _lib.MODE_SC):
+        if fast:
+            raise NotImplementedError("cumulative scans take exact element-wise chains only")
+        run = (f"b2_run_scan<Chain, {_MODE_NAME[spec.mode]}, {_RED_NAME[spec.redop]}, B2_V, {spec.tx}, {spec.ty}, "
+               f"{spec.rpt}, {spec.unroll}, {acc}>(blocks, nblocks, sc);")
     else:
         run = (f"b2_run<Chain, {_MODE_NAME[spec.mode]}, {_RED_NAME[spec.redop]}, B2_V, {spec.tx}, {spec.ty}, "
                f"{spec.rpt}, {spec.unroll}, {acc}>(blocks, nblocks, sc);")

@@ -256,6 +256,12 @@ class Array:
     def argmax(self, axis=None, keepdims=False, split_every=None):
         return self._reduce("argmax", axis, keepdims, None, split_every)
 
+    def cumsum(self, axis=None, dtype=None, out=None, method="sequential"):
+        return cumsum(self, axis=axis, dtype=dtype, out=out, method=method)
+
+    def cumprod(self, axis=None, dtype=None, out=None, method="sequential"):
+        return cumprod(self, axis=axis, dtype=dtype, out=out, method=method)
+
 
 class Compiled:
     """Computed expression(s) plus the replayable launch tape.  Several arrays compiled
@@ -288,6 +294,47 @@ class Compiled:
         for st in self.executor.results.values():
             out.extend(k for k in st.keepalive if isinstance(k, FusedLaunch))
         return out
+
+
+# ----------------------------------------------------------------------------- cumulative scans
+def _cumulative(kind, x, axis, dtype, out, method, nan=False):
+    """``_cumreduction_expr`` (``reductions/_cumulative.py:425-448``).  ``method`` ("sequential" |
+    "blelloch") selects between two task-graph shapes in the reference; both give the same values and
+    the B200 path has one implementation (reduce -> scan of the block totals -> scan with carry)."""
+    from ._reductions import CumReduction
+
+    if out is not None:
+        raise NotImplementedError("out= is not supported")
+    if method not in ("sequential", "blelloch"):
+        raise ValueError("Invalid method for cumulative reduction: choose 'sequential' or 'blelloch'")
+    x = asarray(x)
+    if axis is None:
+        if x.ndim > 1:
+            raise NotImplementedError("cumulative reduction with axis=None flattens the array first "
+                                      "(``_prepare_cumulative`` :77-97): reshape is outside the B200 hot path")
+        axis = 0
+    axis = validate_axis(axis, x.ndim)[0]
+    return Array(CumReduction(x.expr, kind, axis, None if dtype is None else np.dtype(dtype).name, bool(nan)))
+
+
+def cumsum(x, axis=None, dtype=None, out=None, method="sequential"):
+    """``cumsum`` (``reductions/_cumulative.py:451-484``)."""
+    return _cumulative("cumsum", x, axis, dtype, out, method)
+
+
+def cumprod(x, axis=None, dtype=None, out=None, method="sequential"):
+    """``cumprod`` (``reductions/_cumulative.py:487-520``)."""
+    return _cumulative("cumprod", x, axis, dtype, out, method)
+
+
+def nancumsum(x, axis, dtype=None, out=None, *, method="sequential"):
+    """``nancumsum`` (``reductions/_cumulative.py:523-557``)."""
+    return _cumulative("cumsum", x, axis, dtype, out, method, nan=True)
+
+
+def nancumprod(x, axis, dtype=None, out=None, *, method="sequential"):
+    """``nancumprod`` (``reductions/_cumulative.py:560-594``)."""
+    return _cumulative("cumprod", x, axis, dtype, out, method, nan=True)
 
 
 # ----------------------------------------------------------------------------- NaN-aware reducers

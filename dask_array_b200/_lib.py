@@ -18,7 +18,7 @@ B2_MAX_IN = 6
 B2_MAX_ND = 4
 
 # enums (include/b200da.h)
-MODE_EW, MODE_R, MODE_C, MODE_RC = 0, 1, 2, 3
+MODE_EW, MODE_R, MODE_C, MODE_RC, MODE_SR, MODE_SC = 0, 1, 2, 3, 4, 5
 RED_NONE, RED_SUM, RED_MIN, RED_MAX, RED_ARGMIN, RED_ARGMAX, RED_MOMENT, RED_PROD, RED_ANY, RED_ALL = range(10)
 RED_NANMIN, RED_NANMAX = 10, 11
 POST_NONE, POST_MEAN, POST_VAR, POST_STD = range(4)

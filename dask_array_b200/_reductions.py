@@ -150,6 +150,29 @@ class ArgChunk(ArrayExpr):
         return f"ArgChunk({self.operand('kind')}, axis={self.operand('axis')})"
 
 
+class CumReduction(ArrayExpr):
+    """``CumReduction`` (``reductions/_cumulative.py:100-265``; ``cumsum`` :451, ``cumprod`` :487,
+    ``nancumsum`` :523, ``nancumprod`` :560): per-block ``np.cumsum`` plus the running total of the
+    preceding blocks along ``axis``.  Not a Blockwise (never fused).  ``kind``: "cumsum" | "cumprod";
+    ``nan``: NaNs count as the identity (the ``chunk.nancumsum`` variants)."""
+
+    _parameters = ["array", "kind", "axis", "dtype_", "nan"]
+
+    @property
+    def chunks(self):
+        return self.operand("array").chunks
+
+    @property
+    def dtype(self):
+        if self.operand("dtype_") is not None:
+            return np.dtype(self.operand("dtype_"))
+        fn = np.cumsum if self.operand("kind") == "cumsum" else np.cumprod
+        return fn(np.ones((0,), dtype=self.operand("array").dtype)).dtype        # :115-119
+
+    def _tree_label(self):
+        return f"CumReduction({'nan' if self.operand('nan') else ''}{self.operand('kind')}, axis={self.operand('axis')})"
+
+
 class PartialReduce(ArrayExpr):
     """One level of the tree (``PartialReduce`` :900-983): every output block folds a group of
     ``split_every`` input partials in ``lol_tuples`` order."""

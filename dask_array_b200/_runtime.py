@@ -174,6 +174,44 @@ def canonicalize(shape, in_strides, reduce_axes) -> Canon:
         "dimension groups: not supported by the B200 kernels yet")
 
 
+def canonicalize_scan(shape, in_strides, axis) -> Canon:
+    """(B, R, C) view of a block for a cumulative scan along ``axis`` (``_cumulative.py:100-265``):
+    dims before the axis -> B (and R when the axis is innermost), the axis -> R (mode SR, dims after it
+    -> C) or C (mode SC).  The output is written (B, R, C)-contiguous, i.e. in the block's own order."""
+    nd = len(shape)
+    axis %= nd
+    groups = []      # [n, kind, strides]; kinds: "b" before, "x" the axis, "a" after
+    for d in range(nd):
+        if shape[d] == 1 and d != axis:
+            continue
+        kind = "x" if d == axis else ("b" if d < axis else "a")
+        st = [int(s[d]) for s in in_strides]
+        n = int(shape[d])
+        if groups and groups[-1][1] == kind and kind != "x" and all(p == q * n for p, q in zip(groups[-1][2], st)):
+            groups[-1][0] *= n
+            groups[-1][2] = st
+        else:
+            groups.append([n, kind, st])
+    nin = len(in_strides)
+    one = [1, "k", [0] * nin]
+    before = [g for g in groups if g[1] == "b"]
+    after = [g for g in groups if g[1] == "a"]
+    x = next(g for g in groups if g[1] == "x")
+
+    def pack(b, r, c, mode):
+        return Canon(mode, b[0], r[0], c[0], [(b[2][k], r[2][k], c[2][k]) for k in range(nin)], [])
+
+    if after:
+        if len(after) > 1 or len(before) > 1:
+            raise NotImplementedError("cumulative scan over a block whose kept dims are not contiguous")
+        return pack(before[0] if before else one, x, after[0], _lib.MODE_SR)
+    if len(before) > 2:
+        raise NotImplementedError("cumulative scan over a block whose kept dims are not contiguous")
+    while len(before) < 2:
+        before.insert(0, one)
+    return pack(before[0], before[1], x, _lib.MODE_SC)
+
+
 @dataclass
 class BlockArgs:
     """Arguments of one block of a fused launch (all device pointers are ints)."""
@@ -189,7 +227,7 @@ class FusedLaunch:
     """Persistent launch table of one fused expression over its resident blocks."""
 
     def __init__(self, program: cg.Program, redop: int, reduce_axes, blocks: list[BlockArgs],
-                 acc_dtype=None, out_is_contiguous: bool = True, keep_order: bool = False):
+                 acc_dtype=None, out_is_contiguous: bool = True, keep_order: bool = False, scan_axis=None):
         if not blocks:
             raise ValueError("FusedLaunch needs at least one block")
         if len(program.inputs) >= 2 and len(blocks) > 2 and not keep_order:
@@ -200,7 +238,10 @@ class FusedLaunch:
         self.program = program
         self.redop = redop
         nin = len(program.inputs)
-        canons = [canonicalize(b.shape, [st for _, st in b.inputs], reduce_axes) for b in blocks]
+        if scan_axis is not None:
+            canons = [canonicalize_scan(b.shape, [st for _, st in b.inputs], scan_axis) for b in blocks]
+        else:
+            canons = [canonicalize(b.shape, [st for _, st in b.inputs], reduce_axes) for b in blocks]
         modes = {c.mode for c in canons}
         if len(modes) != 1:
             raise NotImplementedError(f"blocks of one launch canonicalise to different modes {modes}")
@@ -224,7 +265,9 @@ class FusedLaunch:
                     layouts[k] = "T"
                     staged += tile_bytes
                     ewt = True
-        sizes = [d.itemsize for d in program.inputs] + ([out_dt.itemsize] if self.mode == _lib.MODE_EW else [])
+        scan = self.mode in (_lib.MODE_SR, _lib.MODE_SC)
+        sizes = [d.itemsize for d in program.inputs] + ([out_dt.itemsize] if self.mode == _lib.MODE_EW else []) \
+            + ([acc_dtype.itemsize] if scan else [])
         vmax = max(1, 16 // max(sizes or [out_dt.itemsize]))
         if self.mode == _lib.MODE_R:
             # the row-lane fold stages 256 x V partials in (static) shared memory: keep <= 32 KiB
@@ -247,6 +290,8 @@ class FusedLaunch:
                             return False
                 if self.mode == _lib.MODE_EW and b.out0 % (v * out_dt.itemsize):
                     return False
+                if scan and b.out0 % min(16, v * acc_dtype.itemsize):
+                    return False
                 for n, sts in c.lead:
                     if any(layouts[k] == "V" and s % v for k, s in enumerate(sts)):
                         return False
@@ -263,6 +308,12 @@ class FusedLaunch:
         geo = cg.choose_geometry(program, self.mode, shapes, v)
         if ewt:      # 64 x 64 output tiles, 256 threads
             geo = dict(vec=v, tx=64 // v, ty=256 // (64 // v), rpt=64, unroll=1)
+        if self.mode == _lib.MODE_SR:     # a thread per column strip walks every row of its block
+            cmax = max(c.C for c in canons)
+            geo = dict(vec=v, tx=min(128, max(32, cg._pow2_ceil(-(-cmax // v)))), ty=1,
+                       rpt=max(c.R for c in canons), unroll=8)
+        elif self.mode == _lib.MODE_SC:   # a warp per row
+            geo = dict(vec=v, tx=32, ty=8, rpt=8, unroll=4)
         variant, mirror, n_primary = "", None, len(blocks)
         if ewt:
             pairing = _mirror_pairs(program, layouts, blocks, canons, v)
@@ -284,7 +335,8 @@ class FusedLaunch:
             lead_elems = math.prod(n for n, _ in c.lead) if c.lead else 1
             inner = c.B * c.R * c.C
             # output elements produced per descriptor and their size (reductions)
-            out_per = {_lib.MODE_EW: inner, _lib.MODE_C: c.B * c.R, _lib.MODE_R: c.B * c.C, _lib.MODE_RC: c.B}[self.mode]
+            out_per = {_lib.MODE_EW: inner, _lib.MODE_C: c.B * c.R, _lib.MODE_R: c.B * c.C, _lib.MODE_RC: c.B,
+                       _lib.MODE_SR: inner, _lib.MODE_SC: inner}[self.mode]
             if self.mode == _lib.MODE_EW or redop in (_lib.RED_MIN, _lib.RED_MAX, _lib.RED_NANMIN, _lib.RED_NANMAX, _lib.RED_ARGMIN, _lib.RED_ARGMAX):
                 out_item = out_dt.itemsize
             elif redop == _lib.RED_MOMENT:
@@ -388,6 +440,16 @@ def _mirror_pairs(program, layouts, blocks, canons, v):
     order = primaries + secondaries
     slot = {i: s for s, i in enumerate(order)}
     return order, [slot[mirror_of[i]] for i in order], len(primaries)
+
+
+def scan_launches(program, redop, axis, blocks, acc_dtype):
+    """Cumulative-scan launches (one per canonical mode among ``blocks``); BlockArgs.out1 = carry."""
+    groups = {}
+    for b in blocks:
+        c = canonicalize_scan(b.shape, [st for _, st in b.inputs], axis)
+        groups.setdefault(c.mode, []).append(b)
+    return [FusedLaunch(program, redop, (), g, acc_dtype=acc_dtype, keep_order=True, scan_axis=axis)
+            for g in groups.values()]
 
 
 def fused_launches(program, redop, reduce_axes, blocks, acc_dtype=None, keep_order=False):

@@ -212,7 +212,7 @@ extern "C" int b2_fused_plan(const b2_kernel* k, b2_block* blocks, int nblocks,
             return fail(B2_ERR_INVALID, "block %d has an empty extent (%lld,%lld,%lld): skip it on the host",
                         i, (long long)b.B, (long long)b.R, (long long)b.C);
         b.tiles_r = cdiv(b.R, g.rpt);
-        b.tiles_c = (g.mode == B2_MODE_C) ? 1 : cdiv(b.C, tile_cols);
+        b.tiles_c = (g.mode == B2_MODE_C || g.mode == B2_MODE_SC) ? 1 : cdiv(b.C, tile_cols);
         b.tile_begin = tiles;
         tiles += b.B * b.tiles_r * b.tiles_c;
         ctr_off[i] = ncounters;

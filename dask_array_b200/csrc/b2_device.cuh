@@ -53,7 +53,7 @@ struct B2Scalars {
     i64 i[8];
 };
 
-enum { B2M_EW = 0, B2M_R = 1, B2M_C = 2, B2M_RC = 3 };
+enum { B2M_EW = 0, B2M_R = 1, B2M_C = 2, B2M_RC = 3, B2M_SR = 4, B2M_SC = 5 };
 enum { B2R_NONE = 0, B2R_SUM = 1, B2R_MIN = 2, B2R_MAX = 3, B2R_ARGMIN = 4, B2R_ARGMAX = 5,
        B2R_MOMENT = 6, B2R_PROD = 7, B2R_ANY = 8, B2R_ALL = 9, B2R_NANMIN = 10, B2R_NANMAX = 11 };
 
@@ -1167,6 +1167,136 @@ __device__ __forceinline__ void b2_run_ewt_sym(const B2Block* __restrict__ block
                 Chain::sym_get(tiles[0], lc * TT + (((lr / V) ^ (tx & 7)) * V) + lr % V, gB[m]);
                 Chain::compute_slow(gB[m], sc, o);
                 b2_store_vec<T, V>(outp + (i64)lr * R, o);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ cumulative scans
+// cumsum / cumprod (reductions/_cumulative.py:100-265, CumReduction): the reference scans every block
+// with np.cumsum, walks the blocks along the axis carrying the running total (`extra`) and adds it
+// to each block in a third pass -- 4 N bytes plus temporaries.  Here the per-segment totals come
+// from the ordinary reduction kernels (1 read), their scan is a tiny launch of THIS kernel, and one
+// pass then writes  out = carry (+|*) local_scan(x)  -- 3 N bytes in total.
+//   mode SR: scan along rows; a thread owns V columns and walks all R rows (running total in
+//            registers, U loads in flight);
+//   mode SC: scan along the contiguous dim; one warp per row walks it in steps of 32*V elements:
+//            lane-local scan, warp shuffle scan of the lane totals, running total in a register.
+template <int REDOP, typename ACC> struct B2ScanOp {
+    __device__ __forceinline__ static ACC ident() { return REDOP == B2R_PROD ? (ACC)1 : (ACC)0; }
+    __device__ __forceinline__ static ACC op(ACC a, ACC b) { return REDOP == B2R_PROD ? (ACC)(a * b) : (ACC)(a + b); }
+};
+template <typename ACC, int V> struct B2ScanState { ACC run[V]; };
+
+template <typename Chain, int MODE, int REDOP, int V, int TX, int TY, int RPT, int U, typename ACC>
+__device__ __forceinline__ void b2_run_scan(const B2Block* __restrict__ blocks, int nblocks, const B2Scalars& sc) {
+    typedef typename Chain::out_t T;
+    typedef B2ScanOp<REDOP, ACC> OP;
+    static_assert(!Chain::HAS_SLOW, "scan kernels take exact chains only");
+    static_assert(sizeof(ACC) == 4 || sizeof(ACC) == 8, "scan accumulators are 32 or 64 bit");
+    constexpr int NT = TX * TY;
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    __shared__ B2Block sblk;
+    {
+        const int bi = b2_find_block(blocks, nblocks, (i64)blockIdx.x);
+        const int nw = (int)(sizeof(B2Block) / 4);
+        const u32* src = reinterpret_cast<const u32*>(blocks + bi);
+        u32* dst = reinterpret_cast<u32*>(&sblk);
+        for (int i = tid; i < nw; i += NT) dst[i] = src[i];
+        __syncthreads();
+    }
+    const B2Block& blk = sblk;
+    i64 t = (i64)blockIdx.x - blk.tile_begin;
+    const i64 tc = t % blk.tiles_c; t /= blk.tiles_c;
+    const i64 tr = t % blk.tiles_r; t /= blk.tiles_r;
+    const i64 b = t;
+    const i64 R = blk.R, C = blk.C;
+    const ACC* const carry = (const ACC*)blk.out1;
+
+    if constexpr (MODE == B2M_SR) {
+        static_assert(TY == 1, "row scans: one thread per column strip");
+        const i64 c = (tc * TX + tx) * V;
+        if (c >= C) return;
+        ACC cv[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) cv[v] = carry ? carry[b * C + c + v] : OP::ident();
+        B2ScanState<ACC, V> st;
+#pragma unroll
+        for (int v = 0; v < V; ++v) st.run[v] = OP::ident();
+        typename Chain::Ptrs P;
+        Chain::setup_rows(blk, b, 0, c, 1, P);
+        ACC* const outp = (ACC*)blk.out0 + (b * R) * C + c;
+        const bool has = carry != nullptr;
+        b2_stream<Chain, V, U>(P, (int)R, sc, st,
+            [&](B2ScanState<ACC, V>& s, int k, const T (&o)[V]) {
+                ACC w[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    s.run[v] = (k == 0) ? b2_cast<ACC>(o[v]) : OP::op(s.run[v], b2_cast<ACC>(o[v]));
+                    w[v] = has ? OP::op(cv[v], s.run[v]) : s.run[v];
+                }
+                b2_store_vec<ACC, V>(outp + (i64)k * C, w);
+            });
+    } else {
+        static_assert(MODE == B2M_SC && TX == 32, "column scans: one warp per row");
+        const int lane = tx;
+        const i64 r0 = tr * RPT;
+        const i64 rend = (r0 + RPT < R) ? (r0 + RPT) : R;
+        const i64 step = (i64)TX * V;
+        const int nfull = (int)(C / step);                 // steps every lane takes
+        const i64 ctail = (i64)nfull * step + (i64)lane * V; // this lane's columns in the ragged last step
+        for (i64 r = r0 + ty; r < rend; r += TY) {         // a warp owns its row: uniform control flow
+            const ACC cv = carry ? carry[b * R + r] : OP::ident();
+            const bool has = carry != nullptr;
+            ACC* const outp = (ACC*)blk.out0 + (b * R + r) * C + (i64)lane * V;
+            B2ScanState<ACC, 1> st;
+            st.run[0] = OP::ident();
+            bool first = true;
+            auto stepfn = [&](B2ScanState<ACC, 1>& s, i64 k, const T (&o)[V], bool valid) {
+                ACC w[V];
+                w[0] = valid ? b2_cast<ACC>(o[0]) : OP::ident();
+#pragma unroll
+                for (int v = 1; v < V; ++v) w[v] = valid ? OP::op(w[v - 1], b2_cast<ACC>(o[v])) : OP::ident();
+                ACC inc = w[V - 1];
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const ACC up = __shfl_up_sync(0xffffffffu, inc, off);
+                    if (lane >= off) inc = OP::op(up, inc);
+                }
+                ACC excl = __shfl_up_sync(0xffffffffu, inc, 1);
+                const ACC total = __shfl_sync(0xffffffffu, inc, 31);
+                // prefix of everything before this lane's chunk: previous steps, then the lanes to the left
+                const bool have_base = !first || lane > 0;
+                ACC base = first ? excl : (lane > 0 ? OP::op(s.run[0], excl) : s.run[0]);
+                if (valid) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        ACC x = have_base ? OP::op(base, w[v]) : w[v];
+                        w[v] = has ? OP::op(cv, x) : x;
+                    }
+                    b2_store_vec<ACC, V>(outp + k * step, w);
+                }
+                s.run[0] = first ? total : OP::op(s.run[0], total);
+                first = false;
+            };
+            if (nfull > 0) {
+                typename Chain::Ptrs P;
+                Chain::setup_cols(blk, b, r, (i64)lane * V, step, P);
+                b2_stream<Chain, V, U>(P, nfull, sc, st,
+                    [&](B2ScanState<ACC, 1>& s, int k, const T (&o)[V]) { stepfn(s, (i64)k, o, true); });
+            }
+            if ((i64)nfull * step < C) {
+                const bool valid = ctail < C;
+                T o[V];
+                if (valid) {
+                    typename Chain::Ptrs P;
+                    typename Chain::Regs g;
+                    Chain::setup_cols(blk, b, r, ctail, step, P);
+                    Chain::load(P, 0, g);
+                    Chain::compute_slow(g, sc, o);
+                }
+                stepfn(st, (i64)nfull, o, valid);
             }
         }
     }

@@ -66,7 +66,11 @@ typedef enum b2_redmode {
     B2_MODE_EW = 0,   /* element-wise, full (B,R,C) output                              */
     B2_MODE_R = 1,    /* reduce rows   -> (B, C)   e.g. x.sum(axis=0) of a 2-D block      */
     B2_MODE_C = 2,    /* reduce cols   -> (B, R)   e.g. x.argmax(axis=1)                  */
-    B2_MODE_RC = 3    /* reduce both   -> (B,)     e.g. x.std() chunk step               */
+    B2_MODE_RC = 3,   /* reduce both   -> (B,)     e.g. x.std() chunk step               */
+    /* cumulative scans (reductions/_cumulative.py:100-265 CumReduction): full (B,R,C) output of the
+     * accumulator type; `out1` = carry of the preceding blocks (NULL for the first block)          */
+    B2_MODE_SR = 4,   /* scan along rows, columns kept: carry[b*C + c]   e.g. x.cumsum(axis=0)   */
+    B2_MODE_SC = 5    /* scan along columns, rows kept:  carry[b*R + r]   e.g. x.cumsum(axis=1)   */
 } b2_redmode;
 
 /* what the last level of a tree reduction applies after combining

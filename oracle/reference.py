@@ -772,3 +772,40 @@ def unify_chunks(operands, policy="auto", limit=UNIFY_CHUNKS_LIMIT):
         changed |= tgt != chunks
         out.append(tgt)
     return chunkss, out, changed
+
+
+# ----------------------------------------------------------------------------- cumulative scans
+def da_cumulative(x, axis, kind="cumsum", nan=False, dtype=None):
+    """``CumReduction._layer`` (``reductions/_cumulative.py:174-264``, sequential method): scan every
+    block (``np.cumsum`` / ``np.cumprod`` or their nan variants, ``_chunk.py`` nancumsum/nancumprod),
+    then walk the blocks along ``axis``: ``extra_i = extra_{i-1} (+|*) last hyperplane of block i-1``
+    (identity for an empty block, ``_cum_tail`` :28-39) and ``result_i = extra_i (+|*) scanned_i``;
+    the first block is its own scan.  Pinned bit for bit by tests/golden/cumulative.npz."""
+    func = {("cumsum", False): np.cumsum, ("cumsum", True): np.nancumsum,
+            ("cumprod", False): np.cumprod, ("cumprod", True): np.nancumprod}[(kind, bool(nan))]
+    binop = np.add if kind == "cumsum" else np.multiply
+    ident = 0 if kind == "cumsum" else 1
+    any_block = next(iter(x.blocks.values()))
+    dtype = np.dtype(dtype) if dtype is not None else func(np.ones((0,), dtype=any_block.dtype), axis=0).dtype
+    nb = x.numblocks
+    out = {}
+    tail = (slice(None),) * axis + (slice(-1, None),)
+    for cid in itertools.product(*[range(n) if d != axis else [0] for d, n in enumerate(nb)]):
+        extra = None
+        prev = None
+        for i in range(nb[axis]):
+            bid = cid[:axis] + (i,) + cid[axis + 1:]
+            scanned = func(x.blocks[bid], axis=axis, dtype=dtype)
+            if i == 0:
+                shape = tuple(1 if d == axis else n for d, n in enumerate(scanned.shape))
+                extra = np.full(shape, ident, dtype=dtype)
+                out[bid] = scanned
+            else:
+                if prev.shape[axis] == 0:
+                    t = np.full(tuple(1 if d == axis else n for d, n in enumerate(prev.shape)), ident, dtype=prev.dtype)
+                else:
+                    t = prev[tail]
+                extra = binop(extra, t)
+                out[bid] = binop(extra, scanned)
+            prev = scanned
+    return Blocked(out, x.chunks)

@@ -219,3 +219,18 @@ def test_unify_chunks_matches_reference(case):
     assert {str(k): list(v) for k, v in chunkss.items()} == rec["chunkss"]
     assert [[list(c) for c in t] for t in targets] == rec["result_chunks"]
     assert changed == rec["changed"]
+
+
+# ----------------------------------------------------------------------------- cumulative scans
+def _cum_golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "cumulative.npz"))
+
+
+@pytest.mark.parametrize("case", sorted({k.split("/")[0] for k in _cum_golden().files}))
+def test_cumulative_matches_reference_graph(case):
+    g = _cum_golden()
+    chunks, axis, kind, nan = eval(str(g[case + "/meta"][0]))
+    xh, want = g[case + "/x"], g[case + "/result"]
+    got = ref.da_cumulative(ref.Blocked.from_array(xh, chunks), axis, kind, nan).to_array()
+    assert got.dtype == want.dtype
+    assert np.array_equal(got, want, equal_nan=True)
