@@ -274,6 +274,24 @@ def run_other(args):
                               "launches_per_replay": (_lib.launch_count() - n0) / args.steps,
                               "result": float(np.asarray(val).ravel()[0]), "n_gpus": 1}))
         return
+    if args.config == "cum":
+        # cumulative scans.  Algorithmic bytes: read N + write N (the kernels move 3 N:
+        # the per-segment totals are a separate read pass).
+        n, cb = 32768, 4096
+        base = np.random.default_rng(0).random((cb, cb), dtype=np.float32)
+        x = da.from_host_blocks(lambda bid: base, (n, n), (cb, cb), np.float32, token="cum-f4").persist()
+        for axis in (0, 1):
+            step = da.compile(x.cumsum(axis=axis))
+            timed(step, 2 * n * n * 4, f"cum: fp32 (32768,32768) chunks 4096^2 cumsum(axis={axis}) (2N bytes; 3N moved)",
+                  {"dtype": "f32"})
+            del step
+        del x
+        m = 1 << 28
+        vb = np.random.default_rng(1).random(1 << 24)
+        v = da.from_host_blocks(lambda bid: vb, (m,), (1 << 24,), np.float64, token="cum-f8").persist()
+        step = da.compile(v.cumsum())
+        timed(step, 2 * m * 8, "cum: fp64 vector 2^28 chunks 2^24 cumsum() (2N bytes; 3N moved)", {"dtype": "f64"})
+        return
     if args.config == "c5":
         import ml_dtypes
         n, cb = 32768, 4096
@@ -366,7 +384,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "cum"],
                     help="c2 = headline (default). c3 / c4 = the other BASELINE configs (extra lines for DESIGN.md)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -311,7 +311,7 @@ class FusedLaunch:
         if self.mode == _lib.MODE_SR:     # a thread per column strip walks every row of its block
             cmax = max(c.C for c in canons)
             geo = dict(vec=v, tx=min(128, max(32, cg._pow2_ceil(-(-cmax // v)))), ty=1,
-                       rpt=max(c.R for c in canons), unroll=8)
+                       rpt=1 << 30, unroll=8)          # one row tile per block (constant: one kernel for all R)
         elif self.mode == _lib.MODE_SC:   # a warp per row
             geo = dict(vec=v, tx=32, ty=8, rpt=8, unroll=4)
         variant, mirror, n_primary = "", None, len(blocks)
