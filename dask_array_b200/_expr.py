@@ -164,13 +164,21 @@ class ArrayExpr:
     def simplify(self):
         return _rewrite(self, "_simplify_down")
 
+    def _lower_rechunk(self):
+        return None
+
     def lower_completely(self):
-        return _rewrite(self, "_lower")
+        return _rewrite(_rewrite(self, "_lower"), "_lower_rechunk")
 
     def optimize(self, fuse: bool = True):
+        """simplify -> rechunk pushdown -> lower (chunk unification inserts rechunks) -> pushdown again
+        (``test_lower_inserted_rechunk_pushes_into_from_array``) -> Rechunk -> TasksRechunk -> fuse."""
         from ._blockwise import optimize_blockwise_fusion
+        from ._rechunk import pushdown_rechunks
 
-        expr = self.simplify().lower_completely().simplify()
+        expr = pushdown_rechunks(self.simplify())
+        expr = pushdown_rechunks(_rewrite(expr, "_lower")).simplify()
+        expr = _rewrite(expr, "_lower_rechunk").simplify()
         return optimize_blockwise_fusion(expr) if fuse else expr
 
     # ---- display (README ``pprint``)

@@ -56,11 +56,12 @@ class Rechunk(ArrayExpr):
         x = self.operand("array")
         if x.chunks == self.chunks:                        # no-op removal (:744)
             return x
-        if isinstance(x, Rechunk):                         # rechunk(rechunk(x)) (:755)
-            return Rechunk(x.operand("array"), self.chunks)
         return None
 
     def _lower(self):
+        return None                                        # deferred: lower-inserted rechunks may still push down
+
+    def _lower_rechunk(self):
         return TasksRechunk(self.operand("array"), self.chunks)
 
     def _tree_label(self):
@@ -74,6 +75,9 @@ class TasksRechunk(Rechunk):
         return None
 
     def _lower(self):
+        return None
+
+    def _lower_rechunk(self):
         return None
 
     def pieces(self, new_bid):
@@ -110,3 +114,83 @@ def rechunk(x_expr, chunks):
     if isinstance(chunks, dict):
         chunks = tuple(chunks.get(d, x_expr.chunks[d]) for d in range(x_expr.ndim))
     return Rechunk(x_expr, normalize_chunks(chunks, x_expr.shape))
+
+
+# ----------------------------------------------------------------------------- pushdown
+def _parent_counts(root) -> dict:
+    """How many distinct parents consume each node (the ``dependents`` the reference's
+    ``_simplify_up`` receives, ``_rechunk.py:104-108``)."""
+    counts, seen, stack = {root._name: 0}, set(), [root]
+    while stack:
+        node = stack.pop()
+        if node._name in seen:
+            continue
+        seen.add(node._name)
+        for name in {d._name: d for d in node.dependencies()}:
+            counts[name] = counts.get(name, 0) + 1
+        stack.extend(node.dependencies())
+    return counts
+
+
+def _push(node: "Rechunk"):
+    """``Rechunk._pushdown`` (``_rechunk.py:755-806``) for the children of the hot path; None = keep.
+    On the GPU a pushed rechunk that reaches a host leaf costs nothing (the upload simply cuts the
+    host array at the new grid) and one that reaches an element-wise chain lets the chain fuse with
+    whatever consumes the rechunked result."""
+    from ._blockwise import Elemwise, Transpose
+    from ._expr import BroadcastTrick, FromArray
+
+    child, target = node.operand("array"), node.chunks
+    if type(child) is Rechunk:                                              # :776-784
+        return Rechunk(child.operand("array"), target)
+    if isinstance(child, Transpose):                                        # :787 / _pushdown_through_transpose
+        axes = tuple(child.operand("axes"))
+        inner = [None] * len(axes)
+        for out_dim, in_dim in enumerate(axes):
+            inner[in_dim] = target[out_dim]
+        return Transpose(Rechunk(child.operand("array"), tuple(inner)), axes)
+    if isinstance(child, Elemwise):                                         # :795 / _pushdown_through_elemwise :970-1032
+        nd = child.ndim
+
+        def fix(a):
+            off = nd - a.ndim
+            new = tuple((1,) if a.shape[d] == 1 else target[d + off] for d in range(a.ndim))
+            return a if new == a.chunks else Rechunk(a, new)
+        return child._map_args(fix)
+    if type(child) is FromArray:                                            # _pushdown_into_io :808-823
+        return FromArray(child.operand("array"), target)
+    if type(child) is BroadcastTrick:
+        return BroadcastTrick(child.operand("value"), child.operand("shape_"), target, child.operand("dtype_"))
+    return None
+
+
+def pushdown_rechunks(root):
+    """Push every ``Rechunk`` as far towards the leaves as the reference does, never into a node that
+    something else also consumes (``tests/test_rechunk_pushdown.py:605-680``: a pushed copy would
+    re-derive the shared node -- a second read, a duplicated chain)."""
+    for _ in range(256):
+        counts = _parent_counts(root)
+        memo, changed = {}, False
+
+        def visit(node):
+            nonlocal changed
+            if node._name in memo:
+                return memo[node._name]
+            out = node
+            if type(node) is Rechunk and not changed:
+                child = node.operand("array")
+                if child.chunks == node.chunks:
+                    out, changed = child, True
+                elif counts.get(child._name, 0) <= 1:
+                    pushed = _push(node)
+                    if pushed is not None:
+                        out, changed = pushed, True
+            if out is node:
+                out = node.map_children(visit)
+            memo[node._name] = out
+            return out
+
+        root = visit(root)
+        if not changed:
+            return root
+    return root

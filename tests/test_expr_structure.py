@@ -70,8 +70,13 @@ def test_transpose_conflict_and_same_mapping():
     assert (a.T.T).optimize().expr._name == a.optimize().expr._name
 
 
+def _opaque(shape, chunks, token):
+    """A leaf that cannot absorb a rechunk (per-block host callbacks), like the reference's opaque IO."""
+    return da.from_host_blocks(lambda bid: None, shape, chunks, np.float64, token=token)
+
+
 def test_rechunk_rules_and_pieces():
-    x = da.from_array(np.zeros((16, 16)), chunks=(16, 2))
+    x = _opaque((16, 16), (16, 2), "rr")
     assert x.rechunk((16, 2)).optimize().expr._name == x.optimize().expr._name      # no-op removed
     r = x.rechunk((4, 8)).rechunk((2, 16)).optimize().expr                            # double rechunk collapses
     assert isinstance(r, TasksRechunk) and r.chunks == ((2,) * 8, (16,))
@@ -79,6 +84,51 @@ def test_rechunk_rules_and_pieces():
     assert len(r.pieces((0, 0))) == 8
     o2n = old_to_new(((4, 4, 3), (2, 2, 2)), ((2, 6, 3), (6,)))
     assert o2n[0][1] == [(0, slice(2, 4)), (1, slice(0, 4))]
+
+
+def _walk(e, acc=None):
+    acc = [] if acc is None else acc
+    acc.append(e)
+    for d in e.dependencies():
+        _walk(d, acc)
+    return acc
+
+
+def test_rechunk_pushdown_mirrors_reference_rules():
+    """dask_array/tests/test_rechunk_pushdown.py: :132 (into FromArray), :168 (through elemwise),
+    :487-528 (through transpose), :682 (lower-inserted rechunks), :605-680 (never into shared nodes)."""
+    from dask_array_b200._expr import FromArray
+    from dask_array_b200._blockwise import Elemwise
+    from dask_array_b200._rechunk import Rechunk, pushdown_rechunks
+    data = np.arange(100 * 50, dtype=np.float64).reshape(100, 50)
+    darr = da.from_array(data, chunks=(25, 25))
+    s = pushdown_rechunks(darr.rechunk((50, 50)).expr.simplify())
+    assert isinstance(s, FromArray) and s.chunks == ((50, 50), (50,))
+    s = pushdown_rechunks(darr.rechunk({0: 50}).expr.simplify())
+    assert isinstance(s, FromArray) and s.chunks == ((50, 50), (25, 25))
+    # through elemwise (incl. a broadcast operand: its extent-1 / missing dims keep their chunks)
+    x, v = da.from_array(data, chunks=(25, 25)), da.from_array(data[0], chunks=10)
+    s = pushdown_rechunks(((x + 1) * v).rechunk((20, 5)).expr.simplify())
+    assert isinstance(s, Elemwise) and not any(type(n) is Rechunk for n in _walk(s))
+    assert {n.chunks for n in _walk(s) if isinstance(n, FromArray)} == {((20,) * 5, (5,) * 10), ((5,) * 10,)}
+    # through transpose: input axis i takes the chunks of the output axis it lands on
+    t = _opaque((2, 3, 4), (1, 1, 2), "tp")
+    got = pushdown_rechunks(t.transpose((2, 0, 1)).rechunk((2, 1, 3)).expr.simplify())
+    want = t.rechunk((1, 3, 2)).transpose((2, 0, 1)).expr.simplify()
+    assert got._name == want._name
+    # rechunks inserted by chunk unification at lowering are absorbed by the reads too
+    a, b = da.from_array(data[:22, :22], chunks=(11, 4)), da.from_array(data[:22, :22], chunks=(4, 11))
+    assert not any("Rechunk" in type(n).__name__ for n in _walk((a + b).optimize().expr))
+    # shared nodes are left alone: one read, the chain is not duplicated
+    y = (x + 1) * 2
+    z = y.sum() + y.rechunk((50, 50)).sum()
+    opt = z.optimize(fuse=False).expr
+    assert len({n._name for n in _walk(opt) if isinstance(n, FromArray)}) == 1
+    assert len({n._name for n in _walk(opt) if isinstance(n, Elemwise)}) == 3      # add, mul, top-level add
+    z2 = x.sum() + x.rechunk((50, 50)).sum()
+    opt2 = z2.optimize(fuse=False).expr
+    assert len({n._name for n in _walk(opt2) if isinstance(n, FromArray)}) == 1
+    assert any("Rechunk" in type(n).__name__ for n in _walk(opt2))
 
 
 def test_elemwise_dtypes_follow_numpy_nep50():
@@ -91,8 +141,8 @@ def test_elemwise_dtypes_follow_numpy_nep50():
 
 
 def test_unaligned_chunks_get_rechunked():
-    a = da.from_array(np.zeros((12, 12)), chunks=(4, 12))
-    b = da.from_array(np.zeros((12, 12)), chunks=(6, 12))
+    a = _opaque((12, 12), (4, 12), "ua")
+    b = _opaque((12, 12), (6, 12), "ub")
     assert any("Rechunk" in l for l in labels((a + b).optimize().expr))
 
 

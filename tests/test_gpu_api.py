@@ -108,16 +108,19 @@ def test_arg_reductions_bit_exact(da, dtype, split_every):
 def test_rechunk_and_transpose_bit_exact(da, dtype):
     n = 512
     xh = np.arange(n * n).reshape(n, n).astype(dtype)
-    x = da.from_array(xh, chunks=(n, 16))
-    r = x.rechunk((16, n))
-    assert r.chunks == ((16,) * 32, (n,))
-    assert np.array_equal(r.compute(), xh)
-    want = ref.rechunk(ref.Blocked.from_array(xh, (n, 16)), (16, n))
-    assert np.array_equal(r.compute(), want.to_array())
+    # persisted (device-resident) sources: the rechunk is the gather kernel; un-persisted host
+    # sources absorb the rechunk into their upload (reference rechunk pushdown) -- both are checked
+    for x in (da.from_array(xh, chunks=(n, 16)).persist(), da.from_array(xh, chunks=(n, 16))):
+        r = x.rechunk((16, n))
+        assert r.chunks == ((16,) * 32, (n,))
+        assert np.array_equal(r.compute(), xh)
+        want = ref.rechunk(ref.Blocked.from_array(xh, (n, 16)), (16, n))
+        assert np.array_equal(r.compute(), want.to_array())
+    x = da.from_array(xh, chunks=(n, 16)).persist()
     # ragged both ways
-    xr = da.from_array(xh[:500, :300], chunks=(130, 70))
-    assert np.array_equal(xr.rechunk((64, 300)).compute(), xh[:500, :300])
-    assert np.array_equal(xr.rechunk({0: 499}).compute(), xh[:500, :300])
+    for xr in (da.from_array(xh[:500, :300], chunks=(130, 70)).persist(), da.from_array(xh[:500, :300], chunks=(130, 70))):
+        assert np.array_equal(xr.rechunk((64, 300)).compute(), xh[:500, :300])
+        assert np.array_equal(xr.rechunk({0: 499}).compute(), xh[:500, :300])
     # x.T + x (square chunks: fused transpose) and non-square chunks (rechunk inserted)
     sq = da.from_array(xh, chunks=(128, 128))
     assert np.array_equal((sq.T + sq).compute(), xh.T + xh)

@@ -41,7 +41,7 @@ def _worker(rank, world, port, case, q):
                 recs[r][i] == bytes([r * 16 + i]) * 80 for r in range(world) for i in range(counts[r]))
             q.put((rank, bool(ok), 0))
         elif case == "rechunk":
-            x = da.from_array(xh, chunks=(n, 8))
+            x = da.from_host_blocks(lambda bid: None, xh.shape, (n, 8), xh.dtype, token="gloo-x")   # opaque leaf: the rechunk stays
             expr = x.rechunk((8, n)).optimize().expr
             src = expr.operand("array")
             mine = {bid: xh[tuple(slice(s, s + k) for s, k in zip(src.block_start(bid), src.block_shape(bid)))].copy()
@@ -158,7 +158,7 @@ def test_rechunk_push_plan_covers_every_new_block_once(world, old, new):
     from dask_array_b200._executor import owner_of, plan_rechunk_push
     n = 64
     xh = np.arange(n * n, dtype=np.float64).reshape(n, n)
-    expr = da.from_array(xh, chunks=old).rechunk(new).optimize().expr
+    expr = da.from_host_blocks(lambda bid: None, xh.shape, old, xh.dtype, token=f"push-{old}").rechunk(new).optimize().expr
     src = expr.operand("array")
     plans = [plan_rechunk_push(expr, world, me) for me in range(world)]
     layout, totals, _ = plans[0]
