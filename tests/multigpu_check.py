@@ -71,6 +71,20 @@ def main():
     a64, b64 = ah.astype(np.float64), bh.astype(np.float64)
     assert np.all(np.abs(got - a64 @ b64) <= 1e-5 * (np.abs(a64) @ np.abs(b64)))
     np.testing.assert_allclose((am @ bm).sum().compute(), (a64 @ b64).sum(), rtol=1e-4, atol=1e-2)
+    # cumulative scans across the partition: totals tables completed by an all-reduce
+    ci = rng.integers(-9, 9, size=(300, 200)).astype(np.int32)
+    cd = da.from_array(ci, chunks=(64, 50)).persist()
+    for axis in (0, 1):
+        step = da.compile(cd.cumsum(axis=axis))
+        step.run(); step.run()                                                      # replay: tables are re-zeroed
+        assert np.array_equal(step.results()[0], np.cumsum(ci, axis=axis)), axis
+    cv = rng.integers(1, 3, size=50000).astype(np.int64)
+    assert np.array_equal(da.from_array(cv, chunks=7000).cumsum().compute(), np.cumsum(cv))
+    assert np.array_equal(da.cumprod(da.from_array(cv[:40], chunks=7)).compute(), np.cumprod(cv[:40]))
+    # operands on different grids: unification + rechunk across the partition
+    gh = rng.random((256, 192))
+    ga, gb = da.from_array(gh, chunks=(64, 64)).persist(), da.from_array(gh, chunks=(128, 32)).persist()
+    assert np.array_equal((ga * 2 + gb).compute(), gh * 2 + gh)
     ones = da.ones((1000, 1000), chunks=(100, 100))
     assert (ones + ones.T).sum().compute() == 2_000_000.0
     dist.barrier()
