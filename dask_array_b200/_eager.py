@@ -151,6 +151,51 @@ def _argmin(a, axis=None, keepdims=False, **kw):
     return r if keepdims else r.reshape(tuple(n for d, n in enumerate(a.shape) if axis is not None and d != axis % a.ndim))
 
 
+# ----------------------------------------------------------------------------- cumulative scans
+def _cumulative(a, redop, axis, dtype, nan):
+    """``np.cumsum`` / ``np.cumprod`` (+ nan variants) of ONE chunk -- what ``CumReduction._layer``
+    (``reductions/_cumulative.py:211-222``) calls per block -- as a single scan launch."""
+    x = _as_chunk(a)
+    if axis is None:
+        if x.ndim != 1:
+            x = copy(x).reshape((x.size,))
+        axis = 0
+    fn = np.cumsum if redop == _lib.RED_SUM else np.cumprod
+    acc = np.dtype(dtype) if dtype is not None else fn(np.ones((0,), dtype=x.dtype)).dtype
+    prog = cg.Program()
+    ref = prog.add_input(x.dtype)
+    if nan and x.dtype.kind == "f":
+        ref = prog.op("where", prog.op("isnan", ref), prog.typed_const(0 if redop == _lib.RED_SUM else 1, x.dtype), ref)
+    prog.set_output(prog.op("astype", ref, dtype=acc))
+    out = DeviceChunk.empty(x.shape, acc, x.device)
+    if x.size:
+        blk = rt.BlockArgs(shape=x.shape, inputs=[(x.ptr, x.strides)], out0=out.ptr)
+        for L in rt.scan_launches(prog, redop, axis % x.ndim, [blk], acc):
+            L.run()
+            out._keep = L
+    return out
+
+
+@implements(np.cumsum)
+def _cumsum(a, axis=None, dtype=None, **kw):
+    return _cumulative(a, _lib.RED_SUM, axis, dtype, False)
+
+
+@implements(np.cumprod)
+def _cumprod(a, axis=None, dtype=None, **kw):
+    return _cumulative(a, _lib.RED_PROD, axis, dtype, False)
+
+
+@implements(np.nancumsum)
+def _nancumsum(a, axis=None, dtype=None, **kw):
+    return _cumulative(a, _lib.RED_SUM, axis, dtype, True)
+
+
+@implements(np.nancumprod)
+def _nancumprod(a, axis=None, dtype=None, **kw):
+    return _cumulative(a, _lib.RED_PROD, axis, dtype, True)
+
+
 # ----------------------------------------------------------------------------- views / movement
 @implements(np.transpose)
 def _transpose(a, axes=None):

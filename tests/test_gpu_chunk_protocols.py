@@ -48,3 +48,26 @@ def test_reference_shaped_chunk_functions_run_on_device_chunks():
         np.testing.assert_allclose(got["M"].to_numpy(), want["M"], rtol=2e-5)
     assert np.array_equal(np.argmax(x, axis=1).to_numpy(), np.argmax(xh, axis=1))
     assert np.array_equal(ref.chunk_max(x, axis=(0,), keepdims=True).to_numpy(), xh.max(axis=0, keepdims=True))
+
+
+def test_reference_cumulative_layer_runs_on_device_chunks():
+    """The reference's sequential CumReduction plan (`_cumulative.py:174-264`): np.cumsum per block,
+    `extra = extra + tail`, `result = extra + block` -- executed here with DeviceChunk blocks."""
+    from dask_array_b200 import DeviceChunk
+    rng = np.random.default_rng(2)
+    xh = rng.integers(-9, 9, size=(90, 40)).astype(np.int32)
+    blocks = [DeviceChunk.from_numpy(np.ascontiguousarray(xh[i:i + 30])) for i in range(0, 90, 30)]
+    scanned = [np.cumsum(b, axis=0) for b in blocks]                     # NEP-18 -> one scan launch each
+    assert all(isinstance(s, DeviceChunk) and s.dtype == np.int64 for s in scanned)
+    out, extra = [scanned[0]], None
+    for prev, cur in zip(scanned, scanned[1:]):
+        tail = prev[-1:]                                                  # _cum_tail: last hyperplane
+        extra = tail if extra is None else extra + tail
+        out.append(extra + cur)
+    got = np.concatenate([o.to_numpy() for o in out], axis=0)
+    assert np.array_equal(got, np.cumsum(xh, axis=0))
+    f = rng.random((7, 33))
+    f[2, 5] = np.nan
+    fd = DeviceChunk.from_numpy(f)
+    np.testing.assert_allclose(np.nancumsum(fd, axis=1).to_numpy(), np.nancumsum(f, axis=1), rtol=1e-12)
+    np.testing.assert_allclose(np.cumprod(fd[:2], axis=1).to_numpy(), np.cumprod(f[:2], axis=1), rtol=1e-12)
