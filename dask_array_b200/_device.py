@@ -249,6 +249,10 @@ class DeviceChunk:
         """Synchronous device -> host copy (strided views are gathered by torch's copy)."""
         if self.size == 0:
             return np.empty(self.shape, self.dtype)
+        if any(s < 0 for s in self.strides):       # reversed views (x[::-1]): torch has no negative strides
+            from ._eager import copy
+
+            return copy(self).to_numpy()
         t = self.as_torch()
         if self.dtype.name in ("uint16", "uint32", "uint64", "bfloat16"):
             host = t.contiguous().view(torch.uint8).cpu().numpy().view(self.dtype)

@@ -221,8 +221,18 @@ def _squeeze(a, axis=None):
 
 
 def copy(a: DeviceChunk) -> DeviceChunk:
-    """Contiguous copy (``getitem``'s copy of small selections, ``_chunk.py:285-317``)."""
-    return array_ufunc(a, np.positive, "__call__", a)
+    """Contiguous copy (``getitem``'s copy of small selections, ``_chunk.py:285-317``): one launch of
+    the identity chain, any strides (negative steps included)."""
+    a = _as_chunk(a)
+    out = DeviceChunk.empty(a.shape, a.dtype, a.device)
+    if a.size:
+        prog = cg.Program()
+        prog.set_output(prog.op("astype", prog.add_input(a.dtype), dtype=a.dtype))
+        blk = rt.BlockArgs(shape=a.shape, inputs=[(a.ptr, a.strides)], out0=out.ptr)
+        for L in rt.fused_launches(prog, _lib.RED_NONE, (), [blk]):
+            L.run()
+            out._keep = L
+    return out
 
 
 @implements(np.concatenate)

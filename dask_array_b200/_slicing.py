@@ -1,4 +1,4 @@
-"""Basic slicing (slices with step 1 and integers).
+"""Basic slicing (slices -- any step, either sign -- and integers).
 
 Mirrors ``dask_array/slicing/_basic.py:357-493`` (``SliceSlicesIntegers``): every output block
 is ``getitem(block, slices)`` of one input block, here a zero-copy strided view of the
@@ -31,9 +31,10 @@ def normalize_index(index, shape):
     for ix, n in zip(index, shape):
         if isinstance(ix, slice):
             start, stop, step = ix.indices(n)
-            if step != 1:
-                raise NotImplementedError("slices with a step are outside the B200 hot path")
-            out.append(slice(start, max(stop, start)))
+            if step == 1:
+                out.append(slice(start, max(stop, start)))
+            else:       # canonical stepped form: start/stop as ``slice.indices`` gives them (stop may be -1)
+                out.append(slice(start, stop, step))
         elif isinstance(ix, (int, np.integer)):
             i = int(ix)
             if i < 0:
@@ -66,10 +67,29 @@ class SliceSlicesIntegers(ArrayExpr):
                 res.append([(b, ix - int(edges[b]))])
                 continue
             pcs = []
-            for b in range(len(ch)):
-                a, e = max(ix.start, int(edges[b])), min(ix.stop, int(edges[b + 1]))
-                if a < e:
-                    pcs.append((b, slice(a - int(edges[b]), e - int(edges[b]))))
+            step = ix.step or 1
+            if step == 1:
+                for b in range(len(ch)):
+                    a, e = max(ix.start, int(edges[b])), min(ix.stop, int(edges[b + 1]))
+                    if a < e:
+                        pcs.append((b, slice(a - int(edges[b]), e - int(edges[b]))))
+            elif step > 1:
+                # ``_slice_1d`` (slicing/_utils.py:279-420): blocks that hold no selected element drop out
+                for b in range(len(ch)):
+                    lo, hi = int(edges[b]), min(int(edges[b + 1]), ix.stop)
+                    k0 = max(0, -(-(lo - ix.start) // step))
+                    first = ix.start + k0 * step
+                    if first < hi:
+                        pcs.append((b, slice(first - lo, hi - lo, step)))
+            else:
+                # negative step: the blocks come out in reverse order (``_slice_1d`` :411-440)
+                for b in range(len(ch) - 1, -1, -1):
+                    lo, hi = int(edges[b]), int(edges[b + 1])
+                    k0 = max(0, -(-(ix.start - (hi - 1)) // -step))
+                    first = ix.start + k0 * step
+                    floor = max(ix.stop, lo - 1)                 # selected indices are > floor
+                    if first > floor:
+                        pcs.append((b, slice(first - lo, (floor - lo) if floor >= lo else None, step)))
             if not pcs:
                 pcs = [(0, slice(0, 0))]
             res.append(pcs)
@@ -79,10 +99,10 @@ class SliceSlicesIntegers(ArrayExpr):
     @property
     def chunks(self):
         out = []
-        for ix, pcs in zip(self.operand("index"), self._per_dim()):
+        for ix, pcs, ch in zip(self.operand("index"), self._per_dim(), self.operand("array").chunks):
             if isinstance(ix, int):
                 continue
-            out.append(tuple(s.stop - s.start for _, s in pcs))
+            out.append(tuple(len(range(*sl.indices(ch[b]))) for b, sl in pcs))
         return tuple(out)
 
     def source(self, out_bid):
@@ -97,9 +117,12 @@ class SliceSlicesIntegers(ArrayExpr):
 
     def _simplify_down(self):
         x, index = self.operand("array"), self.operand("index")
-        if all(isinstance(i, slice) and i.start == 0 and i.stop == n for i, n in zip(index, x.shape)):
+        if all(isinstance(i, slice) and i.start == 0 and i.stop == n and (i.step or 1) == 1
+               for i, n in zip(index, x.shape)):
             return x
-        only_slices = all(isinstance(i, slice) for i in index)
+        # the pushdown rules below are written for unit-step windows; stepped slices stay where they are
+        # (still zero-copy strided views of the blocks)
+        only_slices = all(isinstance(i, slice) and (i.step or 1) == 1 for i in index)
         if isinstance(x, BroadcastTrick) and only_slices:
             shape = tuple(i.stop - i.start for i in index)
             # keep the original chunk size, clipped (``_ones_zeros.py:99-121``)
@@ -119,7 +142,8 @@ class SliceSlicesIntegers(ArrayExpr):
                 sub = tuple(index[off + d] if a.shape[d] != 1 else slice(0, 1) for d in range(a.ndim))
                 return SliceSlicesIntegers(a, sub)
             return x._map_args(push)
-        if isinstance(x, SliceSlicesIntegers) and only_slices and all(isinstance(i, slice) for i in x.operand("index")):
+        if isinstance(x, SliceSlicesIntegers) and only_slices and all(
+                isinstance(i, slice) and (i.step or 1) == 1 for i in x.operand("index")):
             inner = x.operand("index")
             merged = tuple(slice(a.start + b.start, a.start + b.stop) for a, b in zip(inner, index))
             return SliceSlicesIntegers(x.operand("array"), merged)

@@ -57,3 +57,27 @@ def test_nd_elementwise_broadcast_and_transpose(da):
     assert np.array_equal((d.transpose(3, 1, 0, 2) + 1).compute(), four.transpose(3, 1, 0, 2) + 1)
     assert np.array_equal(d[1:3, :, 2:5, 1:].compute(), four[1:3, :, 2:5, 1:])
     assert np.array_equal(d.rechunk((3, 1, 5, 2)).compute(), four)
+
+
+def test_stepped_and_reversed_slices_bit_exact():
+    """SliceSlicesIntegers with steps of either sign (slicing/_basic.py:357-493, `_slice_1d`
+    slicing/_utils.py:279-440): zero-copy strided views per block, blocks reversed for negative steps."""
+    import dask_array_b200 as da
+    rng = np.random.default_rng(9)
+    xh = rng.integers(-100, 100, size=(97, 61)).astype(np.int32)
+    x = da.from_array(xh, chunks=(20, 16)).persist()
+    cases = [np.s_[::2], np.s_[::-1], np.s_[5:90:7, ::3], np.s_[::-3, 2], np.s_[90:3:-4, 60:1:-5],
+             np.s_[3, ::-1], np.s_[::40], np.s_[-1:-98:-1, 1::2], np.s_[10:11:5], np.s_[50:10:3]]
+    for idx in cases:
+        y = x[idx]
+        want = xh[idx]
+        assert y.shape == want.shape, idx
+        assert np.array_equal(y.compute(), want), idx
+        if want.size:
+            assert np.array_equal((y * 2 + 1).compute(), want * 2 + 1), idx          # fused chain on strided views
+            assert (y.sum().compute() == want.sum()) and np.array_equal(y.max(axis=0).compute(), want.max(axis=0)), idx
+    f = rng.random((64, 48))
+    fd = da.from_array(f, chunks=(16, 12)).persist()
+    assert np.array_equal((fd[::-1] - fd).compute(), f[::-1] - f)                      # unification rechunks the view
+    assert np.array_equal(fd[::2, ::-2].T.compute(), f[::2, ::-2].T)
+    assert np.array_equal(fd[::-1].cumsum(axis=0).compute().round(9), np.cumsum(f[::-1], axis=0).round(9))
