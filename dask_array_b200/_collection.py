@@ -182,6 +182,26 @@ class Array:
     def __getitem__(self, index):
         from ._slicing import SliceSlicesIntegers, normalize_index
 
+        if not isinstance(index, tuple):
+            index = (index,)
+        if any(i is None for i in index):
+            # np.newaxis entries (``slice_with_newaxes``, slicing/_basic.py): slice without them, then
+            # insert the unit axes where they land in the result (integers drop their axis)
+            from ._views import expand_dims
+
+            if Ellipsis in index:
+                k = index.index(Ellipsis)
+                n_real = sum(1 for i in index if i is not None and i is not Ellipsis)
+                index = index[:k] + (slice(None),) * (self.ndim - n_real) + index[k + 1:]
+            out = self[tuple(i for i in index if i is not None)]
+            pos = 0
+            for i in index:
+                if i is None:
+                    out = expand_dims(out, pos)
+                    pos += 1
+                elif not isinstance(i, Integral):
+                    pos += 1
+            return out
         return Array(SliceSlicesIntegers(self.expr, normalize_index(index, self.shape)))
 
     # ---- reductions (``_collection.py:1300-1500`` -> ``reductions/_common.py``)

@@ -81,3 +81,14 @@ def test_stepped_and_reversed_slices_bit_exact():
     assert np.array_equal((fd[::-1] - fd).compute(), f[::-1] - f)                      # unification rechunks the view
     assert np.array_equal(fd[::2, ::-2].T.compute(), f[::2, ::-2].T)
     assert np.array_equal(fd[::-1].cumsum(axis=0).compute().round(9), np.cumsum(f[::-1], axis=0).round(9))
+
+
+def test_newaxis_in_index():
+    import dask_array_b200 as da
+    xh = np.arange(60.0).reshape(3, 4, 5)
+    x = da.from_array(xh, chunks=(2, 2, 5)).persist()
+    for idx in [np.s_[None], np.s_[:, None], np.s_[..., None], np.s_[1, None, :, None], np.s_[None, ..., None, 2],
+                np.s_[::-1, None, 1:3]]:
+        assert np.array_equal(x[idx].compute(), xh[idx]), idx
+    v = da.from_array(xh[0, 0], chunks=2).persist()
+    assert np.array_equal((v[:, None] * v[None, :]).compute(), xh[0, 0][:, None] * xh[0, 0][None, :])
