@@ -174,3 +174,23 @@ def test_unsupported_fails_loudly(da):
         x[[0, 2]]                                   # fancy indexing is outside the hot path
     with pytest.raises(NotImplementedError):
         da.elemwise("frexp", x).compute()
+
+
+def test_cuda_graph_replay_matches_tape(da):
+    """`Compiled.capture()`: the launch tape as one CUDA graph gives the same results, repeatedly."""
+    rng = np.random.default_rng(4)
+    xh = rng.random((512, 384), dtype=np.float32)
+    x = da.from_array(xh, chunks=(128, 128)).persist()
+    y = da.sin(x) * 2 + x**2
+    step = da.compile(y.mean(axis=0), y.std(), (x.T[:384] + x[:384, :384].rechunk((96, 384))).sum(axis=1), x.argmax(axis=1))
+    step.run()
+    eager = [np.array(r) for r in step.results()]
+    step.capture()
+    for _ in range(3):
+        step.run()
+    for a, b in zip(eager, step.results()):
+        assert np.array_equal(a, b, equal_nan=True)
+    ones = da.ones((1000, 1000), chunks=(100, 100))
+    s = da.compile((ones + ones.T).sum()).capture()
+    s.run(); s.run()
+    assert s.result() == 2_000_000.0
