@@ -182,7 +182,7 @@ def test_cuda_graph_replay_matches_tape(da):
     xh = rng.random((512, 384), dtype=np.float32)
     x = da.from_array(xh, chunks=(128, 128)).persist()
     y = da.sin(x) * 2 + x**2
-    step = da.compile(y.mean(axis=0), y.std(), (x.T[:384] + x[:384, :384].rechunk((96, 384))).sum(axis=1), x.argmax(axis=1))
+    step = da.compile(y.mean(axis=0), y.std(), (x.T[:, :384] + x[:384, :384].rechunk((96, 384))).sum(axis=1), x.argmax(axis=1))
     step.run()
     eager = [np.array(r) for r in step.results()]
     step.capture()
