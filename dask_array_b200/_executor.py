@@ -154,28 +154,37 @@ class Executor:
         src = self.results[expr.operand("array")._name]
         st = BlockStore(expr)
         x = expr.operand("array")
+        moves = []
         for bid in expr.block_ids():
             ibid, idx = expr.source(bid)
             if self.world.size > 1 and not src.replicated and self.world.owner(x, ibid) != self.world.owner(expr, bid):
-                raise NotImplementedError("slice that moves blocks between GPUs (rechunk first)")
+                moves.append((bid, self.world.owner(x, ibid), (lambda blk, idx=idx: blk[idx]), ibid))
+                continue
             if ibid in src.blocks and (src.replicated or self.mine(expr, bid)):
                 st.blocks[bid] = src.blocks[ibid][idx]
         st.replicated = src.replicated
+        if moves:
+            _push_views(self, expr, st, src, moves)
         return st
 
     def _view_store(self, expr, src_of, view_of):
         """Zero-copy structural expressions: each output block is a view of one input block."""
         st = BlockStore(expr)
         rep = None
+        moves = {}
         for bid in expr.block_ids():
             store, x, ibid = src_of(bid)
             rep = store.replicated if rep is None else (rep and store.replicated)
             if self.world.size > 1 and not store.replicated and self.world.owner(x, ibid) != self.world.owner(expr, bid):
-                raise NotImplementedError(f"{type(expr).__name__} that moves blocks between GPUs (rechunk first)")
+                moves.setdefault(id(store), (store, []))[1].append(
+                    (bid, self.world.owner(x, ibid), (lambda blk, bid=bid: view_of(blk, bid)), ibid))
+                continue
             blk = store.blocks.get(ibid)
             if blk is not None and (store.replicated or self.mine(expr, bid)):
                 st.blocks[bid] = view_of(blk, bid)
         st.replicated = bool(rep)
+        for store, mv in moves.values():
+            _push_views(self, expr, st, store, mv)
         return st
 
     def _run_ExpandDims(self, expr):
@@ -1039,6 +1048,41 @@ def _interleave_remote_reads(blocks, owners, me: int, W: int, in_items, out_item
             if i < len(q):
                 out.append(q[i])
     return out
+
+
+def _push_views(ex: Executor, expr, st: BlockStore, src: BlockStore, moves):
+    """Output blocks of a structural expression (slice, concatenate, expand_dims ...) whose source block
+    lives on ANOTHER GPU: the source's owner stores the selected view straight into the block at its new
+    owner -- one gather launch per rank over peer memory, bracketed by the stream barrier (the same
+    mechanism as the rechunk all-to-all).  ``moves``: [(output block id, source owner, view(block), source
+    block id)] in the same order on every rank."""
+    if not _peer.enabled():
+        raise NotImplementedError(f"{type(expr).__name__} that moves blocks between GPUs needs the peer-memory "
+                                  "path (B2_COMM=peer); rechunk first")
+    W, me = ex.world.size, ex.world.rank
+    item = expr.dtype.itemsize
+    layout, totals = {}, [0] * W
+    for bid, _, _, _ in moves:
+        r = ex.world.owner(expr, bid)
+        layout[bid] = (r, totals[r])
+        totals[r] += -(-math.prod(expr.block_shape(bid)) * item // 512) * 512
+    slab = alloc_bytes(totals[me], ex.device)
+    bases = [p[0] for p in _peer.exchange_pointers(ex.device, [slab.data_ptr()], [1] * W, me)]
+    windows = [slab if r == me else _peer.PeerBuffer(bases[r], ex.device, totals[r], r) for r in range(W)]
+    copies = []
+    for bid, src_owner, view, ibid in moves:
+        r, off = layout[bid]
+        dst = DeviceChunk(windows[r], expr.block_shape(bid), expr.dtype, offset=off // item)
+        if r == me:
+            st.blocks[bid] = dst
+        if src_owner == me:
+            copies.extend(_copy_descs(view(src.blocks[ibid]), dst, item))
+    launch = rt.GatherLaunch(copies)
+    bar = _peer.StreamBarrier(ex.device, me, W)
+    ex._do(bar)
+    ex._do(launch.run)
+    ex._do(bar)
+    st.keepalive.extend([launch, slab, windows])
 
 
 def plan_fused_peer_reads(plan: FusedPlan, replicated, W: int):

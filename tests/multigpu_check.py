@@ -85,6 +85,16 @@ def main():
     gh = rng.random((256, 192))
     ga, gb = da.from_array(gh, chunks=(64, 64)).persist(), da.from_array(gh, chunks=(128, 32)).persist()
     assert np.array_equal((ga * 2 + gb).compute(), gh * 2 + gh)
+    # structural views whose source block lives on another GPU: pushed through peer memory
+    sh = rng.random((600, 64))
+    sd = da.from_array(sh, chunks=(100, 64)).persist()
+    assert np.array_equal(sd[150:].compute(), sh[150:])
+    np.testing.assert_allclose((sd[250:550] * 2).sum(axis=1).compute(), (sh[250:550] * 2).sum(axis=1), rtol=1e-12)
+    assert np.array_equal(sd[::-1].compute(), sh[::-1])
+    assert np.array_equal(da.concatenate([sd[100:], sd[:100]]).compute(), np.concatenate([sh[100:], sh[:100]]))
+    step = da.compile(sd[300:] + 1)
+    step.run(); step.run()
+    assert np.array_equal(step.results()[0], sh[300:] + 1)
     ones = da.ones((1000, 1000), chunks=(100, 100))
     assert (ones + ones.T).sum().compute() == 2_000_000.0
     dist.barrier()
