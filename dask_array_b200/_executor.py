@@ -212,11 +212,6 @@ class Executor:
         return self._view_store(expr, src_of, lambda blk, bid: blk)
 
     # ------------------------------------------------------------------ fused blockwise
-    def _fetch_remote(self, needs):
-        """needs: {(dep expr name): set(block ids)} this rank must read but does not own.
-        All ranks call this with their own needs; the schedule is derived symmetrically."""
-        raise NotImplementedError
-
     def _run_FusedBlockwise(self, expr: FusedBlockwise):
         key = expr._name
         plan = _PLAN_CACHE.get(key)

@@ -6,6 +6,8 @@ tests/golden/cumulative.npz) -- the reference's cases: tests/test_reductions.py 
 Integers (wrap-around arithmetic is associative): bit-exact.  Floats: the scan order inside a block
 differs (warp scans / block totals first), so |got - want| <= rtol * cumsum(|x|) with rtol 1e-5 (fp32)
 and 1e-12 (fp64)."""
+import ast
+
 import numpy as np
 import pytest
 
@@ -37,7 +39,7 @@ def test_golden_cases(da):
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cumulative.npz"))
     for case in sorted({k.split("/")[0] for k in g.files}):
-        chunks, axis, kind, nan = eval(str(g[case + "/meta"][0]))
+        chunks, axis, kind, nan = ast.literal_eval(str(g[case + "/meta"][0]))
         xh, want = g[case + "/x"], g[case + "/result"]
         x = da.from_array(xh, chunks=chunks)
         fn = getattr(da, ("nan" if nan else "") + kind)

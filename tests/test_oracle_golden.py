@@ -4,6 +4,8 @@ Bit-exact: both sides are NumPy on the same inputs in the same order."""
 import json
 import os
 
+import ast
+
 import numpy as np
 import pytest
 
@@ -229,7 +231,7 @@ def _cum_golden():
 @pytest.mark.parametrize("case", sorted({k.split("/")[0] for k in _cum_golden().files}))
 def test_cumulative_matches_reference_graph(case):
     g = _cum_golden()
-    chunks, axis, kind, nan = eval(str(g[case + "/meta"][0]))
+    chunks, axis, kind, nan = ast.literal_eval(str(g[case + "/meta"][0]))
     xh, want = g[case + "/x"], g[case + "/result"]
     got = ref.da_cumulative(ref.Blocked.from_array(xh, chunks), axis, kind, nan).to_array()
     assert got.dtype == want.dtype
