@@ -276,6 +276,16 @@ class Array:
     def argmax(self, axis=None, keepdims=False, split_every=None):
         return self._reduce("argmax", axis, keepdims, None, split_every)
 
+    def map_blocks(self, func, *args, **kwargs):
+        from ._overlap import map_blocks
+
+        return map_blocks(func, self, *args, **kwargs)
+
+    def map_overlap(self, func, depth=None, boundary=None, trim=True, **kwargs):
+        from ._overlap import map_overlap
+
+        return map_overlap(func, self, depth=depth, boundary=boundary, trim=trim, **kwargs)
+
     def cumsum(self, axis=None, dtype=None, out=None, method="sequential"):
         return cumsum(self, axis=axis, dtype=dtype, out=out, method=method)
 

@@ -192,6 +192,61 @@ class Executor:
         src = self.results[x._name]
         return self._view_store(expr, lambda bid: (src, x, expr.source(bid)), lambda blk, bid: expr.view(blk))
 
+    def _run_TrimInternal(self, expr):
+        x = expr.operand("array")
+        src = self.results[x._name]
+        return self._view_store(expr, lambda bid: (src, x, bid), lambda blk, bid: expr.view(blk, bid))
+
+    def _run_OverlapInternal(self, expr):
+        """Halo exchange = the rechunk executor on ``OverlapInternal.pieces``: one gather per device,
+        neighbour rims stored into peer memory when the neighbour block lives on another GPU."""
+        return self._run_TasksRechunk(expr)
+
+    def _run_MapBlocks(self, expr):
+        """``func(*blocks)`` per block on the chunk type (NEP-13 / NEP-18 launches).  The result is
+        copied into a block allocated once, so that a replayed tape keeps feeding the same memory to
+        the launches recorded after it."""
+        from . import _eager
+
+        func = expr.operand("func")
+        template, kw = expr.operand("kwargs")
+        kwargs = dict(kw)
+        stores = [self.results[a._name] for a in expr.operand("arrays")]
+        st = BlockStore(expr)
+        work = []
+        for bid in expr.block_ids():
+            if not self.mine(expr, bid):
+                continue
+            out = DeviceChunk.empty(expr.block_shape(bid), expr.dtype, self.device)
+            st.blocks[bid] = out
+            ins = []
+            for s_ in stores:
+                blk = s_.blocks.get(bid)
+                if blk is None:
+                    raise RuntimeError(f"map_blocks: block {bid} of an argument is not resident on rank {self.world.rank}")
+                ins.append(blk)
+            work.append((out, ins))
+        item = expr.dtype.itemsize
+
+        def run():
+            for out, ins in work:
+                it = iter(ins)
+                args = [next(it) if t is None else t for t in template]
+                res = func(*args, **kwargs)
+                if not isinstance(res, DeviceChunk):
+                    raise TypeError(f"map_blocks: {getattr(func, '__name__', func)!r} returned {type(res).__name__}, "
+                                    "not a DeviceChunk (no host fallback: use NumPy functions the chunk type implements)")
+                if res.shape != out.shape or res.dtype != out.dtype:
+                    raise ValueError(f"map_blocks: block result {res.shape} {res.dtype} does not match the declared "
+                                     f"chunks / dtype {out.shape} {out.dtype}")
+                if out.size:
+                    g = rt.GatherLaunch(_copy_descs(res if res.ndim else res.reshape((1,)),
+                                                    out if out.ndim else out.reshape((1,)), item))
+                    g.run()
+                    out._keep = (g, res)
+        self._do(run)
+        return st
+
     def _run_Squeeze(self, expr):
         x = expr.operand("array")
         src = self.results[x._name]

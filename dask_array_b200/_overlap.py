@@ -1,0 +1,377 @@
+"""Halo ("ghost cell") exchange, ``map_blocks`` and ``map_overlap`` -- SURVEY.md 8f rank 4.
+
+Mirrors ``dask_array/_overlap.py``: ``overlap`` (:906-987) = rechunk so every chunk holds the depth
+(``ensure_minimum_chunksize`` :836-883) -> ``boundaries`` (:803-833: ``periodic`` / ``reflect`` /
+``nearest`` / constant pads built from slices and concatenation) -> ``overlap_internal`` (:53-140, chunks
+``_overlap_internal_chunks`` :29-50) -> trim of the pad blocks; ``trim_internal`` (:643-712) and
+``map_overlap`` (``_map_overlap_direct`` :990-1038).
+
+Where the reference builds one ``getitem`` task per ghost fragment plus one ``concatenate3`` per block
+(``ArrayOverlapLayer``), ``OverlapInternal`` here is ONE tiled gather launch per device: every output
+block is assembled from its own block and the rims of its 3^d - 1 neighbours.  It reuses the rechunk
+executor, so with several GPUs the owner of a neighbour block stores its rim straight into the halo
+of the block at ITS owner over NVLink (peer memory), inside the same launch.
+"""
+from __future__ import annotations
+
+import itertools
+from numbers import Integral
+
+import numpy as np
+
+from ._expr import ArrayExpr
+
+
+# ----------------------------------------------------------------------------- argument coercion
+def coerce_depth(ndim, depth):
+    """``coerce_depth`` (:1303-1322)."""
+    if depth is None:
+        depth = 0
+    if isinstance(depth, Integral):
+        depth = (depth,) * ndim
+    if isinstance(depth, tuple):
+        depth = dict(zip(range(ndim), depth))
+    depth = {ax: depth.get(ax, 0) for ax in range(ndim)}
+    return {ax: tuple(int(v) for v in d) if isinstance(d, tuple) else int(d) for ax, d in depth.items()}
+
+
+def coerce_boundary(ndim, boundary):
+    """``coerce_boundary`` (:1351-1362)."""
+    if boundary is None:
+        boundary = "none"
+    if not isinstance(boundary, (tuple, dict)):
+        boundary = (boundary,) * ndim
+    if isinstance(boundary, tuple):
+        boundary = dict(zip(range(ndim), boundary))
+    return {ax: boundary.get(ax, "none") for ax in range(ndim)}
+
+
+def _sides(depth):
+    return depth if isinstance(depth, tuple) else (depth, depth)
+
+
+def ensure_minimum_chunksize(size, chunks):
+    """``ensure_minimum_chunksize`` (:836-883): merge chunks smaller than ``size`` into their
+    neighbours."""
+    if size <= min(chunks):
+        return tuple(chunks)
+    output, new = [], 0
+    for c in chunks:
+        if c < size:
+            if new > size + (size - c):
+                output.append(new - (size - c))
+                new = size
+            else:
+                new += c
+        if new >= size:
+            output.append(new)
+            new = 0
+        if c >= size:
+            new += c
+    if new >= size:
+        output.append(new)
+    elif output:
+        output[-1] += new
+    else:
+        raise ValueError(f"The overlapping depth {size} is larger than your array {sum(chunks)}.")
+    return tuple(output)
+
+
+def _overlap_rechunked_chunks(x, depth, boundary):
+    """``_get_overlap_rechunked_chunks`` (:885-903)."""
+    out = []
+    for axis, c in enumerate(x.chunks):
+        before, after = _sides(depth.get(axis, 0))
+        c = ensure_minimum_chunksize(max(before, after), c) if max(before, after) else tuple(c)
+        if boundary.get(axis, "none") == "none":
+            if len(c) > 1 and c[0] <= before:
+                c = (c[0] + c[1],) + c[2:]
+            if len(c) > 1 and c[-1] <= after:
+                c = c[:-2] + (c[-2] + c[-1],)
+        out.append(c)
+    return tuple(out)
+
+
+# ----------------------------------------------------------------------------- expressions
+class OverlapInternal(ArrayExpr):
+    """``OverlapInternal`` (:70-140): every block grows by the rims of its neighbours.  Executed by the
+    rechunk executor (one gather launch per device; peer stores across GPUs)."""
+
+    _parameters = ["array", "axes"]          # axes: ((axis, (before, after)), ...)
+
+    @property
+    def dtype(self):
+        return self.operand("array").dtype
+
+    def _depths(self):
+        d = dict(self.operand("axes"))
+        return [d.get(i, (0, 0)) for i in range(self.operand("array").ndim)]
+
+    @property
+    def chunks(self):
+        out = []
+        for bds, (before, after) in zip(self.operand("array").chunks, self._depths()):
+            if len(bds) == 1:
+                out.append(tuple(bds))
+            else:                                        # _overlap_internal_chunks (:29-50)
+                out.append((bds[0] + after,) + tuple(b + before + after for b in bds[1:-1]) + (bds[-1] + before,))
+        return tuple(out)
+
+    def pieces(self, new_bid):
+        """[(source block id, source slices, destination slices)] of one output block."""
+        x = self.operand("array")
+        per_dim = []
+        for d, (b, (before, after)) in enumerate(zip(new_bid, self._depths())):
+            ch = x.chunks[d]
+            segs, pos = [], 0
+            if b > 0 and before:
+                if ch[b - 1] < before:
+                    raise ValueError(f"overlap depth {before} exceeds the neighbouring chunk ({ch[b - 1]}) on axis {d}")
+                segs.append((b - 1, slice(ch[b - 1] - before, ch[b - 1]), slice(0, before)))
+                pos = before
+            segs.append((b, slice(0, ch[b]), slice(pos, pos + ch[b])))
+            pos += ch[b]
+            if b < len(ch) - 1 and after:
+                if ch[b + 1] < after:
+                    raise ValueError(f"overlap depth {after} exceeds the neighbouring chunk ({ch[b + 1]}) on axis {d}")
+                segs.append((b + 1, slice(0, after), slice(pos, pos + after)))
+            per_dim.append(segs)
+        out = []
+        for combo in itertools.product(*per_dim):
+            out.append((tuple(c[0] for c in combo), tuple(c[1] for c in combo), tuple(c[2] for c in combo)))
+        return out
+
+    def _tree_label(self):
+        return f"OverlapInternal({dict(self.operand('axes'))})"
+
+
+class TrimInternal(ArrayExpr):
+    """``trim_internal`` / ``_trim`` (:643-712): cut the halo off every block; at the array's edge only
+    where the boundary condition added one.  Each output block is a view of its input block."""
+
+    _parameters = ["array", "axes", "boundary"]   # ((axis, (front, back)), ...), ((axis, kind), ...)
+
+    @property
+    def dtype(self):
+        return self.operand("array").dtype
+
+    def _cut(self, d, j, n):
+        front, back = dict(self.operand("axes")).get(d, (0, 0))
+        if dict(self.operand("boundary")).get(d, "none") == "none":
+            return (0 if j == 0 else front), (0 if j == n - 1 else back)
+        return front, back
+
+    @property
+    def chunks(self):
+        out = []
+        for d, bd in enumerate(self.operand("array").chunks):
+            out.append(tuple(c - sum(self._cut(d, j, len(bd))) for j, c in enumerate(bd)))
+        return tuple(out)
+
+    def source(self, bid):
+        return bid
+
+    def view(self, chunk, bid):
+        nb = self.operand("array").numblocks
+        idx = []
+        for d, j in enumerate(bid):
+            front, back = self._cut(d, j, nb[d])
+            idx.append(slice(front, chunk.shape[d] - back))
+        return chunk[tuple(idx)]
+
+
+class MapBlocks(ArrayExpr):
+    """``map_blocks`` (``_map_blocks.py``) for block-aligned array arguments: ``func(*blocks, **kwargs)``
+    runs per block on the chunk type -- ``DeviceChunk`` implements NEP-13 / NEP-18, so NumPy-style
+    functions launch kernels; nothing falls back to the host."""
+
+    _parameters = ["func", "arrays", "kwargs", "dtype_", "chunks_", "token"]
+
+    def dependencies(self):
+        return list(self.operand("arrays"))
+
+    def map_children(self, fn):
+        new = tuple(fn(a) for a in self.operand("arrays"))
+        if all(a is b for a, b in zip(new, self.operand("arrays"))):
+            return self
+        return MapBlocks(self.operand("func"), new, self.operand("kwargs"), self.operand("dtype_"),
+                         self.operand("chunks_"), self.operand("token"))
+
+    @property
+    def dtype(self):
+        return np.dtype(self.operand("dtype_"))
+
+    @property
+    def chunks(self):
+        return self.operand("chunks_")
+
+    def _tree_label(self):
+        return f"MapBlocks({getattr(self.operand('func'), '__name__', 'func')})"
+
+
+# ----------------------------------------------------------------------------- collection API
+def overlap_internal(x, axes):
+    """``overlap_internal`` (:53-67)."""
+    from ._collection import Array, asarray
+
+    x = asarray(x)
+    axes = tuple(sorted((int(a), tuple(_sides(d))) for a, d in axes.items() if max(_sides(d)) > 0))
+    if not axes:
+        return x
+    return Array(OverlapInternal(x.expr, axes))
+
+
+def trim_internal(x, axes, boundary=None):
+    """``trim_internal`` (:643-685)."""
+    from ._collection import Array, asarray
+
+    x = asarray(x)
+    boundary = coerce_boundary(x.ndim, boundary)
+    axes = tuple(sorted((int(a), tuple(_sides(d))) for a, d in axes.items()))
+    return Array(TrimInternal(x.expr, axes, tuple(sorted(boundary.items(), key=lambda kv: kv[0]))))
+
+
+def trim_overlap(x, depth, boundary=None):
+    """``trim_overlap`` (:626-640)."""
+    return trim_internal(x, coerce_depth(x.ndim, depth), boundary)
+
+
+def _axis_slice(ndim, axis, sl):
+    return (slice(None),) * axis + (sl,) + (slice(None),) * (ndim - axis - 1)
+
+
+def _one_chunk(a, axis, depth):
+    ch = list(a.chunks)
+    ch[axis] = (depth,)
+    return a.rechunk(tuple(ch))                          # _remove_overlap_boundaries (:792-800)
+
+
+def periodic(x, axis, depth):
+    """``periodic`` (:715-730)."""
+    from ._views import concatenate
+    left, right = x[_axis_slice(x.ndim, axis, slice(0, depth))], x[_axis_slice(x.ndim, axis, slice(-depth, None))]
+    return concatenate([_one_chunk(right, axis, depth), x, _one_chunk(left, axis, depth)], axis=axis)
+
+
+def reflect(x, axis, depth):
+    """``reflect`` (:733-756)."""
+    from ._views import concatenate
+    left = x[_axis_slice(x.ndim, axis, slice(0, 1) if depth == 1 else slice(depth - 1, None, -1))]
+    right = x[_axis_slice(x.ndim, axis, slice(-1, -depth - 1, -1))]
+    return concatenate([_one_chunk(left, axis, depth), x, _one_chunk(right, axis, depth)], axis=axis)
+
+
+def nearest(x, axis, depth):
+    """``nearest`` (:759-773): the edge hyperplane repeated ``depth`` times."""
+    from ._views import concatenate
+    left = x[_axis_slice(x.ndim, axis, slice(0, 1))]
+    right = x[_axis_slice(x.ndim, axis, slice(-1, None))]
+    rep = lambda e: _one_chunk(concatenate([e] * depth, axis=axis), axis, depth)
+    return concatenate([rep(left), x, rep(right)], axis=axis)
+
+
+def constant(x, axis, depth, value):
+    """``constant`` (:776-789)."""
+    from ._collection import full
+    from ._views import concatenate
+    chunks = list(x.chunks)
+    chunks[axis] = (depth,)
+    c = full(tuple(sum(c) for c in chunks), value, chunks=tuple(chunks), dtype=x.dtype)
+    return concatenate([c, x, c], axis=axis)
+
+
+def boundaries(x, depth=None, kind=None):
+    """``boundaries`` (:803-833)."""
+    if not isinstance(kind, dict):
+        kind = dict.fromkeys(range(x.ndim), kind)
+    if not isinstance(depth, dict):
+        depth = dict.fromkeys(range(x.ndim), depth)
+    for i in range(x.ndim):
+        d = depth.get(i, 0)
+        d = max(_sides(d)) if isinstance(d, tuple) else d
+        if d == 0:
+            continue
+        k = kind.get(i, "none")
+        if isinstance(k, str) and k == "none":
+            continue
+        if isinstance(k, str) and k == "periodic":
+            x = periodic(x, i, d)
+        elif isinstance(k, str) and k == "reflect":
+            x = reflect(x, i, d)
+        elif isinstance(k, str) and k == "nearest":
+            x = nearest(x, i, d)
+        elif i in kind:
+            x = constant(x, i, d, k)
+    return x
+
+
+def overlap(x, depth, boundary, *, allow_rechunk=True):
+    """``overlap`` (:906-987): share ``depth`` cells between neighbouring blocks, with the given
+    boundary condition at the array's edges."""
+    from ._collection import asarray
+
+    x = asarray(x)
+    depth2 = coerce_depth(x.ndim, depth)
+    boundary2 = coerce_boundary(x.ndim, boundary)
+    for ax, d in depth2.items():
+        if isinstance(d, tuple) and boundary2.get(ax, "none") != "none" and d[0] != d[1]:
+            raise NotImplementedError("Asymmetric overlap is currently only implemented for boundary='none'")
+    depths = [max(_sides(d)) for d in depth2.values()]
+    if allow_rechunk:
+        x1 = x.rechunk(_overlap_rechunked_chunks(x, depth2, boundary2))
+    else:
+        if any(min(c) < d for d, c in zip(depths, x.chunks)):
+            raise ValueError("Overlap depth is larger than smallest chunksize.\n"
+                             "Please set allow_rechunk=True to rechunk automatically.\n"
+                             f"Overlap depths required: {depths}\nInput chunks: {x.chunks}\n")
+        x1 = x
+    x2 = boundaries(x1, depth2, boundary2)
+    x3 = overlap_internal(x2, depth2)
+    idx = []
+    for ax in range(x.ndim):
+        t = 2 * max(_sides(depth2[ax])) if boundary2.get(ax, "none") != "none" else 0
+        idx.append(slice(t, -t if t else None))           # chunk.trim of the pad blocks (:984-986)
+    return x3[tuple(idx)] if any(i.start for i in idx) else x3
+
+
+def map_blocks(func, *args, dtype=None, chunks=None, token=None, **kwargs):
+    """``map_blocks`` for block-aligned arrays (every array argument must share one block grid; other
+    arguments are passed through).  ``dtype`` defaults to what ``func`` returns for zero-size NumPy
+    inputs, as the reference infers ``_meta`` (``_utils.py:235-288``)."""
+    from ._collection import Array
+
+    arrays = tuple(a for a in args if isinstance(a, Array))
+    if not arrays:
+        raise TypeError("map_blocks needs at least one array argument")
+    grid = arrays[0].numblocks
+    if any(a.numblocks != grid for a in arrays):
+        raise NotImplementedError("map_blocks over arrays with different block grids (rechunk / broadcast first)")
+    template = tuple(None if isinstance(a, Array) else a for a in args)
+    if dtype is None:
+        metas = iter(np.empty((0,) * a.ndim, dtype=a.dtype) for a in arrays)
+        dtype = np.asarray(func(*[next(metas) if t is None and isinstance(a, Array) else a
+                                  for a, t in zip(args, template)], **kwargs)).dtype
+    out_chunks = arrays[0].chunks if chunks is None else tuple(tuple(c) for c in chunks)
+    tok = token if token is not None else f"{getattr(func, '__name__', 'func')}-{id(func):x}"
+    return Array(MapBlocks(func, tuple(a.expr for a in arrays), (template, tuple(sorted(kwargs.items()))),
+                           np.dtype(dtype).name, out_chunks, tok))
+
+
+def map_overlap(func, *args, depth=None, boundary=None, trim=True, allow_rechunk=True, dtype=None, **kwargs):
+    """``map_overlap`` (:1041-1300, the direct path ``_map_overlap_direct`` :990-1038): overlap every
+    array argument, apply ``func`` per block, trim the halo off the result."""
+    from ._collection import Array, asarray
+
+    if isinstance(func, Array) and callable(args[0]):
+        func, args = args[0], (func,) + args[1:]          # legacy map_overlap(x, func, ...)
+    arrays = [asarray(a) for a in args]
+    depth = [coerce_depth(a.ndim, depth) for a in arrays] if not isinstance(depth, list) else \
+        [coerce_depth(a.ndim, d) for a, d in zip(arrays, depth)]
+    boundary = [coerce_boundary(a.ndim, boundary) for a in arrays] if not isinstance(boundary, list) else \
+        [coerce_boundary(a.ndim, b) for a, b in zip(arrays, boundary)]
+    over = [overlap(a, depth=d, boundary=b, allow_rechunk=allow_rechunk) for a, d, b in zip(arrays, depth, boundary)]
+    out = map_blocks(func, *over, dtype=dtype, **kwargs)
+    if trim:
+        i = sorted(enumerate(over), key=lambda v: (v[1].ndim, -v[0]))[-1][0]
+        out = trim_internal(out, depth[i], boundary[i])
+    return out

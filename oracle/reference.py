@@ -809,3 +809,47 @@ def da_cumulative(x, axis, kind="cumsum", nan=False, dtype=None):
                 out[bid] = binop(extra, scanned)
             prev = scanned
     return Blocked(out, x.chunks)
+
+
+# ----------------------------------------------------------------------------- overlap (halo exchange)
+_PAD_MODE = {"periodic": "wrap", "reflect": "symmetric", "nearest": "edge"}
+
+
+def overlap(x, depth, boundary):
+    """``overlap`` (``_overlap.py:906-987``) restated on the whole array: pad every axis as its boundary
+    condition says (``periodic`` :715 = wrap, ``reflect`` :733 = symmetric -- the edge cell is repeated --,
+    ``nearest`` :759 = edge, a value = constant, ``"none"`` = no pad), then every block of the ORIGINAL
+    grid is cut out together with ``depth`` cells on each side (clipped at un-padded edges).  ``x``:
+    Blocked whose chunks already hold the depth; ``depth`` / ``boundary``: {axis: value}.  The docstring
+    example of the reference (:935-962) is asserted in tests/test_gpu_overlap.py."""
+    full = x.to_array()
+    nd = full.ndim
+    padded = full
+    for ax in range(nd):
+        d, kind = depth.get(ax, 0), boundary.get(ax, "none")
+        if d == 0 or (isinstance(kind, str) and kind == "none"):
+            continue
+        width = [(0, 0)] * nd
+        width[ax] = (d, d)
+        if isinstance(kind, str):
+            padded = np.pad(padded, width, mode=_PAD_MODE[kind])
+        else:
+            padded = np.pad(padded, width, mode="constant", constant_values=kind)
+    blocks, chunks = {}, []
+    for ax in range(nd):
+        d, kind = depth.get(ax, 0), boundary.get(ax, "none")
+        has_pad = d > 0 and not (isinstance(kind, str) and kind == "none")
+        n = len(x.chunks[ax])
+        chunks.append(tuple(c + (d if (j > 0 or has_pad) else 0) + (d if (j < n - 1 or has_pad) else 0)
+                            for j, c in enumerate(x.chunks[ax])))
+    for bid in itertools.product(*[range(len(c)) for c in x.chunks]):
+        sl = []
+        for ax, j in enumerate(bid):
+            d, kind = depth.get(ax, 0), boundary.get(ax, "none")
+            has_pad = d > 0 and not (isinstance(kind, str) and kind == "none")
+            start = sum(x.chunks[ax][:j]) + (d if has_pad else 0)          # position in the padded array
+            lo = start - (d if (j > 0 or has_pad) else 0)
+            hi = start + x.chunks[ax][j] + (d if (j < len(x.chunks[ax]) - 1 or has_pad) else 0)
+            sl.append(slice(lo, hi))
+        blocks[bid] = padded[tuple(sl)]
+    return Blocked(blocks, tuple(chunks))

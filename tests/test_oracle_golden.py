@@ -236,3 +236,24 @@ def test_cumulative_matches_reference_graph(case):
     got = ref.da_cumulative(ref.Blocked.from_array(xh, chunks), axis, kind, nan).to_array()
     assert got.dtype == want.dtype
     assert np.array_equal(got, want, equal_nan=True)
+
+
+# ----------------------------------------------------------------------------- overlap
+def test_overlap_known_answer_from_the_reference_docstring():
+    """`_overlap.py:935-962`: the documented output of overlap(depth={0: 2, 1: 1}, boundary={0: 100, 1: 'reflect'})."""
+    x = np.arange(64).reshape((8, 8))
+    got = ref.overlap(ref.Blocked.from_array(x, (4, 4)), {0: 2, 1: 1}, {0: 100, 1: "reflect"})
+    assert got.chunks == ((8, 8), (6, 6))
+    cols = (0, 0, 1, 2, 3, 4, 3, 4, 5, 6, 7, 7)
+    rows = [[100] * 12] * 2 + [[r * 8 + c for c in cols] for r in (0, 1, 2, 3, 4, 5, 2, 3, 4, 5, 6, 7)] + [[100] * 12] * 2
+    assert np.array_equal(got.to_array(), np.array(rows))
+
+
+def test_overlap_host_helpers_match_reference_doctests():
+    import dask_array_b200 as da
+    assert da.overlap.ensure_minimum_chunksize(10, (20, 20, 1)) == (20, 11, 10)      # _overlap.py:849-852
+    assert da.overlap.ensure_minimum_chunksize(3, (1, 1, 3)) == (5,)
+    x = da.from_array(np.zeros((8, 8)), chunks=(4, 4))
+    assert da.overlap.overlap(x, depth={0: 2, 1: 1}, boundary={0: 100, 1: "reflect"}).chunks == ((8, 8), (6, 6))
+    assert da.overlap.overlap(x, depth=1, boundary="none").chunks == ((5, 5), (5, 5))
+    assert da.overlap.trim_internal(da.overlap.overlap(x, depth=1, boundary="none"), {0: 1, 1: 1}).chunks == x.chunks
