@@ -95,6 +95,16 @@ def main():
     step = da.compile(sd[300:] + 1)
     step.run(); step.run()
     assert np.array_equal(step.results()[0], sh[300:] + 1)
+    # halo exchange across the partition: neighbour rims are stored into the peer's block over NVLink
+    oh = rng.integers(0, 1000, size=(80, 60)).astype(np.int32)
+    od = da.from_array(oh, chunks=(20, 15)).persist()
+    for bnd in ("none", "periodic", "reflect"):
+        got = da.overlap.overlap(od, depth={0: 2, 1: 3}, boundary=bnd)
+        want = ref.overlap(ref.Blocked.from_array(oh, (20, 15)), {0: 2, 1: 3}, {0: bnd, 1: bnd})
+        assert got.chunks == want.chunks and np.array_equal(got.compute(), want.to_array()), bnd
+    lap = da.overlap.overlap(od, depth={0: 1, 1: 0}, boundary={0: "periodic", 1: "none"}).map_blocks(
+        lambda b: b[2:] + b[:-2] - 2 * b[1:-1], chunks=od.chunks)
+    assert np.array_equal(lap.compute(), np.roll(oh, -1, 0) + np.roll(oh, 1, 0) - 2 * oh)
     ones = da.ones((1000, 1000), chunks=(100, 100))
     assert (ones + ones.T).sum().compute() == 2_000_000.0
     dist.barrier()

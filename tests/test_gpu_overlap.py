@@ -74,7 +74,7 @@ def test_map_blocks_and_map_overlap_stencils(da):
     want = -4 * xh + np.roll(xh, 1, 0) + np.roll(xh, -1, 0) + np.roll(xh, 1, 1) + np.roll(xh, -1, 1)
     np.testing.assert_allclose(s.compute(), want, rtol=1e-13, atol=1e-13)
     with pytest.raises(TypeError):
-        x.map_blocks(lambda b: b.to_numpy()).compute()          # host results are refused, loudly
+        x.map_blocks(lambda b: b.to_numpy(), dtype=np.float64).compute()      # host results are refused, loudly
 
 
 def test_compiled_replay_with_map_blocks(da):
