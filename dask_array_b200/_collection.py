@@ -276,6 +276,16 @@ class Array:
     def argmax(self, axis=None, keepdims=False, split_every=None):
         return self._reduce("argmax", axis, keepdims, None, split_every)
 
+    def topk(self, k, axis=-1, split_every=None):
+        from ._topk import topk
+
+        return topk(self, k, axis=axis, split_every=split_every)
+
+    def argtopk(self, k, axis=-1, split_every=None):
+        from ._topk import argtopk
+
+        return argtopk(self, k, axis=axis, split_every=split_every)
+
     def map_blocks(self, func, *args, **kwargs):
         from ._overlap import map_blocks
 

@@ -383,6 +383,110 @@ class Executor:
                 st.keepalive.append(launch)
         return st
 
+    # ------------------------------------------------------------------ top-k
+    def _run_TopK(self, expr):
+        """``topk`` / ``argtopk`` (``routines/_topk.py``): per chain of blocks along the axis, level 0 sorts
+        the segments of every block row and keeps their best k (value, global index) candidates; further
+        levels do the same on the candidate rows until one segment is left.  One launch per block at level 0,
+        one per level afterwards."""
+        import ctypes as C
+
+        if self.world.size > 1:
+            raise NotImplementedError("topk across several GPUs (gather the array on one rank first)")
+        x = expr.operand("array")
+        src = self.results[x._name]
+        k, axis, want_arg = expr.operand("k"), expr.operand("axis"), expr.operand("arg")
+        largest, kabs = k > 0, abs(k)
+        item = x.dtype.itemsize
+        seg_max = 4096 if item <= 4 else 2048
+        ntot = x.shape[axis]
+        if min(kabs, ntot) > seg_max // 2 and ntot > seg_max:
+            raise NotImplementedError(f"topk with k > {seg_max // 2} over an axis longer than {seg_max}")
+        code = _lib.dtype_code(x.dtype)
+        st = BlockStore(expr)
+        nd = x.ndim
+        perm = tuple(d for d in range(nd) if d != axis) + (axis,)
+        ident = cg.Program()
+        ident.set_output(ident.op("astype", ident.add_input(x.dtype), dtype=x.dtype))
+
+        def pow2(v):
+            p = 2
+            while p < v:
+                p *= 2
+            return p
+
+        def rows_last(chunk):
+            """(rows, n) contiguous view of a block with the axis moved last (copied once if needed)."""
+            moved = chunk.transpose(perm)
+            if not moved.is_contiguous:
+                out = DeviceChunk.empty(moved.shape, moved.dtype, self.device)
+                if moved.size:
+                    for launch in rt.fused_launches(ident, _lib.RED_NONE, (), [rt.BlockArgs(
+                            shape=moved.shape, inputs=[(moved.ptr, moved.strides)], out0=out.ptr)]):
+                        self._do(launch.run)
+                        st.keepalive.append(launch)
+                moved = out
+            return moved
+
+        def launch(src_ptr, rows, n, pitch, seg, vals, idx, out_pitch, in_idx, off):
+            args = (code, src_ptr, rows, n, pitch, seg, kabs, int(largest), vals, idx, out_pitch, in_idx, off)
+            self._do(lambda: _lib.check(_lib.lib.b2_topk_rows(*args, rt.current_stream_ptr())))
+
+        others = [range(nb) for d, nb in enumerate(x.numblocks) if d != axis]
+        for cid in itertools.product(*others):
+            bids = [cid[:axis] + (i,) + cid[axis:] for i in range(x.numblocks[axis])]
+            oshape = tuple(n for d, n in enumerate(x.block_shape(bids[0])) if d != axis)
+            rows = math.prod(oshape)
+            out_bid = cid[:axis] + (0,) + cid[axis:]
+            keep = min(kabs, ntot)
+            if rows == 0 or ntot == 0:
+                st.blocks[out_bid] = DeviceChunk.empty(expr.block_shape(out_bid), expr.dtype, self.device)
+                continue
+            # ---- level 0: every block of the chain contributes min(k, seg) candidates per segment
+            plan, width = [], 0
+            for bid in bids:
+                n_i = x.block_shape(bid)[axis]
+                if n_i == 0:
+                    continue
+                seg = min(seg_max, pow2(n_i))
+                nseg = -(-n_i // seg)
+                kk = min(kabs, seg)
+                plan.append((bid, n_i, seg, width))
+                width += nseg * kk
+            vals = DeviceChunk.empty((rows, width), x.dtype, self.device)
+            idx = DeviceChunk.empty((rows, width), np.int64, self.device)
+            for bid, n_i, seg, col in plan:
+                blk = rows_last(src.blocks[bid])
+                st.keepalive.append(blk)
+                launch(blk.ptr, rows, n_i, n_i, seg, vals.ptr + col * item, idx.ptr + col * 8, width, None,
+                       x.block_start(bid)[axis])
+            single = len(plan) == 1 and -(-plan[0][1] // plan[0][2]) == 1
+            # ---- further levels on the candidate rows
+            while not single:
+                seg = min(seg_max, pow2(width))
+                nseg = -(-width // seg)
+                kk = min(kabs, seg)
+                nv = DeviceChunk.empty((rows, nseg * kk), x.dtype, self.device)
+                ni = DeviceChunk.empty((rows, nseg * kk), np.int64, self.device)
+                launch(vals.ptr, rows, width, width, seg, nv.ptr, ni.ptr, nseg * kk, idx.ptr, 0)
+                st.keepalive.extend([vals, idx])
+                vals, idx, width = nv, ni, nseg * kk
+                single = nseg == 1
+            res = idx if want_arg else vals
+            # (rows, width) with the best `keep` first -> block shaped like the input with the axis last ...
+            strides = []
+            acc = width
+            for n in reversed(oshape):
+                strides.append(acc)
+                acc *= max(n, 1)
+            view = DeviceChunk(res.buf, oshape + (keep,), res.dtype, strides=tuple(reversed(strides)) + (1,), offset=res.offset)
+            inv = [0] * nd
+            for pos, d in enumerate(perm):
+                inv[d] = pos
+            st.blocks[out_bid] = view.transpose(tuple(inv))         # ... and the axis back in its place (a view)
+            st.keepalive.extend([vals, idx])
+        return st
+
     # ------------------------------------------------------------------ cumulative scans
     def _run_CumReduction(self, expr: CumReduction):
         """cumsum / cumprod (``reductions/_cumulative.py:100-265``) in three steps, 3 N bytes:

@@ -608,6 +608,107 @@ extern "C" int b2_memcpy2d(void* dst, int64_t dst_pitch, const void* src, int64_
     return B2_OK;
 }
 
+// ------------------------------------------------------------------ top-k (AOT)
+// strict weak order "a is better than b": NaN counts as the largest value (np.sort / np.partition put it
+// last), invalid (padding, idx < 0) entries are the worst, ties go to the smaller index.
+template <typename T, bool LARGEST>
+__device__ __forceinline__ bool b2_topk_better(T av, int ai, T bv, int bi) {
+    if (ai < 0 || bi < 0) return bi < 0 && ai >= 0;
+    const bool an = b2_isnan(av), bn = b2_isnan(bv);
+    if (an || bn) {
+        if (an && bn) return ai < bi;
+        return LARGEST ? an : bn;
+    }
+    if (av == bv) return ai < bi;
+    return LARGEST ? (av > bv) : (av < bv);
+}
+
+template <typename T, bool LARGEST>
+__global__ void __launch_bounds__(256) b2_topk_kernel(const T* __restrict__ src, i64 n, i64 src_pitch, int seg, int nseg,
+                                                      int kk, T* __restrict__ out_vals, i64* __restrict__ out_idx,
+                                                      i64 out_pitch, const i64* __restrict__ in_idx, i64 idx_offset) {
+    extern __shared__ __align__(16) unsigned char b2_topk_smem[];
+    T* sv = reinterpret_cast<T*>(b2_topk_smem);
+    int* si = reinterpret_cast<int*>(b2_topk_smem + (size_t)seg * sizeof(T));
+    const i64 row = blockIdx.x / nseg;
+    const int s = (int)(blockIdx.x % nseg);
+    const i64 e0 = (i64)s * seg;
+    const int len = (int)((n - e0 < seg) ? (n - e0) : seg);
+    const T* rp = src + row * src_pitch + e0;
+    for (int i = threadIdx.x; i < seg; i += blockDim.x) {
+        // candidates of an earlier level carry idx = -1 where their segment ran out of elements
+        const bool ok = i < len && !(in_idx && in_idx[row * n + e0 + i] < 0);
+        if (ok) { sv[i] = rp[i]; si[i] = i; } else { sv[i] = T(); si[i] = -1; }
+    }
+    __syncthreads();
+    for (int size = 2; size <= seg; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < seg / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);                 // this sub-sequence sorts best-first
+                const T a = sv[lo], b = sv[hi];
+                const int ia = si[lo], ib = si[hi];
+                const bool swap = up ? b2_topk_better<T, LARGEST>(b, ib, a, ia) : b2_topk_better<T, LARGEST>(a, ia, b, ib);
+                if (swap) { sv[lo] = b; sv[hi] = a; si[lo] = ib; si[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    T* ov = out_vals + row * out_pitch + (i64)s * kk;
+    i64* oi = out_idx + row * out_pitch + (i64)s * kk;
+    for (int j = threadIdx.x; j < kk; j += blockDim.x) {
+        const int li = si[j];
+        ov[j] = sv[j];
+        oi[j] = (li < 0) ? (i64)-1 : (in_idx ? in_idx[row * n + e0 + li] : idx_offset + e0 + li);
+    }
+}
+
+template <typename T>
+static int launch_topk(const void* src, int64_t rows, int64_t n, int64_t src_pitch, int seg, int k, int largest,
+                       void* out_vals, int64_t* out_idx, int64_t out_pitch, const int64_t* in_idx, int64_t idx_offset,
+                       cudaStream_t st) {
+    const int nseg = (int)cdiv(n, (int64_t)seg);
+    const int kk = k < seg ? k : seg;
+    const size_t smem = (size_t)seg * (sizeof(T) + sizeof(int));
+    const unsigned grid = (unsigned)(rows * nseg);
+    if (largest)
+        b2_topk_kernel<T, true><<<grid, 256, smem, st>>>((const T*)src, (i64)n, (i64)src_pitch, seg, nseg, kk, (T*)out_vals,
+                                                        (i64*)out_idx, (i64)out_pitch, (const i64*)in_idx, (i64)idx_offset);
+    else
+        b2_topk_kernel<T, false><<<grid, 256, smem, st>>>((const T*)src, (i64)n, (i64)src_pitch, seg, nseg, kk, (T*)out_vals,
+                                                         (i64*)out_idx, (i64)out_pitch, (const i64*)in_idx, (i64)idx_offset);
+    return B2_OK;
+}
+
+extern "C" int b2_topk_rows(int dtype, const void* src, int64_t rows, int64_t n, int64_t src_pitch, int seg, int k,
+                            int largest, void* out_vals, int64_t* out_idx, int64_t out_pitch, const int64_t* in_idx,
+                            int64_t idx_offset, void* stream) {
+    if (!src || !out_vals || !out_idx || rows < 0 || n < 0 || k <= 0) return fail(B2_ERR_INVALID, "bad argument");
+    if (rows == 0 || n == 0) return B2_OK;
+    if (seg < 2 || (seg & (seg - 1)) != 0) return fail(B2_ERR_INVALID, "topk: segment length %d is not a power of two", seg);
+    if (rows * cdiv(n, (int64_t)seg) > 0x7fffffffLL) return fail(B2_ERR_UNSUPPORTED, "topk: too many segments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = B2_OK;
+#define B2_T(DT, T)                                                                                                     \
+    case DT:                                                                                                            \
+        if ((size_t)seg * (sizeof(T) + 4) > B2_TOPK_SEG_BYTES + 16384)                                                  \
+            return fail(B2_ERR_INVALID, "topk: segment of %d elements does not fit shared memory", seg);                \
+        rc = launch_topk<T>(src, rows, n, src_pitch, seg, k, largest, out_vals, out_idx, out_pitch, in_idx, idx_offset, st); \
+        break;
+    switch (dtype) {
+        B2_T(B2_BOOL, unsigned char) B2_T(B2_I8, signed char) B2_T(B2_U8, unsigned char)
+        B2_T(B2_I16, short) B2_T(B2_U16, unsigned short) B2_T(B2_I32, int) B2_T(B2_U32, unsigned)
+        B2_T(B2_I64, long long) B2_T(B2_U64, unsigned long long) B2_T(B2_F32, float) B2_T(B2_F64, double)
+        default: return fail(B2_ERR_UNSUPPORTED, "topk: dtype %d", dtype);
+    }
+#undef B2_T
+    if (rc != B2_OK) return rc;
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------ peer memory (CUDA IPC)
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
 extern "C" int b2_ipc_export(const void* ptr, b2_ipc_handle* out) {

@@ -230,6 +230,21 @@ int b2_gather_launch(const b2_copy* d_copies, int n, int64_t total_tiles, void* 
  * multiples) and tile_rows * min(row_bytes, B2_GATHER_COL_BYTES) <= 64 KiB (what b2_gather_plan makes). */
 int b2_gather_launch_bulk(const b2_copy* d_copies, int n, int64_t total_tiles, void* stream);
 
+/* Top-k selection along the contiguous axis (chunk.topk / chunk.argtopk and their aggregates,
+ * _chunk.py:200-290; routines/_topk.py:14-80).  Every row of `rows` x `n` elements is cut into segments
+ * of `seg` elements (seg <= B2_TOPK_SEG_BYTES / (itemsize <= 4 ? 8 : 12), a power of two); one CTA sorts
+ * one segment in shared memory (bitonic network on (value, index) pairs; NaN sorts as the largest value,
+ * like np.sort) and writes its first min(k, segment length) entries, best first, to
+ *     out_vals[row * out_pitch + s * kk + j],  out_idx[...] = in_idx ? in_idx[row * n + e] : idx_offset + e
+ * with kk = min(k, seg).  Calling it again on the candidates (n' = nseg * kk, in_idx = the previous out_idx)
+ * until one segment remains gives the k best of every row, sorted.  largest != 0: the k largest, descending;
+ * else the k smallest, ascending.  Segments shorter than kk are padded with out_idx = -1 entries, which
+ * sort last and must be ignored by the caller (`valid` counts come from the lengths).                   */
+#define B2_TOPK_SEG_BYTES 32768
+int b2_topk_rows(int dtype, const void* src, int64_t rows, int64_t n, int64_t src_pitch, int seg, int k,
+                 int largest, void* out_vals, int64_t* out_idx, int64_t out_pitch, const int64_t* in_idx,
+                 int64_t idx_offset, void* stream);
+
 /* ---- peer memory (one process per GPU) ------------------------------------------
  * The reference moves blocks between workers by pickling them through the scheduler
  * (rechunk: _rechunk.py:1171-1323 getitem + concatenate3 tasks; transposed reads:

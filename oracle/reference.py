@@ -853,3 +853,50 @@ def overlap(x, depth, boundary):
             sl.append(slice(lo, hi))
         blocks[bid] = padded[tuple(sl)]
     return Blocked(blocks, tuple(chunks))
+
+
+# ----------------------------------------------------------------------------- topk / argtopk
+def _chunk_topk(a, k, axis):
+    """``chunk.topk`` (``_chunk.py:200-215``): the k largest (k < 0: -k smallest) along axis, unsorted."""
+    if abs(k) >= a.shape[axis]:
+        return a
+    a = np.partition(a, -k, axis=axis)
+    k_slice = slice(-k, None) if k > 0 else slice(-k)
+    return a[tuple(k_slice if i == axis else slice(None) for i in range(a.ndim))]
+
+
+def da_topk(x, k, axis=-1, split_every=4):
+    """``topk`` (``routines/_topk.py:14-40``): ``reduction`` with chunk = combine = ``chunk.topk`` and
+    aggregate = ``chunk.topk_aggregate`` (``_chunk.py:218-229``: topk once more, then sort -- descending for
+    k > 0).  Pinned by tests/golden/topk.npz."""
+    axis %= x.ndim
+    nb = x.numblocks
+    out = {}
+    for cid in itertools.product(*[range(n) if d != axis else [0] for d, n in enumerate(nb)]):
+        parts = [_chunk_topk(x.blocks[cid[:axis] + (i,) + cid[axis + 1:]], k, axis) for i in range(nb[axis])]
+        while len(parts) > split_every:
+            parts = [_chunk_topk(np.concatenate(parts[i:i + split_every], axis=axis), k, axis)
+                     for i in range(0, len(parts), split_every)]
+        a = np.sort(_chunk_topk(np.concatenate(parts, axis=axis), k, axis), axis=axis)
+        if k > 0:
+            a = a[tuple(slice(None, None, -1) if i == axis else slice(None) for i in range(a.ndim))]
+        out[cid] = a
+    keep = min(abs(k), x.shape[axis])
+    return Blocked(out, tuple((keep,) if d == axis else c for d, c in enumerate(x.chunks)))
+
+
+def da_argtopk(x, k, axis=-1):
+    """``argtopk`` (``routines/_topk.py:43-80``; ``chunk.argtopk`` / ``argtopk_aggregate`` ``_chunk.py:240-281``):
+    the positions along ``axis`` of the elements ``topk`` returns, in the same order.  Restated on the
+    whole chain (for distinct values the tree shape cannot change the answer)."""
+    axis %= x.ndim
+    nb = x.numblocks
+    out = {}
+    for cid in itertools.product(*[range(n) if d != axis else [0] for d, n in enumerate(nb)]):
+        a = np.concatenate([x.blocks[cid[:axis] + (i,) + cid[axis + 1:]] for i in range(nb[axis])], axis=axis)
+        order = np.argsort(a, axis=axis, kind="stable")
+        if k > 0:
+            order = order[tuple(slice(None, None, -1) if i == axis else slice(None) for i in range(a.ndim))]
+        out[cid] = order[tuple(slice(0, abs(k)) if i == axis else slice(None) for i in range(a.ndim))].astype(np.intp)
+    keep = min(abs(k), x.shape[axis])
+    return Blocked(out, tuple((keep,) if d == axis else c for d, c in enumerate(x.chunks)))

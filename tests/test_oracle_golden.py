@@ -257,3 +257,20 @@ def test_overlap_host_helpers_match_reference_doctests():
     assert da.overlap.overlap(x, depth={0: 2, 1: 1}, boundary={0: 100, 1: "reflect"}).chunks == ((8, 8), (6, 6))
     assert da.overlap.overlap(x, depth=1, boundary="none").chunks == ((5, 5), (5, 5))
     assert da.overlap.trim_internal(da.overlap.overlap(x, depth=1, boundary="none"), {0: 1, 1: 1}).chunks == x.chunks
+
+
+# ----------------------------------------------------------------------------- topk
+def _topk_golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "topk.npz"))
+
+
+@pytest.mark.parametrize("case", sorted({k.split("/")[0] for k in _topk_golden().files}))
+def test_topk_matches_reference_chunk_functions(case):
+    g = _topk_golden()
+    chunks, k, axis = ast.literal_eval(str(g[case + "/meta"][0]))
+    xh = g[case + "/x"]
+    got = ref.da_topk(ref.Blocked.from_array(xh, chunks), k, axis).to_array()
+    assert np.array_equal(got, g[case + "/topk"], equal_nan=True)
+    if case + "/argtopk" in g.files:
+        gi = ref.da_argtopk(ref.Blocked.from_array(xh, chunks), k, axis).to_array()
+        assert np.array_equal(gi, g[case + "/argtopk"])
