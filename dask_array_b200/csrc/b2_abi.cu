@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(256) b2_topk_kernel(const T* __restrict__ src,
                                                       i64 out_pitch, const i64* __restrict__ in_idx, i64 idx_offset) {
     extern __shared__ __align__(16) unsigned char b2_topk_smem[];
     T* sv = reinterpret_cast<T*>(b2_topk_smem);
-    int* si = reinterpret_cast<int*>(b2_topk_smem + (size_t)seg * sizeof(T));
+    int* si = reinterpret_cast<int*>(b2_topk_smem + (((size_t)seg * sizeof(T) + 15) & ~(size_t)15));
     const i64 row = blockIdx.x / nseg;
     const int s = (int)(blockIdx.x % nseg);
     const i64 e0 = (i64)s * seg;
@@ -670,7 +670,7 @@ static int launch_topk(const void* src, int64_t rows, int64_t n, int64_t src_pit
                        cudaStream_t st) {
     const int nseg = (int)cdiv(n, (int64_t)seg);
     const int kk = k < seg ? k : seg;
-    const size_t smem = (size_t)seg * (sizeof(T) + sizeof(int));
+    const size_t smem = (((size_t)seg * sizeof(T) + 15) & ~(size_t)15) + (size_t)seg * sizeof(int);
     const unsigned grid = (unsigned)(rows * nseg);
     if (largest)
         b2_topk_kernel<T, true><<<grid, 256, smem, st>>>((const T*)src, (i64)n, (i64)src_pitch, seg, nseg, kk, (T*)out_vals,
