@@ -1,0 +1,514 @@
+"""Moving blocks between GPUs (one process per GPU): block-cyclic ownership, the pure planners every
+rank evaluates identically (no negotiation traffic), the peer-memory data path (stores into / loads from
+the peers' HBM over NVLink, ``_peer``) and the packed NCCL exchange kept for comparison
+(``B2_COMM=nccl``).  Used by ``_executor.Executor``; SURVEY.md section 8e.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+
+import numpy as np
+import torch
+
+from . import _peer
+from . import _runtime as rt
+from ._blockwise import FusedPlan
+from ._device import DeviceChunk, alloc_bytes
+from ._expr import ArrayExpr
+from ._rechunk import TasksRechunk
+
+def _copy_descs(src: DeviceChunk, dst: DeviceChunk, item: int):
+    """2-D copy rectangles moving ``src`` into ``dst`` (same shape, arbitrary strides with a
+    unit-stride innermost run)."""
+    shape = [n for n in src.shape]
+    if math.prod(shape) == 0:
+        return []
+    dims = [(n, s, d) for n, s, d in zip(shape, src.strides, dst.strides) if n != 1]
+    if not dims:
+        return [(src.ptr, dst.ptr, 1, item, item, item)]
+    merged = []
+    for n, s, d in dims:
+        if merged and merged[-1][1] == s * n and merged[-1][2] == d * n:
+            merged[-1] = (merged[-1][0] * n, s, d)
+        else:
+            merged.append((n, s, d))
+    if merged[-1][1] != 1 or merged[-1][2] != 1:
+        merged.append((1, 1, 1))        # e.g. a single column: rows of one element each
+    n_in, s_in, d_in = merged[-1]
+    outer = merged[:-1]
+    if not outer:
+        return [(src.ptr, dst.ptr, 1, n_in * item, n_in * item, n_in * item)]
+    rows, s_row, d_row = outer[-1]
+    lead = outer[:-1]
+    out = []
+    for idx in itertools.product(*[range(n) for n, _, _ in lead]):
+        so = sum(i * s for i, (_, s, _) in zip(idx, lead))
+        do = sum(i * d for i, (_, _, d) in zip(idx, lead))
+        out.append((src.ptr + so * item, dst.ptr + do * item, rows, n_in * item, s_row * item, d_row * item))
+    return out
+
+
+# ----------------------------------------------------------------------------- NCCL plumbing
+def _allgather_blocks(ex, src: BlockStore, x):
+    """All-gather the (tiny) per-block partials of ``x`` so every rank can fold the tree."""
+    import torch.distributed as dist
+
+    W, me = ex.world.size, ex.world.rank
+    ids = list(x.block_ids())
+
+    def fields(b):
+        if isinstance(b, dict):
+            return [(k, v) for k, v in sorted(b.items()) if isinstance(v, DeviceChunk)]
+        return [("", b)]
+
+    # layout is derivable on every rank from shapes alone
+    def proto(bid):
+        kshape = x.block_shape(bid)
+        if src.kind == "moment":
+            return [("", tuple(kshape) + (3,), np.dtype(np.float64))]
+        if src.kind == "mean":
+            return [("total", kshape, x.dtype)]
+        if src.kind == "arg":
+            vdt = x.operand("array").dtype
+            return [("arg", kshape, np.dtype(np.int64)), ("vals", kshape, vdt)]
+        return [("", kshape, x.dtype)]
+
+    def nbytes(bid):
+        return sum(-(-math.prod(s) * d.itemsize // 16) * 16 for _, s, d in proto(bid))
+
+    per_rank = [sum(nbytes(b) for b in ids if ex.world.owner(x, b) == r) for r in range(W)]
+    cap = max(max(per_rank), 16)
+    send = alloc_bytes(cap, ex.device)
+    off = 0
+    copies = []
+    for bid in ids:
+        if ex.world.owner(x, bid) != me:
+            continue
+        blk = src.blocks[bid]
+        for (name, chunk), (_, shp, dt) in zip(fields(blk), proto(bid)):
+            nb = math.prod(shp) * dt.itemsize
+            if nb:
+                copies.append((chunk.ptr, send.data_ptr() + off, 1, nb, nb, nb))
+            off += -(-nb // 16) * 16
+    g = rt.GatherLaunch(copies)
+    ex._do(g.run)
+    recv = alloc_bytes(cap * W, ex.device)
+    ex._do(lambda: dist.all_gather_into_tensor(recv, send))
+    out = {}
+    offs = [0] * W
+    for bid in ids:
+        r = ex.world.owner(x, bid)
+        parts = {}
+        for name, shp, dt in proto(bid):
+            nb = math.prod(shp) * dt.itemsize
+            parts[name] = DeviceChunk(recv, shp, dt, offset=(r * cap + offs[r]) // dt.itemsize)
+            offs[r] += -(-nb // 16) * 16
+        if src.kind == "mean":
+            red = x.root if type(x).__name__ == "FusedBlockwise" else x        # the ChunkReduce
+            axes = red.operand("axis")
+            top = red.operand("array")
+            n = math.prod(top.block_shape(bid)[a] for a in axes)
+            out[bid] = {"total": parts["total"], "n": n}
+        elif src.kind == "arg":
+            out[bid] = parts
+        else:
+            out[bid] = parts[""]
+    src.keepalive.extend([send, recv, g])
+    return out
+
+
+def _p2p_exchange(ex, sends, recvs):
+    """sends: [(peer, tensor)], recvs: [(peer, tensor)] in a globally consistent order."""
+    import torch.distributed as dist
+
+    ops = [dist.P2POp(dist.isend, t, p) for p, t in sends] + [dist.P2POp(dist.irecv, t, p) for p, t in recvs]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def owner_of(expr, bid, world_size: int) -> int:
+    """Block-cyclic placement: ``ravel(block id) mod world``."""
+    if world_size == 1:
+        return 0
+    nb = expr.numblocks
+    return (int(np.ravel_multi_index(bid, nb)) if nb else 0) % world_size
+
+
+def plan_fused_exchange(plan: FusedPlan, replicated, W: int, me: int):
+    """Pure (no device) schedule of the blocks a fused expression reads across the partition.
+    Returns (send_items, recv_items): per peer, lists in one global canonical order --
+    every rank derives the same order from the expression metadata, so sends and receives
+    pair up without negotiation.  Items: (leaf index k, leaf block id, nbytes)."""
+    expr = plan.fused
+    wanted = {}
+    for bid in expr.block_ids():
+        r = owner_of(expr, bid, W)
+        for k, (dep, _) in enumerate(plan.leaves):
+            if replicated[k]:
+                continue
+            lbid = plan.leaf_block_id(k, bid)
+            o = owner_of(dep, lbid, W)
+            if o != r:
+                wanted[(r, dep._name, lbid)] = (o, k)
+    send_items = {p: [] for p in range(W)}
+    recv_items = {p: [] for p in range(W)}
+    for (r, name, lbid) in sorted(wanted):
+        o, k = wanted[(r, name, lbid)]
+        dep = plan.leaves[k][0]
+        nb = math.prod(dep.block_shape(lbid)) * dep.dtype.itemsize
+        if o == me:
+            send_items[r].append((k, lbid, nb))
+        if r == me:
+            recv_items[o].append((k, lbid, nb))
+    return send_items, recv_items
+
+
+def plan_block_fetch(wanted, W: int, me: int):
+    """Pure schedule for whole-block reads across the partition.  ``wanted``: iterable of
+    (reader rank, dep expr, block id) over ALL ranks (every rank computes the same list).
+    Returns (send_items, recv_items) per peer: (dep expr, block id, nbytes), canonical order."""
+    uniq = {}
+    for r, dep, bid in wanted:
+        o = owner_of(dep, bid, W)
+        if o != r:
+            uniq[(r, dep._name, bid)] = (o, dep)
+    send_items = {p: [] for p in range(W)}
+    recv_items = {p: [] for p in range(W)}
+    for (r, name, bid) in sorted(uniq):
+        o, dep = uniq[(r, name, bid)]
+        nb = math.prod(dep.block_shape(bid)) * dep.dtype.itemsize
+        if o == me:
+            send_items[r].append((dep, bid, nb))
+        if r == me:
+            recv_items[o].append((dep, bid, nb))
+    return send_items, recv_items
+
+
+def _fetch_blocks(ex, wanted, stores):
+    """Execute a ``plan_block_fetch`` schedule over NCCL; ``stores``: {dep name: BlockStore}.
+    Returns {(dep name, block id): DeviceChunk} for the blocks this rank received."""
+    W, me = ex.world.size, ex.world.rank
+    send_items, recv_items = plan_block_fetch(wanted, W, me)
+    pad = lambda n: -(-n // 256) * 256
+    sends, recvs, keep, out = [], [], [], {}
+    for p in range(W):
+        if send_items[p]:
+            buf = alloc_bytes(sum(pad(nb) for *_, nb in send_items[p]), ex.device)
+            off, copies = 0, []
+            for dep, bid, nb in send_items[p]:
+                blk = stores[dep._name].blocks[bid]
+                flat = DeviceChunk(buf, blk.shape, blk.dtype, offset=off // blk.itemsize)
+                copies.extend(_copy_descs(blk, flat, blk.itemsize))
+                off += pad(nb)
+            g = rt.GatherLaunch(copies)
+            ex._do(g.run)
+            keep.append(g)
+            sends.append((p, buf))
+        if recv_items[p]:
+            buf = alloc_bytes(sum(pad(nb) for *_, nb in recv_items[p]), ex.device)
+            off = 0
+            for dep, bid, nb in recv_items[p]:
+                out[(dep._name, bid)] = DeviceChunk(buf, dep.block_shape(bid), dep.dtype, offset=off // dep.dtype.itemsize)
+                off += pad(nb)
+            recvs.append((p, buf))
+    if sends or recvs:
+        ex._do(lambda: _p2p_exchange(ex, sends, recvs))
+    out["__keep__"] = (keep, sends, recvs)
+    return out
+
+
+def plan_rechunk_exchange(expr: TasksRechunk, W: int, me: int):
+    """Pure schedule of the rectangles a rechunk moves across the partition (the all-to-all of
+    SURVEY.md 8e).  Items: (old block id, new block id, source slices, piece shape, nbytes)."""
+    x = expr.operand("array")
+    item = expr.dtype.itemsize
+    send_items = {p: [] for p in range(W)}
+    recv_items = {p: [] for p in range(W)}
+    for nbid in expr.block_ids():
+        r = owner_of(expr, nbid, W)
+        for obid, sl, dsl in expr.pieces(nbid):
+            o = owner_of(x, obid, W)
+            if o == r:
+                continue
+            shape = tuple(s.stop - s.start for s in sl)
+            nb = math.prod(shape) * item
+            if o == me:
+                send_items[r].append((obid, nbid, sl, shape, nb))
+            if r == me:
+                recv_items[o].append((obid, nbid, sl, shape, nb))
+    return send_items, recv_items
+
+
+def plan_rechunk_push(expr: TasksRechunk, W: int, me: int):
+    """Pure (no device) plan of a rechunk across the partition as ONE gather per rank that stores
+    straight into the owners' memory.  Every rank lays out the new blocks of every rank the same
+    way (one slab per rank, blocks in block-id order, 512-byte aligned).  Returns
+    ``(layout, totals, pushes)``: ``layout[r] = {new block id: byte offset in rank r's slab}``,
+    ``totals[r]`` = slab bytes, ``pushes`` = [(old block id, source slices, owner rank of the new
+    block, new block id, destination slices)] for every piece whose SOURCE block ``me`` owns --
+    local pieces included: the same launch moves them."""
+    x = expr.operand("array")
+    item = expr.dtype.itemsize
+    layout = [dict() for _ in range(W)]
+    totals = [0] * W
+    pushes = []
+    per_dest = [[] for _ in range(W)]
+    for nbid in expr.block_ids():
+        r = owner_of(expr, nbid, W)
+        layout[r][nbid] = totals[r]
+        totals[r] += -(-math.prod(expr.block_shape(nbid)) * item // 512) * 512
+        for obid, sl, dsl in expr.pieces(nbid):
+            if owner_of(x, obid, W) == me:
+                per_dest[r].append((obid, sl, r, nbid, dsl))
+    # All-to-all schedule: consecutive pieces go to DIFFERENT owners, starting with the right-hand
+    # neighbour -- at any moment rank r stores to r+1, r+2, ... and no owner is the target of every
+    # rank at once (in block-id order all ranks would hammer rank 0's NVLink ingress first).
+    rot = [per_dest[(me + 1 + k) % W] for k in range(W)]
+    for i in range(max((len(q) for q in rot), default=0)):
+        for q in rot:
+            if i < len(q):
+                pushes.append(q[i])
+    return layout, totals, pushes
+
+
+def _rechunk_push(ex, expr: TasksRechunk, src: BlockStore, st: BlockStore):
+    """The all-to-all of a rechunk as the rechunk kernel itself: every rank's tiled
+    gather reads its own old blocks and writes the pieces into the new blocks where they live --
+    local HBM or a peer's HBM over NVLink (``_peer``) -- bracketed by two stream-ordered barriers.
+    Bytes per element: one read + one write, wherever the destination is."""
+    W, me = ex.world.size, ex.world.rank
+    item = expr.dtype.itemsize
+    layout, totals, pushes = plan_rechunk_push(expr, W, me)
+    slab = alloc_bytes(totals[me], ex.device)
+    for nbid, off in layout[me].items():
+        st.blocks[nbid] = DeviceChunk(slab, expr.block_shape(nbid), expr.dtype, offset=off // item)
+    bases = [p[0] for p in _peer.exchange_pointers(ex.device, [slab.data_ptr()], [1] * W, me)]
+    windows = [slab if r == me else _peer.PeerBuffer(bases[r], ex.device, totals[r], r) for r in range(W)]
+    copies = []
+    for obid, sl, r, nbid, dsl in pushes:
+        dst = DeviceChunk(windows[r], expr.block_shape(nbid), expr.dtype, offset=layout[r][nbid] // item)
+        copies.extend(_copy_descs(src.blocks[obid][sl], dst[dsl], item))
+    launch = rt.GatherLaunch(copies)
+    bar = _peer.StreamBarrier(ex.device, me, W)
+    ex._do(bar)                 # every owner is done with the previous contents of its slab
+    ex._do(launch.run)
+    ex._do(bar)                 # every piece has landed before anyone reads a new block
+    st.keepalive.extend([launch, slab, bar, windows])
+    return st
+
+
+def _interleave_remote_reads(blocks, owners, me: int, W: int, in_items, out_item: int, band_rows: int = 256):
+    """Element-wise blocks whose operands sit in peers' memory are cut into row bands and dealt so
+    that consecutive bands read from DIFFERENT peers, starting with the right-hand neighbour: every
+    NVLink port pair is busy all the time instead of all ranks pulling from rank 0 first."""
+    if len(owners) != len(blocks) or not any(o != me for o in owners):
+        return blocks
+    per_owner = [[] for _ in range(W)]
+    for b, o in zip(blocks, owners):
+        if len(b.shape) != 2 or b.shape[0] <= band_rows or b.out1:
+            per_owner[o].append(b)
+            continue
+        R, Ccols = b.shape
+        for a in range(0, R, band_rows):
+            n = min(band_rows, R - a)
+            ins = [(ptr + a * st[0] * item, st) for (ptr, st), item in zip(b.inputs, in_items)]
+            per_owner[o].append(rt.BlockArgs(shape=(n, Ccols), inputs=ins, out0=b.out0 + a * Ccols * out_item))
+    rot = [per_owner[(me + 1 + k) % W] for k in range(W)]
+    out = []
+    for i in range(max(len(q) for q in rot)):
+        for q in rot:
+            if i < len(q):
+                out.append(q[i])
+    return out
+
+
+def _push_views(ex, expr, st: BlockStore, src: BlockStore, moves):
+    """Output blocks of a structural expression (slice, concatenate, expand_dims ...) whose source block
+    lives on ANOTHER GPU: the source's owner stores the selected view straight into the block at its new
+    owner -- one gather launch per rank over peer memory, bracketed by the stream barrier (the same
+    mechanism as the rechunk all-to-all).  ``moves``: [(output block id, source owner, view(block), source
+    block id)] in the same order on every rank."""
+    if not _peer.enabled():
+        raise NotImplementedError(f"{type(expr).__name__} that moves blocks between GPUs needs the peer-memory "
+                                  "path (B2_COMM=peer); rechunk first")
+    W, me = ex.world.size, ex.world.rank
+    item = expr.dtype.itemsize
+    layout, totals = {}, [0] * W
+    for bid, _, _, _ in moves:
+        r = ex.world.owner(expr, bid)
+        layout[bid] = (r, totals[r])
+        totals[r] += -(-math.prod(expr.block_shape(bid)) * item // 512) * 512
+    slab = alloc_bytes(totals[me], ex.device)
+    bases = [p[0] for p in _peer.exchange_pointers(ex.device, [slab.data_ptr()], [1] * W, me)]
+    windows = [slab if r == me else _peer.PeerBuffer(bases[r], ex.device, totals[r], r) for r in range(W)]
+    copies = []
+    for bid, src_owner, view, ibid in moves:
+        r, off = layout[bid]
+        dst = DeviceChunk(windows[r], expr.block_shape(bid), expr.dtype, offset=off // item)
+        if r == me:
+            st.blocks[bid] = dst
+        if src_owner == me:
+            copies.extend(_copy_descs(view(src.blocks[ibid]), dst, item))
+    launch = rt.GatherLaunch(copies)
+    bar = _peer.StreamBarrier(ex.device, me, W)
+    ex._do(bar)
+    ex._do(launch.run)
+    ex._do(bar)
+    st.keepalive.extend([launch, slab, windows])
+
+
+def plan_fused_peer_reads(plan: FusedPlan, replicated, W: int):
+    """Pure plan of the remote block reads of a fused expression: ``exports[o]`` = the (leaf index,
+    leaf block id) pairs rank o owns and some other rank reads, in one canonical order;
+    ``readers[(o, i)]`` = the set of ranks reading export i of rank o."""
+    expr = plan.fused
+    wanted = {}
+    for bid in expr.block_ids():
+        r = owner_of(expr, bid, W)
+        for k, (dep, _) in enumerate(plan.leaves):
+            if replicated[k]:
+                continue
+            lbid = plan.leaf_block_id(k, bid)
+            o = owner_of(dep, lbid, W)
+            if o != r:
+                wanted.setdefault((o, dep._name, lbid), [k, set()])[1].add(r)
+    exports = [[] for _ in range(W)]
+    readers = {}
+    for (o, name, lbid) in sorted(wanted):
+        k, rs = wanted[(o, name, lbid)]
+        readers[(o, len(exports[o]))] = rs
+        exports[o].append((k, lbid))
+    return exports, readers
+
+
+def _peer_reads_for_fused(ex, plan: FusedPlan, deps):
+    """Remote operands of a fused expression (``x.T + x`` across the partition) are read IN PLACE:
+    the owners export the blocks once, the fused kernel of the reading rank loads them over NVLink
+    while it computes -- no pack, no send/recv, no staging copy.  Returns {(dep name, block id):
+    DeviceChunk over peer memory}; ``__barrier__`` must bracket the launch on the tape."""
+    import struct
+
+    W, me = ex.world.size, ex.world.rank
+    exports, readers = plan_fused_peer_reads(plan, [d.replicated for d in deps], W)
+    if not any(exports):
+        return {}
+    rec = _peer.HANDLE_BYTES + 8 * 9
+    mine = []
+    for k, lbid in exports[me]:
+        blk = deps[k].blocks[lbid]
+        st = list(blk.strides) + [0] * (8 - blk.ndim)
+        mine.append(_peer.export_handle(blk.ptr) + struct.pack("<9q", blk.ndim, *st))
+    recs = _peer.exchange_records(ex.device, mine, [len(e) for e in exports], rec)
+    out = {}
+    for o in range(W):
+        if o == me:
+            continue
+        for i, (k, lbid) in enumerate(exports[o]):
+            if me not in readers[(o, i)]:
+                continue
+            raw = recs[o][i]
+            meta = struct.unpack("<9q", raw[_peer.HANDLE_BYTES:])
+            dep = plan.leaves[k][0]
+            ptr = _peer.open_handle(raw[: _peer.HANDLE_BYTES])
+            out[(dep._name, lbid)] = DeviceChunk(_peer.PeerBuffer(ptr, ex.device, owner=o), dep.block_shape(lbid),
+                                                 dep.dtype, strides=meta[1: 1 + meta[0]])
+    out["__barrier__"] = _peer.StreamBarrier(ex.device, me, W)
+    return out
+
+
+def _exchange_for_fused(ex, plan: FusedPlan, deps, out_ids):
+    """Blocks of dependencies that some rank's output blocks read but another rank owns are
+    packed per peer, exchanged over NCCL and exposed as DeviceChunks."""
+    W, me = ex.world.size, ex.world.rank
+    if _peer.enabled():
+        return _peer_reads_for_fused(ex, plan, deps)
+    send_items, recv_items = plan_fused_exchange(plan, [d.replicated for d in deps], W, me)
+    if not any(send_items.values()) and not any(recv_items.values()):
+        return {}
+    pad = lambda n: -(-n // 256) * 256
+    sends, recvs, keep, out = [], [], [], {}
+    for p in range(W):
+        if send_items[p]:
+            buf = alloc_bytes(sum(pad(nb) for _, _, nb in send_items[p]), ex.device)
+            off, copies = 0, []
+            for k, lbid, nb in send_items[p]:
+                blk = deps[k].blocks[lbid]
+                flat = DeviceChunk(buf, blk.shape, blk.dtype, offset=off // blk.itemsize)
+                copies.extend(_copy_descs(blk, flat, blk.itemsize))
+                off += pad(nb)
+            g = rt.GatherLaunch(copies)
+            ex._do(g.run)
+            keep.append(g)
+            sends.append((p, buf))
+        if recv_items[p]:
+            buf = alloc_bytes(sum(pad(nb) for _, _, nb in recv_items[p]), ex.device)
+            off = 0
+            for k, lbid, nb in recv_items[p]:
+                dep = plan.leaves[k][0]
+                out[(dep._name, lbid)] = DeviceChunk(buf, dep.block_shape(lbid), dep.dtype, offset=off // dep.dtype.itemsize)
+                off += pad(nb)
+            recvs.append((p, buf))
+    ex._do(lambda: _p2p_exchange(ex, sends, recvs))
+    out["__keep__"] = (keep, sends, recvs)
+    return out
+
+
+def _exchange_for_rechunk(ex, expr: TasksRechunk, src: BlockStore, new_ids):
+    """All-to-all of the rectangles a rechunk moves across the partition: pack (gather kernel)
+    -> NCCL send/recv -> the local gather reads the received pieces in place."""
+    W, me = ex.world.size, ex.world.rank
+    item = expr.dtype.itemsize
+    pad = lambda n: -(-n // 256) * 256
+    send_items, recv_items = plan_rechunk_exchange(expr, W, me)
+    sends, recvs, keep, out = [], [], [], {}
+    for p in range(W):
+        if send_items[p]:
+            buf = alloc_bytes(sum(pad(it[-1]) for it in send_items[p]), ex.device)
+            off, copies = 0, []
+            for obid, nbid, sl, shape, nb in send_items[p]:
+                piece = src.blocks[obid][sl]
+                flat = DeviceChunk(buf, shape, expr.dtype, offset=off // item)
+                copies.extend(_copy_descs(piece, flat, item))
+                off += pad(nb)
+            g = rt.GatherLaunch(copies)
+            ex._do(g.run)
+            keep.append(g)
+            sends.append((p, buf))
+        if recv_items[p]:
+            buf = alloc_bytes(sum(pad(it[-1]) for it in recv_items[p]), ex.device)
+            off = 0
+            for obid, nbid, sl, shape, nb in recv_items[p]:
+                out[(obid, nbid)] = DeviceChunk(buf, shape, expr.dtype, offset=off // item)
+                off += pad(nb)
+            recvs.append((p, buf))
+    ex._do(lambda: _p2p_exchange(ex, sends, recvs))
+    out["__keep__"] = (keep, sends, recvs)
+    return out
+
+
+
+
+# ----------------------------------------------------------------------------- results to host
+def gather_to_host(ex, expr: ArrayExpr, store: BlockStore) -> np.ndarray:
+    """finalize -> concatenate3 (``_core_utils.py:1426-1448``): assemble the blocks on the host.
+    With several ranks every rank returns the full array (blocks travel as host objects)."""
+    torch.cuda.synchronize()
+    local = {bid: blk.to_numpy() for bid, blk in store.blocks.items()}
+    if ex.world.size > 1 and not store.replicated:
+        import torch.distributed as dist
+
+        allb = [None] * ex.world.size
+        dist.all_gather_object(allb, local)
+        local = {k: v for d in allb for k, v in d.items()}
+    if expr.ndim == 0:
+        return local[()].reshape(())[()]
+    out = np.empty(expr.shape, dtype=expr.dtype)
+    for bid in expr.block_ids():
+        start, shape = expr.block_start(bid), expr.block_shape(bid)
+        if math.prod(shape) == 0:
+            continue
+        out[tuple(slice(s, s + n) for s, n in zip(start, shape))] = local[bid]
+    return out
+

@@ -734,658 +734,10 @@ class Executor:
         return _exchange_for_fused(self, plan, deps, out_ids)
 
 
-class _Cum:
-    """Launch builder of one cumulative reduction (see ``Executor._run_CumReduction``)."""
-
-    SEG = 4096            # elements per virtual row of a 1-D block (16-32 KiB: one warp's worth of work)
-
-    def __init__(self, ex: Executor, st: BlockStore, acc, redop):
-        self.ex, self.st, self.acc, self.redop = ex, st, np.dtype(acc), redop
-        self.ident = 0 if redop == _lib.RED_SUM else 1
-        self.prog = None
-        self.same = cg.Program()                   # identity chain on accumulator-typed tables
-        self.same.set_output(self.same.op("positive", self.same.add_input(self.acc)))
-
-    # ---- launches
-    def _run(self, launches):
-        for launch in launches:
-            self.ex._do(launch.run)
-            self.st.keepalive.append(launch)
-
-    def totals(self, prog, blocks, axis):
-        """reduce every block along ``axis`` into its ``out0`` (a row of a totals table)."""
-        for group in self._by_alignment(blocks):
-            self._run(rt.fused_launches(prog, self.redop, (axis,), group, acc_dtype=self.acc))
-
-    def scan(self, prog, blocks, axis):
-        for group in self._by_alignment(blocks):
-            self._run(rt.scan_launches(prog, self.redop, axis, group, self.acc))
-
-    @staticmethod
-    def _by_alignment(blocks):
-        """Ragged remainder rows go into their own launch so the full rows keep 16-byte vectors."""
-        good = [b for b in blocks if b.shape[-1] % 4 == 0]
-        odd = [b for b in blocks if b.shape[-1] % 4]
-        return [g for g in (good, odd) if g]
-
-    def table(self, shape):
-        t = DeviceChunk(alloc_bytes(math.prod(shape) * self.acc.itemsize, self.ex.device, zero=True), shape, self.acc)
-        if self.ex.world.size > 1:
-            self.ex._do(lambda: t.buf.zero_())     # rows of other ranks must be zero before the all-reduce
-        self.st.keepalive.append(t)
-        return t
-
-    def fill_identity(self, chunk):
-        if self.ident != 0 or self.ex.world.size > 1:
-            self.ex._do(lambda: rt.fill(chunk, self.ident))
-
-    # ---- N-d blocks: the blocks along the axis are the segments, one totals table per chain
-    def nd_blocks(self, x, src, axis):
-        ex, st, acc = self.ex, self.st, self.acc
-        nax = x.numblocks[axis]
-        others = [range(n) for d, n in enumerate(x.numblocks) if d != axis]
-        tables, tot, main = [], [], []
-        for cid in itertools.product(*others):
-            bids = [cid[:axis] + (i,) + cid[axis:] for i in range(nax)]
-            kshape = tuple(n for d, n in enumerate(x.block_shape(bids[0])) if d != axis)
-            ksize = math.prod(kshape)
-            tab = self.table((nax,) + kshape) if nax > 1 and ksize else None
-            if tab is not None:
-                tables.append(tab)
-            for i, bid in enumerate(bids):
-                row = tab[i] if tab is not None else None
-                if x.block_shape(bid)[axis] == 0:
-                    if row is not None and (ex.mine(x, bid) or ex.world.size == 1) and self.ident != 0:
-                        self.fill_identity(row)    # an empty block carries the identity (_cum_tail :28-39)
-                    if ex.mine(x, bid):
-                        st.blocks[bid] = DeviceChunk.empty(x.block_shape(bid), acc, ex.device)
-                    continue
-                if not ex.mine(x, bid):
-                    continue
-                c = src.blocks[bid]
-                out = DeviceChunk.empty(c.shape, acc, ex.device)
-                st.blocks[bid] = out
-                if c.size == 0:
-                    continue
-                if row is not None and i < nax - 1:
-                    tot.append(rt.BlockArgs(shape=c.shape, inputs=[(c.ptr, c.strides)], out0=row.ptr))
-                carry = tab[i - 1].ptr if (tab is not None and i > 0) else 0
-                main.append(rt.BlockArgs(shape=c.shape, inputs=[(c.ptr, c.strides)], out0=out.ptr, out1=carry))
-        if tot:
-            self.totals(self.prog, tot, axis)
-        if tables:
-            if ex.world.size > 1:
-                _sum_tables(ex, tables, acc)
-            # in place: row i becomes the total of blocks 0..i = the carry of block i + 1
-            self.scan(self.same, [rt.BlockArgs(shape=t.shape, inputs=[(t.ptr, t.strides)], out0=t.ptr)
-                                  for t in tables], 0)
-        if main:
-            self.scan(self.prog, main, axis)
-
-    # ---- 1-D blocks: rows of SEG elements are the segments
-    def vector_blocks(self, x, src):
-        ex, st, acc, SEG = self.ex, self.st, self.acc, self.SEG
-        item = x.dtype.itemsize
-        rows, nseg = [], 0           # (block id, first element, row length, number of rows, first segment)
-        for bid in x.block_ids():
-            full, rem = divmod(x.block_shape(bid)[0], SEG)
-            for first, length, n in ([(0, SEG, full)] if full else []) + ([(full * SEG, rem, 1)] if rem else []):
-                rows.append((bid, first, length, n, nseg))
-                nseg += n
-        for bid in x.block_ids():
-            if ex.mine(x, bid):
-                st.blocks[bid] = DeviceChunk.empty(x.block_shape(bid), acc, ex.device)
-        if nseg == 0:
-            return
-        # carries[k] = total of the segments before k (carries[0] = identity)
-        carries = self.table((nseg + 1,)) if nseg > 1 else None
-        tot, main = [], []
-        for bid, first, length, n, seg0 in rows:
-            if not ex.mine(x, bid):
-                continue
-            c, out = src.blocks[bid], st.blocks[bid]
-            s0 = c.strides[0]
-            view = [(c.ptr + first * s0 * item, (length * s0, s0))]
-            if carries is not None:
-                tot.append(rt.BlockArgs(shape=(n, length), inputs=view, out0=carries[seg0 + 1:].ptr))
-            main.append(rt.BlockArgs(shape=(n, length), inputs=view, out0=out.ptr + first * acc.itemsize,
-                                     out1=carries[seg0:].ptr if carries is not None else 0))
-        if carries is not None:
-            if tot:
-                self.totals(self.prog, tot, 1)
-            if ex.world.size > 1:
-                _sum_tables(ex, [carries], acc)
-            self.fill_identity(carries[0:1])
-            self.scan_vector(carries[1:])
-        if main:
-            self.scan(self.prog, main, 1)
-
-    def scan_vector(self, vec: DeviceChunk):
-        """In-place inclusive scan of a contiguous accumulator-typed vector (segment totals)."""
-        n, SEG, acc = vec.shape[0], self.SEG, self.acc
-        if n <= 16 * SEG:            # one warp walks it
-            self.scan(self.same, [rt.BlockArgs(shape=(1, n), inputs=[(vec.ptr, (n, 1))], out0=vec.ptr)], 1)
-            return
-        full, rem = divmod(n, SEG)
-        nseg = full + (1 if rem else 0)
-        carries = DeviceChunk(alloc_bytes((nseg + 1) * acc.itemsize, self.ex.device, zero=True), (nseg + 1,), acc)
-        self.st.keepalive.append(carries)
-        if self.ident != 0:
-            self.ex._do(lambda: rt.fill(carries[0:1], self.ident))
-        tot, main = [], []
-        for first, length, rows, seg0 in [(0, SEG, full, 0)] + ([(full * SEG, rem, 1, full)] if rem else []):
-            view = [(vec.ptr + first * acc.itemsize, (length, 1))]
-            tot.append(rt.BlockArgs(shape=(rows, length), inputs=view, out0=carries[seg0 + 1:].ptr))
-            main.append(rt.BlockArgs(shape=(rows, length), inputs=view, out0=vec.ptr + first * acc.itemsize,
-                                     out1=carries[seg0:].ptr))
-        self.totals(self.same, tot, 1)
-        self.scan_vector(carries[1:])
-        self.scan(self.same, main, 1)
-
-
-def _sum_tables(ex: Executor, tables, acc):
-    """Totals tables are zero where another rank owns the block: an all-reduce(SUM) completes them on
-    every rank (exact: every entry has exactly one non-zero contribution)."""
-    import torch.distributed as dist
-
-    for t in tables:
-        n = t.size
-        if not n:
-            continue
-        tdt = {4: torch.int32, 8: torch.int64}[acc.itemsize] if acc.kind in "iu" else \
-            {4: torch.float32, 8: torch.float64}[acc.itemsize]
-        view = t.buf[t.offset * acc.itemsize: (t.offset + n) * acc.itemsize].view(tdt)
-        ex._do(lambda v=view: dist.all_reduce(v))
-
-
-def _copy_descs(src: DeviceChunk, dst: DeviceChunk, item: int):
-    """2-D copy rectangles moving ``src`` into ``dst`` (same shape, arbitrary strides with a
-    unit-stride innermost run)."""
-    shape = [n for n in src.shape]
-    if math.prod(shape) == 0:
-        return []
-    dims = [(n, s, d) for n, s, d in zip(shape, src.strides, dst.strides) if n != 1]
-    if not dims:
-        return [(src.ptr, dst.ptr, 1, item, item, item)]
-    merged = []
-    for n, s, d in dims:
-        if merged and merged[-1][1] == s * n and merged[-1][2] == d * n:
-            merged[-1] = (merged[-1][0] * n, s, d)
-        else:
-            merged.append((n, s, d))
-    if merged[-1][1] != 1 or merged[-1][2] != 1:
-        merged.append((1, 1, 1))        # e.g. a single column: rows of one element each
-    n_in, s_in, d_in = merged[-1]
-    outer = merged[:-1]
-    if not outer:
-        return [(src.ptr, dst.ptr, 1, n_in * item, n_in * item, n_in * item)]
-    rows, s_row, d_row = outer[-1]
-    lead = outer[:-1]
-    out = []
-    for idx in itertools.product(*[range(n) for n, _, _ in lead]):
-        so = sum(i * s for i, (_, s, _) in zip(idx, lead))
-        do = sum(i * d for i, (_, _, d) in zip(idx, lead))
-        out.append((src.ptr + so * item, dst.ptr + do * item, rows, n_in * item, s_row * item, d_row * item))
-    return out
-
-
-# ----------------------------------------------------------------------------- NCCL plumbing
-def _allgather_blocks(ex: Executor, src: BlockStore, x):
-    """All-gather the (tiny) per-block partials of ``x`` so every rank can fold the tree."""
-    import torch.distributed as dist
-
-    W, me = ex.world.size, ex.world.rank
-    ids = list(x.block_ids())
-
-    def fields(b):
-        if isinstance(b, dict):
-            return [(k, v) for k, v in sorted(b.items()) if isinstance(v, DeviceChunk)]
-        return [("", b)]
-
-    # layout is derivable on every rank from shapes alone
-    def proto(bid):
-        kshape = x.block_shape(bid)
-        if src.kind == "moment":
-            return [("", tuple(kshape) + (3,), np.dtype(np.float64))]
-        if src.kind == "mean":
-            return [("total", kshape, x.dtype)]
-        if src.kind == "arg":
-            vdt = x.operand("array").dtype
-            return [("arg", kshape, np.dtype(np.int64)), ("vals", kshape, vdt)]
-        return [("", kshape, x.dtype)]
-
-    def nbytes(bid):
-        return sum(-(-math.prod(s) * d.itemsize // 16) * 16 for _, s, d in proto(bid))
-
-    per_rank = [sum(nbytes(b) for b in ids if ex.world.owner(x, b) == r) for r in range(W)]
-    cap = max(max(per_rank), 16)
-    send = alloc_bytes(cap, ex.device)
-    off = 0
-    copies = []
-    for bid in ids:
-        if ex.world.owner(x, bid) != me:
-            continue
-        blk = src.blocks[bid]
-        for (name, chunk), (_, shp, dt) in zip(fields(blk), proto(bid)):
-            nb = math.prod(shp) * dt.itemsize
-            if nb:
-                copies.append((chunk.ptr, send.data_ptr() + off, 1, nb, nb, nb))
-            off += -(-nb // 16) * 16
-    g = rt.GatherLaunch(copies)
-    ex._do(g.run)
-    recv = alloc_bytes(cap * W, ex.device)
-    ex._do(lambda: dist.all_gather_into_tensor(recv, send))
-    out = {}
-    offs = [0] * W
-    for bid in ids:
-        r = ex.world.owner(x, bid)
-        parts = {}
-        for name, shp, dt in proto(bid):
-            nb = math.prod(shp) * dt.itemsize
-            parts[name] = DeviceChunk(recv, shp, dt, offset=(r * cap + offs[r]) // dt.itemsize)
-            offs[r] += -(-nb // 16) * 16
-        if src.kind == "mean":
-            red = x.root if isinstance(x, FusedBlockwise) else x        # the ChunkReduce
-            axes = red.operand("axis")
-            top = red.operand("array")
-            n = math.prod(top.block_shape(bid)[a] for a in axes)
-            out[bid] = {"total": parts["total"], "n": n}
-        elif src.kind == "arg":
-            out[bid] = parts
-        else:
-            out[bid] = parts[""]
-    src.keepalive.extend([send, recv, g])
-    return out
-
-
-def _p2p_exchange(ex: Executor, sends, recvs):
-    """sends: [(peer, tensor)], recvs: [(peer, tensor)] in a globally consistent order."""
-    import torch.distributed as dist
-
-    ops = [dist.P2POp(dist.isend, t, p) for p, t in sends] + [dist.P2POp(dist.irecv, t, p) for p, t in recvs]
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-
-
-def owner_of(expr, bid, world_size: int) -> int:
-    """Block-cyclic placement: ``ravel(block id) mod world``."""
-    if world_size == 1:
-        return 0
-    nb = expr.numblocks
-    return (int(np.ravel_multi_index(bid, nb)) if nb else 0) % world_size
-
-
-def plan_fused_exchange(plan: FusedPlan, replicated, W: int, me: int):
-    """Pure (no device) schedule of the blocks a fused expression reads across the partition.
-    Returns (send_items, recv_items): per peer, lists in one global canonical order --
-    every rank derives the same order from the expression metadata, so sends and receives
-    pair up without negotiation.  Items: (leaf index k, leaf block id, nbytes)."""
-    expr = plan.fused
-    wanted = {}
-    for bid in expr.block_ids():
-        r = owner_of(expr, bid, W)
-        for k, (dep, _) in enumerate(plan.leaves):
-            if replicated[k]:
-                continue
-            lbid = plan.leaf_block_id(k, bid)
-            o = owner_of(dep, lbid, W)
-            if o != r:
-                wanted[(r, dep._name, lbid)] = (o, k)
-    send_items = {p: [] for p in range(W)}
-    recv_items = {p: [] for p in range(W)}
-    for (r, name, lbid) in sorted(wanted):
-        o, k = wanted[(r, name, lbid)]
-        dep = plan.leaves[k][0]
-        nb = math.prod(dep.block_shape(lbid)) * dep.dtype.itemsize
-        if o == me:
-            send_items[r].append((k, lbid, nb))
-        if r == me:
-            recv_items[o].append((k, lbid, nb))
-    return send_items, recv_items
-
-
-def plan_block_fetch(wanted, W: int, me: int):
-    """Pure schedule for whole-block reads across the partition.  ``wanted``: iterable of
-    (reader rank, dep expr, block id) over ALL ranks (every rank computes the same list).
-    Returns (send_items, recv_items) per peer: (dep expr, block id, nbytes), canonical order."""
-    uniq = {}
-    for r, dep, bid in wanted:
-        o = owner_of(dep, bid, W)
-        if o != r:
-            uniq[(r, dep._name, bid)] = (o, dep)
-    send_items = {p: [] for p in range(W)}
-    recv_items = {p: [] for p in range(W)}
-    for (r, name, bid) in sorted(uniq):
-        o, dep = uniq[(r, name, bid)]
-        nb = math.prod(dep.block_shape(bid)) * dep.dtype.itemsize
-        if o == me:
-            send_items[r].append((dep, bid, nb))
-        if r == me:
-            recv_items[o].append((dep, bid, nb))
-    return send_items, recv_items
-
-
-def _fetch_blocks(ex: Executor, wanted, stores):
-    """Execute a ``plan_block_fetch`` schedule over NCCL; ``stores``: {dep name: BlockStore}.
-    Returns {(dep name, block id): DeviceChunk} for the blocks this rank received."""
-    W, me = ex.world.size, ex.world.rank
-    send_items, recv_items = plan_block_fetch(wanted, W, me)
-    pad = lambda n: -(-n // 256) * 256
-    sends, recvs, keep, out = [], [], [], {}
-    for p in range(W):
-        if send_items[p]:
-            buf = alloc_bytes(sum(pad(nb) for *_, nb in send_items[p]), ex.device)
-            off, copies = 0, []
-            for dep, bid, nb in send_items[p]:
-                blk = stores[dep._name].blocks[bid]
-                flat = DeviceChunk(buf, blk.shape, blk.dtype, offset=off // blk.itemsize)
-                copies.extend(_copy_descs(blk, flat, blk.itemsize))
-                off += pad(nb)
-            g = rt.GatherLaunch(copies)
-            ex._do(g.run)
-            keep.append(g)
-            sends.append((p, buf))
-        if recv_items[p]:
-            buf = alloc_bytes(sum(pad(nb) for *_, nb in recv_items[p]), ex.device)
-            off = 0
-            for dep, bid, nb in recv_items[p]:
-                out[(dep._name, bid)] = DeviceChunk(buf, dep.block_shape(bid), dep.dtype, offset=off // dep.dtype.itemsize)
-                off += pad(nb)
-            recvs.append((p, buf))
-    if sends or recvs:
-        ex._do(lambda: _p2p_exchange(ex, sends, recvs))
-    out["__keep__"] = (keep, sends, recvs)
-    return out
-
-
-def plan_rechunk_exchange(expr: TasksRechunk, W: int, me: int):
-    """Pure schedule of the rectangles a rechunk moves across the partition (the all-to-all of
-    SURVEY.md 8e).  Items: (old block id, new block id, source slices, piece shape, nbytes)."""
-    x = expr.operand("array")
-    item = expr.dtype.itemsize
-    send_items = {p: [] for p in range(W)}
-    recv_items = {p: [] for p in range(W)}
-    for nbid in expr.block_ids():
-        r = owner_of(expr, nbid, W)
-        for obid, sl, dsl in expr.pieces(nbid):
-            o = owner_of(x, obid, W)
-            if o == r:
-                continue
-            shape = tuple(s.stop - s.start for s in sl)
-            nb = math.prod(shape) * item
-            if o == me:
-                send_items[r].append((obid, nbid, sl, shape, nb))
-            if r == me:
-                recv_items[o].append((obid, nbid, sl, shape, nb))
-    return send_items, recv_items
-
-
-def plan_rechunk_push(expr: TasksRechunk, W: int, me: int):
-    """Pure (no device) plan of a rechunk across the partition as ONE gather per rank that stores
-    straight into the owners' memory.  Every rank lays out the new blocks of every rank the same
-    way (one slab per rank, blocks in block-id order, 512-byte aligned).  Returns
-    ``(layout, totals, pushes)``: ``layout[r] = {new block id: byte offset in rank r's slab}``,
-    ``totals[r]`` = slab bytes, ``pushes`` = [(old block id, source slices, owner rank of the new
-    block, new block id, destination slices)] for every piece whose SOURCE block ``me`` owns --
-    local pieces included: the same launch moves them."""
-    x = expr.operand("array")
-    item = expr.dtype.itemsize
-    layout = [dict() for _ in range(W)]
-    totals = [0] * W
-    pushes = []
-    per_dest = [[] for _ in range(W)]
-    for nbid in expr.block_ids():
-        r = owner_of(expr, nbid, W)
-        layout[r][nbid] = totals[r]
-        totals[r] += -(-math.prod(expr.block_shape(nbid)) * item // 512) * 512
-        for obid, sl, dsl in expr.pieces(nbid):
-            if owner_of(x, obid, W) == me:
-                per_dest[r].append((obid, sl, r, nbid, dsl))
-    # All-to-all schedule: consecutive pieces go to DIFFERENT owners, starting with the right-hand
-    # neighbour -- at any moment rank r stores to r+1, r+2, ... and no owner is the target of every
-    # rank at once (in block-id order all ranks would hammer rank 0's NVLink ingress first).
-    rot = [per_dest[(me + 1 + k) % W] for k in range(W)]
-    for i in range(max((len(q) for q in rot), default=0)):
-        for q in rot:
-            if i < len(q):
-                pushes.append(q[i])
-    return layout, totals, pushes
-
-
-def _rechunk_push(ex: Executor, expr: TasksRechunk, src: BlockStore, st: BlockStore):
-    """The all-to-all of a rechunk as the rechunk kernel itself: every rank's tiled
-    gather reads its own old blocks and writes the pieces into the new blocks where they live --
-    local HBM or a peer's HBM over NVLink (``_peer``) -- bracketed by two stream-ordered barriers.
-    Bytes per element: one read + one write, wherever the destination is."""
-    W, me = ex.world.size, ex.world.rank
-    item = expr.dtype.itemsize
-    layout, totals, pushes = plan_rechunk_push(expr, W, me)
-    slab = alloc_bytes(totals[me], ex.device)
-    for nbid, off in layout[me].items():
-        st.blocks[nbid] = DeviceChunk(slab, expr.block_shape(nbid), expr.dtype, offset=off // item)
-    bases = [p[0] for p in _peer.exchange_pointers(ex.device, [slab.data_ptr()], [1] * W, me)]
-    windows = [slab if r == me else _peer.PeerBuffer(bases[r], ex.device, totals[r], r) for r in range(W)]
-    copies = []
-    for obid, sl, r, nbid, dsl in pushes:
-        dst = DeviceChunk(windows[r], expr.block_shape(nbid), expr.dtype, offset=layout[r][nbid] // item)
-        copies.extend(_copy_descs(src.blocks[obid][sl], dst[dsl], item))
-    launch = rt.GatherLaunch(copies)
-    bar = _peer.StreamBarrier(ex.device, me, W)
-    ex._do(bar)                 # every owner is done with the previous contents of its slab
-    ex._do(launch.run)
-    ex._do(bar)                 # every piece has landed before anyone reads a new block
-    st.keepalive.extend([launch, slab, bar, windows])
-    return st
-
-
-def _interleave_remote_reads(blocks, owners, me: int, W: int, in_items, out_item: int, band_rows: int = 256):
-    """Element-wise blocks whose operands sit in peers' memory are cut into row bands and dealt so
-    that consecutive bands read from DIFFERENT peers, starting with the right-hand neighbour: every
-    NVLink port pair is busy all the time instead of all ranks pulling from rank 0 first."""
-    if len(owners) != len(blocks) or not any(o != me for o in owners):
-        return blocks
-    per_owner = [[] for _ in range(W)]
-    for b, o in zip(blocks, owners):
-        if len(b.shape) != 2 or b.shape[0] <= band_rows or b.out1:
-            per_owner[o].append(b)
-            continue
-        R, Ccols = b.shape
-        for a in range(0, R, band_rows):
-            n = min(band_rows, R - a)
-            ins = [(ptr + a * st[0] * item, st) for (ptr, st), item in zip(b.inputs, in_items)]
-            per_owner[o].append(rt.BlockArgs(shape=(n, Ccols), inputs=ins, out0=b.out0 + a * Ccols * out_item))
-    rot = [per_owner[(me + 1 + k) % W] for k in range(W)]
-    out = []
-    for i in range(max(len(q) for q in rot)):
-        for q in rot:
-            if i < len(q):
-                out.append(q[i])
-    return out
-
-
-def _push_views(ex: Executor, expr, st: BlockStore, src: BlockStore, moves):
-    """Output blocks of a structural expression (slice, concatenate, expand_dims ...) whose source block
-    lives on ANOTHER GPU: the source's owner stores the selected view straight into the block at its new
-    owner -- one gather launch per rank over peer memory, bracketed by the stream barrier (the same
-    mechanism as the rechunk all-to-all).  ``moves``: [(output block id, source owner, view(block), source
-    block id)] in the same order on every rank."""
-    if not _peer.enabled():
-        raise NotImplementedError(f"{type(expr).__name__} that moves blocks between GPUs needs the peer-memory "
-                                  "path (B2_COMM=peer); rechunk first")
-    W, me = ex.world.size, ex.world.rank
-    item = expr.dtype.itemsize
-    layout, totals = {}, [0] * W
-    for bid, _, _, _ in moves:
-        r = ex.world.owner(expr, bid)
-        layout[bid] = (r, totals[r])
-        totals[r] += -(-math.prod(expr.block_shape(bid)) * item // 512) * 512
-    slab = alloc_bytes(totals[me], ex.device)
-    bases = [p[0] for p in _peer.exchange_pointers(ex.device, [slab.data_ptr()], [1] * W, me)]
-    windows = [slab if r == me else _peer.PeerBuffer(bases[r], ex.device, totals[r], r) for r in range(W)]
-    copies = []
-    for bid, src_owner, view, ibid in moves:
-        r, off = layout[bid]
-        dst = DeviceChunk(windows[r], expr.block_shape(bid), expr.dtype, offset=off // item)
-        if r == me:
-            st.blocks[bid] = dst
-        if src_owner == me:
-            copies.extend(_copy_descs(view(src.blocks[ibid]), dst, item))
-    launch = rt.GatherLaunch(copies)
-    bar = _peer.StreamBarrier(ex.device, me, W)
-    ex._do(bar)
-    ex._do(launch.run)
-    ex._do(bar)
-    st.keepalive.extend([launch, slab, windows])
-
-
-def plan_fused_peer_reads(plan: FusedPlan, replicated, W: int):
-    """Pure plan of the remote block reads of a fused expression: ``exports[o]`` = the (leaf index,
-    leaf block id) pairs rank o owns and some other rank reads, in one canonical order;
-    ``readers[(o, i)]`` = the set of ranks reading export i of rank o."""
-    expr = plan.fused
-    wanted = {}
-    for bid in expr.block_ids():
-        r = owner_of(expr, bid, W)
-        for k, (dep, _) in enumerate(plan.leaves):
-            if replicated[k]:
-                continue
-            lbid = plan.leaf_block_id(k, bid)
-            o = owner_of(dep, lbid, W)
-            if o != r:
-                wanted.setdefault((o, dep._name, lbid), [k, set()])[1].add(r)
-    exports = [[] for _ in range(W)]
-    readers = {}
-    for (o, name, lbid) in sorted(wanted):
-        k, rs = wanted[(o, name, lbid)]
-        readers[(o, len(exports[o]))] = rs
-        exports[o].append((k, lbid))
-    return exports, readers
-
-
-def _peer_reads_for_fused(ex: Executor, plan: FusedPlan, deps):
-    """Remote operands of a fused expression (``x.T + x`` across the partition) are read IN PLACE:
-    the owners export the blocks once, the fused kernel of the reading rank loads them over NVLink
-    while it computes -- no pack, no send/recv, no staging copy.  Returns {(dep name, block id):
-    DeviceChunk over peer memory}; ``__barrier__`` must bracket the launch on the tape."""
-    import struct
-
-    W, me = ex.world.size, ex.world.rank
-    exports, readers = plan_fused_peer_reads(plan, [d.replicated for d in deps], W)
-    if not any(exports):
-        return {}
-    rec = _peer.HANDLE_BYTES + 8 * 9
-    mine = []
-    for k, lbid in exports[me]:
-        blk = deps[k].blocks[lbid]
-        st = list(blk.strides) + [0] * (8 - blk.ndim)
-        mine.append(_peer.export_handle(blk.ptr) + struct.pack("<9q", blk.ndim, *st))
-    recs = _peer.exchange_records(ex.device, mine, [len(e) for e in exports], rec)
-    out = {}
-    for o in range(W):
-        if o == me:
-            continue
-        for i, (k, lbid) in enumerate(exports[o]):
-            if me not in readers[(o, i)]:
-                continue
-            raw = recs[o][i]
-            meta = struct.unpack("<9q", raw[_peer.HANDLE_BYTES:])
-            dep = plan.leaves[k][0]
-            ptr = _peer.open_handle(raw[: _peer.HANDLE_BYTES])
-            out[(dep._name, lbid)] = DeviceChunk(_peer.PeerBuffer(ptr, ex.device, owner=o), dep.block_shape(lbid),
-                                                 dep.dtype, strides=meta[1: 1 + meta[0]])
-    out["__barrier__"] = _peer.StreamBarrier(ex.device, me, W)
-    return out
-
-
-def _exchange_for_fused(ex: Executor, plan: FusedPlan, deps, out_ids):
-    """Blocks of dependencies that some rank's output blocks read but another rank owns are
-    packed per peer, exchanged over NCCL and exposed as DeviceChunks."""
-    W, me = ex.world.size, ex.world.rank
-    if _peer.enabled():
-        return _peer_reads_for_fused(ex, plan, deps)
-    send_items, recv_items = plan_fused_exchange(plan, [d.replicated for d in deps], W, me)
-    if not any(send_items.values()) and not any(recv_items.values()):
-        return {}
-    pad = lambda n: -(-n // 256) * 256
-    sends, recvs, keep, out = [], [], [], {}
-    for p in range(W):
-        if send_items[p]:
-            buf = alloc_bytes(sum(pad(nb) for _, _, nb in send_items[p]), ex.device)
-            off, copies = 0, []
-            for k, lbid, nb in send_items[p]:
-                blk = deps[k].blocks[lbid]
-                flat = DeviceChunk(buf, blk.shape, blk.dtype, offset=off // blk.itemsize)
-                copies.extend(_copy_descs(blk, flat, blk.itemsize))
-                off += pad(nb)
-            g = rt.GatherLaunch(copies)
-            ex._do(g.run)
-            keep.append(g)
-            sends.append((p, buf))
-        if recv_items[p]:
-            buf = alloc_bytes(sum(pad(nb) for _, _, nb in recv_items[p]), ex.device)
-            off = 0
-            for k, lbid, nb in recv_items[p]:
-                dep = plan.leaves[k][0]
-                out[(dep._name, lbid)] = DeviceChunk(buf, dep.block_shape(lbid), dep.dtype, offset=off // dep.dtype.itemsize)
-                off += pad(nb)
-            recvs.append((p, buf))
-    ex._do(lambda: _p2p_exchange(ex, sends, recvs))
-    out["__keep__"] = (keep, sends, recvs)
-    return out
-
-
-def _exchange_for_rechunk(ex: Executor, expr: TasksRechunk, src: BlockStore, new_ids):
-    """All-to-all of the rectangles a rechunk moves across the partition: pack (gather kernel)
-    -> NCCL send/recv -> the local gather reads the received pieces in place."""
-    W, me = ex.world.size, ex.world.rank
-    item = expr.dtype.itemsize
-    pad = lambda n: -(-n // 256) * 256
-    send_items, recv_items = plan_rechunk_exchange(expr, W, me)
-    sends, recvs, keep, out = [], [], [], {}
-    for p in range(W):
-        if send_items[p]:
-            buf = alloc_bytes(sum(pad(it[-1]) for it in send_items[p]), ex.device)
-            off, copies = 0, []
-            for obid, nbid, sl, shape, nb in send_items[p]:
-                piece = src.blocks[obid][sl]
-                flat = DeviceChunk(buf, shape, expr.dtype, offset=off // item)
-                copies.extend(_copy_descs(piece, flat, item))
-                off += pad(nb)
-            g = rt.GatherLaunch(copies)
-            ex._do(g.run)
-            keep.append(g)
-            sends.append((p, buf))
-        if recv_items[p]:
-            buf = alloc_bytes(sum(pad(it[-1]) for it in recv_items[p]), ex.device)
-            off = 0
-            for obid, nbid, sl, shape, nb in recv_items[p]:
-                out[(obid, nbid)] = DeviceChunk(buf, shape, expr.dtype, offset=off // item)
-                off += pad(nb)
-            recvs.append((p, buf))
-    ex._do(lambda: _p2p_exchange(ex, sends, recvs))
-    out["__keep__"] = (keep, sends, recvs)
-    return out
-
-
-# ----------------------------------------------------------------------------- results to host
-def gather_to_host(ex: Executor, expr: ArrayExpr, store: BlockStore) -> np.ndarray:
-    """finalize -> concatenate3 (``_core_utils.py:1426-1448``): assemble the blocks on the host.
-    With several ranks every rank returns the full array (blocks travel as host objects)."""
-    torch.cuda.synchronize()
-    local = {bid: blk.to_numpy() for bid, blk in store.blocks.items()}
-    if ex.world.size > 1 and not store.replicated:
-        import torch.distributed as dist
-
-        allb = [None] * ex.world.size
-        dist.all_gather_object(allb, local)
-        local = {k: v for d in allb for k, v in d.items()}
-    if expr.ndim == 0:
-        return local[()].reshape(())[()]
-    out = np.empty(expr.shape, dtype=expr.dtype)
-    for bid in expr.block_ids():
-        start, shape = expr.block_start(bid), expr.block_shape(bid)
-        if math.prod(shape) == 0:
-            continue
-        out[tuple(slice(s, s + n) for s, n in zip(start, shape))] = local[bid]
-    return out
+# the multi-GPU plumbing and the cumulative-scan launch builder live in their own modules
+from ._exchange import (  # noqa: E402,F401
+    _allgather_blocks, _copy_descs, _exchange_for_fused, _exchange_for_rechunk, _fetch_blocks, _interleave_remote_reads,
+    _peer_reads_for_fused, _push_views, _rechunk_push, gather_to_host, owner_of, plan_block_fetch, plan_fused_exchange,
+    plan_fused_peer_reads, plan_rechunk_exchange, plan_rechunk_push,
+)
+from ._cumexec import _Cum  # noqa: E402,F401
