@@ -151,6 +151,27 @@ def _argmin(a, axis=None, keepdims=False, **kw):
     return r if keepdims else r.reshape(tuple(n for d, n in enumerate(a.shape) if axis is not None and d != axis % a.ndim))
 
 
+# ----------------------------------------------------------------------------- windows
+@implements(np.lib.stride_tricks.sliding_window_view)
+def _sliding_window_view(x, window_shape, axis=None, **kw):
+    """Zero-copy: the window axes re-use the strides of the axes they slide along (what NumPy's
+    ``as_strided`` does on the host); consumers read the overlapping windows through the descriptors."""
+    x = _as_chunk(x)
+    window_shape = tuple(window_shape) if np.iterable(window_shape) else (window_shape,)
+    if axis is None:
+        axis = tuple(range(x.ndim))
+    axis = tuple(a % x.ndim for a in ((axis,) if np.isscalar(axis) else axis))
+    if len(axis) != len(window_shape):
+        raise ValueError("Must provide matching length window_shape and axis")
+    shape = list(x.shape)
+    for ax, w in zip(axis, window_shape):
+        if w <= 0 or shape[ax] < w:
+            raise ValueError("window shape cannot be larger than input array shape")
+        shape[ax] -= w - 1
+    return DeviceChunk(x.buf, tuple(shape) + window_shape, x.dtype,
+                       strides=tuple(x.strides) + tuple(x.strides[ax] for ax in axis), offset=x.offset)
+
+
 # ----------------------------------------------------------------------------- cumulative scans
 def _cumulative(a, redop, axis, dtype, nan):
     """``np.cumsum`` / ``np.cumprod`` (+ nan variants) of ONE chunk -- what ``CumReduction._layer``

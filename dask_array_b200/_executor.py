@@ -217,33 +217,44 @@ class Executor:
         for bid in expr.block_ids():
             if not self.mine(expr, bid):
                 continue
-            out = DeviceChunk.empty(expr.block_shape(bid), expr.dtype, self.device)
-            st.blocks[bid] = out
             ins = []
-            for s_ in stores:
-                blk = s_.blocks.get(bid)
+            for a, s_ in zip(expr.operand("arrays"), stores):
+                blk = s_.blocks.get(bid[:a.ndim])            # trailing output dims are new axes (one block)
                 if blk is None:
                     raise RuntimeError(f"map_blocks: block {bid} of an argument is not resident on rank {self.world.rank}")
                 ins.append(blk)
-            work.append((out, ins))
-        item = expr.dtype.itemsize
+            work.append((bid, expr.block_shape(bid), ins))
+        ident = cg.Program()
+        ident.set_output(ident.op("astype", ident.add_input(expr.dtype), dtype=expr.dtype))
 
         def run():
-            for out, ins in work:
+            for bid, shape, ins in work:
                 it = iter(ins)
                 args = [next(it) if t is None else t for t in template]
                 res = func(*args, **kwargs)
                 if not isinstance(res, DeviceChunk):
                     raise TypeError(f"map_blocks: {getattr(func, '__name__', func)!r} returned {type(res).__name__}, "
                                     "not a DeviceChunk (no host fallback: use NumPy functions the chunk type implements)")
-                if res.shape != out.shape or res.dtype != out.dtype:
+                if res.shape != tuple(shape) or res.dtype != expr.dtype:
                     raise ValueError(f"map_blocks: block result {res.shape} {res.dtype} does not match the declared "
-                                     f"chunks / dtype {out.shape} {out.dtype}")
+                                     f"chunks / dtype {tuple(shape)} {expr.dtype}")
+                prev = st.blocks.get(bid)
+                if any(res.buf is b.buf for b in ins):
+                    # a VIEW of an argument block (slices, sliding windows ...): pointer-stable across replays,
+                    # so it is the output block itself -- nothing is materialised
+                    if prev is not None and (prev.ptr, prev.strides) != (res.ptr, res.strides):
+                        raise RuntimeError("map_blocks: a view result changed between replays")
+                    st.blocks[bid] = res
+                    continue
+                out = prev if prev is not None else DeviceChunk.empty(shape, expr.dtype, self.device)
+                st.blocks[bid] = out                          # allocated once: replays refill the same memory
                 if out.size:
-                    g = rt.GatherLaunch(_copy_descs(res if res.ndim else res.reshape((1,)),
-                                                    out if out.ndim else out.reshape((1,)), item))
-                    g.run()
-                    out._keep = (g, res)
+                    blk = rt.BlockArgs(shape=res.shape, inputs=[(res.ptr, res.strides)], out0=out.ptr)
+                    keep = [res]
+                    for launch in rt.fused_launches(ident, _lib.RED_NONE, (), [blk]):
+                        launch.run()
+                        keep.append(launch)
+                    out._keep = keep
         self._do(run)
         return st
 

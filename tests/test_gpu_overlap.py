@@ -83,3 +83,26 @@ def test_compiled_replay_with_map_blocks(da):
     step = da.compile((x.map_overlap(lambda b: b + 1, depth=1, boundary="reflect") * 2).sum())
     step.run(); step.run()
     np.testing.assert_allclose(step.result(), ((xh + 1) * 2).sum(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("shape,chunks,window,axis", [((200,), (64,), 7, 0), ((60, 50), (20, 25), 5, 0),
+                                                      ((60, 50), (20, 25), (3, 4), (0, 1)), ((30, 40, 8), (10, 40, 8), 6, 1),
+                                                      ((40,), (3,), 5, 0)])
+def test_sliding_window_view_and_rolling_reductions(da, shape, chunks, window, axis):
+    """`sliding_window_view` (`_overlap.py:1365-1433`) against NumPy's; rolling sum / mean / max read the
+    overlapping windows in place (no window is materialised)."""
+    rng = np.random.default_rng(5)
+    xh = rng.integers(-50, 50, size=shape).astype(np.float64)
+    x = da.from_array(xh, chunks=chunks).persist()
+    v = da.sliding_window_view(x, window, axis=axis)
+    want = np.lib.stride_tricks.sliding_window_view(xh, window, axis=axis)
+    assert v.shape == want.shape
+    assert np.array_equal(v.compute(), want)
+    nwin = len(window) if isinstance(window, tuple) else 1
+    red = tuple(range(-nwin, 0))
+    assert np.array_equal(v.sum(axis=red).compute(), want.sum(axis=red))               # integer-valued: exact
+    assert np.array_equal(v.max(axis=red).compute(), want.max(axis=red))
+    np.testing.assert_allclose(v.mean(axis=red).compute(), want.mean(axis=red), rtol=1e-12)
+    step = da.compile(v.sum(axis=red))
+    step.run(); step.run()
+    assert np.array_equal(step.result(), want.sum(axis=red))
