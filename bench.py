@@ -378,7 +378,9 @@ def run_other(args):
             step = da.compile(sq.T + sq)
             timed(step, 2 * n * n * item, f"c4: x.T + x (16384,16384) {np.dtype(dt).name} chunks 2048^2 "
                   "(2N bytes: mirror-pair kernel, every tile read once)" if world == 1 else
-                  f"c4: x.T + x (16384,16384) {np.dtype(dt).name} chunks 2048^2 (remote operand read in place over NVLink)",
+                  f"c4: x.T + x (16384,16384) {np.dtype(dt).name} chunks 2048^2 " + (
+                      "(remote operand read in place over NVLink)" if os.environ.get("B2_COMM", "peer") != "nccl"
+                      else "(remote blocks fetched with packed NCCL send/recv)"),
                   {"dtype": np.dtype(dt).name})
             del sq, step
     if world > 1:
