@@ -36,11 +36,36 @@ def config_kernels():
     return out
 
 
+def extra_kernels():
+    """(name, program, KernelSpec) of the kernels whose geometry is fixed by the launch builder: the
+    mirror-pair kernel of c4's ``x.T + x`` and the cumulative scans."""
+    out = []
+    for dt, v in (("float32", 4), ("float64", 2)):
+        p = cg.Program()
+        a, b = p.add_input(dt), p.add_input(dt)
+        p.set_output(p.op("add", a, b))
+        out.append((f"c4 x.T + x mirror pair {dt}", p,
+                    cg.KernelSpec(p.key(), ("T", "V"), _lib.MODE_EW, _lib.RED_NONE, vec=v, tx=16, ty=16, rpt=16 * v,
+                                  unroll=1, acc_dtype=dt, variant="sym")))
+        q = cg.Program()
+        q.set_output(q.op("astype", q.add_input(dt), dtype=np.dtype(dt)))
+        out.append((f"cumsum rows {dt}", q, cg.KernelSpec(q.key(), ("V",), _lib.MODE_SR, _lib.RED_SUM, vec=v, tx=128, ty=1,
+                                                        rpt=1 << 30, unroll=8, acc_dtype=dt)))
+        out.append((f"cumsum columns {dt}", q, cg.KernelSpec(q.key(), ("V",), _lib.MODE_SC, _lib.RED_SUM, vec=v, tx=32, ty=8,
+                                                           rpt=8, unroll=4, acc_dtype=dt)))
+    return out
+
+
 def prebuild(verbose: bool = False):
     n = 0
     for name, prog, layouts, mode, redop, shape, vec, acc in config_kernels():
         geo = cg.choose_geometry(prog, mode, [shape], vec)
         spec = cg.KernelSpec(prog.key(), layouts, mode, redop, acc_dtype=acc.name, **geo)
+        cubin = rt.compile_kernel(prog, spec)
+        n += 1
+        if verbose:
+            print(f"{name}: {len(cubin)} bytes ({spec.digest()})")
+    for name, prog, spec in extra_kernels():
         cubin = rt.compile_kernel(prog, spec)
         n += 1
         if verbose:
