@@ -240,6 +240,30 @@ def _remove_conflicting(group):
     return [e for e in group if e._name in reach]
 
 
+def _external_reads(group) -> int:
+    """Upper bound of the kernel inputs of a group: edges from members to array expressions outside it
+    (constant leaves inside the group are immediates; a dependency read through two block mappings
+    counts twice, as the program builder counts it)."""
+    names = {e._name for e in group}
+    return sum(1 for e in group for d in e.dependencies() if d._name not in names)
+
+
+def _reachable(group):
+    """Members still connected to the root through members."""
+    if not group:
+        return group
+    names = {e._name for e in group}
+    by = {e._name: e for e in group}
+    reach, stack = {group[0]._name}, [group[0]]
+    while stack:
+        e = stack.pop()
+        for d in e.dependencies():
+            if d._name in names and d._name not in reach:
+                reach.add(d._name)
+                stack.append(by[d._name])
+    return [e for e in group if e._name in reach]
+
+
 def optimize_blockwise_fusion(expr):
     """``optimize_blockwise_fusion_array`` (:1405-1571): roots are fusable nodes without
     fusable dependents; a dependency joins a group when all its dependents are inside it."""
@@ -285,6 +309,36 @@ def optimize_blockwise_fusion(expr):
                 elif dep_name not in {r._name for r in roots}:
                     roots.append(dep)
         group = _remove_conflicting(group)
+        # a kernel takes at most B2_MAX_IN array inputs: while the group reads more, the operand of the
+        # root with the largest sub-tree is cut out and becomes a group (a kernel, a materialised
+        # intermediate) of its own
+        while len(group) > 1 and _external_reads(group) > cg.MAX_INPUTS:
+            names = {e._name for e in group}
+            by = {e._name: e for e in group}
+
+            def subtree(e, acc):
+                if e._name in acc:
+                    return acc
+                acc.add(e._name)
+                for d in e.dependencies():
+                    if d._name in names:
+                        subtree(by[d._name], acc)
+                return acc
+            # the member whose sub-tree swallows the most inputs while still fitting one kernel
+            def reads(e):
+                sub = subtree(e, set())
+                return sum(1 for n in sub for d in by[n].dependencies() if d._name not in sub)
+            cands = [(reads(e), len(subtree(e, set())), e._name, e) for e in group[1:]]
+            cands = [c for c in cands if 1 < c[0] <= cg.MAX_INPUTS]
+            if not cands:
+                break
+            victim = max(cands)[3]
+            cut = subtree(victim, set())
+            group = [e for e in group if e._name not in cut]
+            # members still reachable from the root only (a cut sub-tree may have shared nodes with the rest)
+            group = _remove_conflicting(_reachable(group))
+            if victim._name not in {r._name for r in roots}:
+                roots.append(victim)
         # every launch is a "fused" launch, also a group of one (single Elemwise / Transpose)
         replacements[group[0]._name] = FusedBlockwise(tuple(group))
         assigned.update(e._name for e in group)

@@ -25,6 +25,7 @@ import numpy as np
 
 from . import _lib
 
+MAX_INPUTS = _lib.B2_MAX_IN   # array inputs of one fused kernel (descriptor table slots)
 CODEGEN_VERSION = "21"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {

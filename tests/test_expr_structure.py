@@ -158,3 +158,20 @@ def test_diamond_group_is_rebuilt_consistently():
         return int(isinstance(e, (Elemwise, Transpose))) + sum(bare(d) for d in e.dependencies())
     assert bare(opt) == 0
     assert len(FusedPlan(opt).leaves) == 1
+
+
+def test_fused_groups_respect_the_kernel_input_limit():
+    """A kernel's descriptor has B2_MAX_IN input slots: wider expressions are cut into several groups,
+    each swallowing as many inputs as fit (found by the fuzz test)."""
+    from dask_array_b200 import _lib
+    from dask_array_b200._blockwise import FusedBlockwise
+    arrs = [_opaque((40, 40), (10, 10), f"lim{i}") for i in range(11)]
+    e = arrs[0]
+    for a in arrs[1:]:
+        e = e * 2 + a
+    fused = {n._name: n for n in _walk(e.optimize().expr) if isinstance(n, FusedBlockwise)}
+    sizes = sorted(len(FusedPlan(f).leaves) for f in fused.values())
+    assert sizes == [6, 6] and max(sizes) <= _lib.B2_MAX_IN
+    t = ((arrs[0] + arrs[1]) + (arrs[2] + arrs[3])) + ((arrs[4] + arrs[5]) + (arrs[6] + arrs[7].T))
+    fused = {n._name: n for n in _walk(t.optimize().expr) if isinstance(n, FusedBlockwise)}
+    assert all(len(FusedPlan(f).leaves) <= _lib.B2_MAX_IN for f in fused.values()) and len(fused) == 2
