@@ -494,7 +494,19 @@ class KernelSpec:
         import os
 
         tune = os.environ.get("B2_MINB", "")
-        return hashlib.sha1((CODEGEN_VERSION + tune + repr(self)).encode()).hexdigest()[:20]
+        return hashlib.sha1((CODEGEN_VERSION + _header_hash() + tune + repr(self)).encode()).hexdigest()[:20]
+
+
+_HEADER_HASH = None
+
+
+def _header_hash() -> str:
+    """Digest of the device header every generated kernel includes (``b2_device.cuh``, embedded in the
+    library): a cached cubin can never outlive a change of the templates it was built from."""
+    global _HEADER_HASH
+    if _HEADER_HASH is None:
+        _HEADER_HASH = hashlib.sha1(_lib.lib.b2_device_header()).hexdigest()[:12]
+    return _HEADER_HASH
 
 
 def packed_bytes(spec: KernelSpec, out_dtype) -> int:
