@@ -20,6 +20,7 @@ from ._views import broadcast_to, concatenate, expand_dims, squeeze, stack  # no
 from . import _overlap as overlap  # noqa: F401,E402  (da.overlap.overlap / trim_internal / map_overlap ...)
 from ._overlap import map_blocks, map_overlap, sliding_window_view  # noqa: F401,E402
 from ._topk import argtopk, topk  # noqa: F401,E402
+from ._routines import diff, flip, fliplr, flipud, roll  # noqa: F401,E402
 
 for _n in UFUNC_NAMES:
     globals()[_n] = _ufunc(_n)

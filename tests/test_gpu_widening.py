@@ -84,3 +84,22 @@ def test_elementwise_over_mismatched_chunks_unifies_like_the_reference():
     z = x + shifted
     assert z.chunks == ((100,) * 4,)                        # golden case "roll_shift"
     assert np.array_equal(z.compute(), xh + np.roll(xh, 50))
+
+
+def test_roll_diff_flip_compositions():
+    """`roll` (manipulation/_roll.py), `diff` (routines/_diff.py), `flip*` (manipulation/_flip.py): the
+    reference composes them from slices / concatenate / subtract, and so does the B200 package."""
+    import dask_array_b200 as da
+    rng = np.random.default_rng(12)
+    xh = rng.integers(-100, 100, size=(37, 50)).astype(np.int64)
+    x = da.from_array(xh, chunks=(10, 16)).persist()
+    for shift, axis in [(3, 1), (-5, 0), (50, 1), ((2, -7), (0, 1)), (0, 0)]:
+        assert np.array_equal(da.roll(x, shift, axis=axis).compute(), np.roll(xh, shift, axis=axis)), (shift, axis)
+    v = da.from_array(xh[0], chunks=7).persist()
+    assert np.array_equal(da.roll(v, 11).compute(), np.roll(xh[0], 11))
+    for n, axis in [(1, -1), (2, 0), (3, 1)]:
+        assert np.array_equal(da.diff(x, n, axis=axis).compute(), np.diff(xh, n, axis=axis)), (n, axis)
+    assert np.array_equal(da.diff(x, axis=1, prepend=0, append=7).compute(), np.diff(xh, axis=1, prepend=0, append=7))
+    assert np.array_equal(da.flip(x).compute(), np.flip(xh))
+    assert np.array_equal(da.flipud(x).compute(), np.flipud(xh)) and np.array_equal(da.fliplr(x).compute(), np.fliplr(xh))
+    assert (da.diff(x, axis=0) ** 2).sum().compute() == (np.diff(xh, axis=0) ** 2).sum()
