@@ -23,27 +23,26 @@ from ._expr import ArrayExpr
 
 
 # ----------------------------------------------------------------------------- argument coercion
+def _per_axis(ndim, value, default):
+    """Scalar / tuple / {axis: value} -> {axis: value} for every axis."""
+    if value is None:
+        value = default
+    if isinstance(value, dict):
+        return {ax: value.get(ax, default) for ax in range(ndim)}
+    if isinstance(value, tuple):
+        return {ax: (value[ax] if ax < len(value) else default) for ax in range(ndim)}
+    return dict.fromkeys(range(ndim), value)
+
+
 def coerce_depth(ndim, depth):
-    """``coerce_depth`` (:1303-1322)."""
-    if depth is None:
-        depth = 0
-    if isinstance(depth, Integral):
-        depth = (depth,) * ndim
-    if isinstance(depth, tuple):
-        depth = dict(zip(range(ndim), depth))
-    depth = {ax: depth.get(ax, 0) for ax in range(ndim)}
-    return {ax: tuple(int(v) for v in d) if isinstance(d, tuple) else int(d) for ax, d in depth.items()}
+    """Depth per axis, ints (or (before, after) pairs of ints) -- ``coerce_depth`` (:1303-1322)."""
+    out = _per_axis(ndim, (depth,) * ndim if isinstance(depth, Integral) else depth, 0)
+    return {ax: (tuple(map(int, d)) if isinstance(d, tuple) else int(d)) for ax, d in out.items()}
 
 
 def coerce_boundary(ndim, boundary):
-    """``coerce_boundary`` (:1351-1362)."""
-    if boundary is None:
-        boundary = "none"
-    if not isinstance(boundary, (tuple, dict)):
-        boundary = (boundary,) * ndim
-    if isinstance(boundary, tuple):
-        boundary = dict(zip(range(ndim), boundary))
-    return {ax: boundary.get(ax, "none") for ax in range(ndim)}
+    """Boundary kind per axis, ``"none"`` where unspecified -- ``coerce_boundary`` (:1351-1362)."""
+    return _per_axis(ndim, boundary, "none")
 
 
 def _sides(depth):
@@ -51,30 +50,39 @@ def _sides(depth):
 
 
 def ensure_minimum_chunksize(size, chunks):
-    """``ensure_minimum_chunksize`` (:836-883): merge chunks smaller than ``size`` into their
-    neighbours."""
-    if size <= min(chunks):
-        return tuple(chunks)
-    output, new = [], 0
+    """Merge chunks smaller than ``size`` into their neighbours so that every chunk can lend ``size``
+    cells to a halo -- same results as the reference's ``ensure_minimum_chunksize`` (:836-883, pinned by
+    tests/golden/structure.json and a randomised comparison in tests/test_structure_golden.py).
+
+    A pending run collects the chunks seen since the last emitted one.  A small chunk joins the pending
+    run -- unless the run is a big chunk with more than ``size`` to spare, which then donates exactly what
+    the small chunk lacks and is emitted without it.  A run that has reached ``size`` is emitted at once;
+    big chunks wait in the run (they may still have to donate); the remainder sticks to the last chunk."""
+    chunks = tuple(chunks)
+    if min(chunks) >= size:
+        return chunks
+    done, pending = [], 0
     for c in chunks:
-        if c < size:
-            if new > size + (size - c):
-                output.append(new - (size - c))
-                new = size
+        small = c < size
+        if small:
+            lack = size - c
+            if pending > size + lack:
+                done.append(pending - lack)
+                pending = size
             else:
-                new += c
-        if new >= size:
-            output.append(new)
-            new = 0
-        if c >= size:
-            new += c
-    if new >= size:
-        output.append(new)
-    elif output:
-        output[-1] += new
+                pending += c
+        if pending >= size:
+            done.append(pending)
+            pending = 0
+        if not small:
+            pending = pending + c
+    if pending >= size:
+        done.append(pending)
+    elif done:
+        done[-1] += pending
     else:
         raise ValueError(f"The overlapping depth {size} is larger than your array {sum(chunks)}.")
-    return tuple(output)
+    return tuple(done)
 
 
 def _overlap_rechunked_chunks(x, depth, boundary):
@@ -240,68 +248,70 @@ def _axis_slice(ndim, axis, sl):
     return (slice(None),) * axis + (sl,) + (slice(None),) * (ndim - axis - 1)
 
 
-def _one_chunk(a, axis, depth):
-    ch = list(a.chunks)
-    ch[axis] = (depth,)
-    return a.rechunk(tuple(ch))                          # _remove_overlap_boundaries (:792-800)
+def _rim(x, axis, sl, depth):
+    """``x[..., sl, ...]`` along ``axis`` as ONE chunk of ``depth`` cells (``_remove_overlap_boundaries``
+    :792-800 rechunks the pads the same way)."""
+    rim = x[_axis_slice(x.ndim, axis, sl)]
+    grid = list(rim.chunks)
+    grid[axis] = (depth,)
+    return rim.rechunk(tuple(grid))
+
+
+def _pads(x, axis, depth, kind):
+    """(low pad, high pad) of ``depth`` cells for one axis: ``periodic`` (:715-730) wraps the far side
+    around, ``reflect`` (:733-756) mirrors the near side including its edge cell, ``nearest`` (:759-773)
+    repeats the edge cell, anything else is a constant fill (:776-789)."""
+    from ._collection import full
+    from ._views import concatenate
+
+    if kind == "periodic":
+        return _rim(x, axis, slice(-depth, None), depth), _rim(x, axis, slice(0, depth), depth)
+    if kind == "reflect":
+        low = slice(0, 1) if depth == 1 else slice(depth - 1, None, -1)
+        return _rim(x, axis, low, depth), _rim(x, axis, slice(-1, -depth - 1, -1), depth)
+    if kind == "nearest":
+        def repeated(sl):
+            edge = x[_axis_slice(x.ndim, axis, sl)]
+            grid = list(edge.chunks)
+            grid[axis] = (depth,)
+            return concatenate([edge] * depth, axis=axis).rechunk(tuple(grid))
+        return repeated(slice(0, 1)), repeated(slice(-1, None))
+    grid = list(x.chunks)
+    grid[axis] = (depth,)
+    fill = full(tuple(sum(c) for c in grid), kind, chunks=tuple(grid), dtype=x.dtype)
+    return fill, fill
 
 
 def periodic(x, axis, depth):
-    """``periodic`` (:715-730)."""
-    from ._views import concatenate
-    left, right = x[_axis_slice(x.ndim, axis, slice(0, depth))], x[_axis_slice(x.ndim, axis, slice(-depth, None))]
-    return concatenate([_one_chunk(right, axis, depth), x, _one_chunk(left, axis, depth)], axis=axis)
+    return boundaries(x, {axis: depth}, {axis: "periodic"})
 
 
 def reflect(x, axis, depth):
-    """``reflect`` (:733-756)."""
-    from ._views import concatenate
-    left = x[_axis_slice(x.ndim, axis, slice(0, 1) if depth == 1 else slice(depth - 1, None, -1))]
-    right = x[_axis_slice(x.ndim, axis, slice(-1, -depth - 1, -1))]
-    return concatenate([_one_chunk(left, axis, depth), x, _one_chunk(right, axis, depth)], axis=axis)
+    return boundaries(x, {axis: depth}, {axis: "reflect"})
 
 
 def nearest(x, axis, depth):
-    """``nearest`` (:759-773): the edge hyperplane repeated ``depth`` times."""
-    from ._views import concatenate
-    left = x[_axis_slice(x.ndim, axis, slice(0, 1))]
-    right = x[_axis_slice(x.ndim, axis, slice(-1, None))]
-    rep = lambda e: _one_chunk(concatenate([e] * depth, axis=axis), axis, depth)
-    return concatenate([rep(left), x, rep(right)], axis=axis)
+    return boundaries(x, {axis: depth}, {axis: "nearest"})
 
 
 def constant(x, axis, depth, value):
-    """``constant`` (:776-789)."""
-    from ._collection import full
-    from ._views import concatenate
-    chunks = list(x.chunks)
-    chunks[axis] = (depth,)
-    c = full(tuple(sum(c) for c in chunks), value, chunks=tuple(chunks), dtype=x.dtype)
-    return concatenate([c, x, c], axis=axis)
+    return boundaries(x, {axis: depth}, {axis: value})
 
 
 def boundaries(x, depth=None, kind=None):
-    """``boundaries`` (:803-833)."""
-    if not isinstance(kind, dict):
-        kind = dict.fromkeys(range(x.ndim), kind)
-    if not isinstance(depth, dict):
-        depth = dict.fromkeys(range(x.ndim), depth)
-    for i in range(x.ndim):
-        d = depth.get(i, 0)
-        d = max(_sides(d)) if isinstance(d, tuple) else d
-        if d == 0:
+    """``boundaries`` (:803-833): pad every axis that has a depth and a boundary condition."""
+    from ._views import concatenate
+
+    kinds = kind if isinstance(kind, dict) else dict.fromkeys(range(x.ndim), kind)
+    depths = depth if isinstance(depth, dict) else dict.fromkeys(range(x.ndim), depth)
+    for axis in range(x.ndim):
+        d = depths.get(axis, 0) or 0
+        d = max(_sides(d))
+        k = kinds.get(axis, "none")
+        if d == 0 or k is None or (isinstance(k, str) and k == "none") or axis not in kinds:
             continue
-        k = kind.get(i, "none")
-        if isinstance(k, str) and k == "none":
-            continue
-        if isinstance(k, str) and k == "periodic":
-            x = periodic(x, i, d)
-        elif isinstance(k, str) and k == "reflect":
-            x = reflect(x, i, d)
-        elif isinstance(k, str) and k == "nearest":
-            x = nearest(x, i, d)
-        elif i in kind:
-            x = constant(x, i, d, k)
+        low, high = _pads(x, axis, d, k)
+        x = concatenate([low, x, high], axis=axis)
     return x
 
 
