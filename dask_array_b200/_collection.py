@@ -326,12 +326,15 @@ class Compiled:
     def capture(self):
         """Capture the launch tape into ONE CUDA graph: a replay is then a single graph launch instead
         of one driver call per kernel (the README example drops from ~11 us per launch to the graph's
-        fixed cost).  Single-GPU steps only: the peer-memory barrier takes a fresh epoch per call, which
-        a captured graph would freeze."""
+        fixed cost).  Multi-GPU steps are capturable on the peer-memory path: its barriers keep their
+        epoch in a device counter (``b2_peer_barrier_dev``), so the captured launches are argument-stable;
+        every rank must then replay the same number of times."""
         import torch
 
-        if self.executor.world.size > 1:
-            raise NotImplementedError("CUDA-graph capture of a multi-GPU step (peer barriers carry per-call epochs)")
+        from . import _peer
+
+        if self.executor.world.size > 1 and not _peer.enabled():
+            raise NotImplementedError("CUDA-graph capture of a multi-GPU step needs the peer-memory path (B2_COMM=peer)")
         for k in self.fused_launches():
             if k.profile:
                 raise RuntimeError("per-launch event profiling and graph capture are mutually exclusive")

@@ -49,72 +49,130 @@ def _copy_descs(src: DeviceChunk, dst: DeviceChunk, item: int):
     return out
 
 
-# ----------------------------------------------------------------------------- NCCL plumbing
+# ----------------------------------------------------------------------------- tree partials
+def _partial_fields(x, kind, bid):
+    """[(field name, shape, dtype)] of the partial block ``bid`` of ``x`` -- derivable on every rank from
+    the expression alone (``mean_chunk`` / ``moment_chunk`` / ``arg_chunk`` results, ``_common.py:270-281,
+    368-404, 704-732``, in their device representation, see ``_reductions``)."""
+    kshape = tuple(x.block_shape(bid))
+    if kind == "moment":
+        return [("", kshape + (3,), np.dtype(np.float64))]
+    if kind == "mean":
+        return [("total", kshape, x.dtype)]
+    if kind == "arg":
+        leaf = x
+        while type(leaf).__name__ == "PartialReduce":
+            leaf = leaf.operand("array")
+        return [("arg", kshape, np.dtype(np.int64)), ("vals", kshape, leaf.operand("array").dtype)]
+    return [("", kshape, x.dtype)]
+
+
+def mean_count(x, bid):
+    """Element count behind the ``total`` of partial block ``bid`` (the ``n`` of ``mean_chunk``
+    ``_common.py:278-279``, summed by ``mean_combine`` :284-305): a host integer, from shapes alone."""
+    if type(x).__name__ == "PartialReduce":
+        for key, members in x.groups():
+            if key == bid:
+                return sum(mean_count(x.operand("array"), m) for m in members)
+        raise KeyError(bid)
+    red = x.root if type(x).__name__ == "FusedBlockwise" else x        # the ChunkReduce
+    top = red.operand("array")
+    return math.prod(top.block_shape(bid)[a] for a in red.operand("axis"))
+
+
+def partials_layout(x, kind, W: int):
+    """One slab per rank holding that rank's partial blocks of ``x`` in block-id order, every field
+    16-byte aligned.  Returns ``(layout, sizes)``: ``layout[r][bid] = [(name, byte offset, shape, dtype)]``."""
+    layout = [dict() for _ in range(W)]
+    sizes = [0] * W
+    for bid in x.block_ids():
+        r = owner_of(x, bid, W)
+        ent = []
+        for name, shp, dt in _partial_fields(x, kind, bid):
+            ent.append((name, sizes[r], shp, dt))
+            sizes[r] += -(-math.prod(shp) * dt.itemsize // 16) * 16
+        layout[r][bid] = ent
+    return layout, sizes
+
+
+def alloc_partials(ex, x, kind):
+    """Allocate this rank's partial blocks of ``x`` inside ONE slab laid out by ``partials_layout`` (the
+    slab is the send buffer of the all-gather: no pack step).  Returns (slab, {bid: {field: DeviceChunk}})."""
+    layout, sizes = partials_layout(x, kind, ex.world.size)
+    me = ex.world.rank
+    slab = alloc_bytes(max(sizes[me], 16), ex.device)
+    out = {}
+    for bid, ent in layout[me].items():
+        out[bid] = {name: DeviceChunk(slab, shp, dt, offset=off // dt.itemsize) for name, off, shp, dt in ent}
+    return slab, out
+
+
+_SMALL_ALLGATHER = 64 * 1024
+
+
 def _allgather_blocks(ex, src: BlockStore, x):
-    """All-gather the (tiny) per-block partials of ``x`` so every rank can fold the tree."""
+    """All-gather the per-block partials of ``x`` so every rank can fold the tree (the exchange between
+    the chunk step and ``PartialReduce``, ``reductions/_reduction.py:751-806``).  Peer path: every rank
+    stores its slab into slot ``rank`` of every rank's window over NVLink between two stream-ordered
+    barriers -- one launch for small payloads (``b2_peer_allgather``), barrier / tiled gather / barrier
+    for big ones.  ``B2_COMM=nccl``: ``all_gather_into_tensor``."""
     import torch.distributed as dist
 
     W, me = ex.world.size, ex.world.rank
-    ids = list(x.block_ids())
-
-    def fields(b):
-        if isinstance(b, dict):
-            return [(k, v) for k, v in sorted(b.items()) if isinstance(v, DeviceChunk)]
-        return [("", b)]
-
-    # layout is derivable on every rank from shapes alone
-    def proto(bid):
-        kshape = x.block_shape(bid)
-        if src.kind == "moment":
-            return [("", tuple(kshape) + (3,), np.dtype(np.float64))]
-        if src.kind == "mean":
-            return [("total", kshape, x.dtype)]
-        if src.kind == "arg":
-            vdt = x.operand("array").dtype
-            return [("arg", kshape, np.dtype(np.int64)), ("vals", kshape, vdt)]
-        return [("", kshape, x.dtype)]
-
-    def nbytes(bid):
-        return sum(-(-math.prod(s) * d.itemsize // 16) * 16 for _, s, d in proto(bid))
-
-    per_rank = [sum(nbytes(b) for b in ids if ex.world.owner(x, b) == r) for r in range(W)]
-    cap = max(max(per_rank), 16)
-    send = alloc_bytes(cap, ex.device)
-    off = 0
-    copies = []
-    for bid in ids:
-        if ex.world.owner(x, bid) != me:
-            continue
-        blk = src.blocks[bid]
-        for (name, chunk), (_, shp, dt) in zip(fields(blk), proto(bid)):
-            nb = math.prod(shp) * dt.itemsize
-            if nb:
-                copies.append((chunk.ptr, send.data_ptr() + off, 1, nb, nb, nb))
-            off += -(-nb // 16) * 16
-    g = rt.GatherLaunch(copies)
-    ex._do(g.run)
+    kind = src.kind
+    layout, sizes = partials_layout(x, kind, W)
+    cap = max(max(sizes), 16)
+    send = getattr(src, "slab", None)
+    keep = []
+    if send is None:
+        send = alloc_bytes(cap, ex.device)
+        copies = []
+        for bid, ent in layout[me].items():
+            blk = src.blocks[bid]
+            for name, off, shp, dt in ent:
+                chunk = blk[name] if isinstance(blk, dict) else blk
+                nb = math.prod(shp) * dt.itemsize
+                if nb:
+                    if not chunk.is_contiguous:
+                        raise NotImplementedError("all-gather of a non-contiguous partial block")
+                    copies.append((chunk.ptr, send.data_ptr() + off, 1, nb, nb, nb))
+        g = rt.GatherLaunch(copies)
+        ex._do(g.run)
+        keep.append(g)
     recv = alloc_bytes(cap * W, ex.device)
-    ex._do(lambda: dist.all_gather_into_tensor(recv, send))
-    out = {}
-    offs = [0] * W
-    for bid in ids:
-        r = ex.world.owner(x, bid)
-        parts = {}
-        for name, shp, dt in proto(bid):
-            nb = math.prod(shp) * dt.itemsize
-            parts[name] = DeviceChunk(recv, shp, dt, offset=(r * cap + offs[r]) // dt.itemsize)
-            offs[r] += -(-nb // 16) * 16
-        if src.kind == "mean":
-            red = x.root if type(x).__name__ == "FusedBlockwise" else x        # the ChunkReduce
-            axes = red.operand("axis")
-            top = red.operand("array")
-            n = math.prod(top.block_shape(bid)[a] for a in axes)
-            out[bid] = {"total": parts["total"], "n": n}
-        elif src.kind == "arg":
-            out[bid] = parts
+    bar = _peer.StreamBarrier(ex.device, me, W) if _peer.enabled() else None
+    if bar is not None and getattr(bar, "allgather", None) is not None:
+        bases = [p[0] for p in _peer.exchange_pointers(ex.device, [recv.data_ptr()], [1] * W, me)]
+        table = torch.tensor(bases, dtype=torch.int64).to(ex.device)
+        nb_me = sizes[me]
+        if cap <= _SMALL_ALLGATHER:
+            ex._do(lambda: bar.allgather(table.data_ptr(), send.data_ptr(), nb_me, cap))
         else:
-            out[bid] = parts[""]
-    src.keepalive.extend([send, recv, g])
+            push = rt.GatherLaunch([(send.data_ptr(), bases[(me + 1 + k) % W] + me * cap, 1, nb_me, nb_me, nb_me)
+                                    for k in range(W)] if nb_me else [])
+            ex._do(bar)
+            ex._do(push.run)
+            ex._do(bar)
+            keep.append(push)
+        keep.append(table)
+    else:
+        if send.numel() != cap:
+            full = alloc_bytes(cap, ex.device)
+            ex._do(lambda: full[: send.numel()].copy_(send))
+            keep.append(send)
+            send = full
+        ex._do(lambda: dist.all_gather_into_tensor(recv, send))
+    out = {}
+    for r in range(W):
+        for bid, ent in layout[r].items():
+            parts = {name: DeviceChunk(recv, shp, dt, offset=(r * cap + off) // dt.itemsize) for name, off, shp, dt in ent}
+            if kind == "mean":
+                out[bid] = {"total": parts["total"], "n": mean_count(x, bid)}
+            elif kind == "arg":
+                out[bid] = parts
+            else:
+                out[bid] = parts[""]
+    src.keepalive.extend([send, recv, keep])
     return out
 
 

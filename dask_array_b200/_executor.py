@@ -40,6 +40,7 @@ class BlockStore:
         self.replicated = replicated
         self.blocks = {}          # bid -> DeviceChunk | dict
         self.keepalive = []       # launch tables / pointer tables the stream may still read
+        self.slab = None          # partial blocks laid out by _exchange.partials_layout (send buffer of the all-gather)
 
 
 class World:
@@ -55,9 +56,6 @@ class World:
 
     def owner(self, expr, bid) -> int:
         return owner_of(expr, bid, self.size)
-
-
-_PLAN_CACHE: dict = {}
 
 
 class Executor:
@@ -279,10 +277,10 @@ class Executor:
 
     # ------------------------------------------------------------------ fused blockwise
     def _run_FusedBlockwise(self, expr: FusedBlockwise):
-        key = expr._name
-        plan = _PLAN_CACHE.get(key)
-        if plan is None:
-            plan = _PLAN_CACHE[key] = FusedPlan(expr)
+        # the plan (kernel program + leaf map) is rebuilt per run: it references the leaves -- host arrays,
+        # resident device blocks -- which a process-wide cache would pin for ever; the expensive part, the
+        # compiled kernel, is cached by structure in _runtime
+        plan = FusedPlan(expr)
         red = plan.reduce
         top = plan.eval_expr
         kind = red.operand("kind") if red is not None else None
@@ -295,9 +293,24 @@ class Executor:
         blocks, block_owner = [], []
         axes = red.operand("axis") if red is not None else ()
         acc_dtype = None
+        if red is not None:
+            # every partial block of this rank inside ONE slab (the send buffer of the tree's all-gather)
+            st.slab, fields = alloc_partials(self, expr, store_kind)
+            if kind == "var":
+                acc_dtype = np.float32 if plan.program.out_dtype == np.float32 else np.float64
+            else:
+                acc_dtype = red.dtype
         for bid in out_ids:
             shape = top.block_shape(bid) if red is not None else expr.block_shape(bid)
-            if math.prod(shape) == 0:
+            if red is not None:
+                f = fields[bid]
+                out = f["total"] if kind == "mean" else f[""]
+                st.blocks[bid] = {"total": out, "n": math.prod(shape[a] for a in axes)} if kind == "mean" else out
+                if math.prod(shape) == 0:
+                    if out.size:
+                        out.as_torch().zero_()
+                    continue
+            elif math.prod(shape) == 0:
                 st.blocks[bid] = self._empty_result(expr, bid, store_kind)
                 continue
             ins = []
@@ -313,27 +326,9 @@ class Executor:
                 ins.append((src.ptr, plan.leaf_strides(k, src, len(shape))))
             if red is None:
                 block_owner.append(remote_owner)
-            out_shape = expr.block_shape(bid)
-            if red is None:
-                out = DeviceChunk.empty(out_shape, expr.dtype, self.device)
-                blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
+                out = DeviceChunk.empty(expr.block_shape(bid), expr.dtype, self.device)
                 st.blocks[bid] = out
-            elif kind == "var":
-                out = DeviceChunk.empty(tuple(out_shape) + (3,), np.float64, self.device)
-                acc_dtype = np.float32 if plan.program.out_dtype == np.float32 else np.float64
-                blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
-                st.blocks[bid] = out
-            elif kind == "mean":
-                out = DeviceChunk.empty(out_shape, red.dtype, self.device)
-                acc_dtype = red.dtype
-                blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
-                n = math.prod(shape[a] for a in axes)
-                st.blocks[bid] = {"total": out, "n": n}
-            else:
-                out = DeviceChunk.empty(out_shape, red.dtype, self.device)
-                acc_dtype = red.dtype
-                blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
-                st.blocks[bid] = out
+            blocks.append(rt.BlockArgs(shape=shape, inputs=ins, out0=out.ptr))
         bar = extra.get("__barrier__")
         keep_order = False
         if bar is not None:
@@ -373,13 +368,12 @@ class Executor:
         prog.set_output(prog.op("positive", prog.add_input(x.dtype)))
         st = BlockStore(expr, "arg")
         blocks = []
+        st.slab, fields = alloc_partials(self, expr, "arg")
         for bid in x.block_ids():
             if not self.mine(x, bid):
                 continue
             c = src.blocks[bid]
-            oshape = expr.block_shape(bid)
-            vals = DeviceChunk.empty(oshape, x.dtype, self.device)
-            arg = DeviceChunk.empty(oshape, np.int64, self.device)
+            vals, arg = fields[bid]["vals"], fields[bid]["arg"]
             start = x.block_start(bid)
             kw = {}
             if ravel:
@@ -527,21 +521,30 @@ class Executor:
         return cum.st
 
     # ------------------------------------------------------------------ tree levels
-    def _gather_partials(self, src: BlockStore, x):
-        """Make every partial block of ``x`` available on this rank (all-gather over NCCL)."""
+    def _gather_partials(self, expr, src: BlockStore, x):
+        """The partial blocks a ``PartialReduce`` level folds on this rank.  Returns ``(blocks, local)``.
+        ``local``: every group's members live on the rank that owns the group's output block (e.g.
+        ``mean(axis=0)`` with the block columns dealt to the ranks): each owner folds its own groups, no
+        exchange at all.  Otherwise the partials are all-gathered (peer memory) and every rank folds the
+        whole level, so the results are replicated."""
         if self.world.size == 1 or src.replicated:
-            return src.blocks
-        return _allgather_blocks(self, src, x)
+            return src.blocks, False
+        W = self.world.size
+        if all(owner_of(x, m, W) == owner_of(expr, key, W) for key, members in expr.groups() for m in members):
+            return src.blocks, True
+        return _allgather_blocks(self, src, x), False
 
     def _run_PartialReduce(self, expr: PartialReduce):
         x = expr.operand("array")
         src = self.results[x._name]
         kind, final = expr.operand("kind"), expr.operand("final")
-        parts = self._gather_partials(src, x)
+        parts, local = self._gather_partials(expr, src, x)
         redop = REDOPS[kind]
-        st = BlockStore(expr, src.kind if not final else "array", replicated=True)
+        st = BlockStore(expr, src.kind if not final else "array", replicated=not local)
         groups, in_dt, out_dt, op = [], None, None, redop
         for key, members in expr.groups():
+            if local and not self.mine(expr, key):
+                continue
             blks = [parts[m] for m in members]
             first = blks[0]
             if src.kind == "mean":
@@ -580,6 +583,8 @@ class Executor:
                 in_dt = out_dt = first.dtype
                 st.blocks[key] = out
             st.keepalive.append(blks)
+        if not groups:                      # this rank owns no output block of the level
+            return st
         launch = rt.CombineGroupsLaunch(op, in_dt, out_dt, groups)       # ONE launch for the whole level
         self._do(launch.run)
         st.keepalive.append(launch)
@@ -747,7 +752,7 @@ class Executor:
 
 # the multi-GPU plumbing and the cumulative-scan launch builder live in their own modules
 from ._exchange import (  # noqa: E402,F401
-    _allgather_blocks, _copy_descs, _exchange_for_fused, _exchange_for_rechunk, _fetch_blocks, _interleave_remote_reads,
+    alloc_partials, mean_count, partials_layout, _allgather_blocks, _copy_descs, _exchange_for_fused, _exchange_for_rechunk, _fetch_blocks, _interleave_remote_reads,
     _peer_reads_for_fused, _push_views, _rechunk_push, gather_to_host, owner_of, plan_block_fetch, plan_fused_exchange,
     plan_fused_peer_reads, plan_rechunk_exchange, plan_rechunk_push,
 )

@@ -95,16 +95,21 @@ class NcclBarrier:
 
         dist.all_reduce(self.flag)
 
+    allgather = None          # the NCCL barrier has no peer windows: callers fall back to all_gather_into_tensor
+
 
 class PeerBarrier:
-    """Stream-ordered barrier through peer memory (``b2_peer_barrier``): every rank stores an epoch
+    """Stream-ordered barrier through peer memory (``b2_peer_barrier_dev``): every rank stores an epoch
     into every peer's signal array over NVLink and waits for its own array to fill.  Everything the
     ranks enqueued before it has completed -- and is visible system-wide -- before anything enqueued
-    after it runs.  One instance per process; all ranks call it in the same order."""
+    after it runs.  The epoch is a device counter the kernel advances itself, so the launch is
+    argument-stable and can be replayed from a CUDA graph.  One instance per process; all ranks call it
+    in the same order."""
 
     def __init__(self, device, rank: int, world: int):
-        self.rank, self.world, self.epoch = rank, world, 0
+        self.rank, self.world, self.device = rank, world, device
         self.sig = torch.zeros(max(world, 2), dtype=torch.int64, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
         # the all-gather inside is ordered after the zero-fill on every rank: no signal can precede it
         ptrs = exchange_pointers(device, [self.sig.data_ptr()], [1] * world, rank)
         self.table = torch.tensor([p[0] for p in ptrs], dtype=torch.int64).to(device)
@@ -112,9 +117,16 @@ class PeerBarrier:
     def __call__(self):
         from ._device import current_stream_ptr
 
-        self.epoch += 1
-        _lib.check(_lib.lib.b2_peer_barrier(self.table.data_ptr(), self.rank, self.world, self.epoch,
-                                            current_stream_ptr()))
+        _lib.check(_lib.lib.b2_peer_barrier_dev(self.table.data_ptr(), self.epoch.data_ptr(), self.rank, self.world,
+                                                current_stream_ptr()))
+
+    def allgather(self, windows_table: int, send_ptr: int, nbytes: int, slot_bytes: int):
+        """``b2_peer_allgather`` on this barrier's signal table: barrier -> my record into slot ``rank`` of
+        every rank's window -> barrier, one launch."""
+        from ._device import current_stream_ptr
+
+        _lib.check(_lib.lib.b2_peer_allgather(self.table.data_ptr(), self.epoch.data_ptr(), windows_table, send_ptr,
+                                              nbytes, slot_bytes, self.rank, self.world, current_stream_ptr()))
 
 
 _BARRIER = None

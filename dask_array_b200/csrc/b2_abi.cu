@@ -781,6 +781,100 @@ extern "C" int b2_peer_barrier(void* const* d_sig_table, int me, int world, uint
     return B2_OK;
 }
 
+// Device-epoch variants: the epoch lives in a device counter that the kernel itself advances, so the
+// launch arguments never change and the launch can sit inside a CUDA graph that is replayed.
+__device__ __forceinline__ void b2_signal_all(unsigned long long* const* sig, int me, int world, unsigned long long epoch) {
+    for (int p = threadIdx.x; p < world; p += blockDim.x) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sig[p] + me), "l"(epoch) : "memory");
+    }
+}
+__device__ __forceinline__ void b2_wait_all(unsigned long long* const* sig, int me, int world, unsigned long long epoch,
+                                            unsigned long long timeout_ns) {
+    for (int p = threadIdx.x; p < world; p += blockDim.x) {
+        const unsigned long long* mine = sig[me] + p;
+        unsigned long long v, t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if (v >= epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) __trap();
+            __nanosleep(40);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) b2_peer_barrier_dev_kernel(unsigned long long* const* __restrict__ sig,
+                                                                 unsigned long long* epoch_ctr, int me, int world,
+                                                                 unsigned long long timeout_ns) {
+    const unsigned long long epoch = *epoch_ctr + 1;     // stream order serialises the launches that touch it
+    b2_signal_all(sig, me, world, epoch);
+    b2_wait_all(sig, me, world, epoch, timeout_ns);
+    __syncwarp();
+    if (threadIdx.x == 0) *epoch_ctr = epoch;
+}
+
+extern "C" int b2_peer_barrier_dev(void* const* d_sig_table, uint64_t* d_epoch, int me, int world, void* stream) {
+    if (!d_sig_table || !d_epoch || world <= 0 || me < 0 || me >= world) return fail(B2_ERR_INVALID, "bad argument");
+    b2_peer_barrier_dev_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long* const*)d_sig_table,
+                                                                   (unsigned long long*)d_epoch, me, world,
+                                                                   120ull * 1000000000ull);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
+// All-gather of small per-rank records through peer memory in ONE launch:
+//   barrier (every rank has consumed the previous contents of the receive windows)
+//   -> store my `nbytes` at slot `me` of every rank's window (16-byte vectors, NVLink stores)
+//   -> barrier (every record has landed and is visible).
+// One CTA: the payloads are the per-block partials of a tree reduction (bytes to a few hundred KiB).
+__global__ void __launch_bounds__(1024) b2_peer_allgather_kernel(unsigned long long* const* __restrict__ sig,
+                                                                 unsigned long long* epoch_ctr,
+                                                                 unsigned char* const* __restrict__ windows,
+                                                                 const unsigned char* __restrict__ send, long long nbytes,
+                                                                 long long slot_bytes, int me, int world,
+                                                                 unsigned long long timeout_ns) {
+    const unsigned long long e0 = *epoch_ctr + 1;
+    if (threadIdx.x < 32) {
+        b2_signal_all(sig, me, world, e0);
+        b2_wait_all(sig, me, world, e0, timeout_ns);
+    }
+    __syncthreads();
+    const long long nvec = nbytes >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(send);
+    for (int k = 0; k < world; ++k) {
+        const int p = (me + 1 + k) % world;          // start at the right-hand neighbour: a permutation at any moment
+        uint4* d4 = reinterpret_cast<uint4*>(windows[p] + (long long)me * slot_bytes);
+        for (long long i = threadIdx.x; i < nvec; i += blockDim.x) d4[i] = s4[i];
+        unsigned char* d1 = windows[p] + (long long)me * slot_bytes;
+        for (long long i = (nvec << 4) + threadIdx.x; i < nbytes; i += blockDim.x) d1[i] = send[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        b2_signal_all(sig, me, world, e0 + 1);
+        b2_wait_all(sig, me, world, e0 + 1, timeout_ns);
+        __syncwarp();
+        if (threadIdx.x == 0) *epoch_ctr = e0 + 1;
+    }
+}
+
+extern "C" int b2_peer_allgather(void* const* d_sig_table, uint64_t* d_epoch, void* const* d_windows, const void* send,
+                                 int64_t nbytes, int64_t slot_bytes, int me, int world, void* stream) {
+    if (!d_sig_table || !d_epoch || !d_windows || world <= 0 || me < 0 || me >= world || nbytes < 0 || nbytes > slot_bytes
+        || (nbytes && !send))
+        return fail(B2_ERR_INVALID, "bad argument");
+    if (((uintptr_t)send & 15) || (slot_bytes & 15)) return fail(B2_ERR_INVALID, "peer_allgather: 16-byte alignment");
+    b2_peer_allgather_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+        (unsigned long long* const*)d_sig_table, (unsigned long long*)d_epoch, (unsigned char* const*)d_windows,
+        (const unsigned char*)send, (long long)nbytes, (long long)slot_bytes, me, world, 120ull * 1000000000ull);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------ fill (AOT)
 template <typename W>
 __global__ void __launch_bounds__(256) b2_fill_kernel(W* dst, i64 n, W value) {

@@ -267,6 +267,18 @@ int b2_ipc_open(const b2_ipc_handle* h, void** ptr);
  * the same order on every rank.  A peer that does not arrive within 120 s traps the kernel (a loud
  * failure instead of a hung GPU). */
 int b2_peer_barrier(void* const* d_sig_table, int me, int world, uint64_t epoch, void* stream);
+/* The same barrier with the epoch kept in a DEVICE counter (*d_epoch, this rank's own memory, zero at
+ * start) that the kernel advances by one: the launch arguments never change, so the launch can be
+ * captured in a CUDA graph and replayed.  All barriers of one signal table must use the same variant. */
+int b2_peer_barrier_dev(void* const* d_sig_table, uint64_t* d_epoch, int me, int world, void* stream);
+/* All-gather of the per-block partials of a tree reduction across ranks (the exchange step between
+ * the chunk Blockwise and the first PartialReduce level, reductions/_reduction.py:751-806, when the
+ * members of a group live on different GPUs) in ONE launch through peer memory: barrier (the receive
+ * windows are free) -> this rank's `nbytes` stored into slot `me` (byte offset me * slot_bytes) of
+ * every rank's window d_windows[p] over NVLink -> barrier (all records visible).  Advances *d_epoch
+ * by two.  `send` and slot_bytes are 16-byte aligned; nbytes <= slot_bytes. */
+int b2_peer_allgather(void* const* d_sig_table, uint64_t* d_epoch, void* const* d_windows, const void* send,
+                      int64_t nbytes, int64_t slot_bytes, int me, int world, void* stream);
 
 /* Strided host<->device block transfer: from_array's per-block getitem of a host array
  * (io/_from_array.py:60-160) and finalize's concatenate3 into the host result

@@ -34,6 +34,30 @@ def main():
     np.testing.assert_allclose(got_mean, want_mean, rtol=1e-5)
     np.testing.assert_allclose(got_std, want_std, rtol=1e-5)
 
+    # the tree exchange through peer memory (b2_peer_allgather) replayed from ONE CUDA graph per rank:
+    # device-side epochs keep the captured barriers valid across replays
+    xp = x.persist()
+    yp = da.sin(xp) * 2 + xp**2
+    step = da.compile(yp.mean(axis=0), yp.std(), yp.sum(axis=1), yp.max())
+    if os.environ.get("B2_COMM", "peer") != "nccl":
+        step.capture()
+    for _ in range(5):
+        step.run()
+    gm, gs, gr, gx = step.results()
+    np.testing.assert_allclose(gm, want_mean, rtol=1e-5)
+    np.testing.assert_allclose(gs, want_std, rtol=1e-5)
+    y64 = np.sin(xh.astype(np.float64)) * 2 + xh.astype(np.float64) ** 2
+    np.testing.assert_allclose(gr, y64.sum(axis=1), rtol=1e-5)
+    np.testing.assert_allclose(gx, y64.max(), rtol=1e-6)
+    # an aggregate that stays with its owners (mean(axis=0): every group is local to one rank) feeding an
+    # element-wise chain on the full grid, and a big partial payload (the tiled-gather all-gather path)
+    np.testing.assert_allclose((x - x.mean(axis=0)).std(axis=0).compute(), xh.astype(np.float64).std(axis=0), rtol=1e-5)
+    wide = rng.random((64, 40000))
+    wd = da.from_array(wide, chunks=(8, 40000))
+    np.testing.assert_allclose(wd.sum(axis=0).compute(), wide.sum(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(wd.var(axis=0, split_every=2).compute(), wide.var(axis=0), rtol=1e-12)
+    assert np.array_equal(wd.argmax(axis=0).compute(), wide.argmax(axis=0))
+
     b = ref.Blocked.from_array(xh, chunks)
     t = np.floor(xh * 50)
     tb, td = ref.Blocked.from_array(t, chunks), da.from_array(t, chunks=chunks)
