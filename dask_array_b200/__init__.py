@@ -22,6 +22,9 @@ from ._overlap import map_blocks, map_overlap, sliding_window_view  # noqa: F401
 from ._topk import argtopk, topk  # noqa: F401,E402
 from ._routines import diff, flip, fliplr, flipud, roll  # noqa: F401,E402
 
+from . import plugin  # noqa: F401,E402  (register / get / lower_reference: the reference-facing boundary)
+from .plugin import get, register  # noqa: F401,E402
+
 for _n in UFUNC_NAMES:
     globals()[_n] = _ufunc(_n)
 for _n in ("sum", "prod", "mean", "var", "std", "min", "max", "any", "all", "argmin", "argmax"):

@@ -435,6 +435,14 @@ class FusedPlan:
                 out = self.program.op("positive", out)
         self.program.set_output(out)
 
+    @classmethod
+    def from_reference(cls, fused):
+        """Plan of a REFERENCE ``FusedBlockwise`` (``dask_array/_blockwise.py:1574-1728``): see
+        ``plugin.fused_plan_from_reference``."""
+        from .plugin import fused_plan_from_reference
+
+        return fused_plan_from_reference(fused)
+
     def _leaf(self, dep, dmap):
         key = (dep._name, dmap)
         if key not in self._leaf_index:

@@ -116,13 +116,18 @@ ALIASES = {
     operator.gt: "greater", operator.ge: "greater_equal", operator.eq: "equal", operator.ne: "not_equal",
     "divide": "true_divide", "mod": "remainder", "abs": "absolute", "bitwise_not": "invert",
     "conjugate": "positive", "conj": "positive",
+    # the reference's own element-wise helpers (reductions/_common.py:625-636: std = safe_sqrt(var))
+    "_sqrt": "sqrt", "safe_sqrt": "sqrt",
 }
 
 
 def canonical_name(op) -> str:
     """Name of an Elemwise ``op`` (operator.* function, np.ufunc or string)."""
-    if op in ALIASES:
-        return ALIASES[op]
+    try:
+        if op in ALIASES:
+            return ALIASES[op]
+    except TypeError:           # unhashable callable object
+        pass
     name = op if isinstance(op, str) else getattr(op, "__name__", None)
     if name in ALIASES:
         return ALIASES[name]

@@ -564,15 +564,34 @@ def full(shape, fill_value, dtype=None, chunks=None, **kw):
 
 
 class _RandomGenerator:
-    """``da.random.default_rng(seed)`` (``random/``): per-block ``SeedSequence.spawn`` children."""
+    """``da.random.default_rng(seed)`` (``random/_generator.py:425-441``): one live ``SeedSequence`` per
+    generator (fresh OS entropy when ``seed`` is None); every draw spawns one child per block from it
+    (``_spawn_bitgens``, ``random/_expr.py:29-32``), which advances the sequence -- successive draws differ,
+    a fixed seed reproduces the same succession, exactly like the reference."""
 
     def __init__(self, seed=None):
-        self.seed = 0 if seed is None else seed
+        if isinstance(seed, np.random.SeedSequence):
+            self._seed_seq = seed
+        elif isinstance(seed, np.random.Generator):
+            self._seed_seq = seed.bit_generator.seed_seq
+        elif isinstance(seed, np.random.BitGenerator):
+            self._seed_seq = seed.seed_seq
+        else:
+            self._seed_seq = np.random.SeedSequence(seed)
 
     def _make(self, dist, size, chunks, dtype, args=()):
-        shape = (size,) if isinstance(size, Integral) else tuple(size)
+        shape = () if size is None else (size,) if isinstance(size, Integral) else tuple(size)
         chunks = normalize_chunks(chunks if chunks is not None and chunks != "auto" else shape, shape)
-        return Array(Random(self.seed, dist, shape, chunks, np.dtype(dtype).name, args))
+        ss = self._seed_seq
+        first = ss.n_children_spawned
+        nblocks = 1
+        for c in chunks:
+            nblocks *= len(c)
+        ss.spawn(nblocks)                       # advance, as _spawn_bitgens does
+        ent = ss.entropy
+        ent = tuple(int(e) for e in ent) if isinstance(ent, (list, tuple, np.ndarray)) else int(ent)
+        seed = (ent, tuple(int(k) for k in ss.spawn_key), int(first))
+        return Array(Random(seed, dist, shape, chunks, np.dtype(dtype).name, args))
 
     def random(self, size=None, dtype=np.float64, chunks="auto", **kw):
         return self._make("random", size, chunks, dtype)

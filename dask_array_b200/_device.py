@@ -189,9 +189,13 @@ class DeviceChunk:
         """Basic indexing only (slices with step 1.., ints, None, Ellipsis): always a view."""
         if not isinstance(index, tuple):
             index = (index,)
+        if any(isinstance(i, (np.ndarray, DeviceChunk, list)) for i in index):
+            from ._eager import fancy_getitem          # the integer-array gathers of _arg_combine
+
+            return fancy_getitem(self, index)
         n_real = sum(1 for i in index if i is not None and i is not Ellipsis)
-        if Ellipsis in index:
-            k = index.index(Ellipsis)
+        if any(i is Ellipsis for i in index):
+            k = next(p for p, i in enumerate(index) if i is Ellipsis)
             index = index[:k] + (slice(None),) * (self.ndim - n_real) + index[k + 1:]
         else:
             index = index + (slice(None),) * (self.ndim - n_real)

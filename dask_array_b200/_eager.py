@@ -369,8 +369,244 @@ def numel(x, **kwargs):
     return np.broadcast_to(np.array(prod, dtype=dtype), new)
 
 
+# ----------------------------------------------------------------------------- integer-array gathers
+def _index_chunk(ix):
+    c = _as_chunk(ix)
+    if c.dtype.kind not in "iu":
+        raise IndexError("arrays used as indices must be of integer type")
+    if c.dtype != np.int64:
+        c = c.astype(np.int64)
+    return c if c.is_contiguous else copy(c)
+
+
+def _take(src: DeviceChunk, idx: DeviceChunk, n: int, inner: int, out_shape) -> DeviceChunk:
+    out = DeviceChunk.empty(out_shape, src.dtype, src.device)
+    if out.size:
+        _lib.check(_lib.lib.b2_take(src.itemsize, src.ptr, idx.ptr, out.ptr, out.size, n, inner, rt.current_stream_ptr()))
+        out._keep = (src, idx)
+    return out
+
+
+def fancy_getitem(a: DeviceChunk, index):
+    """The two integer-array gathers of ``_arg_combine`` (``reductions/_common.py:687-697``):
+    ``vals.ravel()[local_args]`` (one index array on a 1-D chunk) and the take-along-axis spelled with
+    ``np.ogrid``: ``vals[ogrid_0, .., local_args, .., ogrid_k]``.  Anything else is refused."""
+    if not isinstance(index, tuple):
+        index = (index,)
+    if len(index) == 1 and a.ndim == 1:
+        idx = _index_chunk(index[0])
+        src = a if a.is_contiguous else copy(a)
+        return _take(src, idx, a.shape[0], 0, idx.shape)
+    if len(index) != a.ndim:
+        raise NotImplementedError("DeviceChunk integer-array indexing: one index array per axis (np.ogrid form) or a 1-D take")
+    dev = [k for k, ix in enumerate(index) if isinstance(ix, DeviceChunk)]
+    if len(dev) != 1:
+        raise NotImplementedError("DeviceChunk integer-array indexing: exactly one data-dependent index array (the arg positions)")
+    axis = dev[0]
+    local = index[axis]
+    kept = [d for d in range(a.ndim) if d != axis]
+    if local.ndim != len(kept) or any(local.shape[j] != a.shape[d] for j, d in enumerate(kept)):
+        raise NotImplementedError("DeviceChunk take-along-axis: the index array must span every other axis")
+    for j, d in enumerate(kept):
+        g = np.asarray(index[d])
+        want = np.arange(a.shape[d]).reshape(tuple(a.shape[d] if q == j else 1 for q in range(len(kept))))
+        if g.shape != want.shape or not np.array_equal(g, want):
+            raise NotImplementedError("DeviceChunk take-along-axis: the other indices must be the np.ogrid open grid")
+    src = a if a.is_contiguous else copy(a)
+    inner = math.prod(a.shape[axis + 1:])
+    return _take(src, _index_chunk(local), a.shape[axis], max(inner, 1), local.shape)
+
+
+@implements(np.take)
+def _np_take(a, indices, axis=None, **kw):
+    a = _as_chunk(a)
+    if axis is None:
+        a = a.ravel()
+        axis = 0
+    if a.ndim != 1:
+        raise NotImplementedError("np.take on DeviceChunk: 1-D (or axis=None) only")
+    return fancy_getitem(a, (indices,))
+
+
+@implements(np.unravel_index)
+def _unravel_index(indices, shape, order="C"):
+    """``arg_chunk`` ravel path (``_common.py:711``): flat positions -> per-axis coordinates, on the device."""
+    if order != "C":
+        raise NotImplementedError("unravel_index: C order only")
+    idx = _as_chunk(indices)
+    out = []
+    for n in reversed(tuple(shape)):
+        out.append(idx % np.int64(n))
+        idx = idx // np.int64(n)
+    return tuple(reversed(out))
+
+
+@implements(np.ravel_multi_index)
+def _ravel_multi_index(multi_index, dims, mode="raise", order="C"):
+    """``_common.py:713``: coordinates (device chunks and / or host integers) -> flat positions."""
+    if order != "C":
+        raise NotImplementedError("ravel_multi_index: C order only")
+    acc = None
+    for i, n in zip(multi_index, dims):
+        acc = i if acc is None else acc * np.int64(n) + i
+    return acc if isinstance(acc, DeviceChunk) else _as_chunk(np.asarray(acc, dtype=np.int64))
+
+
+# ----------------------------------------------------------------------------- contractions on chunks
+def _matricize(x: DeviceChunk, free, contracted):
+    """(prod(free), prod(contracted)) row-major matrix holding ``x`` with the contracted axes last."""
+    moved = x.transpose(tuple(free) + tuple(contracted))
+    if not moved.is_contiguous:
+        moved = copy(moved)
+    m = math.prod(x.shape[d] for d in free)
+    k = math.prod(x.shape[d] for d in contracted)
+    return moved.reshape((m, k)), m, k
+
+
+def gemm_tn(a2: DeviceChunk, b2: DeviceChunk) -> DeviceChunk:
+    """``a2 @ b2.T`` for row-major (M, K) and (N, K) chunks: bf16 / fp32 on the tensor cores
+    (``b2_gemm_tn_pairs``; fp32 through the bf16 x 3 split), every other NumPy number type through the
+    exact SIMT kernel (``b2_gemm_tn_simt``: fp64 FMA, integer multiply-add in the result type)."""
+    import ctypes as C
+
+    (M, K), (N, K2) = a2.shape, b2.shape
+    assert K == K2
+    dt = np.result_type(a2.dtype, b2.dtype)
+    name = dt.name
+    if a2.dtype == b2.dtype and name in ("float32", "bfloat16") and K % 8 == 0 and a2.ptr % 16 == 0 and b2.ptr % 16 == 0:
+        out = DeviceChunk.empty((M, N), np.float32, a2.device)
+        if not out.size:
+            return out
+        st = rt.current_stream_ptr()
+        if name == "bfloat16":
+            _lib.check(_lib.lib.b2_gemm_tn(_lib.dtype_code("bfloat16"), a2.ptr, K, b2.ptr, K, out.ptr, N, M, N, K, 0, st))
+            out._keep = (a2, b2)
+            return out
+        u16 = np.dtype("uint16")
+        pa = [DeviceChunk.empty(a2.shape, u16, a2.device) for _ in range(3)]
+        pb = [DeviceChunk.empty(b2.shape, u16, b2.device) for _ in range(3)]
+        _lib.check(_lib.lib.b2_split3_bf16(a2.ptr, pa[0].ptr, pa[1].ptr, pa[2].ptr, a2.size, st))
+        _lib.check(_lib.lib.b2_split3_bf16(b2.ptr, pb[0].ptr, pb[1].ptr, pb[2].ptr, b2.size, st))
+        combos = [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0)]
+        arrA = (C.c_void_p * 6)(*[pa[i].ptr for i, _ in combos])
+        arrB = (C.c_void_p * 6)(*[pb[j].ptr for _, j in combos])
+        _lib.check(_lib.lib.b2_gemm_tn_pairs(_lib.dtype_code("bfloat16"), arrA, arrB, 6, K, K, out.ptr, N, M, N, K, 0, st))
+        out._keep = (pa, pb)
+        return out
+    if name not in ("float64", "float32", "int32", "int64", "uint32", "uint64"):
+        if dt.kind in "iub":
+            dt = np.dtype(np.int64) if dt.kind in "ib" else np.dtype(np.uint64)
+        elif dt.kind == "f":
+            dt = np.dtype(np.float32)
+        else:
+            raise NotImplementedError(f"matmul / tensordot of dtype {dt} has no B200 kernel")
+    want = np.result_type(a2.dtype, b2.dtype)
+    a2 = a2 if a2.dtype == dt else a2.astype(dt)
+    b2 = b2 if b2.dtype == dt else b2.astype(dt)
+    out = DeviceChunk.empty((M, N), dt, a2.device)
+    if out.size:
+        if K == 0:
+            rt.fill(out, 0)
+        else:
+            _lib.check(_lib.lib.b2_gemm_tn_simt(_lib.dtype_code(dt), a2.ptr, K, b2.ptr, K, out.ptr, N, M, N, K, 0,
+                                                rt.current_stream_ptr()))
+        out._keep = (a2, b2)
+    return out if out.dtype == want else out.astype(want)
+
+
 def tensordot(a, b, axes=2):
-    raise NotImplementedError("tensordot on DeviceChunk: use the BlockGEMM expression (dask_array_b200._matmul)")
+    """``tensordot_lookup`` implementation (``_core_utils.py:1252-1258``; called per block triple by
+    ``_tensordot``, ``linalg/_tensordot.py:20-42``): matricise both operands and run one GEMM."""
+    a, b = _as_chunk(a), _as_chunk(b)
+    if isinstance(axes, (int, np.integer)):
+        la, lb = tuple(range(a.ndim - axes, a.ndim)), tuple(range(axes))
+    else:
+        la, lb = axes
+        la = (la,) if isinstance(la, (int, np.integer)) else tuple(la)
+        lb = (lb,) if isinstance(lb, (int, np.integer)) else tuple(lb)
+    la, lb = tuple(x % a.ndim for x in la), tuple(x % b.ndim for x in lb)
+    if len(la) != len(lb) or any(a.shape[i] != b.shape[j] for i, j in zip(la, lb)):
+        raise ValueError("shape-mismatch for sum")
+    fa = [d for d in range(a.ndim) if d not in la]
+    fb = [d for d in range(b.ndim) if d not in lb]
+    a2, _, _ = _matricize(a, fa, la)
+    b2, _, _ = _matricize(b, fb, lb)
+    out = gemm_tn(a2, b2)
+    return out.reshape(tuple(a.shape[d] for d in fa) + tuple(b.shape[d] for d in fb))
+
+
+@implements(np.tensordot)
+def _np_tensordot(a, b, axes=2):
+    return tensordot(a, b, axes=axes)
+
+
+@implements(np.matmul, np.dot)
+def _np_matmul(a, b, **kw):
+    a, b = _as_chunk(a), _as_chunk(b)
+    if a.ndim != 2 or b.ndim != 2:
+        raise NotImplementedError("np.matmul on DeviceChunk: 2-D operands")
+    return tensordot(a, b, axes=((1,), (0,)))
+
+
+def einsum(subscripts, *operands, dtype=None, **kwargs):
+    """``einsum_lookup`` implementation (``_dispatch.py:146``; called per block by ``chunk_einsum``,
+    ``_einsum.py:20-34``).  Explicit or implicit subscripts over one or more operands, each label at most
+    once per operand; operands are contracted pairwise, left to right: labels that survive in neither the
+    output nor a later operand are summed, labels shared by both operands AND still needed afterwards
+    (batch labels) are refused -- a per-label GEMM loop is not worth a launch each."""
+    if kwargs.get("out") is not None:
+        raise NotImplementedError("einsum(out=...) on DeviceChunk")
+    subs = subscripts.replace(" ", "")
+    if "." in subs:
+        raise NotImplementedError("einsum ellipsis on DeviceChunk")
+    if "->" in subs:
+        ins, out = subs.split("->")
+    else:
+        ins = subs
+        flat = ins.replace(",", "")
+        out = "".join(sorted(c for c in set(flat) if flat.count(c) == 1))
+    terms = ins.split(",")
+    if len(terms) != len(operands):
+        raise ValueError("einsum: number of subscripts does not match the operands")
+    ops = [_as_chunk(o) for o in operands]
+    for t, o in zip(terms, ops):
+        if len(set(t)) != len(t) or len(t) != o.ndim:
+            raise NotImplementedError("einsum on DeviceChunk: every label at most once per operand")
+    cur, lab = ops[0], terms[0]
+    for k in range(1, len(ops)):
+        nxt, nl = ops[k], terms[k]
+        later = set(out).union(*[set(t) for t in terms[k + 1:]]) if k + 1 < len(terms) else set(out)
+        # labels private to one side and not needed later: summed first
+        for side in (0, 1):
+            x, xl, other = (cur, lab, nl) if side == 0 else (nxt, nl, lab)
+            drop = [i for i, c in enumerate(xl) if c not in other and c not in later]
+            if drop:
+                x = _sum(x, axis=tuple(drop))
+                xl = "".join(c for i, c in enumerate(xl) if i not in drop)
+            if side == 0:
+                cur, lab = x, xl
+            else:
+                nxt, nl = x, xl
+        shared = [c for c in lab if c in nl]
+        if any(c in later for c in shared):
+            raise NotImplementedError("einsum on DeviceChunk: batch labels (shared by two operands and kept) are not supported")
+        cur = tensordot(cur, nxt, axes=([lab.index(c) for c in shared], [nl.index(c) for c in shared]))
+        lab = "".join(c for c in lab if c not in shared) + "".join(c for c in nl if c not in shared)
+    drop = [i for i, c in enumerate(lab) if c not in out]
+    if drop:
+        cur = _sum(cur, axis=tuple(drop))
+        lab = "".join(c for i, c in enumerate(lab) if i not in drop)
+    if sorted(lab) != sorted(out):
+        raise ValueError(f"einsum: output labels {out!r} are not produced by the operands")
+    res = cur.transpose(tuple(lab.index(c) for c in out)) if lab != out else cur
+    if dtype is not None and np.dtype(dtype) != res.dtype:
+        res = res.astype(np.dtype(dtype))
+    return res
+
+
+@implements(np.einsum)
+def _np_einsum(subscripts, *operands, **kw):
+    return einsum(subscripts, *operands, **kw)
 
 
 # ----------------------------------------------------------------------------- install on DeviceChunk

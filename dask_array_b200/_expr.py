@@ -54,9 +54,36 @@ def _tok(obj) -> str:
         return "(" + ",".join(_tok(o) for o in obj) + ")"
     if isinstance(obj, dict):
         return "{" + ",".join(f"{_tok(k)}:{_tok(v)}" for k, v in sorted(obj.items(), key=lambda kv: str(kv[0]))) + "}"
-    if callable(obj) and hasattr(obj, "__name__"):
-        return f"fn:{obj.__name__}"
+    if callable(obj):
+        return _tok_callable(obj)
     return repr(obj)
+
+
+def _tok_callable(fn) -> str:
+    """Identity of a user function inside an expression name: module-level importable callables (NumPy
+    ufuncs, library functions) by their qualified name; lambdas / closures / partials by their code object,
+    constants, defaults and closure contents -- two different lambdas never share a name, the same source
+    evaluated twice does (the reference tokenises ``func`` the same way and treats ``token=`` as a prefix,
+    ``core/_blockwise_funcs.py``)."""
+    import functools
+
+    if isinstance(fn, functools.partial):
+        return f"partial({_tok_callable(fn.func)},{_tok(fn.args)},{_tok(fn.keywords)})"
+    code = getattr(fn, "__code__", None)
+    name = f"{getattr(fn, '__module__', '')}.{getattr(fn, '__qualname__', getattr(fn, '__name__', type(fn).__name__))}"
+    if code is None:
+        return f"fn:{name}" if hasattr(fn, "__name__") else f"fn:{name}@{id(fn):x}"
+    h = hashlib.sha1()
+    h.update(code.co_code)
+    h.update(repr(code.co_consts).encode())
+    h.update(repr(code.co_names).encode())
+    h.update(repr(getattr(fn, "__defaults__", None)).encode())
+    for cell in getattr(fn, "__closure__", None) or ():
+        try:
+            h.update(_tok(cell.cell_contents).encode())
+        except ValueError:                      # empty cell
+            h.update(b"<empty>")
+    return f"fn:{name}#{h.hexdigest()[:12]}"
 
 
 class ArrayExpr:
@@ -298,10 +325,17 @@ class Random(ArrayExpr):
     def dtype(self):
         return np.dtype(self.operand("dtype_"))
 
+    def block_seeds(self):
+        """``_spawn_bitgens`` (``random/_expr.py:29-32``): the children the generator's live SeedSequence
+        spawned for THIS draw.  ``seed`` = (entropy, spawn_key, children spawned before this draw)."""
+        entropy, spawn_key, first = self.operand("seed")
+        nb = self.numblocks
+        return np.random.SeedSequence(entropy, spawn_key=tuple(spawn_key), n_children_spawned=first).spawn(math.prod(nb) or 1)
+
     def host_block(self, bid) -> np.ndarray:
         nb = self.numblocks
         flat = int(np.ravel_multi_index(bid, nb)) if nb else 0
-        child = np.random.SeedSequence(self.operand("seed")).spawn(math.prod(nb) or 1)[flat]
+        child = self.block_seeds()[flat]
         gen = np.random.Generator(np.random.PCG64(child))
         dist = self.operand("distribution")
         shape = self.block_shape(bid)

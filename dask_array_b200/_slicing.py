@@ -139,7 +139,10 @@ class SliceSlicesIntegers(ArrayExpr):
 
             def push(a):
                 off = nd - a.ndim
-                sub = tuple(index[off + d] if a.shape[d] != 1 else slice(0, 1) for d in range(a.ndim))
+                # slice(0, 1) only where the operand is BROADCAST along the dim; a genuine size-1 dim of the
+                # output takes the real index (it may be empty: (a + b)[0:0])
+                sub = tuple(slice(0, 1) if a.shape[d] == 1 and x.shape[off + d] != 1 else index[off + d]
+                            for d in range(a.ndim))
                 return SliceSlicesIntegers(a, sub)
             return x._map_args(push)
         if isinstance(x, SliceSlicesIntegers) and only_slices and all(

@@ -899,6 +899,43 @@ extern "C" int b2_fill(void* dst, int64_t nelem, int itemsize, const void* value
     return B2_OK;
 }
 
+// ------------------------------------------------------------------ take (AOT)
+// Integer-array gather of the arg-reduction combine step (_arg_combine, reductions/_common.py:687-697):
+//   inner == 0 : out[j] = src[idx[j]]                              (vals.ravel()[local_args])
+//   inner  > 0 : out[o, i] = src[o, idx[o, i], i], src (outer, n, inner) contiguous   (vals[ogrid.., local_args, ..])
+// Negative indices wrap like NumPy; out-of-range ones are clamped (no fault on garbage input).
+template <typename W>
+__global__ void __launch_bounds__(256) b2_take_kernel(const W* __restrict__ src, const long long* __restrict__ idx,
+                                                      W* __restrict__ out, i64 count, i64 n, i64 inner) {
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (i64)gridDim.x * blockDim.x) {
+        long long k = idx[j];
+        if (k < 0) k += n;
+        k = k < 0 ? 0 : (k >= n ? n - 1 : k);
+        if (inner == 0) out[j] = src[k];
+        else { const i64 o = j / inner, i = j - o * inner; out[j] = src[(o * n + k) * inner + i]; }
+    }
+}
+
+extern "C" int b2_take(int itemsize, const void* src, const int64_t* idx, void* out, int64_t count, int64_t n,
+                       int64_t inner, void* stream) {
+    if (count < 0 || n <= 0 || inner < 0 || (count && (!src || !idx || !out))) return fail(B2_ERR_INVALID, "bad argument");
+    if (count == 0) return B2_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t g = cdiv(count, 256);
+    if (g > 148 * 16) g = 148 * 16;
+    const long long* ix = (const long long*)idx;
+    switch (itemsize) {
+        case 1: b2_take_kernel<<<(unsigned)g, 256, 0, st>>>((const unsigned char*)src, ix, (unsigned char*)out, count, n, inner); break;
+        case 2: b2_take_kernel<<<(unsigned)g, 256, 0, st>>>((const unsigned short*)src, ix, (unsigned short*)out, count, n, inner); break;
+        case 4: b2_take_kernel<<<(unsigned)g, 256, 0, st>>>((const unsigned*)src, ix, (unsigned*)out, count, n, inner); break;
+        case 8: b2_take_kernel<<<(unsigned)g, 256, 0, st>>>((const unsigned long long*)src, ix, (unsigned long long*)out, count, n, inner); break;
+        default: return fail(B2_ERR_UNSUPPORTED, "take: itemsize %d", itemsize);
+    }
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
 // shared with the other translation units of the library
 extern "C" int b2_set_error_(int code, const char* msg) { return fail(code, "%s", msg); }
 extern "C" void b2_count_launch_(void) { g_launches.fetch_add(1); }

@@ -290,6 +290,14 @@ int b2_memcpy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch
  * creation/_ones_zeros.py:17-137) */
 int b2_fill(void* dst, int64_t nelem, int itemsize, const void* value, void* stream);
 
+/* Integer-array gather used by the arg-reduction combine step on the chunk type (_arg_combine,
+ * reductions/_common.py:687-697: `vals.ravel()[local_args]` and the np.ogrid take-along-axis
+ * `vals[ogrid.., local_args, ..]`).  inner == 0: out[j] = src[idx[j]], j < count, idx in [-n, n).
+ * inner > 0: src is (outer, n, inner) contiguous, idx / out are (outer, inner): out[o,i] = src[o, idx[o,i], i];
+ * count = outer * inner. */
+int b2_take(int itemsize, const void* src, const int64_t* idx, void* out, int64_t count, int64_t n,
+            int64_t inner, void* stream);
+
 /* ------------------------------------------------------------------ contraction
  * matmul / tensordot block GEMM (linalg/_tensordot.py:194-249): C (+)= A @ B^T with
  * A (M,K) and B (N,K) row-major ("TN"), accumulating over the k block index instead
@@ -323,6 +331,12 @@ typedef struct b2_gemm_problem {
 } b2_gemm_problem;
 int b2_gemm_tn_batched(int dtype, const b2_gemm_problem* problems, int nproblems,
                        void* workspace, size_t workspace_bytes, size_t* needed, void* stream);
+/* The same contraction for the NumPy number types the tensor cores do not serve -- float64 (the dtype
+ * of the reference's own matmul / tensordot tests, tests/test_routines.py:321-399), float32 in IEEE
+ * arithmetic, int32 / uint32 / int64 / uint64 -- on the CUDA cores, every product and sum in the
+ * element type (np.matmul semantics per block, linalg/_tensordot.py:207).  C has the operands' dtype. */
+int b2_gemm_tn_simt(int dtype, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                    int64_t M, int64_t N, int64_t K, int accumulate, void* stream);
 /* fp32 -> bf16 hi/mid/lo planes with hi + mid + lo == x to ~2^-24 (operand preparation of the
  * fp32 matmul; tensor cores have no IEEE fp32 mode) */
 int b2_split3_bf16(const float* src, void* hi, void* mid, void* lo, int64_t nelem, void* stream);

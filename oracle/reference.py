@@ -291,21 +291,34 @@ def chunk_max(x, axis=None, keepdims=None):
 
 
 def _kd(fn):
-    """``_chunk.py:137-168 keepdims_wrapper`` for np.argmin/np.argmax."""
+    """``_chunk.py:137-168 keepdims_wrapper`` for np.argmin/np.argmax (the result is indexed as it is --
+    NumPy scalars accept ``r[None, ...]`` -- so a duck-array result stays a duck array)."""
     def wrapped(x, axis=None, keepdims=None):
         r = fn(x, axis=axis)
         if not keepdims:
             return r
         axes = range(x.ndim) if axis is None else ([axis] if np.isscalar(axis) else axis)
-        return np.asarray(r)[tuple(None if d in axes else slice(None) for d in range(x.ndim))]
+        return r[tuple(None if d in axes else slice(None) for d in range(x.ndim))]
+    wrapped.__name__ = fn.__name__
     return wrapped
 
 
 argmin_kd, argmax_kd = _kd(np.argmin), _kd(np.argmax)
 
 
+def _arg_result(vals, arg):
+    """``_common.py:722-731`` / ``:738-746``: a structured array, or -- for chunk types without
+    structured dtypes (``np.empty_like`` raises TypeError) -- a dict."""
+    try:
+        out = np.empty_like(vals, shape=vals.shape, dtype=[("vals", vals.dtype), ("arg", arg.dtype)])
+    except TypeError:
+        out = dict()
+    out["vals"], out["arg"] = vals, arg
+    return out
+
+
 def arg_chunk(func, argfunc, x, axis, offset_info):
-    """``_common.py:704-732`` (structured-array branch)."""
+    """``_common.py:704-732``."""
     arg_axis = None if len(axis) == x.ndim or x.ndim == 1 else axis[0]
     vals = func(x, axis=arg_axis, keepdims=True)
     arg = argfunc(x, axis=arg_axis, keepdims=True)
@@ -313,17 +326,17 @@ def arg_chunk(func, argfunc, x, axis, offset_info):
         if arg_axis is None:
             offset, total_shape = offset_info
             ind = np.unravel_index(arg.ravel()[0], x.shape)
-            arg[:] = np.ravel_multi_index(tuple(o + i for o, i in zip(offset, ind)), total_shape)
+            total_ind = tuple(o + i for (o, i) in zip(offset, ind))
+            arg[:] = np.ravel_multi_index(total_ind, total_shape)
         else:
             arg += offset_info
-    out = np.empty(vals.shape, dtype=[("vals", vals.dtype), ("arg", arg.dtype)])
-    out["vals"], out["arg"] = vals, arg
-    return out
+    return _arg_result(vals, arg)
 
 
 def _arg_combine(data, axis, argfunc, keepdims=False):
-    """``_common.py:675-701``."""
-    axis = None if len(axis) == data.ndim or data.ndim == 1 else axis[0]
+    """``_common.py:675-701`` (both the structured-array and the dict representation)."""
+    ndim = data["vals"].ndim if isinstance(data, dict) else data.ndim
+    axis = None if len(axis) == ndim or ndim == 1 else axis[0]
     vals, arg = data["vals"], data["arg"]
     if axis is None:
         local = argfunc(vals, axis=axis, keepdims=keepdims)
@@ -340,9 +353,7 @@ def _arg_combine(data, axis, argfunc, keepdims=False):
 def arg_combine(argfunc, data, axis):
     """``_common.py:735-746``."""
     arg, vals = _arg_combine(data, axis, argfunc, keepdims=True)
-    out = np.empty(vals.shape, dtype=[("vals", vals.dtype), ("arg", arg.dtype)])
-    out["vals"], out["arg"] = vals, arg
-    return out
+    return _arg_result(vals, arg)
 
 
 def arg_agg(argfunc, data, axis, keepdims=False):

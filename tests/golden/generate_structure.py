@@ -78,6 +78,17 @@ def main():
                                       "result": [list(c) for c in got]})
     for size, chunks in [(10, (20, 20, 1)), (3, (1, 1, 3)), (10, (20, 20, 1, 6)), (5, (3, 3, 3, 3)), (4, (10, 1, 1, 1, 10)), (2, (2, 2, 2)), (7, (1, 20, 1))]:
         out["min_chunksize"].append({"size": size, "chunks": list(chunks), "result": list(O.ensure_minimum_chunksize(size, chunks))})
+    # 2000 random (size, chunks) cases of the same helper (ValueError recorded as null): the product's
+    # rewrite is compared with these DATA, never with reference source executed at test time
+    r2 = random.Random(3)
+    for _ in range(2000):
+        chunks = tuple(r2.randint(1, 30) for _ in range(r2.randint(1, 8)))
+        size = r2.randint(1, 25)
+        try:
+            res = list(O.ensure_minimum_chunksize(size, chunks))
+        except ValueError:
+            res = None
+        out["min_chunksize"].append({"size": size, "chunks": list(chunks), "result": res})
     for ndim, depth, boundary in [(2, 1, "reflect"), (3, {0: 2, 2: (1, 3)}, {1: "periodic"}), (2, (1, 2), None), (1, None, 5)]:
         d = O.coerce_depth(ndim, depth)
         b = O.coerce_boundary(ndim, boundary)

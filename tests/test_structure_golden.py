@@ -49,38 +49,15 @@ def test_overlap_chunks_and_helpers_match_reference():
         axes = {int(a): (tuple(d) if isinstance(d, list) else d) for a, d in rec["axes"].items()}
         norm = tuple(sorted((a, d if isinstance(d, tuple) else (d, d)) for a, d in axes.items()))
         assert [list(c) for c in OverlapInternal(x.expr, norm).chunks] == rec["result"]
+    assert len(GOLD["min_chunksize"]) > 2000        # 7 hand-picked + 2000 random cases recorded from the reference
     for rec in GOLD["min_chunksize"]:
-        assert list(ensure_minimum_chunksize(rec["size"], tuple(rec["chunks"]))) == rec["result"]
+        try:
+            got = list(ensure_minimum_chunksize(rec["size"], tuple(rec["chunks"])))
+        except ValueError:
+            got = None
+        assert got == rec["result"], rec
     for rec in GOLD["coerce"]:
         d = coerce_depth(rec["ndim"], eval(rec["depth"]))
         b = coerce_boundary(rec["ndim"], eval(rec["boundary"]))
         assert {str(k): (list(v) if isinstance(v, tuple) else v) for k, v in d.items()} == rec["depth_out"]
         assert {str(k): v for k, v in b.items()} == rec["boundary_out"]
-
-
-@pytest.mark.skipif(not os.path.exists("/root/reference/dask_array/_overlap.py"),
-                    reason="needs the reference checkout (build container only)")
-def test_ensure_minimum_chunksize_equals_the_reference_on_random_inputs():
-    """The helper is written in this package's own structure; here it is compared with the reference's
-    function (source taken verbatim from the checkout, executed alone) on 5000 random chunkings."""
-    import ast
-    import random
-    from numbers import Integral, Number
-    from dask_array_b200._overlap import ensure_minimum_chunksize
-    ns = {"Integral": Integral, "Number": Number}
-    for node in ast.parse(open("/root/reference/dask_array/_overlap.py").read()).body:
-        if isinstance(node, ast.FunctionDef) and node.name == "ensure_minimum_chunksize":
-            exec(compile(ast.Module([node], []), "reference", "exec"), ns)
-    rng = random.Random(3)
-    for _ in range(5000):
-        chunks = tuple(rng.randint(1, 30) for _ in range(rng.randint(1, 8)))
-        size = rng.randint(1, 25)
-        try:
-            want = tuple(ns["ensure_minimum_chunksize"](size, chunks))
-        except ValueError:
-            want = None
-        try:
-            got = ensure_minimum_chunksize(size, chunks)
-        except ValueError:
-            got = None
-        assert got == want, (size, chunks)
