@@ -12,7 +12,7 @@ from ._device import DeviceChunk  # noqa: F401
 from ._collection import (  # noqa: F401
     UFUNC_NAMES, Array, Compiled, _method, _ufunc, asarray, compile, compute, elemwise, from_array,
     dot, from_host_blocks, full, matmul, nanargmax, nanargmin, nanmax, nanmean, nanmin, nanprod, nanstd, nansum,
-    nanvar, ones, random, tensordot, cumsum, cumprod, nancumsum, nancumprod,
+    nanvar, ones, random, tensordot, einsum, cumsum, cumprod, nancumsum, nancumprod,
     rechunk, transpose, where, zeros,
 )
 

@@ -486,19 +486,17 @@ def nanargmax(a, axis=None, keepdims=False, split_every=None):
 
 
 def tensordot(a, b, axes=2):
-    """``linalg/_tensordot.py:45-136`` for the 2-D contractions the block GEMM covers."""
-    a, b = asarray(a), asarray(b)
-    if isinstance(axes, int):
-        la, lb = tuple(range(a.ndim - axes, a.ndim)), tuple(range(axes))
-    else:
-        la, lb = axes
-        la = (la,) if isinstance(la, int) else tuple(la)
-        lb = (lb,) if isinstance(lb, int) else tuple(lb)
-    if a.ndim != 2 or b.ndim != 2 or len(la) != 1 or len(lb) != 1:
-        raise NotImplementedError("B200 tensordot covers 2-D operands contracted over one axis (use @ for matmul)")
-    aa = a if la[0] % 2 == 1 else a.T
-    bb = b if lb[0] % 2 == 0 else b.T
-    return aa @ bb
+    """``linalg/_tensordot.py:45-136``."""
+    from ._matmul import tensordot as _td
+
+    return _td(a, b, axes=axes)
+
+
+def einsum(*operands, **kwargs):
+    """``_einsum.py:181-271``."""
+    from ._matmul import einsum as _es
+
+    return _es(*operands, **kwargs)
 
 
 def dot(a, b):

@@ -625,16 +625,14 @@ class Executor:
         st.keepalive.extend([launch, remote])
         return st
 
-    # ------------------------------------------------------------------ blocked matmul
+    # ------------------------------------------------------------------ blocked matmul / tensordot
     def _run_BlockGEMM(self, expr):
         """One tcgen05 launch per output block; the k blocks (and, for fp32 operands, the six
         bf16 x 3 split products) are accumulated in TMEM (``b2_gemm_tn_pairs``)."""
-        import ctypes as C
-
         a, bt = expr.operand("a"), expr.operand("bt")
         sa, sb = self.results[a._name], self.results[bt._name]
         st = BlockStore(expr)
-        nk_ = a.numblocks[1]
+        nk = a.numblocks[1]
         mine = [bid for bid in expr.block_ids() if self.mine(expr, bid)]
         if self.world.size > 1:
             # SURVEY 8e: the owner of output block (i, j) gathers row-panel i of a and row-panel j of bt;
@@ -642,7 +640,7 @@ class Executor:
             wanted = []
             for bid in expr.block_ids():
                 r = self.world.owner(expr, bid)
-                for k in range(nk_):
+                for k in range(nk):
                     if not sa.replicated:
                         wanted.append((r, a, (bid[0], k)))
                     if not sb.replicated:
@@ -650,70 +648,160 @@ class Executor:
             got = _fetch_blocks(self, wanted, {a._name: sa, bt._name: sb})
             va, vb = BlockStore(a), BlockStore(bt)
             for (i, j) in mine:
-                for k in range(nk_):
+                for k in range(nk):
                     blk = sa.blocks.get((i, k))
                     va.blocks[(i, k)] = blk if blk is not None else got[(a._name, (i, k))]
                     blk = sb.blocks.get((j, k))
                     vb.blocks[(j, k)] = blk if blk is not None else got[(bt._name, (j, k))]
             sa, sb = va, vb
             st.keepalive.append(got)
-        fp32 = a.dtype == np.float32
+        problems = []
+        for (i, j) in mine:
+            out = DeviceChunk.empty(expr.block_shape((i, j)), expr.dtype, self.device)
+            st.blocks[(i, j)] = out
+            problems.append((out, [(sa.blocks[(i, k)], sb.blocks[(j, k)]) for k in range(nk)]))
+        self._contract(st, problems, a.dtype)
+        return st
+
+    def _run_BlockContract(self, expr):
+        """N-d ``tensordot`` (``linalg/_tensordot.py:45-136``): every operand block is matricised once (free
+        axes x contracted axes, a copy only when the block is not already in that order), every output
+        block is ONE accumulation over the contracted block indices -- the reference's (.., 1, ..) partials
+        and their ``.sum(axis=left_axes)`` tree are never materialised."""
+        a, b = expr.operand("a"), expr.operand("b")
+        la, lb = expr.operand("la"), expr.operand("lb")
+        sa, sb = self.results[a._name], self.results[b._name]
+        if self.world.size > 1 and not (sa.replicated and sb.replicated):
+            raise NotImplementedError("N-d tensordot across several GPUs (2-D matmul shards; gather the operands first)")
+        fa = [d for d in range(a.ndim) if d not in la]
+        fb = [d for d in range(b.ndim) if d not in lb]
+        st = BlockStore(expr)
+        ident = {}
+
+        def matricize(store, x, bid, free, con, cache):
+            if bid not in cache:
+                blk = store.blocks[bid]
+                moved = blk.transpose(tuple(free) + tuple(con))
+                if not moved.is_contiguous or moved.ptr % 16:
+                    out = DeviceChunk.empty(moved.shape, moved.dtype, self.device)
+                    if moved.size:
+                        prog = ident.get(x.dtype)
+                        if prog is None:
+                            prog = ident[x.dtype] = cg.Program()
+                            prog.set_output(prog.op("astype", prog.add_input(x.dtype), dtype=x.dtype))
+                        for launch in rt.fused_launches(prog, _lib.RED_NONE, (), [rt.BlockArgs(
+                                shape=moved.shape, inputs=[(moved.ptr, moved.strides)], out0=out.ptr)]):
+                            self._do(launch.run)
+                            st.keepalive.append(launch)
+                    moved = out
+                m = math.prod(blk.shape[d] for d in free)
+                k = math.prod(blk.shape[d] for d in con)
+                cache[bid] = moved.reshape((m, k))
+            return cache[bid]
+
+        ca, cb = {}, {}
+        kranges = [range(a.numblocks[d]) for d in la]
+        problems = []
+        for bid in expr.block_ids():
+            if not self.mine(expr, bid):
+                continue
+            ia, jb = bid[:len(fa)], bid[len(fa):]
+            pairs = []
+            for kk in itertools.product(*kranges):
+                abid = [0] * a.ndim
+                for d, i in zip(fa, ia):
+                    abid[d] = i
+                for d, i in zip(la, kk):
+                    abid[d] = i
+                bbid = [0] * b.ndim
+                for d, j in zip(fb, jb):
+                    bbid[d] = j
+                for d, i in zip(lb, kk):
+                    bbid[d] = i
+                pairs.append((matricize(sa, a, tuple(abid), fa, la, ca), matricize(sb, b, tuple(bbid), fb, lb, cb)))
+            shape = expr.block_shape(bid)
+            out = DeviceChunk.empty(shape, expr.dtype, self.device)
+            st.blocks[bid] = out
+            m = math.prod(shape[:len(fa)])
+            problems.append((out.reshape((m, math.prod(shape[len(fa):]))), pairs))
+        self._contract(st, problems, np.result_type(a.dtype, b.dtype) if a.dtype != b.dtype else a.dtype)
+        st.keepalive.extend([ca, cb])
+        return st
+
+    def _contract(self, st, problems, in_dtype):
+        """``out (M, N) = sum_p A_p (M, K_p) @ B_p (N, K_p)^T`` for every problem ``(out, [(A_p, B_p)])``.
+        bf16 / fp32 operands whose contraction lengths are multiples of 8: ONE batched tcgen05 launch chain
+        (fp32 through the bf16 x 3 split); everything else: the exact SIMT kernel, pair by pair."""
+        import ctypes as C
+        import os
+
+        if not problems:
+            return
+        in_dtype = np.dtype(in_dtype)
+        name = in_dtype.name
+        tensor = name in ("float32", "bfloat16") and all(
+            A.shape[1] % 8 == 0 and A.ptr % 16 == 0 and B.ptr % 16 == 0 and A.is_contiguous and B.is_contiguous
+            and A.dtype == in_dtype and B.dtype == in_dtype for _, pairs in problems for A, B in pairs)
+        if not tensor:
+            if name == "bfloat16":
+                raise NotImplementedError(
+                    "bfloat16 contraction chunks must be multiples of 8 elements (16-byte TMA row strides): rechunk the contracted axis")
+            return self._contract_exact(st, problems)
+        fp32 = name == "float32"
         bf16 = np.dtype("uint16")          # raw 16-bit planes
+        planes = {}
 
-        def planes(store, x):
-            out = {}
-            for bid, blk in store.blocks.items():
-                if not blk.is_contiguous:
-                    raise NotImplementedError("matmul operand blocks must be contiguous (persist / rechunk first)")
+        def split(blk):
+            key = (blk.ptr, blk.shape)
+            if key not in planes:
                 if not fp32:
-                    out[bid] = (blk,)
-                    continue
-                hi, mid, lo = (DeviceChunk.empty(blk.shape, bf16, self.device) for _ in range(3))
-                self._do(lambda b=blk, h=hi, m=mid, l=lo: _lib.check(_lib.lib.b2_split3_bf16(
-                    b.ptr, h.ptr, m.ptr, l.ptr, b.size, rt.current_stream_ptr())))
-                out[bid] = (hi, mid, lo)
-            return out
+                    planes[key] = (blk,)
+                else:
+                    hi, mid, lo = (DeviceChunk.empty(blk.shape, bf16, self.device) for _ in range(3))
+                    self._do(lambda b=blk, h=hi, m=mid, l=lo: _lib.check(_lib.lib.b2_split3_bf16(
+                        b.ptr, h.ptr, m.ptr, l.ptr, b.size, rt.current_stream_ptr())))
+                    planes[key] = (hi, mid, lo)
+            return planes[key]
 
-        pa, pb = planes(sa, a), planes(sb, bt)
         # products kept for fp32: hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi  (error ~2^-24)
         combos = [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0)] if fp32 else [(0, 0)]
-        nk = a.numblocks[1]
         probs, keep = [], []
-        if not mine:
-            return st
-        for (i, j) in mine:
-            M, N = expr.block_shape((i, j))
-            out = DeviceChunk.empty((M, N), np.float32, self.device)
-            st.blocks[(i, j)] = out
-            ks = [a.block_shape((i, k))[1] for k in range(nk)]
-            if any(kk % 8 for kk in ks):
-                raise NotImplementedError(
-                    f"matmul contraction chunks {tuple(ks)} must be multiples of 8 elements (16-byte TMA row strides): rechunk the contracted axis")
+        for out, pairs in problems:
+            M, N = out.shape
+            if M == 0 or N == 0:
+                continue
+            pairs = [(A, B) for A, B in pairs if A.shape[1] > 0]
+            if not pairs:
+                self._do(lambda o=out: rt.fill(o, 0))
+                continue
+            ks = [A.shape[1] for A, _ in pairs]
             K = max(ks)
-            A, B, Kp = [], [], []
-            for k in range(nk):
-                for ca, cb in combos:
-                    A.append(pa[(i, k)][ca].ptr)
-                    B.append(pb[(j, k)][cb].ptr)
-                    Kp.append(ks[k])
-            arrA = (C.c_void_p * len(A))(*A)
-            arrB = (C.c_void_p * len(B))(*B)
+            Ap, Bp, Kp = [], [], []
+            for (A, B), kk in zip(pairs, ks):
+                pa, pb = split(A), split(B)
+                for ca_, cb_ in combos:
+                    Ap.append(pa[ca_].ptr)
+                    Bp.append(pb[cb_].ptr)
+                    Kp.append(kk)
+            arrA = (C.c_void_p * len(Ap))(*Ap)
+            arrB = (C.c_void_p * len(Bp))(*Bp)
             arrK = (C.c_int64 * len(Kp))(*Kp)
             keep.extend([arrA, arrB, arrK])
             p = _lib.GemmProblem()
             p.A, p.B = C.cast(arrA, C.c_void_p), C.cast(arrB, C.c_void_p)
             p.Kpair = C.cast(arrK, C.c_void_p).value if len(set(ks)) > 1 else None
-            p.npairs, p.accumulate, p.lda, p.ldb = len(A), 0, K, K
+            p.npairs, p.accumulate, p.lda, p.ldb = len(Ap), 0, K, K
             p.C, p.ldc, p.M, p.N, p.K = out.ptr, N, M, N, K
             probs.append(p)
-        import os
+        if not probs:
+            return
         if os.environ.get("B2_GEMM_BATCHED", "1") == "0" and all(not p.Kpair for p in probs):   # diagnostic: one launch per output block
             for p in probs:
                 self._do(lambda p=p: _lib.check(_lib.lib.b2_gemm_tn_pairs(
                     _lib.dtype_code("bfloat16"), p.A, p.B, p.npairs, p.lda, p.ldb, p.C, p.ldc, p.M, p.N, p.K, 0,
                     rt.current_stream_ptr())))
-            st.keepalive.extend([keep, probs, pa, pb])
-            return st
+            st.keepalive.extend([keep, probs, planes])
+            return
         # Long pair lists are issued as several batched launches that accumulate into C.  Same-box
         # A/B (bench --config c5, fp32 split = 48 pairs): 48 pairs/launch 693, 24 -> 763, 12 -> 993,
         # 6 -> 1058 tensor TFLOP/s: in a long launch the CTAs drift out of lockstep and stop sharing
@@ -741,9 +829,33 @@ class Executor:
             self._do(lambda arr=arr, n=len(sub), wptr=wptr, nb=need.value: _lib.check(_lib.lib.b2_gemm_tn_batched(
                 _lib.dtype_code("bfloat16"), arr, n, wptr, nb, None, rt.current_stream_ptr())))
             st.keepalive.extend([arr, ws])
-        st.keepalive.append(keep)
-        st.keepalive.extend([pa, pb])
-        return st
+        st.keepalive.extend([keep, planes])
+
+    def _contract_exact(self, st, problems):
+        """The coverage path of ``_contract``: ``b2_gemm_tn_simt`` per pair, accumulating in the element type
+        (fp64 FMA, IEEE fp32, wrap-around integers -- ``np.matmul`` semantics per block)."""
+        for out, pairs in problems:
+            M, N = out.shape
+            if M == 0 or N == 0:
+                continue
+            dt = out.dtype
+            if dt.name not in ("float64", "float32", "int32", "uint32", "int64", "uint64"):
+                raise NotImplementedError(f"matmul / tensordot with result dtype {dt} has no B200 kernel")
+            first = True
+            for A, B in pairs:
+                K = A.shape[1]
+                if K == 0:
+                    continue
+                if A.dtype != dt or B.dtype != dt or not A.is_contiguous or not B.is_contiguous:
+                    raise NotImplementedError("exact contraction needs contiguous operands of the result dtype "
+                                              "(tensordot() casts at the expression level)")
+                code, acc = _lib.dtype_code(dt), 0 if first else 1
+                self._do(lambda A=A, B=B, K=K, code=code, acc=acc, out=out, M=M, N=N: _lib.check(_lib.lib.b2_gemm_tn_simt(
+                    code, A.ptr, K, B.ptr, K, out.ptr, N, M, N, K, acc, rt.current_stream_ptr())))
+                st.keepalive.extend([A, B])
+                first = False
+            if first:
+                self._do(lambda o=out: rt.fill(o, 0))
 
     # ------------------------------------------------------------------ multi-GPU exchange (fused)
     def _exchange_for_fused(self, plan, deps, out_ids):

@@ -11,7 +11,9 @@ blocks of ``y`` as they are; a plain ``x @ w`` first materialises ``w.T`` with t
 Precision: bf16 operands -> exact products, fp32 accumulation (result dtype float32).  fp32
 operands are split into three bf16 planes (hi + mid + lo, ~2^-24) and the six leading products
 are accumulated, giving fp32-class accuracy (rtol 1e-5 against sgemm; tensor cores have no IEEE
-fp32 mode).  Other dtypes raise NotImplementedError.
+fp32 mode).  float64 and 32/64-bit integer operands -- and N-d ``tensordot`` / ``einsum`` in general -- go
+through ``BlockContract``: the same accumulate-over-k structure, on the exact SIMT GEMM
+(``b2_gemm_tn_simt``) when the dtype has no tensor-core path.
 """
 from __future__ import annotations
 
@@ -44,18 +46,155 @@ class BlockGEMM(ArrayExpr):
         return "BlockGEMM(tcgen05, k-accumulate)"
 
 
+class BlockContract(ArrayExpr):
+    """``tensordot(a, b, axes=(la, lb))`` (``linalg/_tensordot.py:45-136``): output dims = the free axes of
+    ``a`` then the free axes of ``b``; the contracted axes have identical chunks on both operands."""
+
+    _parameters = ["a", "b", "la", "lb"]
+
+    @property
+    def chunks(self):
+        a, b, la, lb = (self.operand(k) for k in ("a", "b", "la", "lb"))
+        return tuple(c for d, c in enumerate(a.chunks) if d not in la) + tuple(c for d, c in enumerate(b.chunks) if d not in lb)
+
+    @property
+    def dtype(self):
+        a, b = self.operand("a"), self.operand("b")
+        if a.dtype == b.dtype and a.dtype in (np.dtype(np.float32), _bf16()):
+            return np.dtype(np.float32)
+        return np.promote_types(a.dtype, b.dtype)
+
+    def _tree_label(self):
+        return f"BlockContract(axes={self.operand('la')},{self.operand('lb')})"
+
+
+_TENSOR_DTYPES = None
+
+
+def _tensor_core(dt) -> bool:
+    return dt in (np.dtype(np.float32), _bf16())
+
+
+def tensordot(a, b, axes=2):
+    """``tensordot`` (``linalg/_tensordot.py:45-136``) for N-d operands and any number of contracted axes.
+    fp32 / bf16 run on the tensor cores; fp64 and integer operands on the exact SIMT GEMM."""
+    from ._blockwise import Elemwise
+    from ._collection import Array, asarray
+    from ._rechunk import Rechunk
+
+    a, b = asarray(a), asarray(b)
+    if isinstance(axes, (int, np.integer)):
+        la, lb = tuple(range(a.ndim - axes, a.ndim)), tuple(range(axes))
+    else:
+        la, lb = axes
+        la = (la,) if isinstance(la, (int, np.integer)) else tuple(la)
+        lb = (lb,) if isinstance(lb, (int, np.integer)) else tuple(lb)
+    la, lb = tuple(x % a.ndim for x in la), tuple(x % b.ndim for x in lb)
+    if len(la) != len(lb) or any(a.shape[i] != b.shape[j] for i, j in zip(la, lb)):
+        raise ValueError("shape-mismatch for sum")
+    ae, be = a.expr, b.expr
+    if a.ndim == 2 and b.ndim == 2 and len(la) == 1 and a.dtype == b.dtype and _tensor_core(a.dtype):
+        # the 2-D tensor-core case is the blocked matmul: operands read K-major as they lie
+        aa = a if la[0] == 1 else a.T
+        bb = b if lb[0] == 0 else b.T
+        return matmul(aa, bb)
+    dt = np.promote_types(a.dtype, b.dtype)
+    if not (a.dtype == b.dtype and _tensor_core(a.dtype)):
+        if dt.kind == "b":
+            dt = np.dtype(np.int64)
+        if dt.kind == "c" or dt.itemsize < 4 and dt.kind in "iu":
+            raise NotImplementedError(f"tensordot of dtype {dt} has no B200 kernel (float32/64, bfloat16, 32/64-bit integers)")
+        if dt == np.dtype(np.float16):
+            dt = np.dtype(np.float32)
+        if ae.dtype != dt:
+            ae = Elemwise("astype", (ae,), (("dtype", dt.name),))
+        if be.dtype != dt:
+            be = Elemwise("astype", (be,), (("dtype", dt.name),))
+    # align the contracted chunks (the blockwise alignment of the reference, ``unify_chunks``)
+    want = list(be.chunks)
+    for i, j in zip(la, lb):
+        want[j] = ae.chunks[i]
+    if tuple(want) != tuple(be.chunks):
+        be = Rechunk(be, tuple(want))
+    return Array(BlockContract(ae, be, la, lb))
+
+
+def einsum(*operands, dtype=None, optimize=False, split_every=None, **kwargs):
+    """``einsum`` (``_einsum.py:181-271``): operands are contracted pairwise, left to right, through
+    ``tensordot``; labels that appear in one operand only and not in the output are summed first; the result
+    is transposed into the requested label order.  Labels repeated inside one operand (diagonals) and batch
+    labels (shared by two operands AND kept) have no B200 kernel and are refused."""
+    from ._collection import asarray
+
+    if not operands or not isinstance(operands[0], str):
+        raise NotImplementedError("einsum: the subscripts-string form is supported")
+    subs, ops = operands[0].replace(" ", ""), [asarray(o) for o in operands[1:]]
+    if "." in subs:
+        raise NotImplementedError("einsum with an ellipsis")
+    if "->" in subs:
+        ins, out = subs.split("->")
+    else:
+        ins = subs
+        flat = ins.replace(",", "")
+        out = "".join(sorted(c for c in set(flat) if flat.count(c) == 1))
+    terms = ins.split(",")
+    if len(terms) != len(ops):
+        raise ValueError("einsum: number of subscripts does not match the operands")
+    for t, o in zip(terms, ops):
+        if len(t) != o.ndim:
+            raise ValueError(f"einsum: operand has {o.ndim} dims but subscripts {t!r}")
+        if len(set(t)) != len(t):
+            raise NotImplementedError("einsum: a label repeated inside one operand (diagonal)")
+    cur, lab = ops[0], terms[0]
+    for k in range(1, len(ops)):
+        nxt, nl = ops[k], terms[k]
+        later = set(out).union(*[set(t) for t in terms[k + 1:]]) if k + 1 < len(terms) else set(out)
+
+        def presum(x, xl, other):
+            drop = tuple(i for i, c in enumerate(xl) if c not in other and c not in later)
+            if drop:
+                x = x.sum(axis=drop, split_every=split_every)
+                xl = "".join(c for i, c in enumerate(xl) if i not in drop)
+            return x, xl
+        cur, lab = presum(cur, lab, nl)
+        nxt, nl = presum(nxt, nl, lab)
+        shared = [c for c in lab if c in nl]
+        if any(c in later for c in shared):
+            raise NotImplementedError("einsum: batch labels (shared by two operands and kept) have no B200 kernel")
+        cur = tensordot(cur, nxt, axes=([lab.index(c) for c in shared], [nl.index(c) for c in shared]))
+        lab = "".join(c for c in lab if c not in shared) + "".join(c for c in nl if c not in shared)
+    drop = tuple(i for i, c in enumerate(lab) if c not in out)
+    if drop:
+        cur = cur.sum(axis=drop, split_every=split_every)
+        lab = "".join(c for i, c in enumerate(lab) if i not in drop)
+    if sorted(lab) != sorted(out):
+        raise ValueError(f"einsum: output labels {out!r} are not produced by the operands")
+    if lab != out:
+        cur = cur.transpose(tuple(lab.index(c) for c in out))
+    want = np.dtype(dtype) if dtype is not None else None
+    if want is not None and cur.dtype != want:
+        cur = cur.astype(want)
+    return cur
+
+
 def matmul(a, b):
-    """``Array.__matmul__`` (``_collection.py:856``) for 2-D operands."""
+    """``Array.__matmul__`` (``_collection.py:856``, ``linalg/_tensordot.py:253-334``) for 2-D operands: bf16 and
+    fp32 on the tensor cores (``BlockGEMM``), every other number type through ``tensordot``'s exact path."""
     from ._collection import Array
     from ._rechunk import Rechunk
 
-    if a.ndim != 2 or b.ndim != 2:
-        raise NotImplementedError("B200 matmul handles 2-D operands (the BASELINE contraction)")
+    if a.ndim == 0 or b.ndim == 0:
+        raise ValueError("`matmul` does not support scalars.")
+    if a.ndim > 2 or b.ndim > 2:
+        raise NotImplementedError("B200 matmul handles 1-D and 2-D operands (stacked / broadcast batch matmul has no kernel)")
+    if a.ndim == 1 or b.ndim == 1:
+        if a.shape[-1] != b.shape[0]:
+            raise ValueError(f"matmul: shapes {a.shape} and {b.shape} are not aligned")
+        return tensordot(a, b, axes=((a.ndim - 1,), (0,)))
     if a.shape[1] != b.shape[0]:
         raise ValueError(f"matmul: shapes {a.shape} and {b.shape} are not aligned")
-    ok = (np.dtype(np.float32), _bf16())
-    if a.dtype not in ok or b.dtype != a.dtype:
-        raise NotImplementedError(f"B200 matmul supports float32 @ float32 and bfloat16 @ bfloat16, got {a.dtype} @ {b.dtype}")
+    if not (a.dtype == b.dtype and _tensor_core(a.dtype)):
+        return tensordot(a, b, axes=((1,), (0,)))
     be = b.expr
     if isinstance(be, Transpose) and tuple(be.operand("axes")) == (1, 0):
         bt = be.operand("array")                       # x @ y.T : y is already (N, K)

@@ -312,6 +312,16 @@ def concrete(seq):
     return seq
 
 
+def _typename(typ):
+    """dask.utils.typename: ``module.qualname`` of a type (of the instance's type when given an instance)."""
+    if not isinstance(typ, type):
+        return _typename(type(typ))
+    mod = getattr(typ, "__module__", None)
+    if not mod or mod == "builtins":
+        return typ.__name__
+    return f"{mod}.{typ.__qualname__}"
+
+
 _UTILS = dict(
     ndimlist=ndimlist, concrete=concrete,
     Dispatch=Dispatch, deepmap=deepmap, derived_from=derived_from, funcname=funcname,
@@ -319,7 +329,7 @@ _UTILS = dict(
     cached_cumsum=cached_cumsum, parse_bytes=parse_bytes, cached_property=functools.cached_property,
     is_cupy_type=lambda x: False, is_series_like=lambda x: False, is_dataframe_like=lambda x: False,
     is_index_like=lambda x: False, format_bytes=lambda n: f"{n} B",
-    typename=lambda t: getattr(t, "__name__", str(t)),
+    typename=lambda t, short=False: _typename(t),
 )
 
 

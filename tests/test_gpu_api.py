@@ -51,7 +51,10 @@ def test_fused_chain_mean_std(da, shape, chunks):
 @pytest.mark.parametrize("dtype", ["float64", "float32", "int32", "int64"])
 def test_reductions_2d(da, dtype):
     rng = np.random.default_rng(1)
-    xh = (rng.random((300, 420)) * 200 - 100).astype(dtype)
+    # floats: positive data, so that sum / mean are well conditioned and north_star's rtol (1e-5 / 1e-12)
+    # applies to the RESULT (the reference's own assert_eq is allclose(rtol=1e-5, atol=1e-8)); sums with
+    # cancellation are covered by test_float_sums_with_cancellation below with the bound stated there
+    xh = (rng.random((300, 420)) * 200 - (100 if np.dtype(dtype).kind == "i" else 0)).astype(dtype)
     chunks = (128, 100)
     x = da.from_array(xh, chunks=chunks)
     b = ref.Blocked.from_array(xh, chunks)
@@ -64,19 +67,86 @@ def test_reductions_2d(da, dtype):
             if np.dtype(dtype).kind == "i":
                 assert np.array_equal(got, want)
             else:
-                np.testing.assert_allclose(got, want, rtol=rtol * 10, atol=1e-9 if dtype == "float64" else 1e-2)
+                np.testing.assert_allclose(got, want, rtol=rtol, atol=1e-8)
             got, want = x.mean(axis=axis, keepdims=kd).compute(), ref.da_mean(b, axis=axis, keepdims=kd)
             assert got.dtype == want.dtype
-            np.testing.assert_allclose(got, want, rtol=rtol * 10, atol=1e-9 if dtype != "float32" else 1e-4)
+            np.testing.assert_allclose(got, want, rtol=rtol, atol=1e-8)
             for ddof in (0, 1):
                 got = x.var(axis=axis, keepdims=kd, ddof=ddof).compute()
                 want = ref.da_var(b, axis=axis, keepdims=kd, ddof=ddof)
                 assert got.dtype == want.dtype
-                np.testing.assert_allclose(got, want, rtol=max(rtol, 1e-11))
+                np.testing.assert_allclose(got, want, rtol=rtol)
             np.testing.assert_allclose(x.std(axis=axis, keepdims=kd).compute(), ref.da_std(b, axis=axis, keepdims=kd),
-                                       rtol=max(rtol, 1e-11))
+                                       rtol=rtol)
             assert np.array_equal(x.min(axis=axis, keepdims=kd).compute(), ref.da_min(b, axis=axis, keepdims=kd))
             assert np.array_equal(x.max(axis=axis, keepdims=kd).compute(), ref.da_max(b, axis=axis, keepdims=kd))
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_float_sums_with_cancellation(da, dtype):
+    """Signed data: the sum is small against sum|x|, so the rounding error of ANY summation order (the
+    reference's included) is bounded relative to sum|x|, not to the result: |got - truth| <= rtol * sum|x|,
+    truth in fp64 (fp32) / extended precision via math.fsum (fp64)."""
+    import math
+    rng = np.random.default_rng(1)
+    xh = (rng.random((300, 420)) * 200 - 100).astype(dtype)
+    x = da.from_array(xh, chunks=(128, 100))
+    rtol = RTOL64 if dtype == "float64" else RTOL32
+    got = x.sum().compute()
+    truth = math.fsum(xh.astype(np.float64).ravel())
+    assert abs(float(got) - truth) <= rtol * float(np.abs(xh.astype(np.float64)).sum())
+    for axis in (0, 1):
+        got = x.sum(axis=axis).compute().astype(np.float64)
+        truth = xh.astype(np.longdouble).sum(axis=axis).astype(np.float64)
+        assert np.all(np.abs(got - truth) <= rtol * np.abs(xh.astype(np.float64)).sum(axis=axis))
+        gm = x.mean(axis=axis).compute().astype(np.float64)
+        assert np.all(np.abs(gm - truth / xh.shape[axis]) <= rtol * np.abs(xh.astype(np.float64)).mean(axis=axis))
+
+
+@pytest.mark.parametrize("offset,spread", [(1000.0, 10.0), (1.0e6, 1.0)])
+@pytest.mark.parametrize("chunks", [(64, 64), (100, 37)])
+def test_fp32_variance_with_mean_far_above_spread(da, offset, spread, chunks):
+    """var / std of fp32 data whose mean dwarfs its spread (the oracle golden case `1000 + 10 u`,
+    tests/golden/generate.py, and a harsher 1e6 + u): a naive single pass sum(x^2) - n mean^2 loses every
+    digit here; the kernel's shifted sums + fp64 Chan merge must stay within rtol 1e-5 of the fp64 truth AND
+    of the reference's two-pass-per-chunk result (moment_chunk, _common.py:393-403)."""
+    rng = np.random.default_rng(5)
+    xh = (offset + spread * rng.random((256, 300))).astype(np.float32)
+    x = da.from_array(xh, chunks=chunks)
+    b = ref.Blocked.from_array(xh, chunks)
+    x64 = xh.astype(np.float64)
+    for axis in (None, 0, 1):
+        got = x.var(axis=axis).compute()
+        np.testing.assert_allclose(got, x64.var(axis=axis), rtol=RTOL32)
+        np.testing.assert_allclose(got, ref.da_var(b, axis=axis), rtol=RTOL32)
+        np.testing.assert_allclose(x.std(axis=axis, ddof=1).compute(), x64.std(axis=axis, ddof=1), rtol=RTOL32)
+    # through a fused chain as well (the chunk step of the std() headline kernel)
+    y = x * 2 + 1
+    np.testing.assert_allclose(y.std().compute(), (x64 * 2 + 1).std(), rtol=RTOL32)
+
+
+def test_random_matches_seed_sequence_spawn_bit_exact(da):
+    """da.random.default_rng(seed).random(...) == the reference's per-block streams (random/_expr.py:29-32,
+    97-126): block k draws from PCG64(SeedSequence(seed).spawn(nblocks)[k]); a second draw from the same
+    generator continues the spawn sequence (different values, reproducible)."""
+    rng = da.random.default_rng(42)
+    a = rng.random((96, 80), chunks=(32, 40), dtype=np.float32)
+    b = rng.random((96, 80), chunks=(32, 40))
+    ss = np.random.SeedSequence(42)
+    for arr, dt in ((a, np.float32), (b, np.float64)):
+        kids = ss.spawn(6)
+        want = np.empty((96, 80), dtype=dt)
+        for k, (i, j) in enumerate((i, j) for i in range(3) for j in range(2)):
+            want[32 * i:32 * i + 32, 40 * j:40 * j + 40] = np.random.Generator(np.random.PCG64(kids[k])).random((32, 40), dtype=dt)
+        got = arr.compute()
+        assert got.dtype == dt and np.array_equal(got, want)
+    assert not np.array_equal(a.compute().astype(np.float64), b.compute())
+    again = da.random.default_rng(42).random((96, 80), chunks=(32, 40), dtype=np.float32)
+    assert again.name == a.name and np.array_equal(again.compute(), a.compute())
+    assert (da.random.random((8,), chunks=4) - da.random.random((8,), chunks=4)).compute().any()
+    n = da.random.default_rng(7).standard_normal((64,), chunks=16)
+    kids = np.random.SeedSequence(7).spawn(4)
+    assert np.array_equal(n.compute(), np.concatenate([np.random.Generator(np.random.PCG64(k)).standard_normal(16) for k in kids]))
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32", "int16"])

@@ -36,7 +36,7 @@ def test_nd_reductions_all_axis_sets(da, shape, chunks):
             assert np.array_equal(x.sum(axis=axes).compute(), xh.sum(axis=axes)), axes
             assert np.array_equal(x.max(axis=axes, keepdims=True).compute(), xh.max(axis=axes, keepdims=True)), axes
             np.testing.assert_allclose(f.mean(axis=axes).compute(), fh.mean(axis=axes), rtol=1e-12, err_msg=str(axes))
-            np.testing.assert_allclose(f.var(axis=axes).compute(), fh.var(axis=axes), rtol=1e-11, err_msg=str(axes))
+            np.testing.assert_allclose(f.var(axis=axes).compute(), fh.var(axis=axes), rtol=1e-12, err_msg=str(axes))
     for ax in range(nd):
         assert np.array_equal(x.argmax(axis=ax).compute(), xh.argmax(axis=ax)), ax
         assert np.array_equal(x.argmin(axis=ax).compute(), xh.argmin(axis=ax)), ax
