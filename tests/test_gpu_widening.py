@@ -34,8 +34,14 @@ def test_structural_views(da):
     t, u = da.from_array(th, chunks=(5, 16)), da.from_array(uh, chunks=(3, 16))      # ragged k blocks: 16, 16, 8
     mm = da.tensordot(t, u, axes=((1,), (1,)))
     np.testing.assert_allclose(mm.compute(), th.astype(np.float64) @ uh.T.astype(np.float64), rtol=1e-5)
+    # contraction chunks that are not multiples of 8 elements cannot be TMA operands: fp32 then runs in IEEE
+    # arithmetic on the exact kernel (b2_gemm_tn_simt); bf16 has no such path and says so
+    got = (da.from_array(th[:, :10], chunks=(5, 4)) @ da.from_array(uh[:, :10], chunks=(3, 4)).T).compute()
+    np.testing.assert_allclose(got, th[:, :10].astype(np.float64) @ uh[:, :10].T.astype(np.float64), rtol=1e-5)
+    import ml_dtypes
+    tb, ub = th[:, :10].astype(ml_dtypes.bfloat16), uh[:, :10].astype(ml_dtypes.bfloat16)
     with pytest.raises(NotImplementedError, match="multiples of 8"):
-        (da.from_array(th[:, :10], chunks=(5, 4)) @ da.from_array(uh[:, :10], chunks=(3, 4)).T).compute()
+        (da.from_array(tb, chunks=(5, 4)) @ da.from_array(ub, chunks=(3, 4)).T).compute()
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
