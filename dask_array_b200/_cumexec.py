@@ -60,8 +60,71 @@ class _Cum:
         if self.ident != 0 or self.ex.world.size > 1:
             self.ex._do(lambda: rt.fill(chunk, self.ident))
 
+    # ---- N-d blocks, one GPU: single pass over chains of blocks (2 N bytes)
+    def nd_chained(self, x, src, axis) -> bool:
+        """Every chain of blocks along ``axis`` is walked by the threads that own its columns (scan along
+        rows) or by the warps that own its rows (scan along the contiguous dim), running total in registers:
+        each element is read once and written once.  Needs enough independent columns / rows to keep HBM
+        busy; returns False (nothing done) when the array is too narrow -- the three-step plan then splits
+        the axis itself."""
+        import os
+
+        ex, st, acc = self.ex, self.st, self.acc
+        if ex.world.size != 1 or os.environ.get("B2_SCAN_CHAINED", "1") != "1":
+            return False
+        nax = x.numblocks[axis]
+        others = [range(n) for d, n in enumerate(x.numblocks) if d != axis]
+        chains, lanes, mode = [], 0, None
+        for cid in itertools.product(*others):
+            bids = [cid[:axis] + (i,) + cid[axis:] for i in range(nax)]
+            ch = []
+            for bid in bids:
+                c = src.blocks[bid]
+                if c.size == 0:
+                    continue
+                canon = rt.canonicalize_scan(c.shape, [c.strides], axis)
+                if mode is None:
+                    mode = canon.mode
+                elif canon.mode != mode:
+                    return False
+                ch.append((bid, c, canon))
+            if not ch:
+                continue
+            canon = ch[0][2]
+            if mode == _lib.MODE_SR:
+                if any(k[2].C != canon.C or k[2].B != canon.B for k in ch):
+                    return False
+                lanes += canon.B * canon.C
+            else:
+                if any(k[2].R != canon.R or k[2].B != canon.B for k in ch):
+                    return False
+                lanes += canon.B * canon.R * 32
+            chains.append(ch)
+        if not chains:
+            return False
+        # independent lanes needed to cover HBM latency: ~4 MB in flight (column strips hold 512 B each,
+        # row warps 4 x 512 B)
+        need = (16384 if mode == _lib.MODE_SR else 32 * 1024) * max(1, 4 // acc.itemsize if mode == _lib.MODE_SR else 1)
+        if lanes < need:
+            return False
+        launch_chains = []
+        for ch in chains:
+            out_chain = []
+            for bid, c, _ in ch:
+                out = DeviceChunk.empty(c.shape, acc, ex.device)
+                st.blocks[bid] = out
+                out_chain.append(rt.BlockArgs(shape=c.shape, inputs=[(c.ptr, c.strides)], out0=out.ptr))
+            launch_chains.append(out_chain)
+        for bid in x.block_ids():                       # empty blocks along the axis
+            if bid not in st.blocks:
+                st.blocks[bid] = DeviceChunk.empty(x.block_shape(bid), acc, ex.device)
+        self._run([rt.chained_scan_launch(self.prog, self.redop, axis, launch_chains, acc)])
+        return True
+
     # ---- N-d blocks: the blocks along the axis are the segments, one totals table per chain
     def nd_blocks(self, x, src, axis):
+        if self.nd_chained(x, src, axis):
+            return
         ex, st, acc = self.ex, self.st, self.acc
         nax = x.numblocks[axis]
         others = [range(n) for d, n in enumerate(x.numblocks) if d != axis]

@@ -53,6 +53,8 @@ def extra_kernels():
                                                         rpt=1 << 30, unroll=8, acc_dtype=dt)))
         out.append((f"cumsum columns {dt}", q, cg.KernelSpec(q.key(), ("V",), _lib.MODE_SC, _lib.RED_SUM, vec=v, tx=32, ty=8,
                                                            rpt=8, unroll=4, acc_dtype=dt)))
+        out.append((f"cumsum rows, chained single pass {dt}", q, cg.KernelSpec(
+            q.key(), ("V",), _lib.MODE_SR, _lib.RED_SUM, vec=v, tx=32, ty=1, rpt=1 << 30, unroll=32 if v == 4 else 16, acc_dtype=dt)))
     return out
 
 

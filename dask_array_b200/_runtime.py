@@ -227,7 +227,10 @@ class FusedLaunch:
     """Persistent launch table of one fused expression over its resident blocks."""
 
     def __init__(self, program: cg.Program, redop: int, reduce_axes, blocks: list[BlockArgs],
-                 acc_dtype=None, out_is_contiguous: bool = True, keep_order: bool = False, scan_axis=None):
+                 acc_dtype=None, out_is_contiguous: bool = True, keep_order: bool = False, scan_axis=None,
+                 chain_links=None, n_heads=None):
+        """``chain_links`` / ``n_heads`` (scan launches): ``blocks`` = the ``n_heads`` first blocks of the chains
+        followed by their successors; ``chain_links[i]`` = table index of the block after block i (0 = none)."""
         if not blocks:
             raise ValueError("FusedLaunch needs at least one block")
         if len(program.inputs) >= 2 and len(blocks) > 2 and not keep_order:
@@ -312,6 +315,10 @@ class FusedLaunch:
             cmax = max(c.C for c in canons)
             geo = dict(vec=v, tx=min(128, max(32, cg._pow2_ceil(-(-cmax // v)))), ty=1,
                        rpt=1 << 30, unroll=8)          # one row tile per block (constant: one kernel for all R)
+            if chain_links is not None:
+                # chained single pass: the only parallelism is over columns, so every thread keeps 32 vector
+                # loads (512 B) in flight and a CTA is one warp (spreads the few warps over all SMs)
+                geo = dict(vec=v, tx=32, ty=1, rpt=1 << 30, unroll=32 if max(sizes) <= 4 else 16)   # (8-byte: 32 spills)
         elif self.mode == _lib.MODE_SC:   # a warp per row
             geo = dict(vec=v, tx=32, ty=8, rpt=8, unroll=4)
         variant, mirror, n_primary = "", None, len(blocks)
@@ -368,9 +375,14 @@ class FusedLaunch:
             assert len(descs) == len(mirror)
             for d, m in zip(descs, mirror):
                 d.mirror = m
+        if chain_links is not None:
+            assert len(descs) == len(chain_links) and mirror is None
+            for d, m in zip(descs, chain_links):
+                d.mirror = m
+            n_primary = n_heads
         # mirror-pair launches tile the primary block of each pair only; the partners sit behind
         # them in the table and are reached through `mirror`
-        self.nblocks = n_primary if mirror is not None else len(descs)
+        self.nblocks = n_primary if (mirror is not None or chain_links is not None) else len(descs)
         arr = (_lib.Block * len(descs))(*descs)
         need = C.c_size_t()
         tiles = C.c_int64()
@@ -450,6 +462,22 @@ def scan_launches(program, redop, axis, blocks, acc_dtype):
         groups.setdefault(c.mode, []).append(b)
     return [FusedLaunch(program, redop, (), g, acc_dtype=acc_dtype, keep_order=True, scan_axis=axis)
             for g in groups.values()]
+
+
+def chained_scan_launch(program, redop, axis, chains, acc_dtype):
+    """ONE single-pass launch over chains of blocks along the scanned axis (``chains``: lists of BlockArgs in
+    axis order, all of one canonical mode): heads first, successors behind them, linked through ``mirror``."""
+    heads = [ch[0] for ch in chains]
+    order, links = list(heads), [0] * len(heads)
+    for h, ch in enumerate(chains):
+        prev = h
+        for b in ch[1:]:
+            order.append(b)
+            links.append(0)
+            links[prev] = len(order) - 1
+            prev = len(order) - 1
+    return FusedLaunch(program, redop, (), order, acc_dtype=acc_dtype, keep_order=True, scan_axis=axis,
+                       chain_links=links, n_heads=len(heads))
 
 
 def fused_launches(program, redop, reduce_axes, blocks, acc_dtype=None, keep_order=False):

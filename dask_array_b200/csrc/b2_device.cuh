@@ -1214,6 +1214,10 @@ __device__ __forceinline__ void b2_run_scan(const B2Block* __restrict__ blocks, 
     const i64 R = blk.R, C = blk.C;
     const ACC* const carry = (const ACC*)blk.out1;
 
+    // Chained launches (single pass, 2 N bytes): the blocks along the scanned axis form a chain -- `mirror`
+    // holds the table index of the NEXT block of the chain (0 = last; heads come first in the table, so 0 is
+    // never a successor) -- and the thread / warp that owns a column strip / row keeps walking from block to
+    // block with its running total in registers: no per-block totals pass, no carry table.
     if constexpr (MODE == B2M_SR) {
         static_assert(TY == 1, "row scans: one thread per column strip");
         const i64 c = (tc * TX + tx) * V;
@@ -1224,79 +1228,96 @@ __device__ __forceinline__ void b2_run_scan(const B2Block* __restrict__ blocks, 
         B2ScanState<ACC, V> st;
 #pragma unroll
         for (int v = 0; v < V; ++v) st.run[v] = OP::ident();
-        typename Chain::Ptrs P;
-        Chain::setup_rows(blk, b, 0, c, 1, P);
-        ACC* const outp = (ACC*)blk.out0 + (b * R) * C + c;
         const bool has = carry != nullptr;
-        b2_stream<Chain, V, U>(P, (int)R, sc, st,
-            [&](B2ScanState<ACC, V>& s, int k, const T (&o)[V]) {
-                ACC w[V];
+        bool started = false;
+        const B2Block* cur = &blk;
+        for (;;) {
+            const i64 Rc = cur->R;
+            typename Chain::Ptrs P;
+            Chain::setup_rows(*cur, b, 0, c, 1, P);
+            ACC* const outp = (ACC*)cur->out0 + (b * Rc) * C + c;
+            const bool fresh = !started;
+            b2_stream<Chain, V, U>(P, (int)Rc, sc, st,
+                [&](B2ScanState<ACC, V>& s, int k, const T (&o)[V]) {
+                    ACC w[V];
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    s.run[v] = (k == 0) ? b2_cast<ACC>(o[v]) : OP::op(s.run[v], b2_cast<ACC>(o[v]));
-                    w[v] = has ? OP::op(cv[v], s.run[v]) : s.run[v];
-                }
-                b2_store_vec<ACC, V>(outp + (i64)k * C, w);
-            });
+                    for (int v = 0; v < V; ++v) {
+                        s.run[v] = (fresh && k == 0) ? b2_cast<ACC>(o[v]) : OP::op(s.run[v], b2_cast<ACC>(o[v]));
+                        w[v] = has ? OP::op(cv[v], s.run[v]) : s.run[v];
+                    }
+                    b2_store_vec<ACC, V>(outp + (i64)k * C, w);
+                });
+            if (Rc > 0) started = true;
+            const int nxt = cur->mirror;
+            if (nxt == 0) break;
+            cur = blocks + nxt;
+        }
     } else {
         static_assert(MODE == B2M_SC && TX == 32, "column scans: one warp per row");
         const int lane = tx;
         const i64 r0 = tr * RPT;
         const i64 rend = (r0 + RPT < R) ? (r0 + RPT) : R;
         const i64 step = (i64)TX * V;
-        const int nfull = (int)(C / step);                 // steps every lane takes
-        const i64 ctail = (i64)nfull * step + (i64)lane * V; // this lane's columns in the ragged last step
         for (i64 r = r0 + ty; r < rend; r += TY) {         // a warp owns its row: uniform control flow
             const ACC cv = carry ? carry[b * R + r] : OP::ident();
             const bool has = carry != nullptr;
-            ACC* const outp = (ACC*)blk.out0 + (b * R + r) * C + (i64)lane * V;
             B2ScanState<ACC, 1> st;
             st.run[0] = OP::ident();
             bool first = true;
-            auto stepfn = [&](B2ScanState<ACC, 1>& s, i64 k, const T (&o)[V], bool valid) {
-                ACC w[V];
-                w[0] = valid ? b2_cast<ACC>(o[0]) : OP::ident();
+            const B2Block* cur = &blk;
+            for (;;) {
+                const i64 Cc = cur->C;
+                const int nfull = (int)(Cc / step);                 // steps every lane takes
+                const i64 ctail = (i64)nfull * step + (i64)lane * V; // this lane's columns in the ragged last step
+                ACC* const outp = (ACC*)cur->out0 + (b * R + r) * Cc + (i64)lane * V;
+                auto stepfn = [&](B2ScanState<ACC, 1>& s, i64 k, const T (&o)[V], bool valid) {
+                    ACC w[V];
+                    w[0] = valid ? b2_cast<ACC>(o[0]) : OP::ident();
 #pragma unroll
-                for (int v = 1; v < V; ++v) w[v] = valid ? OP::op(w[v - 1], b2_cast<ACC>(o[v])) : OP::ident();
-                ACC inc = w[V - 1];
+                    for (int v = 1; v < V; ++v) w[v] = valid ? OP::op(w[v - 1], b2_cast<ACC>(o[v])) : OP::ident();
+                    ACC inc = w[V - 1];
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const ACC up = __shfl_up_sync(0xffffffffu, inc, off);
-                    if (lane >= off) inc = OP::op(up, inc);
-                }
-                ACC excl = __shfl_up_sync(0xffffffffu, inc, 1);
-                const ACC total = __shfl_sync(0xffffffffu, inc, 31);
-                // prefix of everything before this lane's chunk: previous steps, then the lanes to the left
-                const bool have_base = !first || lane > 0;
-                ACC base = first ? excl : (lane > 0 ? OP::op(s.run[0], excl) : s.run[0]);
-                if (valid) {
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        ACC x = have_base ? OP::op(base, w[v]) : w[v];
-                        w[v] = has ? OP::op(cv, x) : x;
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const ACC up = __shfl_up_sync(0xffffffffu, inc, off);
+                        if (lane >= off) inc = OP::op(up, inc);
                     }
-                    b2_store_vec<ACC, V>(outp + k * step, w);
-                }
-                s.run[0] = first ? total : OP::op(s.run[0], total);
-                first = false;
-            };
-            if (nfull > 0) {
-                typename Chain::Ptrs P;
-                Chain::setup_cols(blk, b, r, (i64)lane * V, step, P);
-                b2_stream<Chain, V, U>(P, nfull, sc, st,
-                    [&](B2ScanState<ACC, 1>& s, int k, const T (&o)[V]) { stepfn(s, (i64)k, o, true); });
-            }
-            if ((i64)nfull * step < C) {
-                const bool valid = ctail < C;
-                T o[V];
-                if (valid) {
+                    ACC excl = __shfl_up_sync(0xffffffffu, inc, 1);
+                    const ACC total = __shfl_sync(0xffffffffu, inc, 31);
+                    // prefix of everything before this lane's chunk: previous steps, then the lanes to the left
+                    const bool have_base = !first || lane > 0;
+                    ACC base = first ? excl : (lane > 0 ? OP::op(s.run[0], excl) : s.run[0]);
+                    if (valid) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            ACC x = have_base ? OP::op(base, w[v]) : w[v];
+                            w[v] = has ? OP::op(cv, x) : x;
+                        }
+                        b2_store_vec<ACC, V>(outp + k * step, w);
+                    }
+                    s.run[0] = first ? total : OP::op(s.run[0], total);
+                    first = false;
+                };
+                if (nfull > 0) {
                     typename Chain::Ptrs P;
-                    typename Chain::Regs g;
-                    Chain::setup_cols(blk, b, r, ctail, step, P);
-                    Chain::load(P, 0, g);
-                    Chain::compute_slow(g, sc, o);
+                    Chain::setup_cols(*cur, b, r, (i64)lane * V, step, P);
+                    b2_stream<Chain, V, U>(P, nfull, sc, st,
+                        [&](B2ScanState<ACC, 1>& s, int k, const T (&o)[V]) { stepfn(s, (i64)k, o, true); });
                 }
-                stepfn(st, (i64)nfull, o, valid);
+                if ((i64)nfull * step < Cc) {
+                    const bool valid = ctail < Cc;
+                    T o[V];
+                    if (valid) {
+                        typename Chain::Ptrs P;
+                        typename Chain::Regs g;
+                        Chain::setup_cols(*cur, b, r, ctail, step, P);
+                        Chain::load(P, 0, g);
+                        Chain::compute_slow(g, sc, o);
+                    }
+                    stepfn(st, (i64)nfull, o, valid);
+                }
+                const int nxt = cur->mirror;
+                if (nxt == 0) break;
+                cur = blocks + nxt;
             }
         }
     }
