@@ -43,6 +43,10 @@ def _as_chunk(x):
 def array_ufunc(self, ufunc, method, *inputs, **kwargs):
     if method != "__call__":
         return NotImplemented
+    if ufunc is np.matmul:            # a generalised ufunc, not element-wise: the contraction path
+        if kwargs.get("out") is not None:
+            return NotImplemented
+        return _np_matmul(*inputs)
     out = kwargs.pop("out", None)
     dtype = kwargs.pop("dtype", None)
     kwargs.pop("casting", None)

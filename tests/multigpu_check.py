@@ -109,6 +109,24 @@ def main():
     gh = rng.random((256, 192))
     ga, gb = da.from_array(gh, chunks=(64, 64)).persist(), da.from_array(gh, chunks=(128, 32)).persist()
     assert np.array_equal((ga * 2 + gb).compute(), gh * 2 + gh)
+    peer = os.environ.get("B2_COMM", "peer") != "nccl"
+    if not peer:
+        # views and halos whose source block lives on another GPU are peer-memory only (a loud refusal on the
+        # packed-NCCL comparison path): check the refusal, then finish
+        sd = da.from_array(rng.random((600, 64)), chunks=(100, 64)).persist()
+        try:
+            sd[150:].compute()
+        except NotImplementedError as e:
+            assert "peer-memory" in str(e)
+        else:
+            raise AssertionError("cross-GPU view on the NCCL path should be refused")
+        ones = da.ones((1000, 1000), chunks=(100, 100))
+        assert (ones + ones.T).sum().compute() == 2_000_000.0
+        dist.barrier()
+        if rank == 0:
+            print(f"multigpu_check ok on {world} GPUs (B2_COMM=nccl)")
+        dist.destroy_process_group()
+        return
     # structural views whose source block lives on another GPU: pushed through peer memory
     sh = rng.random((600, 64))
     sd = da.from_array(sh, chunks=(100, 64)).persist()

@@ -108,8 +108,8 @@ def test_float_sums_with_cancellation(da, dtype):
 def test_fp32_variance_with_mean_far_above_spread(da, offset, spread, chunks):
     """var / std of fp32 data whose mean dwarfs its spread (the oracle golden case `1000 + 10 u`,
     tests/golden/generate.py, and a harsher 1e6 + u): a naive single pass sum(x^2) - n mean^2 loses every
-    digit here; the kernel's shifted sums + fp64 Chan merge must stay within rtol 1e-5 of the fp64 truth AND
-    of the reference's two-pass-per-chunk result (moment_chunk, _common.py:393-403)."""
+    digit here; the kernel's shifted sums + fp64 Chan merge must stay within rtol 1e-5 of the fp64 truth, and
+    at least as close to it as the reference's two-pass-per-chunk result (moment_chunk, _common.py:393-403)."""
     rng = np.random.default_rng(5)
     xh = (offset + spread * rng.random((256, 300))).astype(np.float32)
     x = da.from_array(xh, chunks=chunks)
@@ -117,8 +117,17 @@ def test_fp32_variance_with_mean_far_above_spread(da, offset, spread, chunks):
     x64 = xh.astype(np.float64)
     for axis in (None, 0, 1):
         got = x.var(axis=axis).compute()
-        np.testing.assert_allclose(got, x64.var(axis=axis), rtol=RTOL32)
-        np.testing.assert_allclose(got, ref.da_var(b, axis=axis), rtol=RTOL32)
+        truth = x64.var(axis=axis)
+        np.testing.assert_allclose(got, truth, rtol=RTOL32)
+        # The reference's fp32 two-pass-per-chunk result is itself off by 2e-5 (1000 + 10 u) to 1.6e-2
+        # (1e6 + u) here -- its block mean is rounded to fp32 before the deviations are squared (measured on
+        # B200 box, round 2) -- so it cannot be matched to 1e-5; what must hold is that this backend is at
+        # least as close to the fp64 truth as the reference is, and agrees with it within the reference's
+        # own error.
+        want = ref.da_var(b, axis=axis).astype(np.float64)
+        ref_err = np.abs(want - truth)
+        assert np.all(np.abs(got - truth) <= ref_err + RTOL32 * np.abs(truth))
+        assert np.all(np.abs(got - want) <= 2 * ref_err + RTOL32 * np.abs(truth))
         np.testing.assert_allclose(x.std(axis=axis, ddof=1).compute(), x64.std(axis=axis, ddof=1), rtol=RTOL32)
     # through a fused chain as well (the chunk step of the std() headline kernel)
     y = x * 2 + 1
