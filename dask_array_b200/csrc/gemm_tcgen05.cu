@@ -257,6 +257,181 @@ b2_gemm_tn_batched_kernel(const GemmProblem* __restrict__ probs, int nprobs, con
     gemm_tile(base, base + 1, 2, pr.npairs, pr.C, pr.ldc, pr.M, pr.N, pr.K, pr.accumulate, mt * BM, nt * BN);
 }
 
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// Two CTAs of one cluster (the two SMs of a TPC) compute ONE 256 x 256 output tile: CTA r owns rows
+// [m0 + 128 r, +128) of A and of the accumulator (its own TMEM, 128 lanes x 256 columns) and loads HALF of the
+// B tile -- rows [n0 + 128 r, +128) -- into its shared memory; the MMA (M = 256, issued by the leader CTA
+// only) reads both halves.  Per CTA and k step that is 16 KiB of A + 16 KiB of B for the tensor work that
+// costs the single-CTA kernel 16 + 32 KiB: a third less L2 -> SM traffic and shared-memory fill, which is
+// what the power-capped tensor pipe is waiting for, and room for 6 pipeline stages instead of 4.
+constexpr int P_BM = 128, P_BN = 256, P_BNH = 128, P_STAGES = 6;
+constexpr int P_A_BYTES = P_BM * BK * 2, P_B_BYTES = P_BNH * BK * 2, P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;     // shared::cluster address of the SAME offset in CTA 0 of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of the pair; the transaction bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__device__ __forceinline__ void gemm_tile_pair(const CUtensorMap* __restrict__ amaps, const CUtensorMap* __restrict__ bmaps,
+                                               int map_stride, int npairs, float* __restrict__ C, long long ldc,
+                                               int M, int N, int K, int accumulate, int m0, int n0) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = (uint64_t*)(smem + P_STAGES * P_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + P_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + P_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int k_iters = (K + BK - 1) / BK;
+    const int total_iters = npairs * k_iters;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {      // the same warp of BOTH CTAs allocates: 256 TMEM columns in each SM
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(P_BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                   // barriers of both CTAs initialised, TMEM allocated
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(amaps);
+            tma_prefetch_desc(bmaps);
+            for (int it = 0; it < total_iters; ++it) {
+                const int s = it % P_STAGES;
+                const uint32_t ph = (uint32_t)(it / P_STAGES) & 1u;
+                const int p = it / k_iters, kk = it % k_iters;
+                if (kk == 0 && p + 1 < npairs) {
+                    tma_prefetch_desc(amaps + (size_t)(p + 1) * map_stride);
+                    tma_prefetch_desc(bmaps + (size_t)(p + 1) * map_stride);
+                }
+                mbar_wait(&empty_bar[s], ph ^ 1u);                               // own CTA's copy: freed by the multicast commit
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * P_STAGE_BYTES);  // the leader counts both CTAs' bytes
+                uint8_t* sa = smem + s * P_STAGE_BYTES;
+                tma_load_2d_pair(sa, amaps + (size_t)p * map_stride, kk * BK, m0 + (int)rank * P_BM, &full_bar[s]);
+                tma_load_2d_pair(sa + P_A_BYTES, bmaps + (size_t)p * map_stride, kk * BK, n0 + (int)rank * P_BNH, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * P_BM, P_BN);
+            for (int it = 0; it < total_iters; ++it) {
+                const int s = it % P_STAGES;
+                const uint32_t ph = (uint32_t)(it / P_STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + s * P_STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + P_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16_pair(tmem_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+                umma_commit_pair(&empty_bar[s]);        // frees the stage in BOTH CTAs when these MMAs retire
+            }
+            umma_commit_pair(tmem_full_bar);            // accumulators of both CTAs complete
+        }
+    } else {
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const int row = m0 + (int)rank * P_BM + q * 32 + lane;
+        float* crow = C + (long long)row * ldc + n0;
+#pragma unroll 1
+        for (int c = 0; c < P_BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            if (row < M) {
+                if (n0 + c + 32 <= N && (ldc % 4 == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        float4* dst = reinterpret_cast<float4*>(crow + c + j);
+                        if (accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                        *dst = v;
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j) {
+                        if (n0 + c + j < N) {
+                            float v = __uint_as_float(r[j]);
+                            if (accumulate) v += crow[c + j];
+                            crow[c + j] = v;
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                   // neither CTA may free TMEM / exit while the peer still uses it
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(P_BN));
+    }
+}
+
+// every output block of a blocked matmul, one CTA pair per 256 x 256 tile.  Tiles of a block are walked in
+// bands of 8 tile rows, column by column inside a band, so that the ~74 pairs resident at a time cover a
+// near-square 8 x 9 patch of the output (operand rows fetched per wave: 8 x 256 + 9 x 256).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+b2_gemm_tn_pair_kernel(const GemmProblem* __restrict__ probs, int nprobs, const CUtensorMap* __restrict__ maps) {
+    __shared__ GemmProblem pr;
+    const long long tile = blockIdx.x >> 1;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = nprobs - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (probs[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+        }
+        pr = probs[lo];
+    }
+    __syncthreads();
+    const int t = (int)(tile - pr.tile_begin);
+    const int tiles_m = (pr.M + 2 * P_BM - 1) / (2 * P_BM);
+    constexpr int BAND = 8;
+    const int per_band = BAND * pr.tiles_n;
+    const int band = t / per_band, in_band = t - band * per_band;
+    const int rows_here = (tiles_m - band * BAND < BAND) ? (tiles_m - band * BAND) : BAND;
+    const int mt = band * BAND + in_band % rows_here, nt = in_band / rows_here;
+    const CUtensorMap* base = maps + 2 * (size_t)pr.map_begin;
+    gemm_tile_pair(base, base + 1, 2, pr.npairs, pr.C, pr.ldc, pr.M, pr.N, pr.K, pr.accumulate, mt * 2 * P_BM, nt * P_BN);
+}
+
 // fp32 -> three bf16 planes with hi + mid + lo == x to ~2^-24 (x - hi and the next residual are exact)
 __global__ void __launch_bounds__(256) b2_split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                         __nv_bfloat16* __restrict__ mid, __nv_bfloat16* __restrict__ lo,
@@ -354,8 +529,14 @@ extern "C" int b2_gemm_tn_batched(int dtype, const b2_gemm_problem* problems, in
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
         attr_err = cudaFuncSetAttribute(b2_gemm_tn_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(b2_gemm_tn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
     });
     if (attr_err != cudaSuccess) return b2_set_error_(B2_ERR_CUDA, cudaGetErrorString(attr_err));
+    // CTA-pair kernel (256 x 256 tiles) unless B2_GEMM_2CTA=0 asks for the single-CTA one (A/B comparison)
+    static const bool pair = [] { const char* e = getenv("B2_GEMM_2CTA"); return !(e && e[0] == '0'); }();
+    const int box_b = pair ? P_BNH : BN;
+    const int tile_m = pair ? 2 * P_BM : BM;
     void* host = nullptr;
     if (posix_memalign(&host, 64, need)) return b2_set_error_(B2_ERR_INVALID, "out of host memory");
     memset(host, 0, need);
@@ -373,16 +554,16 @@ extern "C" int b2_gemm_tn_batched(int dtype, const b2_gemm_problem* problems, in
             const int64_t la = q.Kpair ? kp : q.lda, lb = q.Kpair ? kp : q.ldb;
             if (kp <= 0 || kp > q.K || la % 8 || lb % 8) { rc = b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_batched: per-pair K must be in (0, K] and a multiple of 8"); break; }
             rc = make_map(&hm[2 * (map_begin + p)], q.A[p], q.M, kp, la, BM);
-            if (rc == B2_OK) rc = make_map(&hm[2 * (map_begin + p) + 1], q.B[p], q.N, kp, lb, BN);
+            if (rc == B2_OK) rc = make_map(&hm[2 * (map_begin + p) + 1], q.B[p], q.N, kp, lb, box_b);
         }
         GemmProblem& g = hp[i];
         g.C = q.C; g.ldc = q.ldc; g.M = (int)q.M; g.N = (int)q.N; g.K = (int)q.K; g.npairs = q.npairs;
         g.accumulate = q.accumulate; g.map_begin = map_begin; g.tile_begin = tiles;
         g.tiles_n = (int)((q.N + BN - 1) / BN);
-        tiles += (long long)((q.M + BM - 1) / BM) * g.tiles_n;
+        tiles += (long long)((q.M + tile_m - 1) / tile_m) * g.tiles_n;
         map_begin += q.npairs;
     }
-    if (rc == B2_OK && tiles > 0x7fffffffLL) rc = b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_batched: too many tiles");
+    if (rc == B2_OK && tiles > 0x3fffffffLL) rc = b2_set_error_(B2_ERR_UNSUPPORTED, "b2_gemm_tn_batched: too many tiles");
     if (rc == B2_OK) {
         // pageable source: the copy is staged before the call returns, so `host` can be freed
         cudaError_t e = cudaMemcpyAsync(workspace, host, need, cudaMemcpyHostToDevice, (cudaStream_t)stream);
@@ -390,8 +571,12 @@ extern "C" int b2_gemm_tn_batched(int dtype, const b2_gemm_problem* problems, in
     }
     free(host);
     if (rc != B2_OK) return rc;
-    b2_gemm_tn_batched_kernel<<<(unsigned)tiles, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
-        (const GemmProblem*)((char*)workspace + probs_off), nproblems, (const CUtensorMap*)workspace);
+    if (pair)
+        b2_gemm_tn_pair_kernel<<<(unsigned)(2 * tiles), NUM_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(
+            (const GemmProblem*)((char*)workspace + probs_off), nproblems, (const CUtensorMap*)workspace);
+    else
+        b2_gemm_tn_batched_kernel<<<(unsigned)tiles, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+            (const GemmProblem*)((char*)workspace + probs_off), nproblems, (const CUtensorMap*)workspace);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return b2_set_error_(B2_ERR_CUDA, cudaGetErrorString(e));
     b2_count_launch_();
