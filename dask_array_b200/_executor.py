@@ -31,6 +31,13 @@ from ._reductions import REDOPS, ArgChunk, ChunkReduce, CumReduction, PartialRed
 from ._slicing import SliceSlicesIntegers
 
 
+import os as _os
+
+# B2_NVTX: 0 = off, 1 (default) = one range per expression while it is planned and first launched,
+# 2 = the replayed tape carries the same ranges (two host calls per expression and replay)
+_NVTX = int(_os.environ.get("B2_NVTX", "1") or 0)
+
+
 class BlockStore:
     """Blocks of one expression held by this rank.  ``kind``: array | mean | moment | arg."""
 
@@ -82,7 +89,20 @@ class Executor:
             raise NotImplementedError(
                 f"{type(expr).__name__} has no B200 execution path (optimise the expression first; "
                 "there is no CPU fallback)")
-        store = fn(expr)
+        # one NVTX range per expression (planning + first launch) and, through the tape markers, per replay:
+        # the timeline of a profiler shows which fused expression a kernel belongs to
+        label = f"b2:{type(expr).__name__}:{expr._name[-12:]}"
+        first = len(self.tape)
+        if _NVTX:
+            torch.cuda.nvtx.range_push(label)
+        try:
+            store = fn(expr)
+        finally:
+            if _NVTX:
+                torch.cuda.nvtx.range_pop()
+        if _NVTX >= 2 and len(self.tape) > first:
+            self.tape.insert(first, lambda label=label: torch.cuda.nvtx.range_push(label))
+            self.tape.append(torch.cuda.nvtx.range_pop)
         self.results[expr._name] = store
         return store
 
