@@ -10,6 +10,9 @@ Headline workload (``configs[1]``, "c2"): fp32 ``x`` in 4096^2 chunks; one step 
   ``std()`` tree needs ONE exchange of (n, mean, M2) triples: a single peer-memory all-gather launch
   (no NCCL in the step).  The step is replayed from one CUDA graph per rank.
 * ``strong``: the SAME step on BASELINE's fixed (32768, 32768) array dealt over the N GPUs.
+* ``first_call_ms`` / ``compute_call_ms``: what the replayed tape leaves out -- the first call (optimise, kernel
+  cubins from the JIT cache, planning, launch) and a plain ``da.compute()`` of the same graph (host planning +
+  launches + the gather of the results), both untimed for ``value``.
 * ``parity``: every rank checks its share of the results against an fp64 ground truth of its own
   blocks; rank 0 also checks against the CPU oracle (the restatement of the reference).
 * ``configs``: the other BASELINE configs, measured in the same run with the same clock sampler:
@@ -425,7 +428,14 @@ def run_c2(ctx: Ctx, strong: bool, with_e2e: bool, with_cpu: bool):
     xh = da.from_host_blocks(lambda bid: store[index[bid]], shape, (BLOCK, BLOCK), np.float32, token=f"{tag}-r{rank}-w{W}")
     x = xh.persist()
     y = chain(x)
-    step = da.compile(y.mean(axis=0), y.std())           # runs once: JIT + plan (untimed)
+    ctx.torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step = da.compile(y.mean(axis=0), y.std())           # runs once: optimise + JIT (or cubin cache) + plan + launch
+    ctx.torch.cuda.synchronize()
+    first_call_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    da.compute(y.mean(axis=0), y.std())                  # a plain compute() call of the same graph: nothing replayed
+    compute_call_ms = (time.perf_counter() - t0) * 1e3
     total_bytes = 2 * shape[0] * shape[1] * ITEM          # both reductions, all ranks
     local_pass_bytes = len(index) * BLOCK * BLOCK * ITEM  # one reduction, this rank
     ms, launches = ctx.timed(step, args.steps, args.warmup, tag)
@@ -433,6 +443,7 @@ def run_c2(ctx: Ctx, strong: bool, with_e2e: bool, with_cpu: bool):
     value = total_bytes / (ms * 1e-3) / 1e9
     out = {"value": value, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches,
            "cuda_graph": step._graph is not None, "clocks": ctx.sampler.summary(tag),
+           "first_call_ms": first_call_ms, "compute_call_ms": compute_call_ms,
            "pct_of_measured_hbm_peak": 100.0 * value / W / ctx.hbm_peak, "pct_of_nominal_8TBps": 100.0 * value / W / 8000.0}
 
     # ---- per-kernel roofline: second pass of K steps with CUDA events around every fused launch

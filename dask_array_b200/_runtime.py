@@ -316,9 +316,24 @@ class FusedLaunch:
             geo = dict(vec=v, tx=min(128, max(32, cg._pow2_ceil(-(-cmax // v)))), ty=1,
                        rpt=1 << 30, unroll=8)          # one row tile per block (constant: one kernel for all R)
             if chain_links is not None:
-                # chained single pass: the only parallelism is over columns, so every thread keeps 32 vector
-                # loads (512 B) in flight and a CTA is one warp (spreads the few warps over all SMs)
-                geo = dict(vec=v, tx=32, ty=1, rpt=1 << 30, unroll=32 if max(sizes) <= 4 else 16)   # (8-byte: 32 spills)
+                # chained single pass: the only parallelism is over columns, so every thread keeps U vector
+                # loads in flight and a CTA is one warp (spreads the warps over all SMs).  Narrow vectors give
+                # more warps for the same bytes in flight: pick the widest V that still leaves >= 24k threads.
+                heads = canons[:n_heads]
+                lanes = sum(c.B * c.C for c in heads)
+                vv = v
+                while vv > 1 and lanes // vv < 24576:
+                    vv //= 2
+                vv = int(os.environ.get("B2_SCAN_SR_VEC", vv))
+                # loads in flight per thread, as deep as 255 registers allow (cuobjdump: 224 / 232-244 / 242 regs):
+                # ncu showed the V=4, U=32 kernel latency-bound at 4 MB in flight (4.5 TB/s, 2.7 % warps active)
+                per = max(sizes) * vv
+                uu = 64 if per <= 4 else 48 if per <= 8 else 32 if max(sizes) <= 4 else 16
+                uu = int(os.environ.get("B2_SCAN_SR_UNROLL", uu))
+                if vv == 1:
+                    layouts = [l if l in ("S", "T") else "G" for l in layouts]
+                v = vv
+                geo = dict(vec=v, tx=32, ty=1, rpt=1 << 30, unroll=uu)   # (8-byte x V=2 x 32 loads spills)
         elif self.mode == _lib.MODE_SC:   # a warp per row
             geo = dict(vec=v, tx=32, ty=8, rpt=8, unroll=4)
         variant, mirror, n_primary = "", None, len(blocks)

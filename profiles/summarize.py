@@ -25,6 +25,9 @@ KEYS = [
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+    "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum.per_second",
 ]
 
 
@@ -43,12 +46,14 @@ def rows_of(rep):
 
 
 def main():
-    summary = {}
-    for name in sorted(os.listdir(SRC)):
-        if name.startswith("prof_r1") and name.endswith(".ncu-rep"):
-            summary[name[:-8]] = rows_of(os.path.join(SRC, name))
-    with open(os.path.join(OUT, "r1_ncu_full_summary.json"), "w") as f:
-        json.dump(summary, f, indent=1)
+    for rnd in ("r1", "r2"):
+        summary = {}
+        for name in sorted(os.listdir(SRC)):
+            if name.startswith("prof_" + rnd) and name.endswith(".ncu-rep"):
+                summary[name[:-8]] = rows_of(os.path.join(SRC, name))
+        if summary:
+            with open(os.path.join(OUT, rnd + "_ncu_full_summary.json"), "w") as f:
+                json.dump(summary, f, indent=1)
     # launch list: per-kernel totals and shares of one timed step
     ll = os.path.join(SRC, "launches_r1.csv")
     if os.path.exists(ll):
