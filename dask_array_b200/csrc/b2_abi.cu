@@ -899,6 +899,168 @@ extern "C" int b2_fill(void* dst, int64_t nelem, int itemsize, const void* value
     return B2_OK;
 }
 
+// ------------------------------------------------------------------ sliding-window reductions (AOT)
+// reduction(sliding_window_view(x, w), axis=window_axis) -- SlidingWindowReduction
+// (reductions/_sliding_window.py:405-560): the reference combines, per block, a SUFFIX scan of the block, the
+// totals of the blocks a window covers whole and a PREFIX scan of the band its right edge sweeps
+// (_sliding_window_banded_reduce :96-160).  The same decomposition with segments of exactly `w` elements
+// (van Herk / Gil-Werman) needs no totals:  out[t] = suffix_seg(t)[t]  (+)  prefix_seg(t)+1[t + w - 1],
+// any associative (+), O(1) operations per element whatever the window, every input element read twice
+// (once per scan direction; the second read is an L1 / L2 hit) and every output written once.
+template <typename T, int OP> __device__ __forceinline__ T b2w_op(T a, T b) {
+    if constexpr (OP == B2R_SUM) return (T)(a + b);
+    else if constexpr (OP == B2R_PROD) return (T)(a * b);
+    else if constexpr (OP == B2R_MIN) return b2_np_min(a, b);
+    else return b2_np_max(a, b);
+}
+
+// window along ROWS of a (B, R, C) block: a thread owns one column of one segment of w output rows
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) b2_window_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, i64 B, i64 R,
+                                                             i64 C, i64 w, int mean, i64 col_tiles, i64 seg_tiles) {
+    const i64 Rout = R - w + 1, nseg = (Rout + w - 1) / w;
+    i64 t = blockIdx.x;
+    const i64 ct = t % col_tiles; t /= col_tiles;
+    const i64 stile = t % seg_tiles; const i64 b = t / seg_tiles;
+    const i64 c = ct * 32 + threadIdx.x, s = stile * 8 + threadIdx.y;
+    if (c >= C || s >= nseg || b >= B) return;
+    const T* x = src + (b * R) * C + c;
+    T* o = dst + (b * Rout) * C + c;
+    const i64 base = s * w;
+    const i64 hi = (base + w < R) ? base + w : R;
+    T h = x[(hi - 1) * C];
+    if (hi - 1 < Rout) o[(hi - 1) * C] = (mean && hi - 1 == base) ? (T)(h / (T)w) : h;
+    for (i64 i = hi - 2; i >= base; --i) {                 // suffix scan of this segment, last row first
+        h = b2w_op<T, OP>(h, x[i * C]);
+        if (i < Rout) o[i * C] = (mean && i == base) ? (T)(h / (T)w) : h;
+    }
+    T g = T(0);
+    for (i64 j = 0; j + 1 < w; ++j) {                      // prefix scan of the next segment completes the windows
+        const i64 r = base + w + j, tt = base + j + 1;
+        if (r >= R || tt >= Rout) break;
+        const T v = x[r * C];
+        g = (j == 0) ? v : b2w_op<T, OP>(g, v);
+        T res = b2w_op<T, OP>(o[tt * C], g);
+        o[tt * C] = mean ? (T)(res / (T)w) : res;
+    }
+}
+
+// window along the CONTIGUOUS axis of (rows, C): a tile of RT rows x L columns is staged in shared memory
+// (coalesced loads), scanned per (row, segment) in both directions, combined and stored coalesced
+template <typename T, int OP, int RT>
+__global__ void __launch_bounds__(256) b2_window_cols_kernel(const T* __restrict__ src, T* __restrict__ dst, i64 rows, i64 C,
+                                                             i64 w, i64 tile_out, int mean, i64 col_tiles) {
+    extern __shared__ __align__(16) unsigned char b2w_smem[];
+    const i64 Cout = C - w + 1;
+    const i64 ct = blockIdx.x % col_tiles, rt = blockIdx.x / col_tiles;
+    const i64 t0 = ct * tile_out, row0 = rt * RT;
+    const i64 nout = (t0 + tile_out <= Cout) ? tile_out : Cout - t0;       // outputs of this tile
+    const int L = (int)(nout + w - 1);                                     // input columns it needs
+    const int Lp = L | 1;                                                  // odd pitch: conflict-free column walks
+    T* H = reinterpret_cast<T*>(b2w_smem);
+    T* G = H + (size_t)RT * Lp;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    for (i64 idx = tid; idx < (i64)RT * L; idx += NT) {
+        const int r = (int)(idx / L), k = (int)(idx % L);
+        T v = T(0);
+        if (row0 + r < rows) v = src[(row0 + r) * C + t0 + k];
+        H[r * Lp + k] = v;
+        G[r * Lp + k] = v;
+    }
+    __syncthreads();
+    const int nsg = (int)((L + w - 1) / w);
+    for (int task = tid; task < 2 * RT * nsg; task += NT) {
+        const int r = task % RT, q = task / RT;
+        const int sg = q % nsg, dir = q / nsg;
+        const int lo = (int)(sg * w), hi = (lo + (int)w < L) ? lo + (int)w : L;
+        if (dir == 0) {                                     // suffix scan within the segment
+            T* p = H + r * Lp;
+            T acc = p[hi - 1];
+            for (int i = hi - 2; i >= lo; --i) { acc = b2w_op<T, OP>(acc, p[i]); p[i] = acc; }
+        } else {                                            // prefix scan within the segment
+            T* p = G + r * Lp;
+            T acc = p[lo];
+            for (int i = lo + 1; i < hi; ++i) { acc = b2w_op<T, OP>(acc, p[i]); p[i] = acc; }
+        }
+    }
+    __syncthreads();
+    for (i64 idx = tid; idx < (i64)RT * nout; idx += NT) {
+        const int r = (int)(idx / nout), k = (int)(idx % nout);
+        if (row0 + r >= rows) continue;
+        T res = H[r * Lp + k];
+        if (k % w != 0) res = b2w_op<T, OP>(res, G[r * Lp + k + (int)w - 1]);   // (k % w == 0: the window IS a segment)
+        dst[(row0 + r) * Cout + t0 + k] = mean ? (T)(res / (T)w) : res;
+    }
+}
+
+template <typename T, int OP>
+static int b2_window_launch(const void* src, void* dst, i64 B, i64 R, i64 C, i64 w, int along_cols, int mean, cudaStream_t st) {
+    if (!along_cols) {
+        const i64 Rout = R - w + 1, nseg = cdiv(Rout, w);
+        const i64 col_tiles = cdiv(C, 32), seg_tiles = cdiv(nseg, 8);
+        const i64 grid = col_tiles * seg_tiles * B;
+        if (grid > 0x7fffffffLL) return fail(B2_ERR_UNSUPPORTED, "window_reduce: too many tiles");
+        b2_window_rows_kernel<T, OP><<<(unsigned)grid, dim3(32, 8), 0, st>>>((const T*)src, (T*)dst, B, R, C, w, mean, col_tiles, seg_tiles);
+    } else {
+        const i64 rows = B * R, Cout = C - w + 1;
+        // outputs per tile: whole segments, about 256 columns; rows per tile as many as shared memory allows
+        const i64 tile_out = w * (cdiv(256, w) > 0 ? cdiv(256, w) : 1);
+        const i64 L = tile_out + w - 1, Lp = L | 1;
+        const size_t per_row = 2 * (size_t)Lp * sizeof(T);
+        const i64 col_tiles = cdiv(Cout, tile_out);
+        int rt = 32;
+        while (rt > 1 && per_row * rt > 200 * 1024) rt /= 2;
+        if (per_row * rt > 200 * 1024)
+            return fail(B2_ERR_UNSUPPORTED, "window_reduce: a window of %lld elements along the contiguous axis does not fit shared memory", (long long)w);
+        const size_t smem = per_row * rt;
+        const i64 grid = col_tiles * cdiv(rows, rt);
+        if (grid > 0x7fffffffLL) return fail(B2_ERR_UNSUPPORTED, "window_reduce: too many tiles");
+#define B2W_COLS(RT_)                                                                                                         \
+        {                                                                                                                      \
+            CUDA_TRY(cudaFuncSetAttribute(b2_window_cols_kernel<T, OP, RT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            b2_window_cols_kernel<T, OP, RT_><<<(unsigned)grid, 256, smem, st>>>((const T*)src, (T*)dst, rows, C, w, tile_out, mean, col_tiles); \
+        }
+        switch (rt) {
+            case 32: B2W_COLS(32) break;
+            case 16: B2W_COLS(16) break;
+            case 8: B2W_COLS(8) break;
+            case 4: B2W_COLS(4) break;
+            case 2: B2W_COLS(2) break;
+            default: B2W_COLS(1) break;
+        }
+#undef B2W_COLS
+    }
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return B2_OK;
+}
+
+template <typename T>
+static int b2_window_dispatch_op(int redop, const void* src, void* dst, i64 B, i64 R, i64 C, i64 w, int along_cols, int mean, cudaStream_t st) {
+    switch (redop) {
+        case B2_RED_SUM: return b2_window_launch<T, B2R_SUM>(src, dst, B, R, C, w, along_cols, mean, st);
+        case B2_RED_PROD: return b2_window_launch<T, B2R_PROD>(src, dst, B, R, C, w, along_cols, mean, st);
+        case B2_RED_MIN: return b2_window_launch<T, B2R_MIN>(src, dst, B, R, C, w, along_cols, mean, st);
+        case B2_RED_MAX: return b2_window_launch<T, B2R_MAX>(src, dst, B, R, C, w, along_cols, mean, st);
+        default: return fail(B2_ERR_UNSUPPORTED, "window_reduce: redop %d (sum, prod, min, max)", redop);
+    }
+}
+
+extern "C" int b2_window_reduce(int redop, int dtype, const void* src, void* dst, int64_t B, int64_t R, int64_t C,
+                                int64_t window, int along_cols, int mean, void* stream) {
+    if (!src || !dst || B <= 0 || R <= 0 || C <= 0 || window <= 0) return fail(B2_ERR_INVALID, "bad argument");
+    if ((along_cols ? C : R) < window) return fail(B2_ERR_INVALID, "window_reduce: window longer than the axis");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case B2_F32: return b2_window_dispatch_op<float>(redop, src, dst, B, R, C, window, along_cols, mean, st);
+        case B2_F64: return b2_window_dispatch_op<double>(redop, src, dst, B, R, C, window, along_cols, mean, st);
+        case B2_I32: return b2_window_dispatch_op<int>(redop, src, dst, B, R, C, window, along_cols, mean, st);
+        case B2_I64: return b2_window_dispatch_op<long long>(redop, src, dst, B, R, C, window, along_cols, mean, st);
+        case B2_U8: case B2_BOOL: return b2_window_dispatch_op<unsigned char>(redop, src, dst, B, R, C, window, along_cols, mean, st);
+        default: return fail(B2_ERR_UNSUPPORTED, "window_reduce: dtype %d (f32, f64, i32, i64, u8/bool)", dtype);
+    }
+}
+
 // ------------------------------------------------------------------ take (AOT)
 // Integer-array gather of the arg-reduction combine step (_arg_combine, reductions/_common.py:687-697):
 //   inner == 0 : out[j] = src[idx[j]]                              (vals.ravel()[local_args])
