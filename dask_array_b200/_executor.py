@@ -645,6 +645,50 @@ class Executor:
         st.keepalive.extend([launch, remote])
         return st
 
+    # ------------------------------------------------------------------ sliding-window reductions
+    def _run_WindowHalo(self, expr):
+        """Blocks + the ``window - 1`` elements that follow them = the rechunk executor on ``WindowHalo.pieces``."""
+        return self._run_TasksRechunk(expr)
+
+    def _run_WindowReduce(self, expr):
+        """``b2_window_reduce`` per block (``reductions/_sliding_window.py:96-160``)."""
+        x = expr.operand("array")
+        src = self.results[x._name]
+        w, ax, kd = expr.operand("window"), expr.operand("axis"), expr.operand("keepdims")
+        redop, mean = REDOPS[expr.operand("redop")], int(bool(expr.operand("mean")))
+        st = BlockStore(expr)
+        for bid in x.block_ids():
+            if not self.mine(x, bid):
+                continue
+            blk = src.blocks[bid]
+            if not blk.is_contiguous:
+                raise RuntimeError("window reduction needs contiguous halo blocks")
+            shape = list(blk.shape)
+            n = shape[ax] - (w - 1)
+            oshape = shape[:ax] + [max(n, 0)] + shape[ax + 1:]
+            out = DeviceChunk.empty(oshape, expr.dtype, self.device)
+            obid = tuple(bid)
+            if kd:
+                wa = expr.operand("window_axis")
+                obid = obid[:wa] + (0,) + obid[wa:]
+                view = out.reshape(tuple(oshape[:wa]) + (1,) + tuple(oshape[wa:]))
+            else:
+                view = out
+            st.blocks[obid] = view
+            if out.size == 0:
+                continue
+            B = math.prod(shape[:ax])
+            Cc = math.prod(shape[ax + 1:])
+            if Cc == 1:
+                args = (1, B, shape[ax], w, 1)            # sliding axis is the contiguous one: (rows, C)
+            else:
+                args = (B, shape[ax], Cc, w, 0)
+            code = _lib.dtype_code(blk.dtype)
+            self._do(lambda blk=blk, out=out, args=args, code=code: _lib.check(_lib.lib.b2_window_reduce(
+                redop, code, blk.ptr, out.ptr, args[0], args[1], args[2], args[3], args[4], mean, rt.current_stream_ptr())))
+            st.keepalive.append(blk)
+        return st
+
     # ------------------------------------------------------------------ blocked matmul / tensordot
     def _run_BlockGEMM(self, expr):
         """One tcgen05 launch per output block; the k blocks (and, for fp32 operands, the six

@@ -368,35 +368,10 @@ def map_blocks(func, *args, dtype=None, chunks=None, token=None, **kwargs):
 
 
 def sliding_window_view(x, window_shape, axis=None, automatic_rechunk=True):
-    """``sliding_window_view`` (``_overlap.py:1365-1433``): overlap by ``window - 1`` on the positive side,
-    then a zero-copy window view per block (NEP-18 ``np.lib.stride_tricks.sliding_window_view`` on the
-    chunk type).  Reductions over the window axes (rolling sum / mean / max ...) read the overlapping
-    windows in place.  ``automatic_rechunk`` only changes how the reference re-balances chunk sizes; here
-    chunks are merged just enough to hold a window (``ensure_minimum_chunksize``)."""
-    from ._collection import asarray
+    """``sliding_window_view`` (``_overlap.py:1365-1433``): see ``_window.SlidingWindowView``."""
+    from ._window import sliding_window_view as _swv
 
-    x = asarray(x)
-    window_shape = tuple(window_shape) if np.iterable(window_shape) else (window_shape,)
-    if any(w <= 0 for w in window_shape):
-        raise ValueError("`window_shape` must contain values > 0")
-    if axis is None:
-        axis = tuple(range(x.ndim))
-        if len(window_shape) != len(axis):
-            raise ValueError(f"Since axis is `None`, must provide window_shape for all dimensions of `x`; got "
-                             f"{len(window_shape)} window_shape elements and `x.ndim` is {x.ndim}.")
-    else:
-        axis = tuple(a % x.ndim for a in ((axis,) if isinstance(axis, Integral) else axis))
-        if len(window_shape) != len(axis):
-            raise ValueError(f"Must provide matching length window_shape and axis; got {len(window_shape)} "
-                             f"window_shape elements and {len(axis)} axes elements.")
-    depths = [0] * x.ndim
-    for ax, w in zip(axis, window_shape):
-        depths[ax] += w - 1
-    safe = tuple(ensure_minimum_chunksize(d + 1, c) if d else tuple(c) for d, c in zip(depths, x.chunks))
-    x = x.rechunk(safe)
-    newchunks = tuple(c[:-1] + (c[-1] - d,) for d, c in zip(depths, x.chunks)) + tuple((w,) for w in window_shape)
-    over = overlap(x, depth={i: (0, d) for i, d in enumerate(depths)}, boundary="none")
-    return map_blocks(np.lib.stride_tricks.sliding_window_view, over, window_shape, axis, dtype=x.dtype, chunks=newchunks)
+    return _swv(x, window_shape, axis=axis, automatic_rechunk=automatic_rechunk)
 
 
 def map_overlap(func, *args, depth=None, boundary=None, trim=True, allow_rechunk=True, dtype=None, **kwargs):

@@ -96,6 +96,16 @@ class Reduction(ArrayExpr):
     def _tree_label(self):
         return f"{self.operand('kind').capitalize()}(axis={self.operand('axis')})"
 
+    def _simplify_down(self):
+        """A reduction over the window axis of a sliding-window view runs on the input's own chunks
+        (``SlidingWindowReduction``; the reference's parent rewrite, ``_overlap.py:500-566``)."""
+        from ._window import SlidingWindowView, native_window_reduction
+
+        x = self.operand("array")
+        if isinstance(x, SlidingWindowView):
+            return native_window_reduction(x, self.operand("kind"), self.operand("axis"), self.operand("keepdims"), self.dtype)
+        return None
+
     def _lower(self):
         """``Reduction._lower`` (:154-226) / ``arg_reduction`` (``_arg_reduction.py:89-150``)."""
         x, kind, axis = self.operand("array"), self.operand("kind"), self.operand("axis")

@@ -1,0 +1,100 @@
+"""Sliding-window reductions (reductions/_sliding_window.py:405-560, _overlap.py:500-566):
+``sliding_window_view(x, w, axis).<reducer>(axis=-1)`` runs as WindowHalo + b2_window_reduce on the input's own
+chunks.  Against NumPy's sliding_window_view reductions: integers / bool / min / max bit-exact, float sums
+within rtol 1e-5 / 1e-12 of |x| summed over the window.  Cases mirror the reference's
+tests/test_sliding_window_reduction.py shapes: chunks smaller than the window, windows spanning several
+blocks, trailing blocks that emit nothing, N-d arrays, both axes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+swv = np.lib.stride_tricks.sliding_window_view
+
+
+@pytest.fixture(scope="module")
+def da():
+    import dask_array_b200 as da
+    return da
+
+
+def _close(got, want, xabs, w, axis, dtype):
+    if np.dtype(dtype).kind != "f":
+        assert np.array_equal(got, want)
+        return
+    rtol = 1e-5 if np.dtype(dtype) == np.float32 else 1e-12
+    bound = swv(xabs, w, axis=axis).sum(axis=-1) * rtol + 1e-30
+    assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= bound)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "int32", "int64"])
+@pytest.mark.parametrize("shape,chunks,axis,w", [
+    ((200, 96), (30, 40), 0, 7), ((200, 96), (30, 40), 1, 7), ((200, 96), (3, 96), 0, 50),       # chunks << window
+    ((64, 300), (64, 17), 1, 120), ((33, 5, 40), (8, 5, 13), 0, 4), ((33, 5, 40), (8, 5, 13), 2, 21),
+    ((1000,), (128,), 0, 300), ((1000,), (1000,), 0, 1), ((50, 70), (50, 70), 1, 70)])
+def test_window_sum_min_max(da, dtype, shape, chunks, axis, w):
+    rng = np.random.default_rng(hash((shape, axis, w)) % 2**32)
+    xh = (rng.random(shape) * 200 - 100).astype(dtype)
+    x = da.from_array(xh, chunks=chunks)
+    v = da.sliding_window_view(x, w, axis=axis)
+    xabs = np.abs(xh.astype(np.float64))
+    r = v.sum(axis=-1)
+    assert type(r.expr.optimize()).__name__ == "WindowReduce"
+    want = swv(xh, w, axis=axis).sum(axis=-1)
+    got = r.compute()
+    assert got.dtype == want.dtype and got.shape == want.shape
+    _close(got, want, xabs, w, axis, dtype)
+    assert np.array_equal(v.max(axis=-1).compute(), swv(xh, w, axis=axis).max(axis=-1))
+    assert np.array_equal(v.min(axis=-1, keepdims=True).compute(), swv(xh, w, axis=axis).min(axis=-1, keepdims=True))
+    if np.dtype(dtype).kind == "f":
+        gm = v.mean(axis=-1).compute()
+        wm = swv(xh, w, axis=axis).mean(axis=-1)
+        assert gm.dtype == wm.dtype
+        bound = swv(xabs, w, axis=axis).mean(axis=-1) * (1e-5 if dtype == "float32" else 1e-12) + 1e-30
+        assert np.all(np.abs(gm.astype(np.float64) - wm.astype(np.float64)) <= bound)
+
+
+def test_window_bool_prod_nan_and_fallbacks(da):
+    rng = np.random.default_rng(3)
+    bh = rng.random((90, 40)) < 0.1
+    b = da.from_array(bh, chunks=(16, 40))
+    v = da.sliding_window_view(b, 9, axis=0)
+    assert np.array_equal(v.any(axis=-1).compute(), swv(bh, 9, axis=0).any(axis=-1))
+    assert np.array_equal(v.all(axis=-1).compute(), swv(bh, 9, axis=0).all(axis=-1))
+    assert np.array_equal(v.sum(axis=-1).compute(), swv(bh, 9, axis=0).sum(axis=-1))           # bool -> int64 counts
+    ph = 1.0 + rng.random((40, 64)) * 0.01
+    p = da.sliding_window_view(da.from_array(ph, chunks=(40, 10)), 25, axis=1)
+    np.testing.assert_allclose(p.prod(axis=-1).compute(), swv(ph, 25, axis=1).prod(axis=-1), rtol=1e-12)
+    nh = rng.random((60, 30))
+    nh[rng.random(nh.shape) < 0.2] = np.nan
+    n = da.sliding_window_view(da.from_array(nh, chunks=(7, 30)), 11, axis=0)
+    np.testing.assert_allclose(da.nansum(n, axis=-1).compute(), np.nansum(swv(nh, 11, axis=0), axis=-1), rtol=1e-12)
+    # max / min propagate NaN like np.maximum / np.minimum
+    assert np.array_equal(n.max(axis=-1).compute(), swv(nh, 11, axis=0).max(axis=-1), equal_nan=True)
+    # not a window-axis reduction, or a reducer without a native kernel: the generic plan (window views) runs
+    g = n.sum(axis=0)
+    assert type(g.expr.optimize()).__name__ != "WindowReduce"
+    np.testing.assert_allclose(da.nansum(n, axis=0).compute(), np.nansum(swv(nh, 11, axis=0), axis=0), rtol=1e-12)
+    np.testing.assert_allclose(n.std(axis=-1).compute()[~np.isnan(swv(nh, 11, axis=0).std(axis=-1))],
+                               swv(nh, 11, axis=0).std(axis=-1)[~np.isnan(swv(nh, 11, axis=0).std(axis=-1))], rtol=1e-10)
+    # the view on its own, and two window axes
+    xh = rng.random((20, 18))
+    x = da.from_array(xh, chunks=(6, 7))
+    assert np.array_equal(da.sliding_window_view(x, 4, axis=1).compute(), swv(xh, 4, axis=1))
+    assert np.array_equal(da.sliding_window_view(x, (3, 2), axis=(0, 1)).max(axis=(-1, -2)).compute(),
+                          swv(xh, (3, 2), axis=(0, 1)).max(axis=(-1, -2)))
+
+
+def test_window_kernel_through_the_c_abi(da):
+    """b2_window_reduce directly (ctypes), both orientations, a window that spans many segments."""
+    from dask_array_b200 import DeviceChunk, _lib
+    from dask_array_b200._device import current_stream_ptr
+    rng = np.random.default_rng(5)
+    for shape, along, w in (((2, 300, 70), 0, 37), ((1, 50, 1000), 1, 256), ((1, 9, 4100), 1, 1500)):
+        xh = rng.integers(-50, 50, shape).astype(np.int64)
+        src = DeviceChunk.from_numpy(xh)
+        B, R, C = shape
+        oshape = (B, R - w + 1, C) if not along else (B, R, C - w + 1)
+        out = DeviceChunk.empty(oshape, np.int64)
+        _lib.check(_lib.lib.b2_window_reduce(_lib.RED_SUM, _lib.dtype_code("int64"), src.ptr, out.ptr, B, R, C, w, along, 0,
+                                             current_stream_ptr()))
+        assert np.array_equal(out.to_numpy(), swv(xh, w, axis=2 if along else 1).sum(axis=-1))
