@@ -17,7 +17,7 @@ Headline workload (``configs[1]``, "c2"): fp32 ``x`` in 4096^2 chunks; one step 
   blocks; rank 0 also checks against the CPU oracle (the restatement of the reference).
 * ``configs``: the other BASELINE configs, measured in the same run with the same clock sampler:
   c3 (fp64 arg/min/max), c4 (rechunk + ``x.T + x``; NVLink all-to-all at N > 1), c5 (blocked
-  matmul, tcgen05) and the cumulative scans.
+  matmul, tcgen05), the cumulative scans and the sliding-window reductions.
 
     python bench.py --gpus N --steps K --warmup W            # this backend
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
@@ -845,6 +845,72 @@ def run_cum(ctx: Ctx):
             "clocks": ctx.sampler.summary("cum"), "gpu_launches": sum(v_["gpu_launches"] for v_ in lines.values())}
 
 
+def run_win(ctx: Ctx):
+    """sliding-window (rolling) reductions over fp32 (32768,32768), chunks 4096^2 --
+    ``sliding_window_view(x, w, axis).sum(axis=-1)`` for a short window on both axes and a window of 1024.
+    Algorithmic bytes: read N + write N (the output is N minus a rim)."""
+    import dask_array_b200 as da
+    from oracle import reference as ref
+
+    args, W = ctx.args, ctx.world
+    if W > 1:
+        return {"skipped": "single-GPU line"}
+    n, cb = 32768, 4096
+    g = n // cb
+    seeds = np.random.SeedSequence(9).spawn(g * g)
+    host = {}
+
+    def gen(bid):
+        host[bid] = np.random.Generator(np.random.PCG64(seeds[bid[0] * g + bid[1]])).random((cb, cb), dtype=np.float32)
+
+    with ThreadPoolExecutor(max_workers=max(1, ctx.threads)) as ex:
+        list(ex.map(gen, [(i, j) for i in range(g) for j in range(g)]))
+    x = da.from_host_blocks(lambda bid: host[bid], (n, n), (cb, cb), np.float32, token="win-f4").persist()
+    swv = np.lib.stride_tricks.sliding_window_view
+    lines = {}
+    for axis, w in ((0, 64), (1, 64), (0, 1024)):
+        step = da.compile(da.sliding_window_view(x, w, axis=axis).sum(axis=-1))
+        ms, launches = ctx.timed(step, args.steps, args.warmup, "win")
+        ctx.torch.cuda.synchronize()
+        # parity sample: one line through all blocks along the axis against NumPy's own window view in fp64
+        j = 5
+        if axis == 0:
+            got = np.concatenate([step.stores[0].blocks[(i, j)][:, 33].to_numpy() for i in range(g)])
+            line = np.concatenate([host[(i, j)][:, 33] for i in range(g)]).astype(np.float64)
+        else:
+            got = np.concatenate([step.stores[0].blocks[(j, i)][33, :].to_numpy() for i in range(g)])
+            line = np.concatenate([host[(j, i)][33, :] for i in range(g)]).astype(np.float64)
+        want = swv(line, w).sum(axis=-1)
+        err = float(np.max(np.abs(got - want) / want))
+        ctx.all_ok(got.shape == want.shape and err <= 1e-5, f"win: rolling sum axis={axis} w={w} vs fp64 (max rel err {err:.2e})")
+        nbytes = n * n * 4 + (n - w + 1) * n * 4
+        lines[f"sum_axis{axis}_w{w}"] = {"ms_per_step": ms, "GBps": nbytes / (ms * 1e-3) / 1e9, "bytes": nbytes,
+                                         "gpu_launches": launches, "max_rel_err_vs_fp64": err}
+        del step
+    worst = min(lines, key=lambda k: lines[k]["GBps"])
+    total_ms = sum(v["ms_per_step"] for v in lines.values())
+    total_bytes = sum(v["bytes"] for v in lines.values())
+    out = {"workload": "win: sliding_window_view(x, w, axis).sum(axis=-1), fp32 (32768,32768) chunks 4096^2: (axis 0, w 64), "
+                       "(axis 1, w 64), (axis 0, w 1024); 2N bytes each",
+           "value": total_bytes / (total_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": total_ms, "n_gpus": 1, "per_op": lines,
+           "roofline": ctx.roofline(lines[worst]["GBps"], f"WindowHalo gather + b2_window_reduce ({worst})", f"win_{worst}",
+                                    lines[worst]["bytes"],
+                                    note="two launches per step: the halo gather (2N) and the window kernel (2N); algorithmic 2N"),
+           "parity": {"checked": True, "vs": "NumPy sliding_window_view(...).sum(-1) in fp64 on one line through all blocks (rtol 1e-5)"},
+           "clocks": ctx.sampler.summary("win"), "gpu_launches": sum(v["gpu_launches"] for v in lines.values())}
+    if not args.no_cpu_baseline:
+        workers = os.cpu_count() or 1
+        xb = ref.Blocked({(i, 0): host[(i, 0)] for i in range(2)}, ((cb, cb), (cb,)))
+        t0 = time.perf_counter()
+        ref.da_sliding_window_reduce(xb, 64, 0, "sum", workers=workers)
+        dt_ = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 2 * (2 * cb * cb * 4) / dt_ / 1e9, "unit": "GB/s", "cores": workers, "kind": "port",
+                               "sample": f"2 of 64 blocks, rolling sum w=64 along axis 0 through NumPy's window view ({dt_:.2f} s)",
+                               "cpu": cpu_model(), "numpy": np.__version__}
+    del x, host
+    return out
+
+
 def run_c1(ctx: Ctx):
     """README example: latency only (80 kB blocks are not a roofline config)."""
     import dask_array_b200 as da
@@ -884,7 +950,7 @@ def run_c1(ctx: Ctx):
             "per_expr": out, "parity": {"checked": True, "bit_exact": True}}
 
 
-CONFIGS = {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c5": run_c5, "cum": run_cum}
+CONFIGS = {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c5": run_c5, "cum": run_cum, "win": run_win}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -896,9 +962,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="all", choices=["all", "c1", "c2", "c3", "c4", "c5", "cum"],
+    ap.add_argument("--config", default="all", choices=["all", "c1", "c2", "c3", "c4", "c5", "cum", "win"],
                     help="all = headline c2 line carrying the other configs (default); cN = that config alone")
-    ap.add_argument("--configs", default="c1,c3,c4,c5,cum", help="secondary configs carried by the default line")
+    ap.add_argument("--configs", default="c1,c3,c4,c5,cum,win", help="secondary configs carried by the default line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -930,7 +996,7 @@ def main():
         if args.config == "all":
             extra = {}
             for name in [c for c in args.configs.split(",") if c]:
-                if W > 1 and name in ("c1", "cum"):
+                if W > 1 and name in ("c1", "cum", "win"):
                     continue
                 try:
                     extra[name] = CONFIGS[name](ctx)

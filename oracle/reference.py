@@ -911,3 +911,38 @@ def da_argtopk(x, k, axis=-1):
         out[cid] = order[tuple(slice(0, abs(k)) if i == axis else slice(None) for i in range(a.ndim))].astype(np.intp)
     keep = min(abs(k), x.shape[axis])
     return Blocked(out, tuple((keep,) if d == axis else c for d, c in enumerate(x.chunks)))
+
+
+# =============================================================================== sliding-window reductions
+def da_sliding_window_reduce(x, window, axis, reducer="sum", workers=0):
+    """``reduction(sliding_window_view(x, window, axis), axis=-1)`` the way the reference's overlap plan
+    evaluates it (``_overlap.py:1365-1433`` + the reduction chunk functions): every block is extended by the
+    ``window - 1`` elements that follow it along ``axis`` and reduced over NumPy's strided window view.
+    (The native-chunk plan ``SlidingWindowReduction``, ``reductions/_sliding_window.py:405-560``, produces the
+    same values from suffix / total / prefix pieces.)  Returns a Blocked with the trimmed chunks (:431-446)."""
+    full = x.to_array()
+    n = full.shape[axis]
+    remaining = n - window + 1
+    emit, starts, pos = [], [], 0
+    for c in x.chunks[axis]:
+        if remaining <= 0:
+            break
+        take = min(c, remaining)
+        emit.append(take)
+        starts.append(pos)
+        pos += c
+        remaining -= take
+    fn = getattr(np, reducer)
+
+    def one(i):
+        sl = [slice(None)] * full.ndim
+        sl[axis] = slice(starts[i], starts[i] + emit[i] + window - 1)
+        blk = full[tuple(sl)]
+        return fn(np.lib.stride_tricks.sliding_window_view(blk, window, axis=axis), axis=-1)
+
+    parts = [p for _, p in sorted(_pmap(lambda i: (i, one(i)), list(range(len(emit))), workers))]
+    out = np.concatenate(parts, axis=axis)
+    chunks = list(x.chunks)
+    chunks[axis] = tuple(emit)
+    return Blocked.from_array(out, tuple(chunks))
+
