@@ -18,9 +18,34 @@ from ._device import DeviceChunk, alloc_bytes
 from ._expr import ArrayExpr
 from ._rechunk import TasksRechunk
 
+_RUN = 4096        # bytes per row a long contiguous run is folded into (== B2_GATHER_COL_BYTES)
+
+
+def _fold_runs(descs):
+    """A rectangle that is ONE contiguous run on both sides (whole blocks, halo bodies: rows == 1 or both
+    pitches == the row length) would be tiled as a single row of 4 KiB column tiles -- a 4 KiB CTA each
+    (measured on B200: 1.7 TB/s).  Folded into rows of 4 KiB the planner makes 64 KiB tiles of it."""
+    out = []
+    for s, d, rows, rb, sp, dp in descs:
+        total = rows * rb
+        if (rows == 1 or (sp == rb and dp == rb)) and total >= 32 * _RUN and s % 16 == 0 and d % 16 == 0:
+            body = total // _RUN
+            out.append((s, d, body, _RUN, _RUN, _RUN))
+            tail = total - body * _RUN
+            if tail:
+                out.append((s + body * _RUN, d + body * _RUN, 1, tail, tail, tail))
+        else:
+            out.append((s, d, rows, rb, sp, dp))
+    return out
+
+
 def _copy_descs(src: DeviceChunk, dst: DeviceChunk, item: int):
     """2-D copy rectangles moving ``src`` into ``dst`` (same shape, arbitrary strides with a
     unit-stride innermost run)."""
+    return _fold_runs(_copy_descs_raw(src, dst, item))
+
+
+def _copy_descs_raw(src: DeviceChunk, dst: DeviceChunk, item: int):
     shape = [n for n in src.shape]
     if math.prod(shape) == 0:
         return []

@@ -657,6 +657,7 @@ class Executor:
         w, ax, kd = expr.operand("window"), expr.operand("axis"), expr.operand("keepdims")
         redop, mean = REDOPS[expr.operand("redop")], int(bool(expr.operand("mean")))
         st = BlockStore(expr)
+        jobs, along = [], None
         for bid in x.block_ids():
             if not self.mine(x, bid):
                 continue
@@ -679,14 +680,26 @@ class Executor:
                 continue
             B = math.prod(shape[:ax])
             Cc = math.prod(shape[ax + 1:])
-            if Cc == 1:
-                args = (1, B, shape[ax], w, 1)            # sliding axis is the contiguous one: (rows, C)
+            job = _lib.WindowJob()
+            job.src, job.dst = blk.ptr, out.ptr
+            if Cc == 1:                                   # the sliding axis is the contiguous one: (rows, C)
+                job.B, job.R, job.C, along_b = 1, B, shape[ax], 1
             else:
-                args = (B, shape[ax], Cc, w, 0)
-            code = _lib.dtype_code(blk.dtype)
-            self._do(lambda blk=blk, out=out, args=args, code=code: _lib.check(_lib.lib.b2_window_reduce(
-                redop, code, blk.ptr, out.ptr, args[0], args[1], args[2], args[3], args[4], mean, rt.current_stream_ptr())))
+                job.B, job.R, job.C, along_b = B, shape[ax], Cc, 0
+            if along is not None and along != along_b:
+                raise NotImplementedError("window reduction over blocks of mixed orientation")
+            along = along_b
+            jobs.append(job)
             st.keepalive.append(blk)
+        if jobs:
+            import ctypes as C
+
+            arr = (_lib.WindowJob * len(jobs))(*jobs)
+            d_jobs = alloc_bytes(C.sizeof(arr), self.device)
+            code = _lib.dtype_code(x.dtype)
+            self._do(lambda: _lib.check(_lib.lib.b2_window_reduce_batched(
+                redop, code, arr, len(jobs), d_jobs.data_ptr(), w, along, mean, rt.current_stream_ptr())))
+            st.keepalive.extend([arr, d_jobs])
         return st
 
     # ------------------------------------------------------------------ blocked matmul / tensordot

@@ -93,6 +93,11 @@ class GemmProblem(C.Structure):
     ]
 
 
+class WindowJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("B", C.c_int64), ("R", C.c_int64), ("C", C.c_int64),
+                ("tile_begin", C.c_int64), ("col_tiles", C.c_int64), ("row_tiles", C.c_int64)]
+
+
 class Copy(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int64), ("row_bytes", C.c_int64),
@@ -107,7 +112,7 @@ SYMBOLS = [
     "b2_jit_compile", "b2_free", "b2_device_header", "b2_kernel_load", "b2_kernel_free",
     "b2_fused_plan", "b2_fused_launch", "b2_combine", "b2_gather_plan", "b2_gather_launch",
     "b2_fill", "b2_gemm_tn", "b2_memcpy2d", "b2_gemm_tn_pairs", "b2_split3_bf16", "b2_combine_groups", "b2_gemm_tn_batched", "b2_gather_launch_bulk",
-    "b2_ipc_export", "b2_ipc_open", "b2_peer_barrier", "b2_topk_rows", "b2_peer_barrier_dev", "b2_peer_allgather", "b2_take", "b2_gemm_tn_simt", "b2_window_reduce",
+    "b2_ipc_export", "b2_ipc_open", "b2_peer_barrier", "b2_topk_rows", "b2_peer_barrier_dev", "b2_peer_allgather", "b2_take", "b2_gemm_tn_simt", "b2_window_reduce_batched",
 ]
 
 
@@ -152,7 +157,7 @@ def _load():
     lib.b2_peer_barrier.argtypes = [vp, i32, i32, C.c_uint64, vp]
     lib.b2_peer_barrier_dev.argtypes = [vp, vp, i32, i32, vp]
     lib.b2_gemm_tn_simt.argtypes = [i32, vp, i64, vp, i64, vp, i64, i64, i64, i64, i32, vp]
-    lib.b2_window_reduce.argtypes = [i32, i32, vp, vp, i64, i64, i64, i64, i32, i32, vp]
+    lib.b2_window_reduce_batched.argtypes = [i32, i32, C.POINTER(WindowJob), i32, vp, i64, i32, i32, vp]
     lib.b2_take.argtypes = [i32, vp, vp, vp, i64, i64, i64, vp]
     lib.b2_peer_allgather.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, vp]
     lib.b2_topk_rows.argtypes = [i32, vp, i64, i64, i64, i32, i32, i32, vp, vp, i64, vp, i64, vp]

@@ -914,65 +914,132 @@ template <typename T, int OP> __device__ __forceinline__ T b2w_op(T a, T b) {
     else return b2_np_max(a, b);
 }
 
-// window along ROWS of a (B, R, C) block: a thread owns one column of one segment of w output rows
-template <typename T, int OP>
-__global__ void __launch_bounds__(256) b2_window_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, i64 B, i64 R,
-                                                             i64 C, i64 w, int mean, i64 col_tiles, i64 seg_tiles) {
+// window along ROWS of a (B, R, C) block: a thread owns V adjacent columns of one segment of w output rows.
+// U row loads are issued before they are consumed (a thread keeps U x 16 B in flight: the scans are serial in
+// the rows, not in the loads).
+struct B2WindowJob {          // == b2_window_job (ABI)
+    const void* src;
+    void* dst;
+    i64 B, R, C;
+    i64 tile_begin, col_tiles, row_tiles;
+};
+__device__ __forceinline__ int b2w_find_job(const B2WindowJob* __restrict__ jobs, int njobs, i64 tile) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <typename T, int OP, int V>
+__global__ void __launch_bounds__(256, 2) b2_window_rows_kernel(const B2WindowJob* __restrict__ jobs, int njobs, i64 w, int mean) {
+    constexpr int U = 4;      // (U = 8 needs 172 registers: one CTA per SM, latency-bound at 2 TB/s on B200)
+    const B2WindowJob job = jobs[b2w_find_job(jobs, njobs, (i64)blockIdx.x)];
+    const T* __restrict__ src = (const T*)job.src;
+    T* __restrict__ dst = (T*)job.dst;
+    const i64 B = job.B, R = job.R, C = job.C, col_tiles = job.col_tiles, seg_tiles = job.row_tiles;
     const i64 Rout = R - w + 1, nseg = (Rout + w - 1) / w;
-    i64 t = blockIdx.x;
+    i64 t = (i64)blockIdx.x - job.tile_begin;
     const i64 ct = t % col_tiles; t /= col_tiles;
     const i64 stile = t % seg_tiles; const i64 b = t / seg_tiles;
-    const i64 c = ct * 32 + threadIdx.x, s = stile * 8 + threadIdx.y;
+    const i64 c = (ct * 32 + threadIdx.x) * V, s = stile * 8 + threadIdx.y;
     if (c >= C || s >= nseg || b >= B) return;
     const T* x = src + (b * R) * C + c;
     T* o = dst + (b * Rout) * C + c;
     const i64 base = s * w;
     const i64 hi = (base + w < R) ? base + w : R;
-    T h = x[(hi - 1) * C];
-    if (hi - 1 < Rout) o[(hi - 1) * C] = (mean && hi - 1 == base) ? (T)(h / (T)w) : h;
-    for (i64 i = hi - 2; i >= base; --i) {                 // suffix scan of this segment, last row first
-        h = b2w_op<T, OP>(h, x[i * C]);
-        if (i < Rout) o[i * C] = (mean && i == base) ? (T)(h / (T)w) : h;
+    const T wdiv = (T)w;
+    T h[V];
+    bool first = true;
+    for (i64 i0 = hi - 1; i0 >= base; i0 -= U) {             // suffix scan of this segment, last row first
+        T v[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i0 - u >= base) b2_load_vec<T, V>(x + (i0 - u) * C, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const i64 i = i0 - u;
+            if (i < base) break;
+            T out[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                h[k] = first ? v[u][k] : b2w_op<T, OP>(h[k], v[u][k]);
+                out[k] = (mean && i == base) ? (T)(h[k] / wdiv) : h[k];
+            }
+            first = false;
+            if (i < Rout) b2_store_vec<T, V>(o + i * C, out);
+        }
     }
-    T g = T(0);
-    for (i64 j = 0; j + 1 < w; ++j) {                      // prefix scan of the next segment completes the windows
-        const i64 r = base + w + j, tt = base + j + 1;
-        if (r >= R || tt >= Rout) break;
-        const T v = x[r * C];
-        g = (j == 0) ? v : b2w_op<T, OP>(g, v);
-        T res = b2w_op<T, OP>(o[tt * C], g);
-        o[tt * C] = mean ? (T)(res / (T)w) : res;
+    i64 jmax = w - 1;                                        // rows of the next segment that complete a window
+    if (R - (base + w) < jmax) jmax = R - (base + w);
+    if (Rout - (base + 1) < jmax) jmax = Rout - (base + 1);
+    T g[V];
+    first = true;
+    for (i64 j0 = 0; j0 < jmax; j0 += U) {
+        T v[U][V], prev[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (j0 + u < jmax) {
+                b2_load_vec<T, V>(x + (base + w + j0 + u) * C, v[u]);
+                const T* op_ = o + (base + j0 + u + 1) * C;   // written by THIS thread in the first phase
+#pragma unroll
+                for (int k = 0; k < V; ++k) prev[u][k] = op_[k];
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (j0 + u >= jmax) break;
+            T out[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                g[k] = first ? v[u][k] : b2w_op<T, OP>(g[k], v[u][k]);
+                const T res = b2w_op<T, OP>(prev[u][k], g[k]);
+                out[k] = mean ? (T)(res / wdiv) : res;
+            }
+            first = false;
+            b2_store_vec<T, V>(o + (base + j0 + u + 1) * C, out);
+        }
     }
 }
 
 // window along the CONTIGUOUS axis of (rows, C): a tile of RT rows x L columns is staged in shared memory
-// (coalesced loads), scanned per (row, segment) in both directions, combined and stored coalesced
+// (coalesced loads, a warp per row), scanned per (row, segment) in both directions, combined and stored
+// coalesced.  All index arithmetic inside the tile is 32-bit.
 template <typename T, int OP, int RT>
-__global__ void __launch_bounds__(256) b2_window_cols_kernel(const T* __restrict__ src, T* __restrict__ dst, i64 rows, i64 C,
-                                                             i64 w, i64 tile_out, int mean, i64 col_tiles) {
+__global__ void __launch_bounds__(256) b2_window_cols_kernel(const B2WindowJob* __restrict__ jobs, int njobs, i64 w64,
+                                                             i64 tile_out, int mean) {
     extern __shared__ __align__(16) unsigned char b2w_smem[];
-    const i64 Cout = C - w + 1;
-    const i64 ct = blockIdx.x % col_tiles, rt = blockIdx.x / col_tiles;
+    const B2WindowJob job = jobs[b2w_find_job(jobs, njobs, (i64)blockIdx.x)];
+    const T* __restrict__ src = (const T*)job.src;
+    T* __restrict__ dst = (T*)job.dst;
+    const i64 rows = job.B * job.R, C = job.C, col_tiles = job.col_tiles;
+    const i64 Cout = C - w64 + 1;
+    const i64 tl = (i64)blockIdx.x - job.tile_begin;
+    const i64 ct = tl % col_tiles, rt = tl / col_tiles;
     const i64 t0 = ct * tile_out, row0 = rt * RT;
-    const i64 nout = (t0 + tile_out <= Cout) ? tile_out : Cout - t0;       // outputs of this tile
-    const int L = (int)(nout + w - 1);                                     // input columns it needs
-    const int Lp = L | 1;                                                  // odd pitch: conflict-free column walks
+    const int w = (int)w64;
+    const int nout = (int)((t0 + tile_out <= Cout) ? tile_out : Cout - t0);   // outputs of this tile
+    const int L = nout + w - 1;                                               // input columns it needs
+    const int Lp = L | 1;                                                     // odd pitch: conflict-free column walks
     T* H = reinterpret_cast<T*>(b2w_smem);
     T* G = H + (size_t)RT * Lp;
-    const int tid = threadIdx.x, NT = blockDim.x;
-    for (i64 idx = tid; idx < (i64)RT * L; idx += NT) {
-        const int r = (int)(idx / L), k = (int)(idx % L);
-        T v = T(0);
-        if (row0 + r < rows) v = src[(row0 + r) * C + t0 + k];
-        H[r * Lp + k] = v;
-        G[r * Lp + k] = v;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nrows = (rows - row0 < RT) ? (int)(rows - row0) : RT;
+    for (int r = warp; r < RT; r += 8) {
+        const T* p = src + (row0 + r) * C + t0;
+        for (int k = lane; k < L; k += 32) {
+            const T v = (r < nrows) ? b2_ld(p + k) : T(0);
+            H[r * Lp + k] = v;
+            G[r * Lp + k] = v;
+        }
     }
     __syncthreads();
-    const int nsg = (int)((L + w - 1) / w);
-    for (int task = tid; task < 2 * RT * nsg; task += NT) {
+    const int nsg = (L + w - 1) / w;
+    const int ntask = 2 * RT * nsg;
+    for (int task = tid; task < ntask; task += 256) {
         const int r = task % RT, q = task / RT;
         const int sg = q % nsg, dir = q / nsg;
-        const int lo = (int)(sg * w), hi = (lo + (int)w < L) ? lo + (int)w : L;
+        const int lo = sg * w, hi = (lo + w < L) ? lo + w : L;
         if (dir == 0) {                                     // suffix scan within the segment
             T* p = H + r * Lp;
             T acc = p[hi - 1];
@@ -984,41 +1051,64 @@ __global__ void __launch_bounds__(256) b2_window_cols_kernel(const T* __restrict
         }
     }
     __syncthreads();
-    for (i64 idx = tid; idx < (i64)RT * nout; idx += NT) {
-        const int r = (int)(idx / nout), k = (int)(idx % nout);
-        if (row0 + r >= rows) continue;
-        T res = H[r * Lp + k];
-        if (k % w != 0) res = b2w_op<T, OP>(res, G[r * Lp + k + (int)w - 1]);   // (k % w == 0: the window IS a segment)
-        dst[(row0 + r) * Cout + t0 + k] = mean ? (T)(res / (T)w) : res;
+    const T wdiv = (T)w;
+    for (int r = warp; r < nrows; r += 8) {
+        T* q = dst + (row0 + r) * Cout + t0;
+        int kmod = lane % w;
+        for (int k = lane; k < nout; k += 32) {
+            T res = H[r * Lp + k];
+            if (kmod != 0) res = b2w_op<T, OP>(res, G[r * Lp + k + w - 1]);   // (k % w == 0: the window IS a segment)
+            q[k] = mean ? (T)(res / wdiv) : res;
+            kmod = (kmod + 32) % w;
+        }
     }
 }
 
+static_assert(sizeof(B2WindowJob) == sizeof(b2_window_job), "B2WindowJob / b2_window_job");
+
 template <typename T, int OP>
-static int b2_window_launch(const void* src, void* dst, i64 B, i64 R, i64 C, i64 w, int along_cols, int mean, cudaStream_t st) {
+static int b2_window_launch(b2_window_job* jobs, int n, void* d_jobs, i64 w, int along_cols, int mean, cudaStream_t st) {
+    i64 tiles = 0;
     if (!along_cols) {
-        const i64 Rout = R - w + 1, nseg = cdiv(Rout, w);
-        const i64 col_tiles = cdiv(C, 32), seg_tiles = cdiv(nseg, 8);
-        const i64 grid = col_tiles * seg_tiles * B;
-        if (grid > 0x7fffffffLL) return fail(B2_ERR_UNSUPPORTED, "window_reduce: too many tiles");
-        b2_window_rows_kernel<T, OP><<<(unsigned)grid, dim3(32, 8), 0, st>>>((const T*)src, (T*)dst, B, R, C, w, mean, col_tiles, seg_tiles);
+        constexpr int VMAX = 16 / (int)sizeof(T);
+        bool vec = VMAX > 1;
+        for (int i = 0; i < n; ++i)
+            vec = vec && jobs[i].C % VMAX == 0 && ((uintptr_t)jobs[i].src % 16 == 0) && ((uintptr_t)jobs[i].dst % 16 == 0);
+        for (int i = 0; i < n; ++i) {
+            const i64 Rout = jobs[i].R - w + 1, nseg = cdiv(Rout, w);
+            jobs[i].col_tiles = cdiv(jobs[i].C, 32 * (vec ? VMAX : 1));
+            jobs[i].row_tiles = cdiv(nseg, 8);
+            jobs[i].tile_begin = tiles;
+            tiles += jobs[i].col_tiles * jobs[i].row_tiles * jobs[i].B;
+        }
+        if (tiles > 0x7fffffffLL) return fail(B2_ERR_UNSUPPORTED, "window_reduce: too many tiles");
+        CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs, (size_t)n * sizeof(b2_window_job), cudaMemcpyHostToDevice, st));
+        if (vec)
+            b2_window_rows_kernel<T, OP, VMAX><<<(unsigned)tiles, dim3(32, 8), 0, st>>>((const B2WindowJob*)d_jobs, n, w, mean);
+        else
+            b2_window_rows_kernel<T, OP, 1><<<(unsigned)tiles, dim3(32, 8), 0, st>>>((const B2WindowJob*)d_jobs, n, w, mean);
     } else {
-        const i64 rows = B * R, Cout = C - w + 1;
         // outputs per tile: whole segments, about 256 columns; rows per tile as many as shared memory allows
         const i64 tile_out = w * (cdiv(256, w) > 0 ? cdiv(256, w) : 1);
         const i64 L = tile_out + w - 1, Lp = L | 1;
         const size_t per_row = 2 * (size_t)Lp * sizeof(T);
-        const i64 col_tiles = cdiv(Cout, tile_out);
         int rt = 32;
-        while (rt > 1 && per_row * rt > 200 * 1024) rt /= 2;
+        while (rt > 1 && per_row * rt > 96 * 1024) rt /= 2;       // <= 96 KiB: two CTAs per SM
         if (per_row * rt > 200 * 1024)
             return fail(B2_ERR_UNSUPPORTED, "window_reduce: a window of %lld elements along the contiguous axis does not fit shared memory", (long long)w);
         const size_t smem = per_row * rt;
-        const i64 grid = col_tiles * cdiv(rows, rt);
-        if (grid > 0x7fffffffLL) return fail(B2_ERR_UNSUPPORTED, "window_reduce: too many tiles");
+        for (int i = 0; i < n; ++i) {
+            jobs[i].col_tiles = cdiv(jobs[i].C - w + 1, tile_out);
+            jobs[i].row_tiles = cdiv(jobs[i].B * jobs[i].R, rt);
+            jobs[i].tile_begin = tiles;
+            tiles += jobs[i].col_tiles * jobs[i].row_tiles;
+        }
+        if (tiles > 0x7fffffffLL) return fail(B2_ERR_UNSUPPORTED, "window_reduce: too many tiles");
+        CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs, (size_t)n * sizeof(b2_window_job), cudaMemcpyHostToDevice, st));
 #define B2W_COLS(RT_)                                                                                                         \
         {                                                                                                                      \
             CUDA_TRY(cudaFuncSetAttribute(b2_window_cols_kernel<T, OP, RT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-            b2_window_cols_kernel<T, OP, RT_><<<(unsigned)grid, 256, smem, st>>>((const T*)src, (T*)dst, rows, C, w, tile_out, mean, col_tiles); \
+            b2_window_cols_kernel<T, OP, RT_><<<(unsigned)tiles, 256, smem, st>>>((const B2WindowJob*)d_jobs, n, w, tile_out, mean); \
         }
         switch (rt) {
             case 32: B2W_COLS(32) break;
@@ -1036,27 +1126,31 @@ static int b2_window_launch(const void* src, void* dst, i64 B, i64 R, i64 C, i64
 }
 
 template <typename T>
-static int b2_window_dispatch_op(int redop, const void* src, void* dst, i64 B, i64 R, i64 C, i64 w, int along_cols, int mean, cudaStream_t st) {
+static int b2_window_dispatch_op(int redop, b2_window_job* jobs, int n, void* d_jobs, i64 w, int along_cols, int mean, cudaStream_t st) {
     switch (redop) {
-        case B2_RED_SUM: return b2_window_launch<T, B2R_SUM>(src, dst, B, R, C, w, along_cols, mean, st);
-        case B2_RED_PROD: return b2_window_launch<T, B2R_PROD>(src, dst, B, R, C, w, along_cols, mean, st);
-        case B2_RED_MIN: return b2_window_launch<T, B2R_MIN>(src, dst, B, R, C, w, along_cols, mean, st);
-        case B2_RED_MAX: return b2_window_launch<T, B2R_MAX>(src, dst, B, R, C, w, along_cols, mean, st);
+        case B2_RED_SUM: return b2_window_launch<T, B2R_SUM>(jobs, n, d_jobs, w, along_cols, mean, st);
+        case B2_RED_PROD: return b2_window_launch<T, B2R_PROD>(jobs, n, d_jobs, w, along_cols, mean, st);
+        case B2_RED_MIN: return b2_window_launch<T, B2R_MIN>(jobs, n, d_jobs, w, along_cols, mean, st);
+        case B2_RED_MAX: return b2_window_launch<T, B2R_MAX>(jobs, n, d_jobs, w, along_cols, mean, st);
         default: return fail(B2_ERR_UNSUPPORTED, "window_reduce: redop %d (sum, prod, min, max)", redop);
     }
 }
 
-extern "C" int b2_window_reduce(int redop, int dtype, const void* src, void* dst, int64_t B, int64_t R, int64_t C,
-                                int64_t window, int along_cols, int mean, void* stream) {
-    if (!src || !dst || B <= 0 || R <= 0 || C <= 0 || window <= 0) return fail(B2_ERR_INVALID, "bad argument");
-    if ((along_cols ? C : R) < window) return fail(B2_ERR_INVALID, "window_reduce: window longer than the axis");
+extern "C" int b2_window_reduce_batched(int redop, int dtype, b2_window_job* jobs, int njobs, void* d_jobs,
+                                        int64_t window, int along_cols, int mean, void* stream) {
+    if (!jobs || !d_jobs || njobs <= 0 || window <= 0) return fail(B2_ERR_INVALID, "bad argument");
+    for (int i = 0; i < njobs; ++i) {
+        const b2_window_job& j = jobs[i];
+        if (!j.src || !j.dst || j.B <= 0 || j.R <= 0 || j.C <= 0) return fail(B2_ERR_INVALID, "window_reduce: bad job %d", i);
+        if ((along_cols ? j.C : j.R) < window) return fail(B2_ERR_INVALID, "window_reduce: window longer than the axis (job %d)", i);
+    }
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
-        case B2_F32: return b2_window_dispatch_op<float>(redop, src, dst, B, R, C, window, along_cols, mean, st);
-        case B2_F64: return b2_window_dispatch_op<double>(redop, src, dst, B, R, C, window, along_cols, mean, st);
-        case B2_I32: return b2_window_dispatch_op<int>(redop, src, dst, B, R, C, window, along_cols, mean, st);
-        case B2_I64: return b2_window_dispatch_op<long long>(redop, src, dst, B, R, C, window, along_cols, mean, st);
-        case B2_U8: case B2_BOOL: return b2_window_dispatch_op<unsigned char>(redop, src, dst, B, R, C, window, along_cols, mean, st);
+        case B2_F32: return b2_window_dispatch_op<float>(redop, jobs, njobs, d_jobs, window, along_cols, mean, st);
+        case B2_F64: return b2_window_dispatch_op<double>(redop, jobs, njobs, d_jobs, window, along_cols, mean, st);
+        case B2_I32: return b2_window_dispatch_op<int>(redop, jobs, njobs, d_jobs, window, along_cols, mean, st);
+        case B2_I64: return b2_window_dispatch_op<long long>(redop, jobs, njobs, d_jobs, window, along_cols, mean, st);
+        case B2_U8: case B2_BOOL: return b2_window_dispatch_op<unsigned char>(redop, jobs, njobs, d_jobs, window, along_cols, mean, st);
         default: return fail(B2_ERR_UNSUPPORTED, "window_reduce: dtype %d (f32, f64, i32, i64, u8/bool)", dtype);
     }
 }

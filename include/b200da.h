@@ -290,16 +290,24 @@ int b2_memcpy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch
  * creation/_ones_zeros.py:17-137) */
 int b2_fill(void* dst, int64_t nelem, int itemsize, const void* value, void* stream);
 
-/* Sliding-window reduction of ONE block: reduction(sliding_window_view(x, window), axis=window_axis) --
- * SlidingWindowReduction / _sliding_window_banded_reduce (reductions/_sliding_window.py:96-160, 405-560) -- for an
- * associative redop (B2_RED_SUM / PROD / MIN / MAX; any / all are MAX / MIN on bool, mean = SUM with `mean` != 0:
- * the result is divided by `window` in the element type, sliding_window_finalize _reduction.py:499-502).
- * src is (B, R, C) contiguous and already carries the window - 1 trailing halo elements along the sliding axis:
- * along_cols == 0 slides along R -> dst (B, R - window + 1, C); along_cols != 0 slides along C ->
- * dst (B, R, C - window + 1).  src and dst have the same element type `dtype` (f32, f64, i32, i64, u8 / bool).
- * O(1) operations per element for any window (two-direction segment scans), 2 N bytes of DRAM traffic. */
-int b2_window_reduce(int redop, int dtype, const void* src, void* dst, int64_t B, int64_t R, int64_t C,
-                     int64_t window, int along_cols, int mean, void* stream);
+/* Sliding-window reductions: reduction(sliding_window_view(x, window), axis=window_axis) -- SlidingWindowReduction /
+ * _sliding_window_banded_reduce (reductions/_sliding_window.py:96-160, 405-560) -- for an associative redop
+ * (B2_RED_SUM / PROD / MIN / MAX; any / all are MAX / MIN on bool, mean = SUM with `mean` != 0: the result is
+ * divided by `window` in the element type, sliding_window_finalize _reduction.py:499-502), over every block of
+ * one launch.  Job i: src is (B, R, C) contiguous and already carries the window - 1 trailing halo elements
+ * along the sliding axis: along_cols == 0 slides along R -> dst (B, R - window + 1, C); along_cols != 0 slides
+ * along C -> dst (B, R, C - window + 1).  src and dst have the element type `dtype` (f32, f64, i32, i64, u8 /
+ * bool).  `jobs` is a HOST array (its tile fields are filled here); `d_jobs` is a caller-owned DEVICE buffer of
+ * njobs * sizeof(b2_window_job) bytes the table is copied to.  O(1) operations per element for any window
+ * (two-direction scans over segments of `window` elements), 2 N bytes of DRAM traffic. */
+typedef struct b2_window_job {
+    const void* src;
+    void* dst;
+    int64_t B, R, C;
+    int64_t tile_begin, col_tiles, row_tiles;   /* filled by the call */
+} b2_window_job;
+int b2_window_reduce_batched(int redop, int dtype, b2_window_job* jobs, int njobs, void* d_jobs,
+                             int64_t window, int along_cols, int mean, void* stream);
 
 /* Integer-array gather used by the arg-reduction combine step on the chunk type (_arg_combine,
  * reductions/_common.py:687-697: `vals.ravel()[local_args]` and the np.ogrid take-along-axis

@@ -85,16 +85,24 @@ def test_window_bool_prod_nan_and_fallbacks(da):
 
 
 def test_window_kernel_through_the_c_abi(da):
-    """b2_window_reduce directly (ctypes), both orientations, a window that spans many segments."""
+    """b2_window_reduce_batched directly (ctypes): both orientations, a window that spans many segments, two jobs."""
+    import ctypes as C
     from dask_array_b200 import DeviceChunk, _lib
-    from dask_array_b200._device import current_stream_ptr
+    from dask_array_b200._device import alloc_bytes, current_stream_ptr
     rng = np.random.default_rng(5)
-    for shape, along, w in (((2, 300, 70), 0, 37), ((1, 50, 1000), 1, 256), ((1, 9, 4100), 1, 1500)):
-        xh = rng.integers(-50, 50, shape).astype(np.int64)
-        src = DeviceChunk.from_numpy(xh)
-        B, R, C = shape
-        oshape = (B, R - w + 1, C) if not along else (B, R, C - w + 1)
-        out = DeviceChunk.empty(oshape, np.int64)
-        _lib.check(_lib.lib.b2_window_reduce(_lib.RED_SUM, _lib.dtype_code("int64"), src.ptr, out.ptr, B, R, C, w, along, 0,
-                                             current_stream_ptr()))
-        assert np.array_equal(out.to_numpy(), swv(xh, w, axis=2 if along else 1).sum(axis=-1))
+    for shapes, along, w in (([(2, 300, 70), (1, 41, 70)], 0, 37), ([(1, 50, 1000)], 1, 256), ([(1, 9, 4100), (1, 3, 1700)], 1, 1500)):
+        hosts = [rng.integers(-50, 50, sh).astype(np.int64) for sh in shapes]
+        srcs = [DeviceChunk.from_numpy(h) for h in hosts]
+        outs, jobs = [], []
+        for (B, R, Cc), src in zip(shapes, srcs):
+            out = DeviceChunk.empty((B, R - w + 1, Cc) if not along else (B, R, Cc - w + 1), np.int64)
+            j = _lib.WindowJob()
+            j.src, j.dst, j.B, j.R, j.C = src.ptr, out.ptr, B, R, Cc
+            outs.append(out)
+            jobs.append(j)
+        arr = (_lib.WindowJob * len(jobs))(*jobs)
+        d_jobs = alloc_bytes(C.sizeof(arr))
+        _lib.check(_lib.lib.b2_window_reduce_batched(_lib.RED_SUM, _lib.dtype_code("int64"), arr, len(jobs), d_jobs.data_ptr(),
+                                                     w, along, 0, current_stream_ptr()))
+        for h, out in zip(hosts, outs):
+            assert np.array_equal(out.to_numpy(), swv(h, w, axis=2 if along else 1).sum(axis=-1))
