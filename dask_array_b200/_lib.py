@@ -95,7 +95,7 @@ class GemmProblem(C.Structure):
 
 class WindowJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("B", C.c_int64), ("R", C.c_int64), ("C", C.c_int64),
-                ("tile_begin", C.c_int64), ("col_tiles", C.c_int64), ("row_tiles", C.c_int64)]
+                ("src_pitch", C.c_int64), ("tile_begin", C.c_int64), ("col_tiles", C.c_int64), ("row_tiles", C.c_int64)]
 
 
 class Copy(C.Structure):

@@ -921,6 +921,7 @@ struct B2WindowJob {          // == b2_window_job (ABI)
     const void* src;
     void* dst;
     i64 B, R, C;
+    i64 src_pitch;
     i64 tile_begin, col_tiles, row_tiles;
 };
 __device__ __forceinline__ int b2w_find_job(const B2WindowJob* __restrict__ jobs, int njobs, i64 tile) {
@@ -933,8 +934,9 @@ __device__ __forceinline__ int b2w_find_job(const B2WindowJob* __restrict__ jobs
 }
 
 template <typename T, int OP, int V>
-__global__ void __launch_bounds__(256, 2) b2_window_rows_kernel(const B2WindowJob* __restrict__ jobs, int njobs, i64 w, int mean) {
-    constexpr int U = 4;      // (U = 8 needs 172 registers: one CTA per SM, latency-bound at 2 TB/s on B200)
+__global__ void __launch_bounds__(256, 3) b2_window_rows_kernel(const B2WindowJob* __restrict__ jobs, int njobs, i64 w, int mean) {
+    constexpr int U = 4;      // (U = 8 needs 172 registers: one CTA per SM, latency-bound at 2 TB/s on B200;
+                              //  U = 4 at two CTAs per SM: 2.7 TB/s; three CTAs per SM keep 48 KiB per SM in flight)
     const B2WindowJob job = jobs[b2w_find_job(jobs, njobs, (i64)blockIdx.x)];
     const T* __restrict__ src = (const T*)job.src;
     T* __restrict__ dst = (T*)job.dst;
@@ -1013,6 +1015,7 @@ __global__ void __launch_bounds__(256) b2_window_cols_kernel(const B2WindowJob* 
     const T* __restrict__ src = (const T*)job.src;
     T* __restrict__ dst = (T*)job.dst;
     const i64 rows = job.B * job.R, C = job.C, col_tiles = job.col_tiles;
+    const i64 pitch = job.src_pitch ? job.src_pitch : C;       // elements between consecutive source rows
     const i64 Cout = C - w64 + 1;
     const i64 tl = (i64)blockIdx.x - job.tile_begin;
     const i64 ct = tl % col_tiles, rt = tl / col_tiles;
@@ -1026,11 +1029,14 @@ __global__ void __launch_bounds__(256) b2_window_cols_kernel(const B2WindowJob* 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nrows = (rows - row0 < RT) ? (int)(rows - row0) : RT;
     for (int r = warp; r < RT; r += 8) {
-        const T* p = src + (row0 + r) * C + t0;
-        for (int k = lane; k < L; k += 32) {
-            const T v = (r < nrows) ? b2_ld(p + k) : T(0);
-            H[r * Lp + k] = v;
-            G[r * Lp + k] = v;
+        const T* p = src + (row0 + r) * pitch + t0;
+        for (int k0 = lane; k0 < L; k0 += 128) {             // four independent loads in flight per thread
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (r < nrows && k0 + 32 * u < L) ? b2_ld(p + k0 + 32 * u) : T(0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k0 + 32 * u < L) { H[r * Lp + k0 + 32 * u] = v[u]; G[r * Lp + k0 + 32 * u] = v[u]; }
         }
     }
     __syncthreads();
@@ -1143,6 +1149,7 @@ extern "C" int b2_window_reduce_batched(int redop, int dtype, b2_window_job* job
         const b2_window_job& j = jobs[i];
         if (!j.src || !j.dst || j.B <= 0 || j.R <= 0 || j.C <= 0) return fail(B2_ERR_INVALID, "window_reduce: bad job %d", i);
         if ((along_cols ? j.C : j.R) < window) return fail(B2_ERR_INVALID, "window_reduce: window longer than the axis (job %d)", i);
+        if (j.src_pitch && (!along_cols || j.src_pitch < j.C)) return fail(B2_ERR_INVALID, "window_reduce: src_pitch is for along_cols jobs and >= C (job %d)", i);
     }
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {

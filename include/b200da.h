@@ -304,6 +304,7 @@ typedef struct b2_window_job {
     const void* src;
     void* dst;
     int64_t B, R, C;
+    int64_t src_pitch;                          /* along_cols only: elements between source rows (0 = C, dense) */
     int64_t tile_begin, col_tiles, row_tiles;   /* filled by the call */
 } b2_window_job;
 int b2_window_reduce_batched(int redop, int dtype, b2_window_job* jobs, int njobs, void* d_jobs,
