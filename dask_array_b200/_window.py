@@ -108,8 +108,8 @@ def native_window_reduction(view: SlidingWindowView, kind, axis, keepdims, dtype
     if work.name not in _KERNEL_DTYPES or (kind in ("mean",) and work.kind != "f"):
         return None
     w = int(view.operand("window_shape")[0])
-    if int(view.operand("axes")[0]) == x.ndim - 1 and 2 * ((2 * w - 1) | 1) * work.itemsize > 200 * 1024:
-        return None        # along the contiguous axis one row of the tile (2w - 1 elements, twice) must fit shared memory
+    if int(view.operand("axes")[0]) == x.ndim - 1 and 2 * ((8 * w - 1) | 1) * work.itemsize > 200 * 1024:
+        return None        # along the contiguous axis one row of the tile (8 segments, twice) must fit shared memory
     return SlidingWindowReduction(x, int(view.operand("window_shape")[0]), int(view.operand("axes")[0]), x.ndim,
                                   bool(keepdims), kind, dtype.name)
 

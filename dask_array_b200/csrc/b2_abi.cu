@@ -1028,17 +1028,29 @@ __global__ void __launch_bounds__(256) b2_window_cols_kernel(const B2WindowJob* 
     T* G = H + (size_t)RT * Lp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nrows = (rows - row0 < RT) ? (int)(rows - row0) : RT;
+    // stage the tile: every element is one asynchronous global -> shared copy (4- and 8-byte types), so a
+    // thread has its whole share of the tile in flight at once instead of a few register loads
     for (int r = warp; r < RT; r += 8) {
         const T* p = src + (row0 + r) * pitch + t0;
-        for (int k0 = lane; k0 < L; k0 += 128) {             // four independent loads in flight per thread
-            T v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (r < nrows && k0 + 32 * u < L) ? b2_ld(p + k0 + 32 * u) : T(0);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (k0 + 32 * u < L) { H[r * Lp + k0 + 32 * u] = v[u]; G[r * Lp + k0 + 32 * u] = v[u]; }
+        T* hrow = H + r * Lp;
+        if (r < nrows) {
+            if constexpr (sizeof(T) == 4 || sizeof(T) == 8) {
+                for (int k = lane; k < L; k += 32) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(hrow + k);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(p + k), "n"((int)sizeof(T)) : "memory");
+                }
+            } else {
+                for (int k = lane; k < L; k += 32) hrow[k] = b2_ld(p + k);
+            }
+        } else {
+            for (int k = lane; k < L; k += 32) hrow[k] = T(0);
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (int r = warp; r < RT; r += 8)
+        for (int k = lane; k < L; k += 32) G[r * Lp + k] = H[r * Lp + k];
     __syncthreads();
     const int nsg = (L + w - 1) / w;
     const int ntask = 2 * RT * nsg;
@@ -1094,12 +1106,15 @@ static int b2_window_launch(b2_window_job* jobs, int n, void* d_jobs, i64 w, int
         else
             b2_window_rows_kernel<T, OP, 1><<<(unsigned)tiles, dim3(32, 8), 0, st>>>((const B2WindowJob*)d_jobs, n, w, mean);
     } else {
-        // outputs per tile: whole segments, about 256 columns; rows per tile as many as shared memory allows
-        const i64 tile_out = w * (cdiv(256, w) > 0 ? cdiv(256, w) : 1);
+        // outputs per tile: SEVEN whole segments (the tile then holds 8 segments: 2 scan directions x 16 rows x 8
+        // segments = 256 scan tasks, one per thread; halo overhead 1/7) unless the window is short, then about
+        // 256 columns; rows per tile: 16, fewer when shared memory (<= 96 KiB: two CTAs per SM) demands it
+        i64 tile_out = 7 * w;
+        if (tile_out < 256) tile_out = w * cdiv(256, w);
         const i64 L = tile_out + w - 1, Lp = L | 1;
         const size_t per_row = 2 * (size_t)Lp * sizeof(T);
-        int rt = 32;
-        while (rt > 1 && per_row * rt > 96 * 1024) rt /= 2;       // <= 96 KiB: two CTAs per SM
+        int rt = 16;
+        while (rt > 1 && per_row * rt > 96 * 1024) rt /= 2;
         if (per_row * rt > 200 * 1024)
             return fail(B2_ERR_UNSUPPORTED, "window_reduce: a window of %lld elements along the contiguous axis does not fit shared memory", (long long)w);
         const size_t smem = per_row * rt;
@@ -1117,7 +1132,6 @@ static int b2_window_launch(b2_window_job* jobs, int n, void* d_jobs, i64 w, int
             b2_window_cols_kernel<T, OP, RT_><<<(unsigned)tiles, 256, smem, st>>>((const B2WindowJob*)d_jobs, n, w, tile_out, mean); \
         }
         switch (rt) {
-            case 32: B2W_COLS(32) break;
             case 16: B2W_COLS(16) break;
             case 8: B2W_COLS(8) break;
             case 4: B2W_COLS(4) break;
