@@ -312,9 +312,50 @@ class Compiled:
 
         self.executor = Executor()
         self.exprs = [a.expr.optimize() for a in arrays]
-        self.stores = [self.executor.run(e) for e in self.exprs]
+        self.stores, self.segments = [], []          # segments: tape index range each top-level expression added
+        for e in self.exprs:
+            lo = len(self.executor.tape)
+            self.stores.append(self.executor.run(e))
+            self.segments.append((lo, len(self.executor.tape)))
         self.tape = list(self.executor.tape)
         self._graph = None
+
+    def _independent_lanes(self):
+        """Tape segments of top-level expressions that may run on concurrent streams inside the captured graph:
+        no computed sub-expression in common (leaves that are already resident do not count) and at most one
+        segment with cross-rank synchronisation (those keep one global order).  Returns [] when the tape has to
+        stay on one stream."""
+        import os
+
+        from . import _executor
+
+        if os.environ.get("B2_GRAPH_LANES", "1") != "1" or len(self.exprs) < 2 or _executor._NVTX >= 2:
+            return []
+        def names(e, acc):
+            if e._name in acc:
+                return acc
+            acc.add(e._name)
+            for d in e.dependencies():
+                names(d, acc)
+            return acc
+
+        lanes = []
+        coll = set(self.executor.collectives)
+        n_coll = 0
+        for e, (lo, hi) in zip(self.exprs, self.segments):
+            if hi <= lo:
+                continue
+            for n in names(e, set()):
+                a, b = self.executor.tape_span.get(n, (0, 0))
+                if b > a and not (lo <= a and b <= hi):
+                    return []            # reads something another segment's launches produce
+            if any(lo <= c < hi for c in coll):
+                n_coll += 1
+            lanes.append((lo, hi))
+        covered = sum(hi - lo for lo, hi in lanes)
+        if n_coll > 1 or len(lanes) < 2 or covered != len(self.tape):
+            return []
+        return lanes
 
     def run(self):
         if self._graph is not None:
@@ -339,11 +380,27 @@ class Compiled:
             if k.profile:
                 raise RuntimeError("per-launch event profiling and graph capture are mutually exclusive")
         torch.cuda.synchronize()
+        lanes = self._independent_lanes()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for fn in self.tape:
-                fn()
+            if not lanes:
+                for fn in self.tape:
+                    fn()
+            else:
+                # independent expressions become parallel branches of the graph: the tail of one expression's big
+                # kernel (its last partial wave) overlaps the start of the next one's instead of idling the SMs
+                main = torch.cuda.current_stream()
+                side = [torch.cuda.Stream() for _ in lanes[1:]]
+                for s_ in side:
+                    s_.wait_stream(main)
+                for (lo, hi), s_ in zip(lanes, [main] + side):
+                    with torch.cuda.stream(s_):
+                        for fn in self.tape[lo:hi]:
+                            fn()
+                for s_ in side:
+                    main.wait_stream(s_)
         self._graph = g
+        self.lanes = len(lanes) or 1
         return self
 
     def results(self):

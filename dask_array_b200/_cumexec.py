@@ -239,6 +239,6 @@ def _sum_tables(ex, tables, acc):
         tdt = {4: torch.int32, 8: torch.int64}[acc.itemsize] if acc.kind in "iu" else \
             {4: torch.float32, 8: torch.float64}[acc.itemsize]
         view = t.buf[t.offset * acc.itemsize: (t.offset + n) * acc.itemsize].view(tdt)
-        ex._do(lambda v=view: dist.all_reduce(v))
+        ex._do(lambda v=view: dist.all_reduce(v), collective=True)
 
 

@@ -171,13 +171,13 @@ def _allgather_blocks(ex, src: BlockStore, x):
         table = torch.tensor(bases, dtype=torch.int64).to(ex.device)
         nb_me = sizes[me]
         if cap <= _SMALL_ALLGATHER:
-            ex._do(lambda: bar.allgather(table.data_ptr(), send.data_ptr(), nb_me, cap))
+            ex._do(lambda: bar.allgather(table.data_ptr(), send.data_ptr(), nb_me, cap), collective=True)
         else:
             push = rt.GatherLaunch([(send.data_ptr(), bases[(me + 1 + k) % W] + me * cap, 1, nb_me, nb_me, nb_me)
                                     for k in range(W)] if nb_me else [])
-            ex._do(bar)
+            ex._do(bar, collective=True)
             ex._do(push.run)
-            ex._do(bar)
+            ex._do(bar, collective=True)
             keep.append(push)
         keep.append(table)
     else:
@@ -186,7 +186,7 @@ def _allgather_blocks(ex, src: BlockStore, x):
             ex._do(lambda: full[: send.numel()].copy_(send))
             keep.append(send)
             send = full
-        ex._do(lambda: dist.all_gather_into_tensor(recv, send))
+        ex._do(lambda: dist.all_gather_into_tensor(recv, send), collective=True)
     out = {}
     for r in range(W):
         for bid, ent in layout[r].items():
@@ -297,7 +297,7 @@ def _fetch_blocks(ex, wanted, stores):
                 off += pad(nb)
             recvs.append((p, buf))
     if sends or recvs:
-        ex._do(lambda: _p2p_exchange(ex, sends, recvs))
+        ex._do(lambda: _p2p_exchange(ex, sends, recvs), collective=True)
     out["__keep__"] = (keep, sends, recvs)
     return out
 
@@ -375,9 +375,9 @@ def _rechunk_push(ex, expr: TasksRechunk, src: BlockStore, st: BlockStore):
         copies.extend(_copy_descs(src.blocks[obid][sl], dst[dsl], item))
     launch = rt.GatherLaunch(copies)
     bar = _peer.StreamBarrier(ex.device, me, W)
-    ex._do(bar)                 # every owner is done with the previous contents of its slab
+    ex._do(bar, collective=True)                 # every owner is done with the previous contents of its slab
     ex._do(launch.run)
-    ex._do(bar)                 # every piece has landed before anyone reads a new block
+    ex._do(bar, collective=True)                 # every piece has landed before anyone reads a new block
     st.keepalive.extend([launch, slab, bar, windows])
     return st
 
@@ -436,9 +436,9 @@ def _push_views(ex, expr, st: BlockStore, src: BlockStore, moves):
             copies.extend(_copy_descs(view(src.blocks[ibid]), dst, item))
     launch = rt.GatherLaunch(copies)
     bar = _peer.StreamBarrier(ex.device, me, W)
-    ex._do(bar)
+    ex._do(bar, collective=True)
     ex._do(launch.run)
-    ex._do(bar)
+    ex._do(bar, collective=True)
     st.keepalive.extend([launch, slab, windows])
 
 
@@ -533,7 +533,7 @@ def _exchange_for_fused(ex, plan: FusedPlan, deps, out_ids):
                 out[(dep._name, lbid)] = DeviceChunk(buf, dep.block_shape(lbid), dep.dtype, offset=off // dep.dtype.itemsize)
                 off += pad(nb)
             recvs.append((p, buf))
-    ex._do(lambda: _p2p_exchange(ex, sends, recvs))
+    ex._do(lambda: _p2p_exchange(ex, sends, recvs), collective=True)
     out["__keep__"] = (keep, sends, recvs)
     return out
 
@@ -566,7 +566,7 @@ def _exchange_for_rechunk(ex, expr: TasksRechunk, src: BlockStore, new_ids):
                 out[(obid, nbid)] = DeviceChunk(buf, shape, expr.dtype, offset=off // item)
                 off += pad(nb)
             recvs.append((p, buf))
-    ex._do(lambda: _p2p_exchange(ex, sends, recvs))
+    ex._do(lambda: _p2p_exchange(ex, sends, recvs), collective=True)
     out["__keep__"] = (keep, sends, recvs)
     return out
 

@@ -73,9 +73,16 @@ class Executor:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.results: dict[str, BlockStore] = {}
         self.tape = []            # every device action in issue order: replaying it repeats the step
+        self.collectives = []     # tape indices of the actions that synchronise with other ranks
+        self.tape_span = {}       # expression name -> (first, end) tape indices of its own device actions
 
-    def _do(self, fn):
+    def _do(self, fn, collective: bool = False):
+        """Run a device action now and record it on the tape.  ``collective``: the action synchronises with the
+        other ranks (peer barrier / all-gather, NCCL call): such actions keep their global order on every rank,
+        so a tape that holds any is never split over concurrent streams."""
         fn()
+        if collective:
+            self.collectives.append(len(self.tape))
         self.tape.append(fn)
 
     # ------------------------------------------------------------------ driver
@@ -100,6 +107,7 @@ class Executor:
         finally:
             if _NVTX:
                 torch.cuda.nvtx.range_pop()
+        self.tape_span[expr._name] = (first, len(self.tape))      # tape entries this expression itself added
         if _NVTX >= 2 and len(self.tape) > first:
             self.tape.insert(first, lambda label=label: torch.cuda.nvtx.range_push(label))
             self.tape.append(torch.cuda.nvtx.range_pop)
@@ -352,7 +360,7 @@ class Executor:
         bar = extra.get("__barrier__")
         keep_order = False
         if bar is not None:
-            self._do(bar)         # the owners have produced the blocks this rank reads in place
+            self._do(bar, collective=True)         # the owners have produced the blocks this rank reads in place
             if red is None:
                 blocks, keep_order = _interleave_remote_reads(
                     blocks, block_owner, self.world.rank, self.world.size,
@@ -364,7 +372,7 @@ class Executor:
                 st.keepalive.append(launch)
             st.keepalive.append(extra)
         if bar is not None:
-            self._do(bar)         # ... and every reader is done before an owner may reuse them
+            self._do(bar, collective=True)         # ... and every reader is done before an owner may reuse them
         return st
 
     def _empty_result(self, expr, bid, kind):

@@ -40,7 +40,7 @@ def main():
     yp = da.sin(xp) * 2 + xp**2
     step = da.compile(yp.mean(axis=0), yp.std(), yp.sum(axis=1), yp.max())
     if os.environ.get("B2_COMM", "peer") != "nccl":
-        step.capture()
+        step.capture()           # independent expressions become parallel graph branches (one may hold collectives)
     for _ in range(5):
         step.run()
     gm, gs, gr, gx = step.results()
