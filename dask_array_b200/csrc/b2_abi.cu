@@ -271,13 +271,29 @@ __device__ __forceinline__ void b2_post_store(void* out0, i64 e, T total, int po
 template <typename T, int OP, typename OUT>
 __device__ __forceinline__ void b2_combine_one(const void* const* __restrict__ parts, const void* const* __restrict__ parts1,
                                                int fanin, i64 e, void* out0, void* out1, int post, double count, double ddof) {
+    // The partials are fetched EIGHT AT A TIME before they are folded (pointer and value loads of a batch are
+    // independent, the fold keeps the given order): a level with fan-in 16 costs two memory round trips instead
+    // of sixteen -- these launches are a few threads wide, so their duration IS that dependent-load chain
+    // (ncu, C2 std() tree: 11.4 us -> see profiles/).
     if constexpr (OP == B2R_SUM || OP == B2R_PROD) {
         T acc = ((const T*)parts[0])[e];
-        for (int g = 1; g < fanin; ++g) { T v = ((const T*)parts[g])[e]; acc = (OP == B2R_SUM) ? (T)(acc + v) : (T)(acc * v); }
+        for (int g0 = 1; g0 < fanin; g0 += 8) {
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (g0 + u < fanin) v[u] = ((const T*)parts[g0 + u])[e];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (g0 + u < fanin) acc = (OP == B2R_SUM) ? (T)(acc + v[u]) : (T)(acc * v[u]);
+        }
         b2_post_store<T, OUT>(out0, e, acc, post, count);
     } else if constexpr (OP == B2R_MIN || OP == B2R_MAX) {
         T acc = ((const T*)parts[0])[e];
-        for (int g = 1; g < fanin; ++g) { T v = ((const T*)parts[g])[e]; acc = (OP == B2R_MAX) ? b2_np_max(acc, v) : b2_np_min(acc, v); }
+        for (int g0 = 1; g0 < fanin; g0 += 8) {
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (g0 + u < fanin) v[u] = ((const T*)parts[g0 + u])[e];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (g0 + u < fanin) acc = (OP == B2R_MAX) ? b2_np_max(acc, v[u]) : b2_np_min(acc, v[u]);
+        }
         ((T*)out0)[e] = acc;
     } else if constexpr (OP == B2R_NANMIN || OP == B2R_NANMAX) {
         T acc = ((const T*)parts[0])[e];
@@ -302,9 +318,16 @@ __device__ __forceinline__ void b2_combine_one(const void* const* __restrict__ p
         ((i64*)out1)[e] = bi;
     } else {   // MOMENT: packed (n, mean, M2) fp64 triples
         B2AccMoment<double, double> acc; acc.init();
-        for (int g = 0; g < fanin; ++g) {
-            const double* q = (const double*)parts[g] + 3 * e;
-            acc.chan(q[0], q[1], q[2]);
+        for (int g0 = 0; g0 < fanin; g0 += 8) {
+            double q[8][3];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (g0 + u < fanin) {
+                    const double* p = (const double*)parts[g0 + u] + 3 * e;
+                    q[u][0] = p[0]; q[u][1] = p[1]; q[u][2] = p[2];
+                }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (g0 + u < fanin) acc.chan(q[u][0], q[u][1], q[u][2]);
         }
         if (post == B2_POST_NONE) {
             double* q = (double*)out0 + 3 * e;
