@@ -879,10 +879,18 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                 if (ty == 0 && c < C) {
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
+                        // partials are fetched eight at a time (independent L2 loads), merged in tile order:
+                        // the fold is ONE thread deep per column, so its duration is the load chain
+                        // (52 row tiles x ~0.5 us when fetched one by one)
                         A tot; tot.unpack(b2_load_cg(&work[(b * tiles_r) * Cpad + c + v]));
-                        for (i64 k = 1; k < tiles_r; ++k) {
-                            A part; part.unpack(b2_load_cg(&work[(b * tiles_r + k) * Cpad + c + v]));
-                            tot.merge(part);
+                        for (i64 k0 = 1; k0 < tiles_r; k0 += 8) {
+                            P_t raw[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (k0 + u < tiles_r) raw[u] = b2_load_cg(&work[(b * tiles_r + k0 + u) * Cpad + c + v]);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (k0 + u < tiles_r) { A part; part.unpack(raw[u]); tot.merge(part); }
                         }
                         b2_store_result<REDOP, T, ACC>(blk, b * C + c + v, tot, blk.arg_offset);
                     }
@@ -934,7 +942,13 @@ __device__ __forceinline__ void b2_run(const B2Block* __restrict__ blocks, int n
                     const i64 per = (ntile + NT - 1) / NT;
                     const i64 k0 = (i64)tid * per;
                     const i64 k1 = (k0 + per < ntile) ? (k0 + per) : ntile;
-                    for (i64 k = k0; k < k1; ++k) { A part; part.unpack(b2_load_cg(&work[b * ntile + k])); tot.merge(part); }
+                    for (i64 kb = k0; kb < k1; kb += 4) {      // four independent loads, merged in order
+                        P_t raw[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) if (kb + u < k1) raw[u] = b2_load_cg(&work[b * ntile + kb + u]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) if (kb + u < k1) { A part; part.unpack(raw[u]); tot.merge(part); }
+                    }
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) tot.shfl(off, 32);
