@@ -715,11 +715,12 @@ def choose_geometry(program: Program, mode: int, shapes, vec: int) -> dict:
         target = 1024 * 1024
         # Small launches (BASELINE config 2 dealt over 8 GPUs: 8 blocks = 512 MiB per rank): with 1 MiB tiles
         # that is 512 CTAs for 444 resident slots -- 1.15 waves, the kernel ran at 71 % of its large-launch
-        # bandwidth (B200 x 8, round 2; 2.3 waves: 89 %, 4.6 waves: 97 %).  Shrink the tile until the launch
-        # is >= ~4 waves, never below 64 KiB; not further: at 4.6 waves 1 MiB tiles still beat 200-row tiles
-        # by 2 % (same box).
+        # bandwidth (B200 x 8, round 2).  Sweep of that launch on one B200 (profiles/r2_small_launch_sweep.py,
+        # mean / std kernel in us): rows per tile 16: 174 / 155, 32: 133 / 129, 64: 115 / 116, 128: 109 / 113,
+        # 256: 120 / 127 -- ~2.3 waves is the sweet spot between wave quantisation and per-tile fixed cost
+        # (descriptor fetch, two-stage partial, fold); never below 64 KiB.
         total = sum(s[0] * s[1] * s[2] for s in shapes) * max(sizes)
-        target = int(min(target, max(64 * 1024, total // (4 * 444))))
+        target = int(min(target, max(64 * 1024, total // 1024)))
     if mode == _lib.MODE_C:
         # B200 sweep (c3, fp64 rows of 128 KiB): 2 loads in flight per thread at 4 CTAs/SM beat 8 at 3
         # (argmax 5.6-5.9 -> 6.8 TB/s, max 6.7 -> 7.2 TB/s): a CTA then walks its row nearly in order and
