@@ -956,9 +956,6 @@ __device__ __forceinline__ int b2w_find_job(const B2WindowJob* __restrict__ jobs
     return lo;
 }
 
-// consecutive segments one thread walks (rows kernel): 4 when the block has plenty of segments, fewer when not
-__host__ __device__ __forceinline__ i64 b2w_segs_per_thread(i64 nseg) { return nseg >= 32 ? 4 : nseg >= 16 ? 2 : 1; }
-
 template <typename T, int OP, int V>
 __global__ void __launch_bounds__(256, 3) b2_window_rows_kernel(const B2WindowJob* __restrict__ jobs, int njobs, i64 w, int mean) {
     constexpr int U = 4;      // (U = 8 needs 172 registers: one CTA per SM, latency-bound at 2 TB/s on B200;
@@ -971,20 +968,13 @@ __global__ void __launch_bounds__(256, 3) b2_window_rows_kernel(const B2WindowJo
     i64 t = (i64)blockIdx.x - job.tile_begin;
     const i64 ct = t % col_tiles; t /= col_tiles;
     const i64 stile = t % seg_tiles; const i64 b = t / seg_tiles;
-    // A thread walks G CONSECUTIVE segments: the forward pass over segment k+1 (completing the windows of
-    // segment k) is followed at once by the backward pass over the same rows (the suffix scan of segment k+1),
-    // and the read-modify-write of an output row comes one segment after its first write -- both re-uses hit
-    // L2 / L1.  (One segment per thread left that distance to the scheduler: ncu showed 2.05 x the needed DRAM
-    // traffic, 444 resident CTAs x 256 KiB of segments ~ the whole L2.)
-    const i64 G = b2w_segs_per_thread(nseg);
-    const i64 c = (ct * 32 + threadIdx.x) * V, s0 = (stile * 8 + threadIdx.y) * G;
-    if (c >= C || s0 >= nseg || b >= B) return;
+    const i64 c = (ct * 32 + threadIdx.x) * V, s = stile * 8 + threadIdx.y;
+    if (c >= C || s >= nseg || b >= B) return;
     const T* x = src + (b * R) * C + c;
     T* o = dst + (b * Rout) * C + c;
-    const T wdiv = (T)w;
-  for (i64 s = s0; s < s0 + G && s < nseg; ++s) {
     const i64 base = s * w;
     const i64 hi = (base + w < R) ? base + w : R;
+    const T wdiv = (T)w;
     T h[V];
     bool first = true;
     for (i64 i0 = hi - 1; i0 >= base; i0 -= U) {             // suffix scan of this segment, last row first
@@ -1035,7 +1025,6 @@ __global__ void __launch_bounds__(256, 3) b2_window_rows_kernel(const B2WindowJo
             b2_store_vec<T, V>(o + (base + j0 + u + 1) * C, out);
         }
     }
-  }
 }
 
 // window along the CONTIGUOUS axis of (rows, C): a tile of RT rows x L columns is staged in shared memory
@@ -1129,7 +1118,7 @@ static int b2_window_launch(b2_window_job* jobs, int n, void* d_jobs, i64 w, int
         for (int i = 0; i < n; ++i) {
             const i64 Rout = jobs[i].R - w + 1, nseg = cdiv(Rout, w);
             jobs[i].col_tiles = cdiv(jobs[i].C, 32 * (vec ? VMAX : 1));
-            jobs[i].row_tiles = cdiv(nseg, 8 * b2w_segs_per_thread(nseg));   // 8 threads (y) x G consecutive segments each
+            jobs[i].row_tiles = cdiv(nseg, 8);
             jobs[i].tile_begin = tiles;
             tiles += jobs[i].col_tiles * jobs[i].row_tiles * jobs[i].B;
         }
