@@ -13,7 +13,7 @@ from ._collection import (  # noqa: F401
     UFUNC_NAMES, Array, Compiled, _method, _ufunc, asarray, compile, compute, elemwise, from_array,
     dot, from_host_blocks, full, matmul, nanargmax, nanargmin, nanmax, nanmean, nanmin, nanprod, nanstd, nansum,
     nanvar, ones, random, tensordot, einsum, cumsum, cumprod, nancumsum, nancumprod,
-    rechunk, transpose, where, zeros,
+    rechunk, transpose, where, zeros, divmod, modf, frexp,
 )
 
 from ._views import broadcast_to, concatenate, expand_dims, squeeze, stack  # noqa: F401,E402
@@ -21,6 +21,26 @@ from . import _overlap as overlap  # noqa: F401,E402  (da.overlap.overlap / trim
 from ._overlap import map_blocks, map_overlap, sliding_window_view  # noqa: F401,E402
 from ._topk import argtopk, topk  # noqa: F401,E402
 from ._routines import diff, flip, fliplr, flipud, roll  # noqa: F401,E402
+
+from ._window import moving_window  # noqa: F401,E402
+
+
+def move_sum(x, window, min_count=None, axis=-1):
+    """bottleneck ``move_sum`` semantics (``MovingWindowReduction``, ``reductions/_sliding_window.py:249-400``)."""
+    return moving_window(x, window, "move_sum", min_count, axis)
+
+
+def move_mean(x, window, min_count=None, axis=-1):
+    return moving_window(x, window, "move_mean", min_count, axis)
+
+
+def move_min(x, window, min_count=None, axis=-1):
+    return moving_window(x, window, "move_min", min_count, axis)
+
+
+def move_max(x, window, min_count=None, axis=-1):
+    return moving_window(x, window, "move_max", min_count, axis)
+
 
 from . import plugin  # noqa: F401,E402  (register / get / lower_reference: the reference-facing boundary)
 from .plugin import get, register  # noqa: F401,E402

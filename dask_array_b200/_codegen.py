@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib
 
 MAX_INPUTS = _lib.B2_MAX_IN   # array inputs of one fused kernel (descriptor table slots)
-CODEGEN_VERSION = "21"     # part of every kernel's cache key: bump when generated code changes
+CODEGEN_VERSION = "22"     # part of every kernel's cache key: bump when generated code changes
 
 CTYPE = {
     "bool": "bool", "int8": "signed char", "uint8": "unsigned char", "int16": "short",
@@ -149,6 +149,11 @@ def infer_dtype(name, args, **kw):
     """Result dtype the way Elemwise._info does it (``_blockwise.py:941-946``)."""
     if name == "astype":
         return np.dtype(kw["dtype"])
+    if name in ("frexp_mantissa", "frexp_exponent"):
+        dummy = np.empty((1,), dtype=args[0].dtype) if not args[0].weak else args[0].value
+        with np.errstate(all="ignore"):
+            m, e = np.frexp(dummy)
+        return np.asarray(m if name == "frexp_mantissa" else e).dtype
     dummies = [np.empty((1,), dtype=a.dtype) if not a.weak else a.value for a in args]
     with np.errstate(all="ignore"):
         return np.asarray(_np_func(name)(*dummies)).dtype
@@ -458,6 +463,17 @@ def _emit(name, args, out, kw) -> str:
         return f"(({T})({a(0)} * {literal(np.pi / 180.0, out)}))"
     if name in ("rad2deg", "degrees"):
         return f"(({T})({a(0)} * {literal(180.0 / np.pi, out)}))"
+    if name in ("frexp_mantissa", "frexp_exponent"):
+        # np.frexp (``_ufunc.py:429-436``, the two DoubleOutputs): x = m * 2**e with 0.5 <= |m| < 1; zero, inf and
+        # NaN keep x as the mantissa and report exponent 0, like NumPy / glibc
+        src = np.dtype(args[0].dtype) if not args[0].weak else np.dtype(np.float64)
+        if src.kind != "f":
+            src = np.dtype(np.float64)
+        fx = "frexpf" if src == np.float32 else "frexp"
+        xs = a(0, src)
+        if name == "frexp_mantissa":
+            return f"([&]{{ int e_ = 0; const {ctype(src)} m_ = {fx}({xs}, &e_); return isfinite({xs}) ? m_ : {xs}; }}())"
+        return f"([&]{{ int e_ = 0; (void){fx}({xs}, &e_); return (isfinite({xs}) && {xs} != 0) ? e_ : 0; }}())"
     if name == "where":
         return f"(({a(0, np.bool_)}) ? {a(1)} : {a(2)})"
     if name == "clip":

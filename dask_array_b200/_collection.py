@@ -29,13 +29,42 @@ def _as_operand(x):
     raise TypeError(f"cannot use {type(x).__name__} as an operand of a dask_array_b200 Array")
 
 
-def elemwise(op, *args, **kwargs):
-    """``elemwise()`` (``core/_blockwise_funcs.py:207``)."""
+def elemwise(op, *args, out=None, where=True, dtype=None, **kwargs):
+    """``elemwise()`` (``core/_blockwise_funcs.py:207-300``).  ``where=mask`` keeps ``out``'s values where the mask is
+    False (``_elemwise_handle_where``, ``_core_utils.py:1031-1036``: the ufunc writes into a copy of ``out``), which
+    is ``where(mask, op(...), out)`` inside the same fused kernel; without ``out`` those positions would be
+    uninitialised memory in NumPy -- refused.  ``out=`` (an Array) is overwritten in place: it takes the result's
+    expression (``handle_out``), and is returned.  ``dtype=`` casts the result (``_enforce_dtype`` :1078)."""
     name = cg.canonical_name(op)
     ops = tuple(_as_operand(a) for a in args)
     if not any(isinstance(o, ArrayExpr) for o in ops):
         raise TypeError("elemwise needs at least one Array operand")
-    return Array(Elemwise(name, ops, tuple(sorted(kwargs.items()))))
+    if isinstance(out, tuple):
+        if len(out) != 1:
+            raise NotImplementedError("The out parameter is not fully supported: one output only")
+        out = out[0]
+    if out is not None and not isinstance(out, Array):
+        raise NotImplementedError("The out parameter is not fully supported. Received type "
+                                  f"{type(out).__name__}, expected a dask_array_b200 Array")
+    res = Array(Elemwise(name, ops, tuple(sorted(kwargs.items()))))
+    if dtype is not None and np.dtype(dtype) != res.dtype:
+        res = res.astype(dtype)
+    if where is not True:
+        if where is False or where is None:
+            where = np.bool_(False)
+        if out is None:
+            raise NotImplementedError("elemwise(where=mask) without out=: the unselected positions are uninitialised "
+                                      "memory in NumPy and have no defined value to reproduce")
+        keep = out if out.dtype == res.dtype else out.astype(res.dtype)
+        res = Array(Elemwise("where", (_as_operand(where), res.expr, keep.expr), ()))
+    if out is not None:
+        if out.shape != res.shape:
+            raise ValueError(f"Mismatched shapes between `out` parameter and result: {out.shape} vs {res.shape}")
+        if res.dtype != out.dtype:
+            res = res.astype(out.dtype)
+        out.expr = res.expr
+        return out
+    return res
 
 
 class Array:
@@ -147,10 +176,15 @@ class Array:
         return matmul(self, other)
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
-        """``Array.__array_ufunc__`` (:1702): NumPy ufuncs on Arrays stay lazy."""
-        if method != "__call__" or kwargs:
+        """``Array.__array_ufunc__`` (:1702): NumPy ufuncs on Arrays stay lazy (``out=`` / ``where=`` / ``dtype=``
+        included; the two-output ufuncs ``frexp / modf / divmod`` return a pair of Arrays)."""
+        if method != "__call__" or set(kwargs) - {"out", "where", "dtype"}:
             return NotImplemented
-        return elemwise(ufunc.__name__, *inputs)
+        if ufunc.nout == 2 and ufunc.__name__ in ("frexp", "modf", "divmod") and not kwargs:
+            return globals()[ufunc.__name__](*inputs)
+        if ufunc.nout != 1:
+            return NotImplemented
+        return elemwise(ufunc.__name__, *inputs, **kwargs)
 
     def astype(self, dtype, **kwargs):
         """``Array.astype`` (:1569-1609)."""
@@ -695,6 +729,28 @@ UFUNC_NAMES = [
 
 def where(cond, x, y):
     return elemwise("where", cond, x, y)
+
+
+def divmod(x, y):   # noqa: A001
+    """``divmod`` (``_ufunc.py:447-451``): ``(x // y, x % y)``."""
+    return elemwise("floor_divide", x, y), elemwise("remainder", x, y)
+
+
+def modf(x):
+    """``modf`` (``_ufunc.py:438-444``): fractional and integral parts, both with the sign of ``x`` (``modf(-2.) ==
+    (-0., -2.)``, ``modf(inf) == (0., inf)``), each ONE fused kernel."""
+    x = asarray(x)
+    if x.dtype.kind != "f":
+        x = x.astype(np.result_type(x.dtype, np.float64) if x.dtype.itemsize > 2 else np.float32 if x.dtype.itemsize == 2 else np.float16)
+    ip = elemwise("trunc", x)
+    frac = elemwise("copysign", elemwise("where", elemwise("isinf", x), 0.0, elemwise("subtract", x, ip)), x)
+    return frac.astype(x.dtype), ip
+
+
+def frexp(x):
+    """``frexp`` (``_ufunc.py:429-436``): mantissa and int32 exponent."""
+    x = asarray(x)
+    return elemwise("frexp_mantissa", x), elemwise("frexp_exponent", x)
 
 
 def _method(name):

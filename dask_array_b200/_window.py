@@ -239,5 +239,49 @@ class WindowReduce(ArrayExpr):
         return f"WindowReduce({self.operand('redop')}{'/w' if self.operand('mean') else ''}, window={self.operand('window')})"
 
 
+# ----------------------------------------------------------------------------- trailing windows (bottleneck move_*)
+MOVING_REDUCERS = {"move_sum": "nansum", "move_mean": "nanmean", "move_min": "nanmin", "move_max": "nanmax"}
+
+
+def moving_window(x, window, reducer="move_sum", min_count=None, axis=-1):
+    """``MovingWindowReduction`` (``reductions/_sliding_window.py:183-246, 249-400``; bottleneck ``move_*`` semantics, the
+    reference's rewrite of ``map_overlap(bottleneck.move_sum, depth={axis: (window - 1, 0)})``): output position ``t``
+    reduces the TRAILING window ``[t - window + 1, t]`` clipped at the array's start, skipping NaNs; windows with
+    fewer than ``min_count`` (default ``window``) valid values are NaN.  Built from the sliding-window kernel: the
+    NaN-free values and the valid flags are padded with ``window - 1`` identities in front and window-reduced on the
+    input's own chunks (two ``b2_window_reduce`` launches), then combined in one fused element-wise kernel."""
+    from ._collection import asarray, elemwise, full
+    from ._views import concatenate
+
+    if reducer not in MOVING_REDUCERS:
+        raise ValueError(f"unknown moving-window reducer {reducer!r}")
+    x = asarray(x)
+    window = int(window)
+    if window < 1:
+        raise ValueError("window must be >= 1")
+    limit = window if min_count is None else int(min_count)
+    if not 1 <= limit <= window:
+        raise ValueError("min_count must be in [1, window]")
+    axis = axis % x.ndim
+    dt = x.dtype if x.dtype.kind == "f" else np.dtype(np.float64)
+    xf = x.astype(dt)
+    ident = {"move_sum": 0.0, "move_mean": 0.0, "move_min": np.inf, "move_max": -np.inf}[reducer]
+    valid = elemwise("logical_not", elemwise("isnan", xf))
+    vals = elemwise("where", valid, xf, dt.type(ident))
+    cnt_in = valid.astype(dt)
+    if window > 1:
+        pad_shape = tuple(window - 1 if d == axis else n for d, n in enumerate(x.shape))
+        pad_chunks = tuple((window - 1,) if d == axis else c for d, c in enumerate(x.chunks))
+        vals = concatenate([full(pad_shape, ident, dtype=dt, chunks=pad_chunks), vals], axis=axis)
+        cnt_in = concatenate([full(pad_shape, 0.0, dtype=dt, chunks=pad_chunks), cnt_in], axis=axis)
+    op = {"move_sum": "sum", "move_mean": "sum", "move_min": "min", "move_max": "max"}[reducer]
+    red = getattr(sliding_window_view(vals, window, axis=axis), op)(axis=-1)
+    cnt = sliding_window_view(cnt_in, window, axis=axis).sum(axis=-1)
+    if reducer == "move_mean":
+        red = elemwise("true_divide", red, cnt)
+    out = elemwise("where", elemwise("less", cnt, dt.type(limit)), dt.type(np.nan), red)
+    return out.astype(dt)
+
+
 def block_ids_of(expr):
     return itertools.product(*[range(len(c)) for c in expr.chunks])

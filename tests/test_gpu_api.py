@@ -298,3 +298,44 @@ def test_graph_capture_with_parallel_lanes_replays_correctly(da):
     step2.run(); step2.run()
     for got, w in zip(step2.results(), want2):
         assert np.array_equal(got, w)
+
+
+def test_two_output_ufuncs_and_where_out(da):
+    """frexp / modf / divmod (_ufunc.py:429-451) and elemwise(where=, out=) (_core_utils.py:1031-1036)."""
+    xh = np.array([1.5, -2.0, 0.0, -0.0, np.inf, -np.inf, np.nan, 1e-310, 123456.789, -0.3], dtype=np.float64)
+    x = da.from_array(xh, chunks=4)
+    for dt in (np.float64, np.float32):
+        xx, hh = x.astype(dt), xh.astype(dt)
+        m, e = da.frexp(xx)
+        wm, we = np.frexp(hh)
+        assert m.dtype == wm.dtype and e.dtype == we.dtype
+        assert np.array_equal(m.compute(), wm, equal_nan=True) and np.array_equal(e.compute(), we)
+        f, i = da.modf(xx)
+        wf, wi = np.modf(hh)
+        gf, gi = f.compute(), i.compute()
+        assert np.array_equal(gf, wf, equal_nan=True) and np.array_equal(gi, wi, equal_nan=True)
+        assert np.array_equal(np.signbit(gf), np.signbit(wf)) and np.array_equal(np.signbit(gi), np.signbit(wi))
+    ih = np.array([7, -7, 9, -9, 0, 5], dtype=np.int32)
+    q, r = da.divmod(da.from_array(ih, chunks=3), 4)
+    wq, wr = np.divmod(ih, 4)
+    assert np.array_equal(q.compute(), wq) and np.array_equal(r.compute(), wr)
+    q2, r2 = np.divmod(x, 0.7)                                   # through __array_ufunc__
+    with np.errstate(all="ignore"):
+        wq2, wr2 = np.divmod(xh, 0.7)
+    assert np.array_equal(q2.compute(), wq2, equal_nan=True)
+    # where= with out=: unselected positions keep out's values; out is overwritten in place and returned
+    ah = np.arange(12.0).reshape(3, 4)
+    mask = (ah % 3 == 0)
+    a = da.from_array(ah, chunks=(2, 2))
+    out = da.full((3, 4), -1.0, chunks=(2, 2))
+    ret = np.multiply(a, 10, out=out, where=da.from_array(mask, chunks=(2, 2)))
+    assert ret is out
+    want = np.full((3, 4), -1.0)
+    np.multiply(ah, 10, out=want, where=mask)
+    assert np.array_equal(out.compute(), want)
+    out2 = da.zeros((3, 4), dtype=np.float32, chunks=(2, 2))
+    np.sin(a, out=out2)                                          # out= alone: cast to out's dtype
+    np.testing.assert_allclose(out2.compute(), np.sin(ah).astype(np.float32), rtol=3e-7)
+    with pytest.raises(NotImplementedError, match="uninitialised"):
+        np.add(a, 1, where=da.from_array(mask, chunks=(2, 2)))
+    assert np.add(a, 1, dtype=np.float32).dtype == np.float32

@@ -106,3 +106,36 @@ def test_window_kernel_through_the_c_abi(da):
                                                      w, along, 0, current_stream_ptr()))
         for h, out in zip(hosts, outs):
             assert np.array_equal(out.to_numpy(), swv(h, w, axis=2 if along else 1).sum(axis=-1))
+
+
+def _move_ref(x, w, reducer, min_count, axis):
+    """bottleneck move_* semantics in plain NumPy: trailing window, NaN-skipping, NaN below min_count."""
+    x = np.moveaxis(np.asarray(x, dtype=np.float64), axis, -1)
+    n = x.shape[-1]
+    out = np.full(x.shape, np.nan)
+    limit = w if min_count is None else min_count
+    fn = {"move_sum": np.nansum, "move_mean": np.nanmean, "move_min": np.nanmin, "move_max": np.nanmax}[reducer]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for t in range(n):
+            win = x[..., max(0, t - w + 1):t + 1]
+            cnt = (~np.isnan(win)).sum(axis=-1)
+            val = np.where(cnt > 0, fn(np.where(cnt[..., None] > 0, win, 0.0) if reducer in ("move_min", "move_max") else win, axis=-1), np.nan)
+            out[..., t] = np.where(cnt >= limit, val, np.nan)
+    return np.moveaxis(out, -1, axis)
+
+
+@pytest.mark.parametrize("reducer", ["move_sum", "move_mean", "move_min", "move_max"])
+@pytest.mark.parametrize("shape,chunks,axis,w,min_count", [((60, 24), (7, 24), 0, 10, None), ((60, 24), (7, 24), 0, 10, 3),
+                                                          ((16, 90), (16, 11), 1, 25, 1), ((200,), (33,), 0, 40, 20)])
+def test_moving_window_trailing_nan_skipping(da, reducer, shape, chunks, axis, w, min_count):
+    """MovingWindowReduction (reductions/_sliding_window.py:183-246, 249-400): chunks smaller than the window,
+    windows clipped at the array start, NaNs skipped, min_count."""
+    rng = np.random.default_rng(7)
+    xh = rng.random(shape) * 10 - 5
+    xh[rng.random(shape) < 0.15] = np.nan
+    got = getattr(da, reducer)(da.from_array(xh, chunks=chunks), w, min_count=min_count, axis=axis).compute()
+    want = _move_ref(xh, w, reducer, min_count, axis)
+    assert got.shape == want.shape and got.dtype == np.float64
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12, equal_nan=True)
