@@ -424,9 +424,8 @@ class Executor:
         one per level afterwards."""
         import ctypes as C
 
-        if self.world.size > 1:
-            raise NotImplementedError("topk across several GPUs (gather the array on one rank first)")
         x = expr.operand("array")
+        multi = self.world.size > 1
         src = self.results[x._name]
         k, axis, want_arg = expr.operand("k"), expr.operand("axis"), expr.operand("arg")
         largest, kabs = k > 0, abs(k)
@@ -488,11 +487,22 @@ class Executor:
                 width += nseg * kk
             vals = DeviceChunk.empty((rows, width), x.dtype, self.device)
             idx = DeviceChunk.empty((rows, width), np.int64, self.device)
+            if multi and not src.replicated:
+                # every rank fills the candidate columns of ITS blocks; the rest is zero, so a byte-wise
+                # all-reduce(SUM) completes both tables exactly (no arithmetic on the values) and every rank
+                # runs the remaining levels redundantly: the result is replicated
+                self._do(lambda v=vals, i=idx: (v.buf.zero_(), i.buf.zero_()))
             for bid, n_i, seg, col in plan:
+                if multi and not src.replicated and not self.mine(x, bid):
+                    continue
                 blk = rows_last(src.blocks[bid])
                 st.keepalive.append(blk)
                 launch(blk.ptr, rows, n_i, n_i, seg, vals.ptr + col * item, idx.ptr + col * 8, width, None,
                        x.block_start(bid)[axis])
+            if multi and not src.replicated:
+                import torch.distributed as dist
+
+                self._do(lambda v=vals, i=idx: (dist.all_reduce(v.buf), dist.all_reduce(i.buf)), collective=True)
             single = len(plan) == 1 and -(-plan[0][1] // plan[0][2]) == 1
             # ---- further levels on the candidate rows
             while not single:
@@ -518,6 +528,7 @@ class Executor:
                 inv[d] = pos
             st.blocks[out_bid] = view.transpose(tuple(inv))         # ... and the axis back in its place (a view)
             st.keepalive.extend([vals, idx])
+        st.replicated = multi
         return st
 
     # ------------------------------------------------------------------ cumulative scans

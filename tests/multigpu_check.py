@@ -109,6 +109,15 @@ def main():
     gh = rng.random((256, 192))
     ga, gb = da.from_array(gh, chunks=(64, 64)).persist(), da.from_array(gh, chunks=(128, 32)).persist()
     assert np.array_equal((ga * 2 + gb).compute(), gh * 2 + gh)
+    # top-k across the partition: per-rank candidates, byte-wise all-reduce, remaining levels on every rank
+    kh = rng.random((300, 257))
+    kd = da.from_array(kh, chunks=(64, 50))
+    for axis in (0, 1):
+        srt = np.sort(kh, axis=axis)
+        assert np.array_equal(kd.topk(5, axis=axis).compute(), np.flip(np.take(srt, range(kh.shape[axis] - 5, kh.shape[axis]), axis=axis), axis=axis))
+        assert np.array_equal(kd.topk(-3, axis=axis).compute(), np.take(srt, range(3), axis=axis))
+        ai = kd.argtopk(4, axis=axis).compute()
+        assert np.array_equal(np.take_along_axis(kh, ai, axis=axis), np.flip(np.take(srt, range(kh.shape[axis] - 4, kh.shape[axis]), axis=axis), axis=axis))
     peer = os.environ.get("B2_COMM", "peer") != "nccl"
     if not peer:
         # views and halos whose source block lives on another GPU are peer-memory only (a loud refusal on the
