@@ -298,6 +298,13 @@ class Array:
 
         return squeeze(self, axis)
 
+    def ravel(self):
+        from ._views import ravel
+
+        return ravel(self)
+
+    flatten = ravel
+
     def any(self, axis=None, keepdims=False, split_every=None):
         return self._reduce("any", axis, keepdims, None, split_every)
 
@@ -468,8 +475,9 @@ def _cumulative(kind, x, axis, dtype, out, method, nan=False):
     x = asarray(x)
     if axis is None:
         if x.ndim > 1:
-            raise NotImplementedError("cumulative reduction with axis=None flattens the array first "
-                                      "(``_prepare_cumulative`` :77-97): reshape is outside the B200 hot path")
+            from ._views import ravel
+
+            x = ravel(x)            # ``_prepare_cumulative`` (:77-97): flatten first, then scan the vector
         axis = 0
     axis = validate_axis(axis, x.ndim)[0]
     return Array(CumReduction(x.expr, kind, axis, None if dtype is None else np.dtype(dtype).name, bool(nan)))

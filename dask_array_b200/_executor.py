@@ -284,6 +284,11 @@ class Executor:
         self._do(run)
         return st
 
+    def _run_Ravel(self, expr):
+        x = expr.operand("array")
+        src = self.results[x._name]
+        return self._view_store(expr, lambda bid: (src, x, expr.source(bid)), lambda blk, bid: expr.view(blk))
+
     def _run_Squeeze(self, expr):
         x = expr.operand("array")
         src = self.results[x._name]

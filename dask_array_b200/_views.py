@@ -33,6 +33,52 @@ class ExpandDims(ArrayExpr):
         return chunk[tuple(slice(None) for _ in range(ax)) + (None,)]
 
 
+class Ravel(ArrayExpr):
+    """C-order flatten of an array whose trailing axes are single-chunk (``reshape(-1)`` after the rechunk the
+    reference's ``reshape`` / ``_prepare_cumulative`` performs, ``reductions/_cumulative.py:77-97``): every block
+    (c0, n1, n2, ...) is contiguous in the flattened order, so the output block is a reshaped VIEW of it."""
+
+    _parameters = ["array"]
+
+    @property
+    def chunks(self):
+        x = self.operand("array")
+        if any(len(c) != 1 for c in x.chunks[1:]):
+            raise ValueError("Ravel needs single-chunk trailing axes (rechunk first)")
+        inner = 1
+        for n in x.shape[1:]:
+            inner *= n
+        return (tuple(c * inner for c in x.chunks[0]),) if x.ndim else ((1,),)
+
+    @property
+    def dtype(self):
+        return self.operand("array").dtype
+
+    def source(self, bid):
+        x = self.operand("array")
+        return (bid[0],) + (0,) * (x.ndim - 1) if x.ndim else ()
+
+    def view(self, chunk):
+        from ._eager import copy
+
+        return (chunk if chunk.is_contiguous else copy(chunk)).reshape((chunk.size,))
+
+
+def ravel(x):
+    """``Array.ravel`` / ``flatten`` for the layouts the hot path needs: the trailing axes are made single-chunk by a
+    rechunk (one tiled gather), then every block is viewed flat."""
+    from ._collection import Array, asarray
+
+    x = asarray(x)
+    if x.ndim == 1:
+        return x
+    if x.ndim == 0:
+        return x[None] if hasattr(x, "__getitem__") else x
+    if any(len(c) != 1 for c in x.chunks[1:]):
+        x = x.rechunk((x.chunks[0],) + tuple((n,) for n in x.shape[1:]))
+    return Array(Ravel(x.expr))
+
+
 class Squeeze(ArrayExpr):
     _parameters = ["array", "axes"]
 

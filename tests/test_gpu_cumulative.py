@@ -106,10 +106,23 @@ def test_long_vector_two_level_carries(da):
         _executor._Cum.SEG = old
 
 
+@pytest.mark.parametrize("shape,chunks", [((5, 4, 3), (2, 2, 3)), ((37, 22), (8, 5)), ((6, 1, 9), (4, 1, 2))])
+def test_cumsum_axis_none_nd(da, shape, chunks):
+    """``cumsum(axis=None)`` / ``cumprod`` of an N-d array (``_prepare_cumulative``, _cumulative.py:77-97): the trailing
+    axes are rechunked to one chunk, every block is viewed flat, the vector is scanned; also ``ravel`` on its own."""
+    rng = np.random.default_rng(4)
+    xh = rng.integers(-5, 6, size=shape).astype(np.int64)
+    x = da.from_array(xh, chunks=chunks)
+    assert np.array_equal(x.ravel().compute(), xh.ravel())
+    assert np.array_equal(x.cumsum().compute(), np.cumsum(xh))
+    fh = 1.0 + rng.random(shape) * 1e-3
+    np.testing.assert_allclose(da.cumprod(da.from_array(fh, chunks=chunks), axis=None).compute(), np.cumprod(fh), rtol=1e-12)
+    assert np.array_equal((x.T * 2).ravel().compute(), (xh.T * 2).ravel())
+
+
 def test_errors(da):
     x = da.from_array(np.zeros((4, 4)), chunks=2)
-    with pytest.raises(NotImplementedError):
-        x.cumsum()                                  # axis=None on N-d needs flatten (out of the hot path)
+    assert x.cumsum().shape == (16,)               # axis=None on N-d: flattened first (test_cumsum_axis_none_nd)
     with pytest.raises(ValueError):
         x.cumsum(axis=0, method="nope")
     with pytest.raises(np.exceptions.AxisError):
