@@ -120,6 +120,14 @@ def partials_layout(x, kind, W: int):
     return layout, sizes
 
 
+def level_is_local(expr, W: int) -> bool:
+    """Pure: does every group of the ``PartialReduce`` level ``expr`` live on the rank that owns the group's output
+    block?  Then each owner folds its own groups and the level needs no exchange (``mean(axis=0)`` with the block
+    columns dealt to the ranks, ``argmax(axis=1)`` of row panels); otherwise the partials are all-gathered."""
+    x = expr.operand("array")
+    return all(owner_of(x, m, W) == owner_of(expr, key, W) for key, members in expr.groups() for m in members)
+
+
 def alloc_partials(ex, x, kind):
     """Allocate this rank's partial blocks of ``x`` inside ONE slab laid out by ``partials_layout`` (the
     slab is the send buffer of the all-gather: no pack step).  Returns (slab, {bid: {field: DeviceChunk}})."""

@@ -573,8 +573,7 @@ class Executor:
         whole level, so the results are replicated."""
         if self.world.size == 1 or src.replicated:
             return src.blocks, False
-        W = self.world.size
-        if all(owner_of(x, m, W) == owner_of(expr, key, W) for key, members in expr.groups() for m in members):
+        if level_is_local(expr, self.world.size):
             return src.blocks, True
         return _allgather_blocks(self, src, x), False
 
@@ -1003,7 +1002,7 @@ class Executor:
 
 # the multi-GPU plumbing and the cumulative-scan launch builder live in their own modules
 from ._exchange import (  # noqa: E402,F401
-    alloc_partials, mean_count, partials_layout, _allgather_blocks, _copy_descs, _exchange_for_fused, _exchange_for_rechunk, _fetch_blocks, _interleave_remote_reads,
+    alloc_partials, level_is_local, mean_count, partials_layout, _allgather_blocks, _copy_descs, _exchange_for_fused, _exchange_for_rechunk, _fetch_blocks, _interleave_remote_reads,
     _peer_reads_for_fused, _push_views, _rechunk_push, gather_to_host, owner_of, plan_block_fetch, plan_fused_exchange,
     plan_fused_peer_reads, plan_rechunk_exchange, plan_rechunk_push,
 )
