@@ -411,6 +411,8 @@ class Compiled:
         fixed cost).  Multi-GPU steps are capturable on the peer-memory path: its barriers keep their
         epoch in a device counter (``b2_peer_barrier_dev``), so the captured launches are argument-stable;
         every rank must then replay the same number of times."""
+        import os
+
         import torch
 
         from . import _peer
@@ -430,16 +432,30 @@ class Compiled:
             else:
                 # independent expressions become parallel branches of the graph: the tail of one expression's big
                 # kernel (its last partial wave) overlaps the start of the next one's instead of idling the SMs
+                # The lane with the longest chain of launches (the std() tree: chunk kernel -> exchange -> two levels
+                # -> sqrt) runs on a HIGH-priority stream: its big kernel is scheduled first, and its serial tail of
+                # small launches then overlaps the other lanes' big kernels instead of trailing the whole step.
                 main = torch.cuda.current_stream()
-                side = [torch.cuda.Stream() for _ in lanes[1:]]
-                for s_ in side:
-                    s_.wait_stream(main)
-                for (lo, hi), s_ in zip(lanes, [main] + side):
-                    with torch.cuda.stream(s_):
+                order = sorted(range(len(lanes)), key=lambda i: lanes[i][0] - lanes[i][1])      # longest first
+                prio = os.environ.get("B2_LANE_PRIORITY", "1") == "1"
+                streams = {}
+                for rank_, i in enumerate(order):
+                    if rank_ == 0 and prio:
+                        streams[i] = torch.cuda.Stream(priority=-1)
+                    elif (rank_ == 1 and prio) or (rank_ == 0 and not prio):
+                        streams[i] = main
+                    else:
+                        streams[i] = torch.cuda.Stream()
+                for s_ in streams.values():
+                    if s_ is not main:
+                        s_.wait_stream(main)
+                for i, (lo, hi) in enumerate(lanes):
+                    with torch.cuda.stream(streams[i]):
                         for fn in self.tape[lo:hi]:
                             fn()
-                for s_ in side:
-                    main.wait_stream(s_)
+                for s_ in streams.values():
+                    if s_ is not main:
+                        main.wait_stream(s_)
         self._graph = g
         self.lanes = len(lanes) or 1
         return self
