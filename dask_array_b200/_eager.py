@@ -376,6 +376,8 @@ def numel(x, **kwargs):
 # ----------------------------------------------------------------------------- integer-array gathers
 def _index_chunk(ix):
     c = _as_chunk(ix)
+    if c.dtype.kind == "b":
+        raise NotImplementedError("boolean-mask indexing of a DeviceChunk (data-dependent shape; outside the hot path)")
     if c.dtype.kind not in "iu":
         raise IndexError("arrays used as indices must be of integer type")
     if c.dtype != np.int64:

@@ -323,3 +323,31 @@ def test_chunk_level_tensordot_einsum_and_exact_gemm():
         np.testing.assert_allclose(got.to_numpy(), want, rtol=1e-12, err_msg=subs)
     with pytest.raises(NotImplementedError, match="batch"):
         _eager.einsum("bij,bjk->bik", A, DeviceChunk.from_numpy(rng.random((5, 7, 2))))
+
+
+def test_get_graph_walking_on_host_objects(monkeypatch):
+    """The scheduler's graph handling without a GPU (device upload patched out): legacy tuples with nested key
+    lists and inline tasks, GraphNode-like values, aliases, literals, nested result keys, and a chain deep enough
+    to break a recursive walker."""
+    monkeypatch.setattr(plugin, "_gpu", lambda: True)
+    monkeypatch.setattr(plugin, "to_device", lambda x: x)
+    add = lambda a, b: a + b                                        # noqa: E731
+    dsk = {"a": 1, "b": (add, "a", 10), "c": (sum, ["a", "b", (add, "b", 1)]), "alias": "c",
+           ("x", 0): np.arange(4.0), ("x", 1): (np.multiply, ("x", 0), 2.0)}
+    assert plugin.get(dsk, "alias") == 1 + 11 + 12
+    out = plugin.get(dsk, [["a", "b"], [("x", 1)]])
+    assert out[0] == [1, 11] and np.array_equal(out[1][0], np.arange(4.0) * 2)
+
+    class Node:
+        def __init__(self, fn, *deps):
+            self.fn, self.deps, self.dependencies = fn, deps, frozenset(deps)
+
+        def __call__(self, values):
+            return self.fn(*[values[d] for d in self.deps])
+
+    g = {"n0": Node(lambda: 0)}
+    for i in range(1, 5000):                                        # deeper than Python's recursion limit
+        g[f"n{i}"] = Node(lambda v: v + 1, f"n{i - 1}")
+    assert plugin.get(g, "n4999") == 4999
+    with pytest.raises(KeyError):
+        plugin.get({"a": (add, "missing-is-a-literal", 1)}, "nope")
