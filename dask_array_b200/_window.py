@@ -274,13 +274,20 @@ def moving_window(x, window, reducer="move_sum", min_count=None, axis=-1):
         pad_chunks = tuple((window - 1,) if d == axis else c for d, c in enumerate(x.chunks))
         vals = concatenate([full(pad_shape, ident, dtype=dt, chunks=pad_chunks), vals], axis=axis)
         cnt_in = concatenate([full(pad_shape, 0.0, dtype=dt, chunks=pad_chunks), cnt_in], axis=axis)
+        # put the pad's length on the LAST block: the window reduction trims window - 1 there (:431-446), so the
+        # result comes out on the input's own chunks ("same shape and chunks as the input", :253)
+        along = x.chunks[axis][:-1] + (x.chunks[axis][-1] + window - 1,)
+        if min(along) >= window - 1:
+            target = tuple(along if d == axis else c for d, c in enumerate(x.chunks))
+            vals, cnt_in = vals.rechunk(target), cnt_in.rechunk(target)
     op = {"move_sum": "sum", "move_mean": "sum", "move_min": "min", "move_max": "max"}[reducer]
     red = getattr(sliding_window_view(vals, window, axis=axis), op)(axis=-1)
     cnt = sliding_window_view(cnt_in, window, axis=axis).sum(axis=-1)
     if reducer == "move_mean":
         red = elemwise("true_divide", red, cnt)
-    out = elemwise("where", elemwise("less", cnt, dt.type(limit)), dt.type(np.nan), red)
-    return out.astype(dt)
+    out = elemwise("where", elemwise("less", cnt, dt.type(limit)), dt.type(np.nan), red).astype(dt)
+    # chunks shorter than the window were merged for the halo exchange: restore the input's block structure
+    return out if out.chunks == x.chunks else out.rechunk(x.chunks)
 
 
 def block_ids_of(expr):

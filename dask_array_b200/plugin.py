@@ -237,6 +237,31 @@ def _axes(axis, ndim):
     return tuple(sorted(a % ndim for a in axis))
 
 
+def _contraction_kind(e):
+    """``"_tensordot"`` / ``"_matmul"`` when ``e`` is the reference's contraction Blockwise, else None."""
+    if _cls(e) != "Blockwise":
+        return None
+    names = _funcnames(e.func)
+    return next((n for n in ("_tensordot", "_matmul") if n in names), None)
+
+
+def _cast(e, dtype):
+    from ._blockwise import Elemwise
+
+    want = np.dtype(dtype)
+    return e if e.dtype == want else Elemwise("astype", (e,), (("dtype", want.name),))
+
+
+def _matmul_of(inner, rec):
+    from . import _matmul as mm
+    from ._collection import Array
+
+    lhs, _, rhs, _ = list(inner.args)[:4]
+    if lhs.ndim != 2 or rhs.ndim != 2:
+        raise NotImplementedError("stacked / broadcast batch matmul has no B200 kernel")
+    return mm.matmul(Array(rec(lhs)), Array(rec(rhs))).expr
+
+
 def lower_reference(expr, _memo=None):
     """Convert a reference expression (``dask_array._expr.ArrayExpr`` tree, lowered or not, fused or not) into
     this package's expression tree.  Unknown node types raise ``NotImplementedError`` naming the class --
@@ -247,6 +272,8 @@ def lower_reference(expr, _memo=None):
     from ._collection import Array
     from ._rechunk import rechunk as _rechunk
     from ._slicing import SliceSlicesIntegers, normalize_index
+    from . import _matmul as mm
+    from . import _window as win
 
     memo = {} if _memo is None else _memo
     key = getattr(expr, "_name", None) or id(expr)
@@ -286,6 +313,34 @@ def lower_reference(expr, _memo=None):
         if isinstance(arr, DeviceChunk):
             arr = arr.to_numpy()                          # re-blocked below; device leaves go through from_array
         out = ex.FromArray(np.asarray(arr), ex.normalize_chunks(expr.chunks, np.asarray(arr).shape))
+    elif name == "Sum" and _contraction_kind(expr.array) == "_tensordot":
+        # tensordot (linalg/_tensordot.py:100-136): Blockwise(_tensordot, concatenate=False) keeps the contracted
+        # axes as size-1 chunks and ``.sum(axis=left_axes)`` folds them -- ONE accumulate-over-k node here
+        inner = expr.array
+        lhs, _, rhs, _ = list(inner.args)[:4]
+        la, lb = ({**(_attr(inner, "kwargs", None) or {}), **_partial_kwargs(inner.func)})["axes"]
+        la, lb = tuple(int(a) % lhs.ndim for a in la), tuple(int(b) % rhs.ndim for b in lb)
+        if _axes(_attr(expr, "axis"), inner.ndim) != tuple(sorted(la)) or bool(_attr(expr, "keepdims", False)):
+            raise NotImplementedError("a Sum over a tensordot partial that is not its own contraction fold")
+        out = _cast(mm.tensordot(Array(rec(lhs)), Array(rec(rhs)), axes=(la, lb)).expr, expr.dtype)
+    elif name == "Reduction" and _contraction_kind(expr.array) == "_matmul" \
+            and "_chunk_sum" in _funcnames(_attr(expr, "chunk")):
+        # matmul (linalg/_tensordot.py:253-334): Blockwise(_matmul) partials (M, 1, N) + ``_sum_wo_cat`` over k
+        out = _cast(_matmul_of(expr.array, rec), expr.dtype)
+    elif name == "Squeeze" and _contraction_kind(expr.array) == "_matmul" \
+            and _axes(_attr(expr, "axis"), expr.array.ndim) == (expr.array.ndim - 2,):
+        out = _cast(_matmul_of(expr.array, rec), expr.dtype)     # one k block: ``_sum_wo_cat`` is a squeeze (:243-246)
+    elif name == "SlidingWindowReduction":
+        x = rec(expr.array)
+        out = win.SlidingWindowReduction(x, int(expr.window), int(expr.sliding_axis) % x.ndim, int(expr.window_axis),
+                                         bool(expr.keepdims), str(expr.reducer), np.dtype(expr.dtype).name)
+        if win.native_window_reduction(win.SlidingWindowView(x, (int(expr.window),), (int(expr.sliding_axis) % x.ndim,)),
+                                       str(expr.reducer), (x.ndim,), bool(expr.keepdims), np.dtype(expr.dtype)) is None:
+            raise NotImplementedError(f"SlidingWindowReduction({expr.reducer}, {np.dtype(expr.dtype)}) has no B200 kernel")
+    elif name == "MovingWindowReduction":
+        x = Array(rec(expr.array))
+        out = _cast(win.moving_window(x, int(expr.window), str(expr.reducer), int(expr.min_count),
+                                      int(expr.sliding_axis)).expr, expr.dtype)
     elif name in _TYPED or name in _TYPED_NAN:
         x = Array(rec(expr.array))
         axis = _axes(_attr(expr, "axis"), x.ndim)

@@ -135,7 +135,10 @@ def test_moving_window_trailing_nan_skipping(da, reducer, shape, chunks, axis, w
     rng = np.random.default_rng(7)
     xh = rng.random(shape) * 10 - 5
     xh[rng.random(shape) < 0.15] = np.nan
-    got = getattr(da, reducer)(da.from_array(xh, chunks=chunks), w, min_count=min_count, axis=axis).compute()
+    x = da.from_array(xh, chunks=chunks)
+    y = getattr(da, reducer)(x, w, min_count=min_count, axis=axis)
+    assert y.chunks == x.chunks                       # "same shape and chunks as the input" (:253)
+    got = y.compute()
     want = _move_ref(xh, w, reducer, min_count, axis)
     assert got.shape == want.shape and got.dtype == np.float64
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12, equal_nan=True)

@@ -144,6 +144,74 @@ def test_lower_reference_lowered_tree_by_function_names():
         assert want.chunks == ours.chunks
 
 
+def _ref_contraction(kind, ah, bh, achunks, bchunks, axes=None):
+    """Stand-ins for the reference's contraction lowering (linalg/_tensordot.py:100-136, 253-334)."""
+    def _tensordot(a, b, axes=None, is_sparse=False): ...
+    def _matmul(a, b): ...
+    def _chunk_sum(a, axis=None, dtype=None, keepdims=None): ...
+
+    a, b = ref_from_array(ah, achunks), ref_from_array(bh, bchunks)
+    if kind == "tensordot":
+        la, lb = axes
+        ndim = ah.ndim + bh.ndim - len(lb)
+        inner = node("Blockwise", func=_tensordot, args=(a, tuple(range(ah.ndim)), b, None), ndim=ndim,
+                     kwargs={"axes": (la, lb), "is_sparse": False}, concatenate=False, dtype=np.result_type(ah, bh))
+        return node("Sum", array=inner, axis=tuple(la), keepdims=False, dtype=np.result_type(ah, bh), split_every=None,
+                    aggregate=None)
+    inner = node("Blockwise", func=_matmul, args=(a, (0, 1), b, (1, 2)), ndim=3, kwargs=None, concatenate=False,
+                 dtype=np.result_type(ah, bh))
+    if len(a.chunks[1]) == 1:
+        return node("Squeeze", array=inner, axis=(1,), dtype=inner.dtype)
+    return node("Reduction", array=inner, chunk=_chunk_sum, aggregate=_chunk_sum, axis=(1,), keepdims=False,
+                dtype=inner.dtype, concatenate=False)
+
+
+def test_lower_reference_contractions_become_one_accumulating_node():
+    rng = np.random.default_rng(7)
+    ah, bh = rng.random((64, 48)), rng.random((48, 32))
+    mm = plugin.lower_reference(_ref_contraction("matmul", ah, bh, ((32, 32), (16,) * 3), ((16,) * 3, (32,))))
+    assert type(mm).__name__ == "BlockContract" and mm.shape == (64, 32) and mm.dtype == np.float64
+    one_k = plugin.lower_reference(_ref_contraction("matmul", ah, bh, ((32, 32), (48,)), ((48,), (32,))))
+    assert type(one_k).__name__ == "BlockContract" and one_k.shape == (64, 32)
+    f32 = plugin.lower_reference(_ref_contraction("matmul", ah.astype("f4"), bh.astype("f4"), ((32, 32), (16,) * 3),
+                                                  ((16,) * 3, (32,))))
+    assert type(f32).__name__ == "BlockGEMM" and f32.dtype == np.float32          # tensor-core path
+    th, uh = rng.random((8, 6, 10)), rng.random((10, 6, 4))
+    td = plugin.lower_reference(_ref_contraction("tensordot", th, uh, ((4, 4), (6,), (5, 5)), ((5, 5), (6,), (4,)),
+                                                 axes=((2, 1), (0, 1))))
+    assert type(td).__name__ == "BlockContract" and td.shape == (8, 4)
+    assert td.operand("la") == (2, 1) and td.operand("lb") == (0, 1)
+    # a Sum over the partial that is NOT the contraction fold is refused, not silently mis-lowered
+    bad = _ref_contraction("tensordot", th, uh, ((4, 4), (6,), (5, 5)), ((5, 5), (6,), (4,)), axes=((2, 1), (0, 1)))
+    bad.axis = (0,)
+    with pytest.raises(NotImplementedError, match="contraction fold"):
+        plugin.lower_reference(bad)
+    # stacked matmul has no kernel
+    s3 = _ref_contraction("matmul", rng.random((2, 4, 4)), rng.random((2, 4, 4)), ((2,), (4,), (2, 2)), ((2,), (2, 2), (4,)))
+    with pytest.raises(NotImplementedError, match="batch matmul"):
+        plugin.lower_reference(s3)
+
+
+def _ref_window(xh, chunks, window, axis, reducer, keepdims=False, dtype=None):
+    x = ref_from_array(xh, chunks)
+    return node("SlidingWindowReduction", array=x, window=window, sliding_axis=axis, window_axis=xh.ndim,
+                keepdims=keepdims, reducer=reducer, dtype=np.dtype(dtype or xh.dtype))
+
+
+def test_lower_reference_window_reductions():
+    xh = np.random.default_rng(8).random((40, 64), dtype=np.float32)
+    sw = plugin.lower_reference(_ref_window(xh, ((20, 20), (32, 32)), 5, 1, "sum"))
+    assert type(sw).__name__ == "SlidingWindowReduction" and sw.shape == (40, 60) and sw.chunks == ((20, 20), (32, 28))
+    low = sw.lower_completely() if hasattr(sw, "lower_completely") else sw._lower()
+    assert type(low).__name__ == "WindowReduce"
+    with pytest.raises(NotImplementedError, match="no B200 kernel"):
+        plugin.lower_reference(_ref_window(xh, ((20, 20), (32, 32)), 5, 1, "var"))
+    mv = node("MovingWindowReduction", array=ref_from_array(xh, ((20, 20), (32, 32))), window=4, min_count=2,
+              sliding_axis=1, reducer="move_mean", dtype=np.dtype("f4"))
+    out = plugin.lower_reference(mv)
+    assert out.shape == xh.shape and out.dtype == np.float32 and out.chunks == ((20, 20), (32, 32))
+
+
 def test_get_walks_graphs_and_needs_a_gpu():
     import torch
 
@@ -351,3 +419,36 @@ def test_get_graph_walking_on_host_objects(monkeypatch):
     assert plugin.get(g, "n4999") == 4999
     with pytest.raises(KeyError):
         plugin.get({"a": (add, "missing-is-a-literal", 1)}, "nope")
+
+
+@pytest.mark.gpu
+def test_plugin_compute_of_reference_contractions_and_windows():
+    rng = np.random.default_rng(9)
+    ah, bh = rng.random((64, 48)), rng.random((48, 32))
+    got = plugin.compute(_ref_contraction("matmul", ah, bh, ((32, 32), (16,) * 3), ((16,) * 3, (32,))), optimize=False)
+    np.testing.assert_allclose(got, ah @ bh, rtol=1e-12)
+    got = plugin.compute(_ref_contraction("matmul", ah, bh, ((32, 32), (48,)), ((48,), (32,))), optimize=False)
+    np.testing.assert_allclose(got, ah @ bh, rtol=1e-12)
+    ih, jh = rng.integers(-9, 9, (32, 24)), rng.integers(-9, 9, (24, 16))
+    got = plugin.compute(_ref_contraction("matmul", ih, jh, ((16, 16), (8,) * 3), ((8,) * 3, (16,))), optimize=False)
+    assert got.dtype == np.int64 and np.array_equal(got, ih @ jh)
+    th, uh = rng.random((8, 6, 10)), rng.random((10, 6, 4))
+    got = plugin.compute(_ref_contraction("tensordot", th, uh, ((4, 4), (6,), (5, 5)), ((5, 5), (6,), (4,)),
+                                          axes=((2, 1), (0, 1))), optimize=False)
+    np.testing.assert_allclose(got, np.tensordot(th, uh, axes=((2, 1), (0, 1))), rtol=1e-12)
+    xh = rng.random((40, 64), dtype=np.float32)
+    view = np.lib.stride_tricks.sliding_window_view
+    got = plugin.compute(_ref_window(xh, ((20, 20), (32, 32)), 5, 1, "max"), optimize=False)
+    assert np.array_equal(got, view(xh, 5, axis=1).max(axis=-1))
+    got = plugin.compute(_ref_window(xh, ((20, 20), (32, 32)), 7, 0, "sum", dtype="f4"), optimize=False)
+    np.testing.assert_allclose(got, view(xh, 7, axis=0).sum(axis=-1, dtype=np.float64), rtol=1e-5)
+    xn = xh.copy(); xn[3, 10:14] = np.nan
+    mv = node("MovingWindowReduction", array=ref_from_array(xn, ((20, 20), (32, 32))), window=4, min_count=2,
+              sliding_axis=1, reducer="move_sum", dtype=np.dtype("f4"))
+    got = plugin.compute(mv, optimize=False)
+    want = np.full(xn.shape, np.nan, dtype=np.float64)
+    for t in range(xn.shape[1]):
+        w = xn[:, max(0, t - 3):t + 1].astype(np.float64)
+        ok = (~np.isnan(w)).sum(axis=1)
+        want[:, t] = np.where(ok >= 2, np.nansum(w, axis=1), np.nan)
+    np.testing.assert_allclose(got, want, rtol=1e-5, equal_nan=True)

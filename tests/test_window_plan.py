@@ -65,3 +65,20 @@ def test_rewrite_rules():
     assert da.sliding_window_view(xi, 6, axis=0).any(axis=-1).dtype == np.bool_
     with pytest.raises(ValueError):
         da.sliding_window_view(x, 31, axis=0)
+
+
+def test_moving_window_keeps_the_input_chunks():
+    """MovingWindowReduction has the input's shape AND chunks (reductions/_sliding_window.py:253): the front pad is
+    moved onto the last block before the window kernel, or -- chunks shorter than the window -- the result is
+    re-blocked."""
+    import dask_array_b200 as da
+
+    for shape, chunks, axis, w in (((40, 64), (20, 32), 1, 4), ((60, 24), (7, 24), 0, 10), ((200,), (33,), 0, 40),
+                                   ((16, 90), (16, 11), 1, 25), ((8, 8), (8, 8), 0, 1)):
+        x = da.from_array(np.zeros(shape), chunks=chunks)
+        for red in ("move_sum", "move_mean", "move_min", "move_max"):
+            y = getattr(da, red)(x, w, axis=axis)
+            assert y.chunks == x.chunks and y.shape == x.shape and y.dtype == np.float64
+    x = da.from_array(np.zeros((40, 64), dtype="f4"), chunks=(20, 32))
+    tree = da.move_sum(x, 4, axis=1).expr.optimize().tree_repr()
+    assert tree.count("TasksRechunk") == 2 and "(32, 35)" in tree     # values + counts: ONE re-block each, before the halo
