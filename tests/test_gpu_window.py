@@ -128,7 +128,8 @@ def _move_ref(x, w, reducer, min_count, axis):
 
 @pytest.mark.parametrize("reducer", ["move_sum", "move_mean", "move_min", "move_max"])
 @pytest.mark.parametrize("shape,chunks,axis,w,min_count", [((60, 24), (7, 24), 0, 10, None), ((60, 24), (7, 24), 0, 10, 3),
-                                                          ((16, 90), (16, 11), 1, 25, 1), ((200,), (33,), 0, 40, 20)])
+                                                          ((16, 90), (16, 11), 1, 25, 1), ((200,), (33,), 0, 40, 20),
+                                                          ((40, 64), (20, 32), 1, 4, 2), ((96, 8), (32, 8), 0, 33, None)])
 def test_moving_window_trailing_nan_skipping(da, reducer, shape, chunks, axis, w, min_count):
     """MovingWindowReduction (reductions/_sliding_window.py:183-246, 249-400): chunks smaller than the window,
     windows clipped at the array start, NaNs skipped, min_count."""
