@@ -274,6 +274,7 @@ def lower_reference(expr, _memo=None):
     from ._slicing import SliceSlicesIntegers, normalize_index
     from . import _matmul as mm
     from . import _window as win
+    from . import _views as vw
 
     memo = {} if _memo is None else _memo
     key = getattr(expr, "_name", None) or id(expr)
@@ -330,6 +331,29 @@ def lower_reference(expr, _memo=None):
     elif name == "Squeeze" and _contraction_kind(expr.array) == "_matmul" \
             and _axes(_attr(expr, "axis"), expr.array.ndim) == (expr.array.ndim - 2,):
         out = _cast(_matmul_of(expr.array, rec), expr.dtype)     # one k block: ``_sum_wo_cat`` is a squeeze (:243-246)
+    elif name in ("Concatenate", "Stack"):
+        arrs = [Array(rec(a)) for a in expr.args]          # ``args`` = array + the trailing operands (:24-25)
+        out = (vw.concatenate if name == "Concatenate" else vw.stack)(arrs, axis=int(expr.axis)).expr
+    elif name == "ExpandDims":
+        x = Array(rec(expr.array))
+        for ax in sorted(int(a) for a in expr.axes):       # positions in OUTPUT coordinates (manipulation/_expand.py:26)
+            x = vw.expand_dims(x, ax)
+        out = x.expr
+    elif name == "Squeeze":
+        out = vw.squeeze(Array(rec(expr.array)), axis=_attr(expr, "axis")).expr
+    elif name == "BroadcastTo":
+        out = vw.broadcast_to(Array(rec(expr.array)), tuple(expr._shape), chunks=_attr(expr, "_chunks")).expr
+    elif name in ("CumReduction", "CumReductionBlelloch"):
+        names = _funcnames(expr.func)
+        kind = next((n for n in names if n in ("cumsum", "cumprod", "nancumsum", "nancumprod")), None)
+        if kind is None:
+            raise NotImplementedError(f"cumulative reduction {names} has no B200 kernel")
+        x = rec(expr.array)
+        dt = _attr(expr, "_dtype")
+        out = red.CumReduction(x, kind[3:] if kind.startswith("nan") else kind, int(expr.axis) % x.ndim,
+                               None if dt is None else np.dtype(dt).name, kind.startswith("nan"))
+    elif name == "Slice":
+        out = Array(rec(expr.array))[tuple(expr.index)].expr
     elif name == "SlidingWindowReduction":
         x = rec(expr.array)
         out = win.SlidingWindowReduction(x, int(expr.window), int(expr.sliding_axis) % x.ndim, int(expr.window_axis),

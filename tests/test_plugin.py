@@ -212,6 +212,46 @@ def test_lower_reference_window_reductions():
     assert out.shape == xh.shape and out.dtype == np.float32 and out.chunks == ((20, 20), (32, 32))
 
 
+def _ref_views(xh, yh, chunks):
+    x, y = ref_from_array(xh, chunks), ref_from_array(yh, chunks)
+    cat = node("Concatenate", array=x, args=[x, y], axis=1, meta=None)
+    stk = node("Stack", array=x, args=[x, y], axis=0, meta=None)
+    exp = node("ExpandDims", array=x, axes=(0, 2))
+    sqz = node("Squeeze", array=exp, axis=(0,))
+    row = node("Slice", array=x, index=(slice(0, 1), slice(None)), allow_getitem_optimization=False)
+    bto = node("BroadcastTo", array=row, _shape=(3,) + (1, xh.shape[1]), _chunks=((1,) * 3, (1,), chunks[1]),
+               _meta_override=None)
+    sl = node("Slice", array=x, index=(slice(3, None, 2), 5), allow_getitem_optimization=False)
+    return dict(cat=cat, stk=stk, exp=exp, sqz=sqz, bto=bto, sl=sl)
+
+
+def _ref_cum(xh, chunks, func, axis, method="sequential", dtype=None):
+    x = ref_from_array(xh, chunks)
+    if method == "blelloch":
+        return node("CumReductionBlelloch", array=x, func=func, preop=np.sum, binop=operator.add, axis=axis, _dtype=dtype)
+    return node("CumReduction", array=x, func=func, binop=operator.add, ident=0, axis=axis, _dtype=dtype)
+
+
+def test_lower_reference_views_and_cumulative():
+    xh, yh = np.arange(48.0).reshape(6, 8), -np.arange(48.0).reshape(6, 8)
+    v = {k: plugin.lower_reference(e) for k, e in _ref_views(xh, yh, ((3, 3), (4, 4))).items()}
+    assert v["cat"].shape == (6, 16) and v["cat"].chunks == ((3, 3), (4,) * 4)
+    assert v["stk"].shape == (2, 6, 8) and v["stk"].chunks == ((1, 1), (3, 3), (4, 4))
+    assert v["exp"].shape == (1, 6, 1, 8) and v["sqz"].shape == (6, 1, 8)
+    assert v["bto"].shape == (3, 1, 8) and v["sl"].shape == (2,)
+    def nancumsum(x, axis=None, dtype=None): ...
+    for func, kind, nan in ((np.cumsum, "cumsum", False), (np.cumprod, "cumprod", False), (nancumsum, "cumsum", True)):
+        for method in ("sequential", "blelloch"):
+            c = plugin.lower_reference(_ref_cum(xh, ((3, 3), (4, 4)), func, 1, method))
+            assert type(c).__name__ == "CumReduction" and c.operand("kind") == kind and c.operand("nan") is nan
+            assert c.chunks == ((3, 3), (4, 4)) and c.dtype == np.float64
+    c = plugin.lower_reference(_ref_cum(xh.astype("i4"), ((3, 3), (4, 4)), np.cumsum, 0, dtype="i8"))
+    assert c.dtype == np.int64
+    def cummax(x, axis=None): ...
+    with pytest.raises(NotImplementedError, match="cumulative"):
+        plugin.lower_reference(_ref_cum(xh, ((3, 3), (4, 4)), cummax, 0))
+
+
 def test_get_walks_graphs_and_needs_a_gpu():
     import torch
 
@@ -452,3 +492,24 @@ def test_plugin_compute_of_reference_contractions_and_windows():
         ok = (~np.isnan(w)).sum(axis=1)
         want[:, t] = np.where(ok >= 2, np.nansum(w, axis=1), np.nan)
     np.testing.assert_allclose(got, want, rtol=1e-5, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_plugin_compute_of_reference_views_and_cumulative():
+    rng = np.random.default_rng(10)
+    xh, yh = rng.random((6, 8)), rng.random((6, 8))
+    v = _ref_views(xh, yh, ((3, 3), (4, 4)))
+    want = dict(cat=np.concatenate([xh, yh], axis=1), stk=np.stack([xh, yh]), exp=xh[None, :, None, :],
+                sqz=xh[:, None, :], bto=np.broadcast_to(xh[0:1], (3, 1, 8)), sl=xh[3::2, 5])
+    for k, e in v.items():
+        assert np.array_equal(plugin.compute(e, optimize=False), want[k]), k
+    def nancumsum(x, axis=None, dtype=None): ...
+    xn = xh.copy(); xn[2, 3] = np.nan
+    for func, ref_fn, src in ((np.cumsum, np.cumsum, xh), (np.cumprod, np.cumprod, xh), (nancumsum, np.nancumsum, xn)):
+        for axis in (0, 1):
+            for method in ("sequential", "blelloch"):
+                got = plugin.compute(_ref_cum(src, ((3, 3), (4, 4)), func, axis, method), optimize=False)
+                np.testing.assert_allclose(got, ref_fn(src, axis=axis), rtol=1e-12)
+    ih = rng.integers(-5, 5, (6, 8)).astype("i4")
+    got = plugin.compute(_ref_cum(ih, ((3, 3), (4, 4)), np.cumsum, 0, dtype="i8"), optimize=False)
+    assert got.dtype == np.int64 and np.array_equal(got, np.cumsum(ih, axis=0, dtype="i8"))
