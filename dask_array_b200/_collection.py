@@ -25,7 +25,7 @@ def _as_operand(x):
     if isinstance(x, np.ndarray):
         if x.ndim == 0:
             return x[()]
-        return FromArray(x, normalize_chunks(x.shape, x.shape))
+        return FromArray(x, normalize_chunks("auto", x.shape, dtype=x.dtype))
     raise TypeError(f"cannot use {type(x).__name__} as an operand of a dask_array_b200 Array")
 
 
@@ -243,7 +243,7 @@ class Array:
         if kind in ("argmin", "argmax") and axis is not None and not isinstance(axis, Integral):
             raise TypeError(f"axis must be either `None` or int, got '{axis}'")
         ax = validate_axis(axis, self.ndim)
-        if ax == () and self.ndim > 0:
+        if ax == () and (self.ndim > 0 or kind not in ("argmin", "argmax")):
             # axis=(): nothing is reduced (NumPy semantics) -- an element-wise identity / cast
             from ._reductions import result_dtype
 
@@ -635,7 +635,7 @@ def compute(*arrays):
 
 def from_host_blocks(get_block, shape, chunks, dtype, token=None):
     """Array whose blocks come from ``get_block(block id) -> host ndarray``."""
-    chunks = normalize_chunks(chunks, tuple(shape))
+    chunks = normalize_chunks(chunks, tuple(shape), dtype=np.dtype(dtype))
     token = token if token is not None else f"{id(get_block):x}"
     return Array(HostBlocks(get_block, chunks, np.dtype(dtype).name, token))
 
@@ -644,9 +644,7 @@ def from_host_blocks(get_block, shape, chunks, dtype, token=None):
 def from_array(x, chunks="auto", **kwargs):
     """``da.from_array`` (``io/_from_array.py``)."""
     x = np.asarray(x)
-    if chunks == "auto":
-        chunks = x.shape
-    return Array(FromArray(x, normalize_chunks(chunks, x.shape)))
+    return Array(FromArray(x, normalize_chunks(chunks, x.shape, dtype=x.dtype)))
 
 
 def asarray(x, **kwargs):
@@ -655,10 +653,9 @@ def asarray(x, **kwargs):
 
 def _creation(value, shape, chunks, dtype):
     shape = (shape,) if isinstance(shape, Integral) else tuple(shape)
-    if chunks is None:
-        chunks = shape
     dtype = np.dtype(dtype if dtype is not None else np.float64)
-    return Array(BroadcastTrick(value, shape, normalize_chunks(chunks, shape), dtype.name))
+    chunks = "auto" if chunks is None else chunks            # the reference's default (creation/_ones_zeros.py)
+    return Array(BroadcastTrick(value, shape, normalize_chunks(chunks, shape, dtype=dtype), dtype.name))
 
 
 def ones(shape, dtype=None, chunks=None, **kw):
@@ -694,7 +691,7 @@ class _RandomGenerator:
 
     def _make(self, dist, size, chunks, dtype, args=()):
         shape = () if size is None else (size,) if isinstance(size, Integral) else tuple(size)
-        chunks = normalize_chunks(chunks if chunks is not None and chunks != "auto" else shape, shape)
+        chunks = normalize_chunks("auto" if chunks is None else chunks, shape, dtype=np.dtype(dtype))   # random/_expr.py:86-90
         ss = self._seed_seq
         first = ss.n_children_spawned
         nblocks = 1

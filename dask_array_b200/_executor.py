@@ -65,6 +65,25 @@ class World:
         return owner_of(expr, bid, self.size)
 
 
+def _fill_identity(out, kind):
+    """Write the identity of fold ``kind`` into the partial ``out`` (zero-size blocks)."""
+    dt = out.dtype
+    if kind in ("prod", "all"):
+        val = 1
+    elif kind in ("min", "nanmin", "max", "nanmax"):
+        low = kind in ("max", "nanmax")
+        if dt.kind == "f" or dt.name == "bfloat16":
+            val = -np.inf if low else np.inf
+        elif dt.kind == "b":
+            val = not low
+        else:
+            info = np.iinfo(dt)
+            val = info.min if low else info.max
+    else:
+        val = 0
+    DeviceChunk.from_numpy(np.full(out.shape, val, dtype=dt), out=out)
+
+
 class Executor:
     def __init__(self, world: World | None = None):
         if not torch.cuda.is_available():
@@ -333,6 +352,9 @@ class Executor:
                 acc_dtype = np.float32 if plan.program.out_dtype == np.float32 else np.float64
             else:
                 acc_dtype = red.dtype
+        if kind in ("min", "max", "nanmin", "nanmax") and math.prod(top.shape[a] for a in axes) == 0:
+            ufunc = {"min": "minimum", "max": "maximum", "nanmin": "fmin", "nanmax": "fmax"}[kind]
+            raise ValueError(f"zero-size array to reduction operation {ufunc} which has no identity")
         for bid in out_ids:
             shape = top.block_shape(bid) if red is not None else expr.block_shape(bid)
             if red is not None:
@@ -340,8 +362,10 @@ class Executor:
                 out = f["total"] if kind == "mean" else f[""]
                 st.blocks[bid] = {"total": out, "n": math.prod(shape[a] for a in axes)} if kind == "mean" else out
                 if math.prod(shape) == 0:
+                    # a zero-size block contributes the fold's identity (``chunk_min`` / ``chunk_max`` return an
+                    # empty partial that vanishes in the aggregate's concatenate, _common.py:92-105)
                     if out.size:
-                        out.as_torch().zero_()
+                        _fill_identity(out, kind)
                     continue
             elif math.prod(shape) == 0:
                 st.blocks[bid] = self._empty_result(expr, bid, store_kind)
@@ -406,6 +430,9 @@ class Executor:
             if not self.mine(x, bid):
                 continue
             c = src.blocks[bid]
+            if c.size == 0:
+                # np.argmax of an empty block raises inside the reference's ``arg_chunk`` too (_common.py:730-779)
+                raise ValueError(f"attempt to get {kind} of an empty sequence (block {bid} has shape {c.shape})")
             vals, arg = fields[bid]["vals"], fields[bid]["arg"]
             start = x.block_start(bid)
             kw = {}

@@ -13,31 +13,129 @@ from __future__ import annotations
 import hashlib
 import itertools
 import math
+from numbers import Number
 
 import numpy as np
 
 
-def normalize_chunks(chunks, shape):
-    """Regular-chunk subset of ``_core_utils.py:731 normalize_chunks``."""
-    if isinstance(chunks, (int, np.integer)):
-        chunks = (int(chunks),) * len(shape)
+CHUNK_SIZE_BYTES = 128 * 2**20          # ``array.chunk-size`` default ("128MiB", dask 2025.12 array schema)
+
+_BYTE_UNITS = {"": 1, "b": 1, "kb": 10**3, "mb": 10**6, "gb": 10**9, "tb": 10**12, "pb": 10**15,
+               "kib": 2**10, "mib": 2**20, "gib": 2**30, "tib": 2**40, "pib": 2**50,
+               "k": 10**3, "m": 10**6, "g": 10**9, "t": 10**12, "p": 10**15,
+               "ki": 2**10, "mi": 2**20, "gi": 2**30, "ti": 2**40, "pi": 2**50}
+
+
+def _parse_bytes(text) -> int:
+    """``dask.utils.parse_bytes``: "128MiB" -> 134217728, "1e6 kB" -> 10**9, 123 -> 123."""
+    if isinstance(text, (int, float, np.integer, np.floating)):
+        return int(text)
+    t = str(text).replace(" ", "")
+    k = len(t)
+    while k and t[k - 1].isalpha():
+        k -= 1
+    number, unit = t[:k] or "1", t[k:].lower()
+    if unit not in _BYTE_UNITS:
+        raise ValueError(f"Could not interpret {unit!r} as a byte unit")
+    return int(float(number) * _BYTE_UNITS[unit])
+
+
+def _regular(n, c):
+    """``blockdims_from_blockshape`` for one axis: ``c`` repeated, the remainder last; a zero-length axis is (0,)."""
+    n, c = int(n), int(c)
+    if n == 0:
+        return (0,)
+    if c <= 0:
+        raise ValueError(f"chunk size must be positive, got {c}")
+    full, rest = divmod(n, c)
+    return (c,) * full + ((rest,) if rest else ())
+
+
+def _auto_sizes(chunks, shape, limit, dtype):
+    """The ``previous_chunks=None`` branch of ``auto_chunks`` (``_core_utils.py:662-677``): every "auto" axis gets
+    the same edge length such that one block is ``limit`` bytes; axes shorter than that become one block and the
+    edge is recomputed for the rest."""
+    chunks = list(chunks)
+    if dtype is None:
+        raise TypeError("dtype must be known for auto-chunking")
+    dtype = np.dtype(dtype)
+    if dtype.hasobject:
+        raise NotImplementedError("Can not use auto rechunking with object dtype")
+    if dtype.itemsize == 0:
+        raise ValueError("auto-chunking with dtype.itemsize == 0 is not supported, please pass in `chunks` explicitly")
+    limit = max(1, CHUNK_SIZE_BYTES if limit is None else _parse_bytes(limit))
+    while True:
+        autos = [i for i, c in enumerate(chunks) if isinstance(c, str)]
+        if not autos:
+            return tuple(chunks)
+        fixed = math.prod(c if isinstance(c, Number) else max(c) for c in chunks if not isinstance(c, str))
+        edge = (limit / dtype.itemsize / fixed) ** (1 / len(autos))
+        small = [i for i in autos if shape[i] < edge]
+        if small:
+            for i in small:
+                chunks[i] = (int(shape[i]),)
+            continue
+        for i in autos:
+            # ``round_to`` (:507-521): edge <= axis length here, so the edge itself with a ragged last block
+            chunks[i] = max(1, int(edge))
+        return tuple(chunks)
+
+
+def normalize_chunks(chunks, shape, dtype=None, limit=None):
+    """``normalize_chunks`` (``_core_utils.py:731-885``) for known shapes: a block edge for every axis (int), one
+    per axis (tuple of ints; -1 / None = the whole axis), explicit block lengths per axis (zero-length blocks
+    allowed), ``{axis: size}``, "auto" and byte-size strings ("1kiB") -- edges chosen so a block holds
+    ``array.chunk-size`` (128 MiB) of ``dtype`` -- and the 0-d / zero-size conventions (``(1,)`` on ``()`` -> ``()``,
+    ``()`` on ``(0, 0)`` -> ``((0,), (0,))``).  ``previous_chunks=`` (re-chunking towards an aspect ratio) is not
+    mirrored."""
+    shape = tuple(int(n) for n in shape)
+    if chunks is None:
+        raise ValueError("You must specify a chunks= keyword argument.")
+    if isinstance(chunks, np.ndarray):
+        chunks = chunks.tolist()
+    if isinstance(chunks, list):
+        chunks = tuple(chunks)
+    if isinstance(chunks, (Number, str)):
+        chunks = (chunks,) * len(shape)
+    if isinstance(chunks, dict):
+        chunks = tuple(chunks.get(i, None) for i in range(len(shape)))
+    if not chunks and shape and all(n == 0 for n in shape):
+        chunks = ((0,),) * len(shape)
+    if len(shape) == 1 and len(chunks) > 1 and all(isinstance(c, (Number, str)) for c in chunks):
+        if any(isinstance(c, str) for c in chunks):
+            raise ValueError(f"String values are not supported inside explicit chunk tuples. Got chunks={chunks}")
+        chunks = (chunks,)
+    if not shape:
+        return ()                                                # ``normalize_chunks((1,), ())`` -> ``()``
     if len(chunks) != len(shape):
-        raise ValueError(f"chunks {chunks} do not match shape {shape}")
+        raise ValueError(f"Chunks and shape must be of the same length/dimension. Got chunks={chunks}, shape={shape}")
+    chunks = tuple(n if c is None or (isinstance(c, Number) and c == -1) else c for c, n in zip(chunks, shape))
+    for c in chunks:
+        if isinstance(c, str) and c != "auto":
+            text = c.replace(" ", "")
+            if not text or not text[-1].isalpha():
+                raise ValueError("String chunk sizes must be 'auto' or byte sizes with a byte unit like 'B', 'MB', "
+                                 f"or 'MiB'. Got {c!r}")
+            parsed = _parse_bytes(c)
+            if parsed < 0:
+                raise ValueError(f"String chunk byte sizes must not be negative. Got {c!r}")
+            if limit is None:
+                limit = parsed
+            elif parsed != _parse_bytes(limit):
+                raise ValueError(f"Only one consistent value of limit or chunk is allowed. Used {parsed} != {limit}")
+    chunks = tuple("auto" if isinstance(c, str) else c for c in chunks)
+    if any(isinstance(c, str) for c in chunks):
+        chunks = _auto_sizes(chunks, shape, limit, dtype)
     out = []
     for c, n in zip(chunks, shape):
         if isinstance(c, (tuple, list)):
+            if not c:
+                raise ValueError("Empty tuples are not allowed in chunks. Express zero length dimensions with 0(s) in chunks")
             if sum(c) != n:
-                raise ValueError(f"chunks {c} do not add up to {n}")
+                raise ValueError(f"Chunks do not add up to shape. Got chunks={chunks}, shape={shape}")
             out.append(tuple(int(v) for v in c))
         else:
-            c = int(c)
-            if c == -1 or c >= n:
-                out.append((int(n),))
-            else:
-                if c <= 0:
-                    raise ValueError(f"bad chunk size {c}")
-                full, rest = divmod(n, c)
-                out.append((c,) * full + ((rest,) if rest else ()))
+            out.append(_regular(n, c))
     return tuple(out)
 
 

@@ -113,7 +113,12 @@ def rechunk(x_expr, chunks):
     """``rechunk()`` (:1452): normalise the request ({axis: size} dicts, -1, ints)."""
     if isinstance(chunks, dict):
         chunks = tuple(chunks.get(d, x_expr.chunks[d]) for d in range(x_expr.ndim))
-    return Rechunk(x_expr, normalize_chunks(chunks, x_expr.shape))
+    probe = (chunks,) if isinstance(chunks, str) else chunks if isinstance(chunks, (tuple, list)) else ()
+    if any(isinstance(c, str) for c in probe):
+        # "auto" / byte sizes re-block towards the aspect ratio of the CURRENT chunks in the reference
+        # (``auto_chunks(previous_chunks=...)``, _core_utils.py:584-660), which is not mirrored
+        raise NotImplementedError('rechunk to "auto" / byte-size chunks: pass explicit block sizes')
+    return Rechunk(x_expr, normalize_chunks(chunks, x_expr.shape, dtype=x_expr.dtype))
 
 
 # ----------------------------------------------------------------------------- pushdown

@@ -340,6 +340,7 @@ class _Config:
 
     values = {
         "array.chunk-size": "128MiB",
+        "array.chunk-size-tolerance": 1.25,       # dask 2025.12 default (quoted in dask_array/_shuffle.py:97)
         "array.rechunk.threshold": 32,   # raised by dask_array/__init__.py:21-29
         "array.rechunk.method": "tasks",
         "array.slicing.split-large-chunks": None,

@@ -1,0 +1,159 @@
+"""The reference's own edge cases for the reduction path (dask_array/tests/test_reductions.py), re-stated against
+NumPy on the GPU: 0-d inputs (:163-183), zero-length blocks (:433-440), negative axes (:549-557), NaN-skipping on a
+tiny ragged array (:560-573), result types of 0-d results (:606-614), reductions over a 0-d comparison (:617-619),
+arrays with a zero-length axis (:622-635), values under every split_every of the tree-depth test (:646-681), the
+cumulative axis / method / NaN matrix (:791-808) and dtype= (:811-830).  Parts of those tests that index with a
+boolean mask (unknown chunk sizes) are outside the path and not restated.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def da():
+    import dask_array_b200 as da
+    return da
+
+
+def assert_eq(got, want, rtol=1e-12):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert got.dtype == want.dtype, (got.dtype, want.dtype)
+    if want.dtype.kind in "biu":
+        assert np.array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want, rtol=rtol, equal_nan=True)
+
+
+REDUCTIONS_0D = [("sum", np.sum), ("prod", np.prod), ("mean", np.mean), ("var", np.var), ("std", np.std), ("min", np.min),
+                 ("max", np.max), ("any", np.any), ("all", np.all), ("nansum", np.nansum), ("nanprod", np.nanprod),
+                 ("nanmean", np.mean), ("nanvar", np.var), ("nanstd", np.std), ("nanmin", np.nanmin), ("nanmax", np.nanmax)]
+
+
+@pytest.mark.parametrize("name,npfunc", REDUCTIONS_0D)
+def test_reductions_0D(da, name, npfunc):
+    x = np.int_(3)
+    a = da.from_array(x, chunks=(1,))                    # normalize_chunks((1,), ()) == ()
+    assert a.shape == () and a.chunks == ()
+    assert_eq(getattr(da, name)(a).compute(), npfunc(x))
+
+
+@pytest.mark.parametrize("name", ["max", "min", "nanmax", "nanmin", "sum", "prod", "mean", "var", "any", "all"])
+def test_zero_length_block_in_the_middle(da, name):
+    """test_min_max_empty_chunks (:438-440), widened to every fold: a zero-size block contributes the identity.
+    The values sit away from 0 on both sides so that a zero-filled partial would be caught."""
+    for x in (np.arange(10) + 20, np.arange(10) - 40):
+        a = da.from_array(x, chunks=((5, 0, 5),))
+        assert a.numblocks == (3,)
+        assert_eq(getattr(da, name)(a).compute(), getattr(np, name)(x))
+        y = (x[:, None] * np.array([1.0, -1.0, 0.5, 2.0]))
+        b = da.from_array(y, chunks=((0, 5, 0, 5), (3, 1)))
+        assert_eq(getattr(da, name)(b, axis=0).compute(), getattr(np, name)(y, axis=0))
+        assert_eq(getattr(da, name)(b).compute(), getattr(np, name)(y))
+
+
+def test_empty_reductions_fail_like_numpy(da):
+    a = da.from_array(np.arange(10), chunks=((5, 0, 5),))
+    with pytest.raises(ValueError, match="empty sequence"):        # np.argmax inside arg_chunk raises in the reference too
+        a.argmax().compute()
+    e = da.ones((0,), chunks=1)
+    for name in ("max", "min", "nanmax", "nanmin"):
+        with pytest.raises(ValueError, match="zero-size array"):   # :446-448
+            getattr(da, name)(e).compute()
+    assert e.sum().compute() == 0.0 and e.prod().compute() == 1.0
+
+
+def test_reductions_with_negative_axes(da):
+    x = np.random.default_rng(0).random((4, 4, 4))
+    a = da.from_array(x, chunks=2)
+    assert_eq(a.argmin(axis=-1).compute(), x.argmin(axis=-1))
+    assert_eq(a.argmin(axis=-1, split_every=2).compute(), x.argmin(axis=-1))
+    assert_eq(a.sum(axis=-1).compute(), x.sum(axis=-1))
+    assert_eq(a.sum(axis=(0, -1)).compute(), x.sum(axis=(0, -1)))
+
+
+def test_nan(da):
+    x = np.array([[1, np.nan, 3, 4], [5, 6, 7, np.nan], [9, 10, 11, 12]])
+    d = da.from_array(x, chunks=(2, 2))
+    assert_eq(da.nansum(d).compute(), np.nansum(x))
+    assert_eq(da.nansum(d, axis=0).compute(), np.nansum(x, axis=0))
+    assert_eq(da.nanmean(d, axis=1).compute(), np.nanmean(x, axis=1))
+    assert_eq(da.nanmin(d, axis=1).compute(), np.nanmin(x, axis=1))
+    assert_eq(da.nanmax(d, axis=(0, 1)).compute(), np.nanmax(x, axis=(0, 1)))
+    assert_eq(da.nanvar(d).compute(), np.nanvar(x))
+    assert_eq(da.nanstd(d, axis=0).compute(), np.nanstd(x, axis=0))
+    assert_eq(da.nanargmin(d, axis=0).compute(), np.nanargmin(x, axis=0))
+    assert_eq(da.nanargmax(d, axis=0).compute(), np.nanargmax(x, axis=0))
+    assert_eq(da.nanprod(d).compute(), np.nanprod(x))
+
+
+def test_0d_array(da):
+    da.mean(da.ones(4, chunks=4), axis=()).compute()
+    x = da.mean(da.ones(4, chunks=4), axis=0).compute()
+    assert type(x) == type(np.mean(np.ones(4)))
+    x = da.sum(da.zeros(4, chunks=1)).compute()
+    assert type(x) == type(np.sum(np.zeros(4)))
+
+
+def test_reduction_on_scalar(da):
+    x = da.from_array(np.array(1.0), chunks=())
+    assert bool((x == x).all().compute())
+
+
+def test_reductions_with_empty_array(da):
+    for shape in ((10, 0, 5), (0, 0, 0)):
+        dx = da.ones(shape, chunks=4)
+        x = dx.compute()
+        assert x.shape == shape
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)           # Mean of empty slice
+            assert_eq(dx.mean().compute(), x.mean())
+            assert_eq(dx.mean(axis=()).compute(), x.mean(axis=()))
+            assert_eq(dx.mean(axis=0).compute(), x.mean(axis=0))
+            assert_eq(dx.mean(axis=1).compute(), x.mean(axis=1))
+            assert_eq(dx.mean(axis=2).compute(), x.mean(axis=2))
+
+
+def test_tree_reduce_depth_values(da):
+    xh = np.arange(11 * 22 * 29).reshape((11, 22, 29))
+    x = da.from_array(xh, chunks=(3, 4, 5))
+    thresh = {0: 2, 1: 3, 2: 4}
+    for axis in (None, (), 0, 1, 2, (0, 1), (0, 2), (1, 2)):
+        for se in (thresh, 20, 40):
+            assert_eq(x.sum(axis=axis, split_every=se).compute(), xh.sum(axis=axis))
+    yh = np.arange(242).reshape((11, 22))
+    y = da.from_array(yh, chunks=(3, 4))
+    for axis in (None, (), 0, 1):
+        for se in ({0: 2, 1: 3}, 20):
+            assert_eq(y.sum(axis=axis, split_every=se).compute(), yh.sum(axis=axis))
+
+
+@pytest.mark.parametrize("func", ["cumsum", "cumprod", "nancumsum", "nancumprod"])
+@pytest.mark.parametrize("use_nan", [False, True])
+@pytest.mark.parametrize("axis", [None, 0, 1, -1])
+def test_array_cumreduction_axis(da, func, use_nan, axis):
+    s = (10, 11, 12)
+    a = np.arange(np.prod(s), dtype=float).reshape(s)
+    if use_nan:
+        a[1] = np.nan
+    d = da.from_array(a, chunks=(4, 5, 6))
+    with np.errstate(over="ignore", invalid="ignore"):
+        want = getattr(np, func)(a, axis=axis)
+        for method in ("sequential", "blelloch"):
+            got = getattr(da, func)(d, axis=axis, method=method).compute()
+            finite = np.isfinite(want)
+            assert got.shape == want.shape and got.dtype == want.dtype
+            np.testing.assert_allclose(got[finite], want[finite], rtol=1e-12)
+            assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isposinf(got), np.isposinf(want))
+
+
+@pytest.mark.parametrize("func", ["cumsum", "cumprod", "nancumsum", "nancumprod"])
+@pytest.mark.parametrize("target_dtype", [None, int, float])
+def test_array_cumreduction_dtype(da, func, target_dtype):
+    a = np.arange(1, 13).reshape(3, 4).astype(np.int32)
+    d = da.from_array(a, chunks=(2, 3))
+    assert_eq(getattr(da, func)(d, axis=0, dtype=target_dtype).compute(), getattr(np, func)(a, axis=0, dtype=target_dtype))
