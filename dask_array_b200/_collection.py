@@ -480,8 +480,12 @@ class Compiled:
 # ----------------------------------------------------------------------------- cumulative scans
 def _cumulative(kind, x, axis, dtype, out, method, nan=False):
     """``_cumreduction_expr`` (``reductions/_cumulative.py:425-448``).  ``method`` ("sequential" |
-    "blelloch") selects between two task-graph shapes in the reference; both give the same values and
-    the B200 path has one implementation (reduce -> scan of the block totals -> scan with carry)."""
+    "blelloch") selects between two task-graph shapes in the reference; the B200 path has one implementation
+    (reduce -> scan of the block totals -> scan with carry, or the chained single pass) which -- like
+    "blelloch" -- combines block totals with each other before applying them: same values up to rounding,
+    except that a product whose INTERMEDIATE block-total products overflow can give inf/NaN where a strict
+    left-to-right product would not (the reference's own blelloch test expects that warning,
+    tests/test_reductions.py:800-803)."""
     from ._reductions import CumReduction
 
     if out is not None:

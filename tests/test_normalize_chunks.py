@@ -1,0 +1,108 @@
+"""``normalize_chunks`` (dask_array/_core_utils.py:731-885) -- the chunk conventions every creation function
+goes through.  Fixed cases are the reference's own doctest examples plus outputs recorded from the reference here;
+the randomised equivalence runs against the reference's function itself (build container only, through
+tests/golden/_refshim.py)."""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+from dask_array_b200._expr import normalize_chunks
+
+HAVE_REF = os.path.exists("/root/reference/dask_array/_core_utils.py")
+
+CASES = [
+    # (chunks, shape, dtype, expected) -- the doctest examples of the reference (:744-823)
+    ((2, 2), (5, 6), None, ((2, 2, 1), (2, 2, 2))),
+    (((2, 2, 1), (2, 2, 2)), (5, 6), None, ((2, 2, 1), (2, 2, 2))),
+    ([[2, 2], [3, 3]], (4, 6), None, ((2, 2), (3, 3))),
+    (10, (30, 5), None, ((10, 10, 10), (5,))),
+    ((-1,), (10,), None, ((10,),)),
+    ((3, None), (9, 9), None, ((3, 3, 3), (9,))),
+    (("auto",), (20,), "uint8", None),             # with limit=5 below
+    ("auto", (2, 3), "int32", ((2,), (3,))),
+    ("1kiB", (2000,), "float32", ((256, 256, 256, 256, 256, 256, 256, 208),)),
+    ((), (), None, ()),
+    ((1,), (), None, ()),
+    ((), (0, 0), None, ((0,), (0,))),
+    # recorded from the reference in the build container
+    ("auto", (32768, 32768), "float32", ((5792,) * 5 + (3808,),) * 2),
+    (("auto", 4096), (32768, 32768), "float32", ((8192,) * 4, (4096,) * 8)),
+    ({0: 10}, (25, 7), "float32", ((10, 10, 5), (7,))),
+    ((5, 0, 5), (10,), None, ((5, 0, 5),)),
+    (4, (10, 0, 5), None, ((4, 4, 2), (0,), (4, 1))),
+    (np.array([2, 3]), (10, 10), None, ((2,) * 5, (3, 3, 3, 1))),
+    ("auto", (0, 5), "float64", ((0,), (5,))),
+]
+
+
+@pytest.mark.parametrize("chunks,shape,dtype,want", CASES)
+def test_fixed_cases(chunks, shape, dtype, want):
+    if want is None:
+        assert normalize_chunks(chunks, shape, dtype=dtype, limit=5) == ((5, 5, 5, 5),)
+    else:
+        assert normalize_chunks(chunks, shape, dtype=dtype) == want
+
+
+def test_errors():
+    with pytest.raises(ValueError, match="same length"):
+        normalize_chunks((2, 2, 2), (4, 4))
+    with pytest.raises(ValueError, match="add up"):
+        normalize_chunks(((2, 3), (4,)), (4, 4))
+    with pytest.raises(ValueError, match="Empty tuples"):
+        normalize_chunks(((), (4,)), (0, 4))
+    with pytest.raises(ValueError, match="String values"):
+        normalize_chunks((5, "auto"), (10,))
+    with pytest.raises(ValueError, match="byte unit"):
+        normalize_chunks("12", (10,), dtype="f4")
+    with pytest.raises(ValueError, match="consistent"):
+        normalize_chunks(("1MiB", "2MiB"), (4000, 4000), dtype="f4")
+    with pytest.raises(TypeError, match="dtype must be known"):
+        normalize_chunks("auto", (10,))
+    with pytest.raises(ValueError, match="chunks="):
+        normalize_chunks(None, (10,))
+
+
+def test_creation_defaults_follow_the_reference():
+    """chunks="auto" is the default of from_array / ones / random (io/_from_array.py:134, creation/_ones_zeros.py,
+    random/_expr.py:86-90): 128 MiB blocks, so the block structure -- and with it the per-block random streams --
+    is the reference's."""
+    import dask_array_b200 as da
+
+    assert da.ones((40000, 40000)).chunks[0] == (4096,) * 9 + (3136,)
+    assert da.random.default_rng(0).random((32768, 32768), dtype=np.float32).numblocks == (6, 6)
+    assert da.from_array(np.zeros((100, 100))).chunks == ((100,), (100,))
+    assert da.from_array(np.int_(3), chunks=(1,)).chunks == ()
+    x = da.ones((10, 10), chunks=5)
+    with pytest.raises(NotImplementedError, match="auto"):
+        x.rechunk("auto")
+    assert x.rechunk({0: -1}).chunks == ((10,), (5, 5)) and x.rechunk((2, -1)).chunks == ((2,) * 5, (10,))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference (build container)")
+def test_randomised_equivalence_with_the_reference():
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import _refshim
+
+    _refshim.install()
+    from dask_array._core_utils import normalize_chunks as ref
+
+    rng = random.Random(1)
+    for _ in range(2000):
+        nd = rng.randint(0, 4)
+        shape = tuple(rng.choice([0, 1, 7, 100, 5000, 40000, 123457]) for _ in range(nd))
+        chunks = tuple(rng.choice(["auto", "auto", -1, None, 1, 3, 64, 1000, "2MiB", (1,)]) for _ in range(nd))
+        chunks = tuple((shape[i],) if c == (1,) else c for i, c in enumerate(chunks))
+        if rng.random() < 0.2:
+            chunks = rng.choice(["auto", 5, "64MiB", -1, {0: 3}])
+        dt = rng.choice(["f4", "f8", "i1", "i8", "c16"])
+        limit = rng.choice([None, None, "1MiB", 5000, 10**9])
+
+        def call(fn, dtype):
+            try:
+                return fn(chunks, shape, limit=limit, dtype=dtype)
+            except Exception as e:          # noqa: BLE001 -- the error TYPE is part of the behaviour compared
+                return type(e).__name__
+        assert call(ref, np.dtype(dt)) == call(normalize_chunks, dt), (chunks, shape, dt, limit)
