@@ -16,7 +16,7 @@ from collections import defaultdict
 import numpy as np
 
 from . import _codegen as cg
-from ._expr import ArrayExpr, BroadcastTrick, _rewrite
+from ._expr import ArrayExpr, BroadcastTrick
 
 
 def _is_scalar(x) -> bool:

@@ -25,10 +25,9 @@ from . import _peer
 from . import _runtime as rt
 from ._blockwise import FusedBlockwise, FusedPlan
 from ._device import DeviceChunk, alloc_bytes, contiguous_strides as _contig
-from ._expr import ArrayExpr, BroadcastTrick, FromArray, HostBlocks, Random, Resident
+from ._expr import ArrayExpr
 from ._rechunk import TasksRechunk
-from ._reductions import REDOPS, ArgChunk, ChunkReduce, CumReduction, PartialReduce
-from ._slicing import SliceSlicesIntegers
+from ._reductions import REDOPS, ArgChunk, CumReduction, PartialReduce
 
 
 import os as _os

@@ -30,7 +30,6 @@ from __future__ import annotations
 
 import functools
 import importlib
-import math
 from numbers import Number
 
 import numpy as np

@@ -2,7 +2,6 @@
 rules the reference documents (README.md:52-57, tests/test_collection.py:996-1135,
 tests/test_reductions.py:646-681), reproduced by the host-side front-end."""
 import numpy as np
-import pytest
 
 import dask_array_b200 as da
 from dask_array_b200._blockwise import FusedBlockwise, FusedPlan

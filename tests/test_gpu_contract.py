@@ -3,7 +3,6 @@
 1-D / 2-D rows of test_matmul with seed 3732, test_tensordot, test_tensordot_2,
 test_tensordot_double_contraction_*).  Contract: fp64 rtol 1e-12; integers bit-exact; fp32 on the tensor
 cores |err| <= 1e-5 * (|A| . |B|) (the bf16 x 3 split; stated in DESIGN.md)."""
-import itertools
 
 import numpy as np
 import pytest

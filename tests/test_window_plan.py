@@ -1,7 +1,6 @@
 """Host logic of the sliding-window reductions on CPU: the parent rewrite, the trimmed output chunks
 (reductions/_sliding_window.py:431-446) and ``WindowHalo.pieces`` -- simulated with NumPy blocks and checked
 against the oracle's restatement of the reference's overlap-plan result."""
-import itertools
 
 import numpy as np
 import pytest
