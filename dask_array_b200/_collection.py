@@ -207,11 +207,12 @@ class Array:
 
     T = property(lambda self: self.transpose())
 
-    def rechunk(self, chunks, **kwargs):
-        """``Array.rechunk`` (:1056)."""
+    def rechunk(self, chunks="auto", threshold=None, block_size_limit=None, balance=False, method=None):
+        """``Array.rechunk`` (:1056).  ``threshold`` / ``method`` shape the reference's task graph only: the
+        re-blocking here is always one gather pass (``TasksRechunk``)."""
         from ._rechunk import rechunk
 
-        return Array(rechunk(self.expr, chunks))
+        return Array(rechunk(self.expr, chunks, block_size_limit, balance))
 
     def __getitem__(self, index):
         from ._slicing import SliceSlicesIntegers, normalize_index
@@ -789,8 +790,8 @@ def transpose(a, axes=None):
     return asarray(a).transpose(axes) if axes is not None else asarray(a).transpose()
 
 
-def rechunk(a, chunks, **kw):
-    return asarray(a).rechunk(chunks)
+def rechunk(a, chunks="auto", threshold=None, block_size_limit=None, balance=False, method=None):
+    return asarray(a).rechunk(chunks, threshold, block_size_limit, balance, method)
 
 
 def matmul(a, b):

@@ -51,10 +51,79 @@ def _regular(n, c):
     return (c,) * full + ((rest,) if rest else ())
 
 
-def _auto_sizes(chunks, shape, limit, dtype):
-    """The ``previous_chunks=None`` branch of ``auto_chunks`` (``_core_utils.py:662-677``): every "auto" axis gets
-    the same edge length such that one block is ``limit`` bytes; axes shorter than that become one block and the
-    edge is recomputed for the rest."""
+CHUNK_SIZE_TOLERANCE = 1.25             # ``array.chunk-size-tolerance`` default (dask 2025.12)
+
+
+def _auto_from_previous(chunks, shape, limit, itemsize, previous):
+    """The ``previous_chunks`` branch of ``auto_chunks`` (``_core_utils.py:584-660``), the one ``rechunk("auto")``
+    takes: grow or shrink the "auto" axes from the MEDIAN of their current block lengths by a common factor so that
+    a block holds ``limit`` bytes.  Growing keeps existing block boundaries (neighbouring blocks are merged up to the
+    proposed length); shrinking -- or growing an axis whose largest block already exceeds the proposal by the
+    tolerance -- picks a regular edge rounded to the axis' dominant block length.  An axis that outgrows its length
+    becomes one block and the factor is redistributed over the remaining axes."""
+    autos = {i for i, c in enumerate(chunks) if isinstance(c, str)}
+    fixed = math.prod(c if isinstance(c, Number) else max(c) for c in chunks if not isinstance(c, str))
+    median = {a: np.median(previous[a]) for a in autos}
+
+    def factor(sizes):
+        return limit / itemsize / fixed / math.prod(max(r) if isinstance(r, tuple) else r for r in sizes.values() if r)
+
+    mult = factor(median)
+    shrinking = mult < 1
+    # when shrinking, the running sizes ARE the result: every pass refines them and the factor is recomputed from them
+    result = median if shrinking else {}
+    dominant = []
+    for i, n in enumerate(shape):
+        counts = {}
+        for c in previous[i]:
+            counts[c] = counts.get(c, 0) + 1
+        mode, count = max(counts.items(), key=lambda kv: kv[1])
+        dominant.append(mode if mode > 1 and count >= len(previous[i]) / 2 else n)
+    again = True
+    while again:
+        live = len(autos)
+        again = False
+        for a in sorted(autos):
+            proposed = median[a] * mult ** (1 / live)
+            ceiling = proposed * CHUNK_SIZE_TOLERANCE ** (1 / live)
+            if proposed > shape[a]:
+                # the axis is exhausted: one block, and the others share what is left of the factor
+                chunks[a] = shape[a]
+                autos.remove(a)
+                del median[a]
+                fixed *= shape[a]
+                result[a] = (shape[a],)
+                again = True
+            elif shrinking or max(previous[a]) > ceiling:
+                step = dominant[a]
+                result[a] = max(1, int(proposed)) if proposed <= step else proposed // step * step
+                if proposed < 1:
+                    again = True
+                    autos.discard(a)
+            else:
+                merged, run = [], 0
+                for c in previous[a]:
+                    if run + c <= proposed:
+                        run += c
+                    else:
+                        if run > 0:
+                            merged.append(run)
+                        run = c
+                if run > 0:
+                    merged.append(run)
+                result[a] = tuple(merged)
+        if again or shrinking:
+            before, mult = mult, factor(median)
+            again = again or mult != before
+    for a, v in result.items():
+        chunks[a] = v if v else 0
+    return tuple(chunks)
+
+
+def _auto_sizes(chunks, shape, limit, dtype, previous=None):
+    """``auto_chunks`` (``_core_utils.py:524-677``).  Without ``previous``: every "auto" axis gets the same edge
+    length such that one block is ``limit`` bytes; axes shorter than that become one block and the edge is
+    recomputed for the rest (:662-677).  With ``previous``: ``_auto_from_previous``."""
     chunks = list(chunks)
     if dtype is None:
         raise TypeError("dtype must be known for auto-chunking")
@@ -64,6 +133,8 @@ def _auto_sizes(chunks, shape, limit, dtype):
     if dtype.itemsize == 0:
         raise ValueError("auto-chunking with dtype.itemsize == 0 is not supported, please pass in `chunks` explicitly")
     limit = max(1, CHUNK_SIZE_BYTES if limit is None else _parse_bytes(limit))
+    if previous:
+        return _auto_from_previous(chunks, shape, limit, dtype.itemsize, previous)
     while True:
         autos = [i for i, c in enumerate(chunks) if isinstance(c, str)]
         if not autos:
@@ -81,13 +152,13 @@ def _auto_sizes(chunks, shape, limit, dtype):
         return tuple(chunks)
 
 
-def normalize_chunks(chunks, shape, dtype=None, limit=None):
+def normalize_chunks(chunks, shape, dtype=None, limit=None, previous_chunks=None):
     """``normalize_chunks`` (``_core_utils.py:731-885``) for known shapes: a block edge for every axis (int), one
     per axis (tuple of ints; -1 / None = the whole axis), explicit block lengths per axis (zero-length blocks
     allowed), ``{axis: size}``, "auto" and byte-size strings ("1kiB") -- edges chosen so a block holds
     ``array.chunk-size`` (128 MiB) of ``dtype`` -- and the 0-d / zero-size conventions (``(1,)`` on ``()`` -> ``()``,
-    ``()`` on ``(0, 0)`` -> ``((0,), (0,))``).  ``previous_chunks=`` (re-chunking towards an aspect ratio) is not
-    mirrored."""
+    ``()`` on ``(0, 0)`` -> ``((0,), (0,))``).  ``previous_chunks=`` (the current blocks of an array being
+    re-chunked) makes "auto" scale those instead of starting from a cube."""
     shape = tuple(int(n) for n in shape)
     if chunks is None:
         raise ValueError("You must specify a chunks= keyword argument.")
@@ -125,7 +196,10 @@ def normalize_chunks(chunks, shape, dtype=None, limit=None):
                 raise ValueError(f"Only one consistent value of limit or chunk is allowed. Used {parsed} != {limit}")
     chunks = tuple("auto" if isinstance(c, str) else c for c in chunks)
     if any(isinstance(c, str) for c in chunks):
-        chunks = _auto_sizes(chunks, shape, limit, dtype)
+        prev = None
+        if previous_chunks is not None:
+            prev = tuple(_regular(n, c) if isinstance(c, Number) else tuple(c) for n, c in zip(shape, previous_chunks))
+        chunks = _auto_sizes(chunks, shape, limit, dtype, prev)
     out = []
     for c, n in zip(chunks, shape):
         if isinstance(c, (tuple, list)):

@@ -109,16 +109,50 @@ def _short(chunks):
     return tuple((c[0],) if len(set(c)) == 1 else c for c in chunks)
 
 
-def rechunk(x_expr, chunks):
-    """``rechunk()`` (:1452): normalise the request ({axis: size} dicts, -1, ints)."""
+def balance_chunksizes(chunks):
+    """``_balance_chunksizes`` (:529-560): among the regular blockings whose edge lies within half a median of the
+    median block length and that give the same number of blocks (one fewer when the smallest block is at most half
+    the largest), take the one with the smallest spread; unchanged when none exists or a block is empty."""
+    if min(chunks) == 0:
+        return tuple(chunks)
+    total = sum(chunks)
+    median = int(np.median(chunks))
+    want = len(chunks) - (1 if min(chunks) <= 0.5 * max(chunks) else 0)
+    best = None
+    for edge in range(median - median // 2, median + median // 2 + 1):
+        full, rest = divmod(total, edge)
+        cand = (edge,) * full + ((rest,) if rest else ())
+        if len(cand) == want and (best is None or max(cand) - min(cand) < max(best) - min(best)):
+            best = cand
+    if best is None:
+        import warnings
+
+        warnings.warn("chunk size balancing not possible with given chunks. Try increasing the chunk size.")
+        return tuple(chunks)
+    return best
+
+
+def rechunk(x_expr, chunks="auto", block_size_limit=None, balance=False):
+    """``rechunk()`` (:1452) / ``Rechunk.chunks`` (:690-718): ``{axis: size}`` dicts (negative axes, missing / None
+    entries keep the current blocks), None entries in tuples, -1, ints, explicit blocks, and "auto" / byte sizes,
+    which scale the CURRENT blocks (``previous_chunks=x.chunks``) up to ``block_size_limit`` (default 128 MiB)."""
+    nd = x_expr.ndim
     if isinstance(chunks, dict):
-        chunks = tuple(chunks.get(d, x_expr.chunks[d]) for d in range(x_expr.ndim))
-    probe = (chunks,) if isinstance(chunks, str) else chunks if isinstance(chunks, (tuple, list)) else ()
-    if any(isinstance(c, str) for c in probe):
-        # "auto" / byte sizes re-block towards the aspect ratio of the CURRENT chunks in the reference
-        # (``auto_chunks(previous_chunks=...)``, _core_utils.py:584-660), which is not mirrored
-        raise NotImplementedError('rechunk to "auto" / byte-size chunks: pass explicit block sizes')
-    return Rechunk(x_expr, normalize_chunks(chunks, x_expr.shape, dtype=x_expr.dtype))
+        given = {}
+        for ax, v in chunks.items():
+            if not -nd <= ax < nd:
+                raise ValueError(f"axis {ax} is out of bounds for array of dimension {nd}")
+            given[ax % nd] = v
+        chunks = tuple(x_expr.chunks[d] if given.get(d) is None else given[d] for d in range(nd))
+    if isinstance(chunks, (tuple, list)):
+        chunks = tuple(cur if c is None else c for c, cur in zip(chunks, x_expr.chunks)) if len(chunks) == nd else tuple(chunks)
+    new = normalize_chunks(chunks, x_expr.shape, dtype=x_expr.dtype, limit=block_size_limit,
+                           previous_chunks=x_expr.chunks)
+    if len(new) != nd:
+        raise ValueError("Provided chunks are not consistent with shape")
+    if balance:
+        new = tuple(balance_chunksizes(c) for c in new)
+    return Rechunk(x_expr, new)
 
 
 # ----------------------------------------------------------------------------- pushdown

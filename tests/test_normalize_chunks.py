@@ -76,9 +76,77 @@ def test_creation_defaults_follow_the_reference():
     assert da.from_array(np.zeros((100, 100))).chunks == ((100,), (100,))
     assert da.from_array(np.int_(3), chunks=(1,)).chunks == ()
     x = da.ones((10, 10), chunks=5)
-    with pytest.raises(NotImplementedError, match="auto"):
-        x.rechunk("auto")
     assert x.rechunk({0: -1}).chunks == ((10,), (5, 5)) and x.rechunk((2, -1)).chunks == ((2,) * 5, (10,))
+    assert x.rechunk({-1: 2, 0: None}).chunks == ((5, 5), (2,) * 5) and x.rechunk((None, 10)).chunks == ((5, 5), (10,))
+    with pytest.raises(ValueError, match="out of bounds"):
+        x.rechunk({2: 1})
+
+
+def test_rechunk_auto_scales_the_current_blocks():
+    """``rechunk("auto")`` (``Rechunk.chunks`` _rechunk.py:690-718 -> ``auto_chunks(previous_chunks=x.chunks)``):
+    expected values recorded from the reference's ``normalize_chunks`` in the build container."""
+    import dask_array_b200 as da
+
+    x = da.ones((32768, 32768), dtype="f4", chunks=(4096, 256))
+    # growing keeps the aspect ratio of the median block (16 : 1) and merges existing blocks: 20480 x 1280 = 100 MiB
+    assert x.rechunk().chunks == ((20480, 12288), (1280,) * 25 + (768,))
+    assert x.rechunk(("auto", -1)).chunks == ((1024,) * 32, (32768,))
+    assert x.rechunk("1MiB").chunks == ((2048,) * 16, (128,) * 256)       # shrinking: regular edges, same aspect ratio
+    assert x.rechunk({0: "auto"}, block_size_limit=2**20).chunks == ((1024,) * 32, (256,) * 128)
+    y = da.ones((1000,), chunks=((300, 300, 300, 100),))
+    assert y.rechunk(250, balance=True).chunks == ((250,) * 4,)
+    assert y.rechunk(400, balance=True).chunks == ((500, 500),)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference (build container)")
+def test_auto_from_previous_and_balance_match_the_reference():
+    import warnings
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import _refshim
+
+    _refshim.install()
+    from dask_array._core_utils import normalize_chunks as ref
+    from dask_array._rechunk import _balance_chunksizes as ref_balance
+    from dask_array_b200._rechunk import balance_chunksizes
+
+    rng = random.Random(7)
+
+    def blocks(n):
+        if rng.random() < 0.5:
+            c = min(n, rng.choice([1, 2, 5, 10, 64, 100, 1000, 4096, n]))
+            full, rest = divmod(n, c)
+            return (c,) * full + ((rest,) if rest else ())
+        parts, rem = [], n
+        while rem > 0:
+            t = rng.randint(1, max(1, min(rem, rng.choice([3, 50, 2000, 100000]))))
+            parts.append(t)
+            rem -= t
+        return tuple(parts)
+
+    for _ in range(1500):
+        nd = rng.randint(1, 4)
+        shape = tuple(rng.choice([1, 7, 100, 5000, 40000, 123457]) for _ in range(nd))
+        prev = tuple(blocks(n) for n in shape)
+        chunks = tuple(rng.choice(["auto", "auto", "auto", -1, None, 3, 64, "2MiB"]) for _ in range(nd))
+        chunks = tuple(prev[i] if c is None else c for i, c in enumerate(chunks))
+        if rng.random() < 0.2:
+            chunks = rng.choice(["auto", "64MiB", "10kiB"])
+        dt = rng.choice(["f4", "f8", "i1", "c16"])
+        limit = rng.choice([None, None, None, "1MiB", 5000, 10**9, 100])
+
+        def call(fn, dtype):
+            try:
+                return fn(chunks, shape, limit=limit, dtype=dtype, previous_chunks=prev)
+            except Exception as e:          # noqa: BLE001
+                return type(e).__name__
+        assert call(ref, np.dtype(dt)) == call(normalize_chunks, dt), (chunks, shape, prev, dt, limit)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(1500):
+            ch = blocks(rng.choice([5, 17, 100, 1000, 4097])) if rng.random() < 0.6 else \
+                tuple(rng.randint(1, rng.choice([3, 20, 500])) for _ in range(rng.randint(1, 12)))
+            assert tuple(int(v) for v in ref_balance(ch)) == balance_chunksizes(ch), ch
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference (build container)")
