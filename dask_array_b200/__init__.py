@@ -13,7 +13,7 @@ from ._collection import (  # noqa: F401
     UFUNC_NAMES, Array, Compiled, _method, _ufunc, asarray, compile, compute, elemwise, from_array,
     dot, from_host_blocks, full, matmul, nanargmax, nanargmin, nanmax, nanmean, nanmin, nanprod, nanstd, nansum,
     nanvar, ones, random, tensordot, einsum, cumsum, cumprod, nancumsum, nancumprod,
-    rechunk, transpose, where, zeros, divmod, modf, frexp,
+    rechunk, transpose, where, zeros, divmod, modf, frexp, arange, linspace,
 )
 
 from ._views import broadcast_to, concatenate, expand_dims, ravel, squeeze, stack  # noqa: F401,E402
@@ -51,5 +51,5 @@ for _n in ("sum", "prod", "mean", "var", "std", "min", "max", "any", "all", "arg
     globals()[_n] = _method(_n)
 del _n
 
-__all__ = ["Array", "from_array", "asarray", "ones", "zeros", "full", "random", "elemwise", "where",
+__all__ = ["Array", "from_array", "asarray", "ones", "zeros", "full", "arange", "linspace", "random", "elemwise", "where",
            "transpose", "rechunk", "matmul"] + UFUNC_NAMES

@@ -678,6 +678,61 @@ def full(shape, fill_value, dtype=None, chunks=None, **kw):
     return _creation(fill_value, shape, chunks, dtype)
 
 
+_NO_START = object()
+
+
+def _host_sequence(label, params, dtype, chunks, make_block):
+    import hashlib
+
+    token = hashlib.sha1(repr((label, params, dtype.name, chunks)).encode()).hexdigest()[:16]
+    return Array(HostBlocks(make_block, chunks, dtype.name, f"{label}-{token}"))
+
+
+def arange(start=_NO_START, stop=None, step=1, *, chunks="auto", like=None, dtype=None):
+    """``da.arange`` (``creation/_arange.py:127-185``): block ``k`` is ``np.arange`` over its own
+    ``[start + first_k * step, start + (first_k + len_k) * step)`` (``Arange._layer`` :102-123, ``_chunk.arange``
+    :320-332), generated on the host and staged once like the random streams."""
+    if start is _NO_START:
+        if stop is None:
+            raise TypeError("arange() requires stop to be specified.")
+        start = 0
+    elif stop is None:
+        start, stop = 0, start
+    if start != 0 and not np.isclose(start + step - start, step, atol=0):
+        # very large start with a small float step: build from zero and shift (:180-183)
+        return arange(0, stop - start, step, chunks=chunks, dtype=dtype) + start
+    num = int(max(np.ceil((stop - start) / step), 0))
+    dt = np.dtype(dtype) if dtype is not None else np.arange(type(start)(0), type(stop)(0), step).dtype
+    blocks = normalize_chunks(chunks, (num,), dtype=dt)
+    firsts = np.concatenate([[0], np.cumsum(blocks[0])]).tolist()
+
+    def make_block(bid):
+        first, n = firsts[bid[0]], blocks[0][bid[0]]
+        res = np.arange(start + first * step, start + (first + n) * step, step, dtype=dt)
+        return res[:-1] if len(res) > n else res
+    return _host_sequence("arange", (start, stop, step), dt, blocks, make_block)
+
+
+def linspace(start, stop, num=50, endpoint=True, retstep=False, chunks="auto", dtype=None):
+    """``da.linspace`` (``creation/_linspace.py:104-145``): ``step = (stop - start) / (num - 1 | num)``; block ``k``
+    is ``np.linspace`` from its running start over its own length (``Linspace._layer`` :84-101)."""
+    num = int(num)
+    dt = np.dtype(dtype) if dtype is not None else np.linspace(0, 1, 1).dtype
+    div = (num - 1) if endpoint else num
+    step = float(stop - start) / (div if div else 1)
+    blocks = normalize_chunks(chunks, (num,), dtype=dt)
+    edges, at = [], start
+    for n in blocks[0]:
+        edges.append((at, at + ((n - 1) if endpoint else n) * step))
+        at = at + step * n
+
+    def make_block(bid):
+        lo, hi = edges[bid[0]]
+        return np.linspace(lo, hi, blocks[0][bid[0]], endpoint=endpoint, dtype=dt)
+    out = _host_sequence("linspace", (start, stop, num, bool(endpoint)), dt, blocks, make_block)
+    return (out, step) if retstep else out
+
+
 class _RandomGenerator:
     """``da.random.default_rng(seed)`` (``random/_generator.py:425-441``): one live ``SeedSequence`` per
     generator (fresh OS entropy when ``seed`` is None); every draw spawns one child per block from it

@@ -308,6 +308,15 @@ def lower_reference(expr, _memo=None):
         value = {"Ones": 1, "Zeros": 0, "Empty": 0}.get(name, kw.get("fill_value", 0))
         out = ex.BroadcastTrick(value, tuple(expr.shape), ex.normalize_chunks(expr.chunks, tuple(expr.shape)),
                                 np.dtype(expr.dtype).name)
+    elif name == "Arange":
+        from . import _collection as col
+
+        out = col.arange(expr.start, expr.stop, expr.step, chunks=tuple(expr.chunks), dtype=np.dtype(expr.dtype)).expr
+    elif name == "Linspace":
+        from . import _collection as col
+
+        out = col.linspace(expr.start, expr.stop, int(_attr(expr, "num", 50)), endpoint=bool(_attr(expr, "endpoint", True)),
+                           chunks=tuple(expr.chunks), dtype=np.dtype(expr.dtype)).expr
     elif name == "FromArray":
         arr = expr.array
         if isinstance(arr, DeviceChunk):

@@ -174,3 +174,41 @@ def test_randomised_equivalence_with_the_reference():
             except Exception as e:          # noqa: BLE001 -- the error TYPE is part of the behaviour compared
                 return type(e).__name__
         assert call(ref, np.dtype(dt)) == call(normalize_chunks, dt), (chunks, shape, dt, limit)
+
+
+def _host_values(a):
+    e = a.expr
+    get = e.operand("get_block")
+    return np.concatenate([get((k,)) for k in range(len(e.chunks[0]))])
+
+
+@pytest.mark.parametrize("args,kw", [((10,), {}), ((2, 20, 3), {"chunks": 4}), ((0, 1, 0.1), {"chunks": 3}),
+                                      ((77, 130, 1), {"chunks": 5}), ((10, 0, -2), {"chunks": 2}),
+                                      ((5,), {"dtype": "f4", "chunks": 2}), ((0,), {}), ((1, 31.3, 2.5), {"chunks": 7}),
+                                      ((2**63 - 10000, 2**63 - 1, 100), {"chunks": 30})])
+def test_arange_blocks(args, kw):
+    """creation/_arange.py:102-123 (tests/test_creation.py arange cases): every block is generated from its own
+    start / stop; the concatenation is NumPy's arange."""
+    import dask_array_b200 as da
+
+    a = da.arange(*args, **kw)
+    want = np.arange(*args, dtype=kw.get("dtype"))
+    assert a.dtype == want.dtype and a.shape == want.shape
+    assert sum(a.chunks[0]) == want.size and (want.size == 0 or max(a.chunks[0]) <= kw.get("chunks", want.size))
+    np.testing.assert_allclose(_host_values(a), want, rtol=1e-15)
+    assert da.arange(*args, **kw).name == a.name                        # deterministic names
+
+
+@pytest.mark.parametrize("args,kw", [((6, 49), {"chunks": 5, "num": 13}), ((1.4, 4.9), {"chunks": 5, "num": 13}),
+                                      ((0, 1), {"num": 50, "endpoint": False, "chunks": 7}),
+                                      ((6, 49), {"chunks": 5, "num": 13, "dtype": int}), ((0, 1), {"num": 1}), ((0, 1), {"num": 0})])
+def test_linspace_blocks(args, kw):
+    import dask_array_b200 as da
+
+    a = da.linspace(*args, **kw)
+    want = np.linspace(*args, **{k: v for k, v in kw.items() if k != "chunks"})
+    assert a.dtype == want.dtype and a.shape == want.shape
+    np.testing.assert_allclose(_host_values(a), want, rtol=1e-13)
+    _, step = da.linspace(*args, retstep=True, **kw)
+    if want.size > 1:
+        assert step == pytest.approx(np.linspace(*args, retstep=True, **{k: v for k, v in kw.items() if k != "chunks"})[1])

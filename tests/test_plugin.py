@@ -250,6 +250,11 @@ def test_lower_reference_views_and_cumulative():
     def cummax(x, axis=None): ...
     with pytest.raises(NotImplementedError, match="cumulative"):
         plugin.lower_reference(_ref_cum(xh, ((3, 3), (4, 4)), cummax, 0))
+    ar = plugin.lower_reference(node("Arange", start=3, stop=40, step=4, chunks=((4, 4, 2),), like=None, dtype=np.dtype("i8")))
+    assert ar.shape == (10,) and ar.chunks == ((4, 4, 2),) and ar.dtype == np.int64
+    assert np.array_equal(np.concatenate([ar.operand("get_block")((k,)) for k in range(3)]), np.arange(3, 40, 4))
+    ls = plugin.lower_reference(node("Linspace", start=0.0, stop=1.0, num=11, endpoint=True, chunks=((6, 5),), dtype=np.dtype("f8")))
+    np.testing.assert_allclose(np.concatenate([ls.operand("get_block")((k,)) for k in range(2)]), np.linspace(0, 1, 11), rtol=1e-15)
 
 
 def test_get_walks_graphs_and_needs_a_gpu():
