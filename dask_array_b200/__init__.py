@@ -13,7 +13,8 @@ from ._collection import (  # noqa: F401
     UFUNC_NAMES, Array, Compiled, _method, _ufunc, asarray, compile, compute, elemwise, from_array,
     dot, from_host_blocks, full, matmul, nanargmax, nanargmin, nanmax, nanmean, nanmin, nanprod, nanstd, nansum,
     nanvar, ones, random, tensordot, einsum, cumsum, cumprod, nancumsum, nancumprod,
-    rechunk, transpose, where, zeros, divmod, modf, frexp, arange, linspace,
+    rechunk, transpose, where, zeros, divmod, modf, frexp, arange, linspace, clip, round, around, swapaxes, moveaxis,
+    rollaxis, real, imag, conj, conjugate,
 )
 
 from ._views import broadcast_to, concatenate, expand_dims, ravel, squeeze, stack  # noqa: F401,E402
@@ -52,4 +53,4 @@ for _n in ("sum", "prod", "mean", "var", "std", "min", "max", "any", "all", "arg
 del _n
 
 __all__ = ["Array", "from_array", "asarray", "ones", "zeros", "full", "arange", "linspace", "random", "elemwise", "where",
-           "transpose", "rechunk", "matmul"] + UFUNC_NAMES
+           "transpose", "rechunk", "matmul", "clip", "round", "around", "swapaxes", "moveaxis", "rollaxis"] + UFUNC_NAMES

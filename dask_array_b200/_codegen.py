@@ -444,6 +444,11 @@ def _emit(name, args, out, kw) -> str:
                 return a(0)
             raise NotImplementedError(f"{name} on dtype {out}")
         return f"{_UNARY_MATH[name][fidx]}({a(0)})"
+    if name == "fmod" and not isf:
+        # C's % truncates toward zero like np.fmod; NumPy gives 0 for a zero divisor, and x % -1 is 0 (INT_MIN too)
+        if out.kind == "u":
+            return f"((({a(1)}) == 0) ? ({T})0 : ({T})(({a(0)}) % ({a(1)})))"
+        return f"((({a(1)}) == 0 || ({a(1)}) == ({T})-1) ? ({T})0 : ({T})(({a(0)}) % ({a(1)})))"
     if name in _BINARY_MATH:
         if not isf:
             raise NotImplementedError(f"{name} on dtype {out}")

@@ -6,6 +6,7 @@ the blocks device-resident under the same expression name (:285-300).
 """
 from __future__ import annotations
 
+import math
 import operator
 from numbers import Integral, Number
 
@@ -206,6 +207,29 @@ class Array:
         return Array(Transpose(self.expr, axes))
 
     T = property(lambda self: self.transpose())
+
+    def swapaxes(self, axis1, axis2):
+        return swapaxes(self, axis1, axis2)
+
+    # ---- small conveniences of the reference's collection (``_collection.py:585-700, 1611-1700``)
+    itemsize = property(lambda self: self.dtype.itemsize)
+    npartitions = property(lambda self: math.prod(self.numblocks))
+    chunksize = property(lambda self: tuple(max(c) for c in self.chunks))
+    real = property(lambda self: real(self))
+    imag = property(lambda self: imag(self))
+
+    def copy(self):
+        """Arrays are immutable descriptions: a copy shares the expression (``Array.copy`` :1688)."""
+        return Array(self.expr)
+
+    def conj(self):
+        return conj(self)
+
+    def clip(self, min=None, max=None):
+        return clip(self, min, max)
+
+    def round(self, decimals=0):
+        return round(self, decimals)
 
     def rechunk(self, chunks="auto", threshold=None, block_size_limit=None, balance=False, method=None):
         """``Array.rechunk`` (:1056).  ``threshold`` / ``method`` shape the reference's task graph only: the
@@ -804,7 +828,7 @@ UFUNC_NAMES = [
     "logical_and", "logical_or", "logical_xor", "logical_not", "maximum", "minimum", "fmax", "fmin",
     "bitwise_and", "bitwise_or", "bitwise_xor", "bitwise_not", "invert", "left_shift", "right_shift",
     "isfinite", "isinf", "isnan", "signbit", "copysign", "nextafter", "floor", "ceil", "trunc", "rint",
-    "fabs", "sign", "absolute", "abs", "clip",
+    "fabs", "sign", "absolute", "abs",
 ]
 
 
@@ -843,6 +867,107 @@ def _method(name):
 
 def transpose(a, axes=None):
     return asarray(a).transpose(axes) if axes is not None else asarray(a).transpose()
+
+
+def swapaxes(a, axis1, axis2):
+    """``swapaxes`` (``manipulation/_transpose.py:243-261``)."""
+    a = asarray(a)
+    if axis1 == axis2:
+        return a
+    order = list(range(a.ndim))
+    i, j = validate_axis(axis1, a.ndim)[0], validate_axis(axis2, a.ndim)[0]
+    order[i], order[j] = order[j], order[i]
+    return a.transpose(order)
+
+
+def moveaxis(a, source, destination):
+    """``moveaxis`` (``manipulation/_transpose.py:264-285``)."""
+    a = asarray(a)
+    src = tuple(s % a.ndim for s in ((source,) if isinstance(source, Integral) else source))
+    dst = tuple(d % a.ndim for d in ((destination,) if isinstance(destination, Integral) else destination))
+    if len(src) != len(dst):
+        raise ValueError("`source` and `destination` arguments must have the same number of elements")
+    order = [n for n in range(a.ndim) if n not in src]
+    for d, s_ in sorted(zip(dst, src)):
+        order.insert(d, s_)
+    return a.transpose(order)
+
+
+def rollaxis(a, axis, start=0):
+    """``rollaxis`` (``manipulation/_transpose.py:288-313``)."""
+    a = asarray(a)
+    n = a.ndim
+    axis = validate_axis(axis, n)[0]
+    if start < 0:
+        start += n
+    if not 0 <= start < n + 1:
+        raise ValueError("'%s' arg requires %d <= %s < %d, but %d was passed in" % ("start", -n, "start", n + 1, start))
+    if axis < start:
+        start -= 1
+    if axis == start:
+        return a
+    order = list(range(n))
+    order.remove(axis)
+    order.insert(start, axis)
+    return a.transpose(order)
+
+
+def clip(a, a_min=None, a_max=None, **kwargs):
+    """``clip`` (``_ufunc.py``): one-sided bounds are ``maximum`` / ``minimum``."""
+    a_min = kwargs.pop("min", a_min)
+    a_max = kwargs.pop("max", a_max)
+    if kwargs:
+        raise TypeError(f"clip() got unexpected arguments {sorted(kwargs)}")
+    if a_min is None and a_max is None:
+        raise ValueError("One of max or min must be given")
+    if a_min is None:
+        return elemwise("minimum", a, a_max)
+    if a_max is None:
+        return elemwise("maximum", a, a_min)
+    return elemwise("clip", a, a_min, a_max)
+
+
+def round(a, decimals=0):   # noqa: A001
+    """``round`` / ``around`` (``_ufunc.py:453-462``): NumPy's own scheme -- scale by ``10**decimals``, ``rint``,
+    scale back (``decimals < 0``: divide first) -- as one fused kernel; integers with ``decimals >= 0`` are unchanged."""
+    a = asarray(a)
+    decimals = int(decimals)
+    if a.dtype.kind in "biu":
+        if decimals >= 0:
+            return a
+        raise NotImplementedError("round of an integer array to negative decimals")
+    if decimals == 0:
+        return elemwise("rint", a)
+    scale = a.dtype.type(10.0 ** abs(decimals))
+    if decimals > 0:
+        return elemwise("true_divide", elemwise("rint", elemwise("multiply", a, scale)), scale)
+    return elemwise("multiply", elemwise("rint", elemwise("true_divide", a, scale)), scale)
+
+
+around = round
+
+
+def _no_complex(a):
+    a = asarray(a)
+    if a.dtype.kind == "c":
+        raise NotImplementedError("complex arrays have no B200 kernels")
+    return a
+
+
+def real(a):
+    return _no_complex(a)
+
+
+def conj(a):
+    return _no_complex(a)
+
+
+conjugate = conj
+
+
+def imag(a):
+    a = _no_complex(a)
+    return Array(BroadcastTrick(0, a.shape, a.chunks, a.dtype.name))
 
 
 def rechunk(a, chunks="auto", threshold=None, block_size_limit=None, balance=False, method=None):

@@ -167,15 +167,3 @@ def test_array_cumreduction_dtype(da, func, target_dtype):
     a = np.arange(1, 13).reshape(3, 4).astype(np.int32)
     d = da.from_array(a, chunks=(2, 3))
     assert_eq(getattr(da, func)(d, axis=0, dtype=target_dtype).compute(), getattr(np, func)(a, axis=0, dtype=target_dtype))
-
-
-def test_arange_and_linspace(da):
-    """creation/_arange.py, creation/_linspace.py: host-generated per block, staged once, then on the device path."""
-    a = da.arange(2, 2000, 3, chunks=100)
-    assert_eq(a.compute(), np.arange(2, 2000, 3))
-    assert_eq((a * 2 + 1).sum().compute(), (np.arange(2, 2000, 3) * 2 + 1).sum())
-    assert_eq(a[::-7].compute(), np.arange(2, 2000, 3)[::-7])
-    f = da.linspace(1.4, 4.9, 1300, chunks=500)
-    assert_eq(f.compute(), np.linspace(1.4, 4.9, 1300), rtol=1e-13)
-    assert_eq(f.mean().compute(), np.linspace(1.4, 4.9, 1300).mean(), rtol=1e-12)
-    assert da.arange(0).compute().shape == (0,)

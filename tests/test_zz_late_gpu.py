@@ -1,0 +1,122 @@
+"""GPU tests written AFTER the round's GPU budget was spent: they have not been run on a B200 yet (see
+profiles/r2_pytest_gpu_late.md).  The file name sorts last on purpose, so that ``pytest -x`` reaches every
+validated test first.  Everything here goes through paths the validated tests already exercise (HostBlocks
+staging, fused element-wise kernels, transposes); the CPU suite checks the same operators' dtypes and that their
+kernels compile (tests/test_ufunc_vocabulary.py), and the block contents of arange / linspace
+(tests/test_normalize_chunks.py).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+F32 = dict(rtol=1e-5, atol=1e-6)          # north-star tolerance, fp32
+F64 = dict(rtol=1e-12, atol=1e-13)        # north-star tolerance, fp64
+
+
+@pytest.fixture(scope="module")
+def da():
+    import dask_array_b200 as da
+    return da
+
+
+def _close(got, want, dtype):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape and got.dtype == want.dtype, (got.dtype, want.dtype)
+    if want.dtype.kind in "biu":
+        assert np.array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want, equal_nan=True, **(F32 if np.dtype(dtype) == np.float32 else F64))
+
+
+def test_arange_and_linspace(da):
+    """creation/_arange.py, creation/_linspace.py: host-generated per block, staged once, then on the device path."""
+    a = da.arange(2, 2000, 3, chunks=100)
+    _close(a.compute(), np.arange(2, 2000, 3), "i8")
+    _close((a * 2 + 1).sum().compute(), (np.arange(2, 2000, 3) * 2 + 1).sum(), "i8")
+    _close(a[::-7].compute(), np.arange(2, 2000, 3)[::-7], "i8")
+    f = da.linspace(1.4, 4.9, 1300, chunks=500)
+    _close(f.compute(), np.linspace(1.4, 4.9, 1300), "f8")
+    _close(f.mean().compute(), np.linspace(1.4, 4.9, 1300).mean(), "f8")
+    assert da.arange(0).compute().shape == (0,)
+
+
+# operator -> (lo, hi) of the inputs; everything else draws from (-3, 3)
+_DOMAIN = {"log": (0.05, 9), "log2": (0.05, 9), "log10": (0.05, 9), "log1p": (-0.9, 9), "sqrt": (0, 9), "arcsin": (-1, 1),
+           "arccos": (-1, 1), "arccosh": (1, 9), "arctanh": (-0.99, 0.99), "tan": (-1.3, 1.3), "reciprocal": (0.2, 3),
+           "power": (0.1, 3), "float_power": (0.1, 3), "exp": (-5, 5), "exp2": (-5, 5), "expm1": (-5, 5),
+           "sinh": (-5, 5), "cosh": (-5, 5)}
+_UNARY = ["negative", "positive", "exp", "exp2", "log", "log2", "log10", "log1p", "expm1", "sqrt", "square", "cbrt",
+          "reciprocal", "sin", "cos", "tan", "arcsin", "arccos", "arctan", "sinh", "cosh", "tanh", "arcsinh", "arccosh",
+          "arctanh", "deg2rad", "rad2deg", "degrees", "radians", "isfinite", "isinf", "isnan", "signbit", "floor", "ceil",
+          "trunc", "rint", "fabs", "sign", "absolute", "logical_not"]
+_BINARY = ["add", "subtract", "multiply", "divide", "true_divide", "floor_divide", "power", "float_power", "remainder",
+           "mod", "fmod", "logaddexp", "arctan2", "hypot", "greater", "greater_equal", "less", "less_equal", "not_equal",
+           "equal", "logical_and", "logical_or", "logical_xor", "maximum", "minimum", "fmax", "fmin", "copysign", "nextafter"]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_float_vocabulary_values(da, dtype):
+    """Appendix A: every float operator against NumPy on a ragged 2-D array (two blocks per axis), special values
+    (NaN, +-inf, +-0) included where the operator's domain is the whole line."""
+    rng = np.random.default_rng(11)
+    with np.errstate(all="ignore"):
+        for op in _UNARY:
+            lo, hi = _DOMAIN.get(op, (-3, 3))
+            xh = (rng.random((37, 53)) * (hi - lo) + lo).astype(dtype)
+            if op not in _DOMAIN:
+                xh[0, :5] = [np.nan, np.inf, -np.inf, 0.0, -0.0]
+            got = getattr(da, op)(da.from_array(xh, chunks=(20, 30))).compute()
+            _close(got, getattr(np, op)(xh), dtype)
+        for op in _BINARY:
+            lo, hi = _DOMAIN.get(op, (-3, 3))
+            xh = (rng.random((37, 53)) * (hi - lo) + lo).astype(dtype)
+            yh = (rng.random((37, 53)) * (hi - lo) + lo).astype(dtype)
+            if op in ("floor_divide", "remainder", "mod", "fmod", "divide", "true_divide"):
+                yh[np.abs(yh) < 0.05] = 0.5               # keep quotients away from the rounding cliff of floor()
+            if op in ("maximum", "minimum", "fmax", "fmin", "add", "less", "equal", "not_equal", "copysign"):
+                xh[0, :4] = [np.nan, 1.0, np.inf, -0.0]
+                yh[0, :4] = [1.0, np.nan, -np.inf, 0.0]
+            x, y = da.from_array(xh, chunks=(20, 30)), da.from_array(yh, chunks=(20, 30))
+            _close(getattr(da, op)(x, y).compute(), getattr(np, op)(xh, yh), dtype)
+
+
+def test_integer_vocabulary_values(da):
+    rng = np.random.default_rng(12)
+    xh = rng.integers(-50, 50, (37, 53)).astype(np.int32)
+    yh = rng.integers(-7, 8, (37, 53)).astype(np.int32)
+    x, y = da.from_array(xh, chunks=(20, 30)), da.from_array(yh, chunks=(20, 30))
+    with np.errstate(all="ignore"):
+        for op in ("bitwise_not", "invert", "negative", "positive", "square", "absolute", "sign", "logical_not"):
+            _close(getattr(da, op)(x).compute(), getattr(np, op)(xh), "i4")
+        for op in ("bitwise_and", "bitwise_or", "bitwise_xor", "add", "subtract", "multiply", "maximum", "minimum",
+                   "greater", "equal", "true_divide"):
+            _close(getattr(da, op)(x, y).compute(), getattr(np, op)(xh, yh), "f8")
+        nz = np.where(yh == 0, 3, yh).astype(np.int32)                       # division by zero is tested apart
+        ynz = da.from_array(nz, chunks=(20, 30))
+        for op in ("floor_divide", "remainder", "mod", "fmod"):
+            _close(getattr(da, op)(x, ynz).compute(), getattr(np, op)(xh, nz), "i4")
+            _close(getattr(da, op)(x, y).compute(), getattr(np, op)(xh, yh), "i4")      # NumPy: x // 0 == x % 0 == 0
+        sh = np.abs(yh)
+        s = da.from_array(sh, chunks=(20, 30))
+        for op in ("left_shift", "right_shift"):
+            _close(getattr(da, op)(x, s).compute(), getattr(np, op)(xh, sh), "i4")
+        _close(da.power(x, s).compute(), np.power(xh, sh), "i4")
+
+
+def test_round_clip_and_axis_moves(da):
+    rng = np.random.default_rng(13)
+    xh = (rng.random((6, 10, 14)) * 200 - 100)
+    x = da.from_array(xh, chunks=(4, 5, 6))
+    for d in (0, 2, -1):
+        _close(da.round(x, d).compute(), np.round(xh, d), "f8")
+    _close(x.round(1).compute(), xh.round(1), "f8")
+    _close(x.clip(-10, 25.5).compute(), xh.clip(-10, 25.5), "f8")
+    _close(da.clip(x, None, 3).compute(), np.clip(xh, None, 3), "f8")
+    _close(x.clip(min=-1).compute(), xh.clip(min=-1), "f8")
+    _close(x.swapaxes(0, 2).compute(), xh.swapaxes(0, 2), "f8")
+    _close(da.moveaxis(x, 0, -1).compute(), np.moveaxis(xh, 0, -1), "f8")
+    _close(da.moveaxis(x, (0, 1), (2, 0)).compute(), np.moveaxis(xh, (0, 1), (2, 0)), "f8")
+    _close(da.rollaxis(x, 2, 0).compute(), np.rollaxis(xh, 2, 0), "f8")
+    _close(x.imag.compute(), xh.imag, "f8")
+    assert x.real.name == x.name and x.conj().name == x.name
