@@ -46,6 +46,46 @@ def test_fixed_cases(chunks, shape, dtype, want):
         assert normalize_chunks(chunks, shape, dtype=dtype) == want
 
 
+def _unrle(runs):
+    return tuple(v for v, n in runs for _ in range(n))
+
+
+def _golden():
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "chunks.json")) as f:
+        return json.load(f)
+
+
+def _outcome(fn, *a, **k):
+    try:
+        return fn(*a, **k)
+    except Exception as e:      # noqa: BLE001 -- the error TYPE is part of the recorded behaviour
+        return type(e).__name__
+
+
+def test_golden_cases_recorded_from_the_reference():
+    """tests/golden/chunks.json (generate_chunks.py): 1100 seeded requests answered by the reference's own
+    ``normalize_chunks`` (with and without ``previous_chunks``) and ``_balance_chunksizes``."""
+    from dask_array_b200._rechunk import balance_chunksizes
+
+    g = _golden()
+    assert len(g["normalize"]) == 400 and len(g["previous"]) == 400 and len(g["balance"]) == 300
+    for case in g["normalize"] + g["previous"]:
+        req = tuple(case["chunks"]) if isinstance(case["chunks"], list) else case["chunks"]
+        prev = tuple(_unrle(p) for p in case["previous"]) if "previous" in case else None
+        want = case["out"] if isinstance(case["out"], str) else tuple(_unrle(c) for c in case["out"])
+        got = _outcome(normalize_chunks, req, tuple(case["shape"]), dtype=case["dtype"], limit=case["limit"],
+                       previous_chunks=prev)
+        assert got == want, case
+    for case in g["balance"]:
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert balance_chunksizes(_unrle(case["chunks"])) == _unrle(case["out"]), case
+
+
 def test_errors():
     with pytest.raises(ValueError, match="same length"):
         normalize_chunks((2, 2, 2), (4, 4))
