@@ -18,6 +18,7 @@ from ._collection import (  # noqa: F401
 )
 
 from ._views import broadcast_to, concatenate, expand_dims, ravel, squeeze, stack  # noqa: F401,E402
+from ._reshape import reshape  # noqa: F401,E402
 from . import _overlap as overlap  # noqa: F401,E402  (da.overlap.overlap / trim_internal / map_overlap ...)
 from ._overlap import map_blocks, map_overlap, sliding_window_view  # noqa: F401,E402
 from ._topk import argtopk, topk  # noqa: F401,E402

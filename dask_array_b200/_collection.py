@@ -211,6 +211,14 @@ class Array:
     def swapaxes(self, axis1, axis2):
         return swapaxes(self, axis1, axis2)
 
+    def reshape(self, *shape, merge_chunks=True, limit=None):
+        """``Array.reshape`` (``manipulation/_reshape.py:460-522``)."""
+        from ._reshape import reshape
+
+        if len(shape) == 1 and not isinstance(shape[0], Integral):
+            shape = shape[0]
+        return reshape(self, shape, merge_chunks=merge_chunks, limit=limit)
+
     # ---- small conveniences of the reference's collection (``_collection.py:585-700, 1611-1700``)
     itemsize = property(lambda self: self.dtype.itemsize)
     npartitions = property(lambda self: math.prod(self.numblocks))

@@ -307,6 +307,12 @@ class Executor:
         src = self.results[x._name]
         return self._view_store(expr, lambda bid: (src, x, expr.source(bid)), lambda blk, bid: expr.view(blk))
 
+    def _run_Reshape(self, expr):
+        """Every output block is the same-rank input block viewed with its own shape (``ReshapeLowered._layer``)."""
+        x = expr.operand("array")
+        src = self.results[x._name]
+        return self._view_store(expr, lambda bid: (src, x, expr.source(bid)), lambda blk, bid: expr.view(blk, bid))
+
     def _run_Squeeze(self, expr):
         x = expr.operand("array")
         src = self.results[x._name]

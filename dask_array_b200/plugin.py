@@ -360,6 +360,12 @@ def lower_reference(expr, _memo=None):
         dt = _attr(expr, "_dtype")
         out = red.CumReduction(x, kind[3:] if kind.startswith("nan") else kind, int(expr.axis) % x.ndim,
                                None if dt is None else np.dtype(dt).name, kind.startswith("nan"))
+    elif name in ("Reshape", "ReshapeLowered"):
+        from ._reshape import reshape as _reshape
+
+        out = _reshape(Array(rec(expr.array)), tuple(int(n) for n in expr._shape)).expr
+        if tuple(out.chunks) != tuple(tuple(c) for c in expr.chunks):
+            raise NotImplementedError("a ReshapeLowered whose input was not blocked by reshape_rechunk")
     elif name == "Slice":
         out = Array(rec(expr.array))[tuple(expr.index)].expr
     elif name == "SlidingWindowReduction":

@@ -250,6 +250,10 @@ def test_lower_reference_views_and_cumulative():
     def cummax(x, axis=None): ...
     with pytest.raises(NotImplementedError, match="cumulative"):
         plugin.lower_reference(_ref_cum(xh, ((3, 3), (4, 4)), cummax, 0))
+    x3 = ref_from_array(np.arange(120.0).reshape(6, 5, 4), ((3, 3), (2, 2, 1), (2, 2)))
+    rs = plugin.lower_reference(node("Reshape", array=x3, _shape=(30, 4), chunks=((5,) * 6, (2, 2))))
+    assert type(rs).__name__ == "Reshape" and rs.shape == (30, 4) and rs.chunks == ((5,) * 6, (2, 2))
+    assert type(rs.operand("array")).__name__ == "Rechunk" and rs.operand("array").chunks == ((1,) * 6, (5,), (2, 2))
     ar = plugin.lower_reference(node("Arange", start=3, stop=40, step=4, chunks=((4, 4, 2),), like=None, dtype=np.dtype("i8")))
     assert ar.shape == (10,) and ar.chunks == ((4, 4, 2),) and ar.dtype == np.int64
     assert np.array_equal(np.concatenate([ar.operand("get_block")((k,)) for k in range(3)]), np.arange(3, 40, 4))

@@ -120,3 +120,22 @@ def test_round_clip_and_axis_moves(da):
     _close(da.rollaxis(x, 2, 0).compute(), np.rollaxis(xh, 2, 0), "f8")
     _close(x.imag.compute(), xh.imag, "f8")
     assert x.real.name == x.name and x.conj().name == x.name
+
+
+def test_reshape_values(da):
+    """manipulation/_reshape.py (tests/test_reshape.py value cases): merges, splits, kept axes, -1, one block,
+    merge_chunks=False, and a reshape between device ops."""
+    rng = np.random.default_rng(14)
+    xh = rng.random((6, 5, 4))
+    x = da.from_array(xh, chunks=(3, 2, 2))
+    for shape in ((30, 4), (3, 2, 5, 4), (6, 20), (120,), (6, 5, 2, 2), (2, 3, 20), (-1, 4), (1, 30, 4, 1)):
+        _close(x.reshape(shape).compute(), xh.reshape(shape), "f8")
+    _close(da.from_array(xh, chunks=(6, 5, 4)).reshape((4, 5, 6)).compute(), xh.reshape((4, 5, 6)), "f8")
+    _close(x.reshape((30, 4), merge_chunks=False).compute(), xh.reshape((30, 4)), "f8")
+    y = (x.T * 2).reshape((20, 6))                       # non-contiguous blocks in front of the views
+    _close(y.compute(), (xh.T * 2).reshape((20, 6)), "f8")
+    _close(y.reshape((4, 5, 6)).sum(axis=1).compute(), (xh.T * 2).reshape((4, 5, 6)).sum(axis=1), "f8")
+    ih = np.arange(64 * 48, dtype=np.int32).reshape(64, 48)
+    i = da.from_array(ih, chunks=(16, 12))
+    assert np.array_equal(i.reshape((8, 8, 48)).compute(), ih.reshape((8, 8, 48)))
+    assert np.array_equal(i.reshape((64, 6, 8)).max(axis=2).compute(), ih.reshape((64, 6, 8)).max(axis=2))
