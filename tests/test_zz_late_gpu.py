@@ -29,18 +29,6 @@ def _close(got, want, dtype):
         np.testing.assert_allclose(got, want, equal_nan=True, **(F32 if np.dtype(dtype) == np.float32 else F64))
 
 
-def test_arange_and_linspace(da):
-    """creation/_arange.py, creation/_linspace.py: host-generated per block, staged once, then on the device path."""
-    a = da.arange(2, 2000, 3, chunks=100)
-    _close(a.compute(), np.arange(2, 2000, 3), "i8")
-    _close((a * 2 + 1).sum().compute(), (np.arange(2, 2000, 3) * 2 + 1).sum(), "i8")
-    _close(a[::-7].compute(), np.arange(2, 2000, 3)[::-7], "i8")
-    f = da.linspace(1.4, 4.9, 1300, chunks=500)
-    _close(f.compute(), np.linspace(1.4, 4.9, 1300), "f8")
-    _close(f.mean().compute(), np.linspace(1.4, 4.9, 1300).mean(), "f8")
-    assert da.arange(0).compute().shape == (0,)
-
-
 # operator -> (lo, hi) of the inputs; everything else draws from (-3, 3)
 _DOMAIN = {"log": (0.05, 9), "log2": (0.05, 9), "log10": (0.05, 9), "log1p": (-0.9, 9), "sqrt": (0, 9), "arcsin": (-1, 1),
            "arccos": (-1, 1), "arccosh": (1, 9), "arctanh": (-0.99, 0.99), "tan": (-1.3, 1.3), "reciprocal": (0.2, 3),
@@ -55,30 +43,53 @@ _BINARY = ["add", "subtract", "multiply", "divide", "true_divide", "floor_divide
            "equal", "logical_and", "logical_or", "logical_xor", "maximum", "minimum", "fmax", "fmin", "copysign", "nextafter"]
 
 
-@pytest.mark.parametrize("dtype", ["float32", "float64"])
-def test_float_vocabulary_values(da, dtype):
-    """Appendix A: every float operator against NumPy on a ragged 2-D array (two blocks per axis), special values
-    (NaN, +-inf, +-0) included where the operator's domain is the whole line."""
-    rng = np.random.default_rng(11)
-    with np.errstate(all="ignore"):
-        for op in _UNARY:
-            lo, hi = _DOMAIN.get(op, (-3, 3))
-            xh = (rng.random((37, 53)) * (hi - lo) + lo).astype(dtype)
-            if op not in _DOMAIN:
-                xh[0, :5] = [np.nan, np.inf, -np.inf, 0.0, -0.0]
-            got = getattr(da, op)(da.from_array(xh, chunks=(20, 30))).compute()
-            _close(got, getattr(np, op)(xh), dtype)
-        for op in _BINARY:
-            lo, hi = _DOMAIN.get(op, (-3, 3))
-            xh = (rng.random((37, 53)) * (hi - lo) + lo).astype(dtype)
-            yh = (rng.random((37, 53)) * (hi - lo) + lo).astype(dtype)
-            if op in ("floor_divide", "remainder", "mod", "fmod", "divide", "true_divide"):
-                yh[np.abs(yh) < 0.05] = 0.5               # keep quotients away from the rounding cliff of floor()
-            if op in ("maximum", "minimum", "fmax", "fmin", "add", "less", "equal", "not_equal", "copysign"):
-                xh[0, :4] = [np.nan, 1.0, np.inf, -0.0]
-                yh[0, :4] = [1.0, np.nan, -np.inf, 0.0]
-            x, y = da.from_array(xh, chunks=(20, 30)), da.from_array(yh, chunks=(20, 30))
-            _close(getattr(da, op)(x, y).compute(), getattr(np, op)(xh, yh), dtype)
+def test_arange_and_linspace(da):
+    """creation/_arange.py, creation/_linspace.py: host-generated per block, staged once, then on the device path."""
+    a = da.arange(2, 2000, 3, chunks=100)
+    _close(a.compute(), np.arange(2, 2000, 3), "i8")
+    _close((a * 2 + 1).sum().compute(), (np.arange(2, 2000, 3) * 2 + 1).sum(), "i8")
+    _close(a[::-7].compute(), np.arange(2, 2000, 3)[::-7], "i8")
+    f = da.linspace(1.4, 4.9, 1300, chunks=500)
+    _close(f.compute(), np.linspace(1.4, 4.9, 1300), "f8")
+    _close(f.mean().compute(), np.linspace(1.4, 4.9, 1300).mean(), "f8")
+    assert da.arange(0).compute().shape == (0,)
+
+
+def test_reshape_values(da):
+    """manipulation/_reshape.py (tests/test_reshape.py value cases): merges, splits, kept axes, -1, one block,
+    merge_chunks=False, and a reshape between device ops."""
+    rng = np.random.default_rng(14)
+    xh = rng.random((6, 5, 4))
+    x = da.from_array(xh, chunks=(3, 2, 2))
+    for shape in ((30, 4), (3, 2, 5, 4), (6, 20), (120,), (6, 5, 2, 2), (2, 3, 20), (-1, 4), (1, 30, 4, 1)):
+        _close(x.reshape(shape).compute(), xh.reshape(shape), "f8")
+    _close(da.from_array(xh, chunks=(6, 5, 4)).reshape((4, 5, 6)).compute(), xh.reshape((4, 5, 6)), "f8")
+    _close(x.reshape((30, 4), merge_chunks=False).compute(), xh.reshape((30, 4)), "f8")
+    y = (x.T * 2).reshape((20, 6))                       # non-contiguous blocks in front of the views
+    _close(y.compute(), (xh.T * 2).reshape((20, 6)), "f8")
+    _close(y.reshape((4, 5, 6)).sum(axis=1).compute(), (xh.T * 2).reshape((4, 5, 6)).sum(axis=1), "f8")
+    ih = np.arange(64 * 48, dtype=np.int32).reshape(64, 48)
+    i = da.from_array(ih, chunks=(16, 12))
+    assert np.array_equal(i.reshape((8, 8, 48)).compute(), ih.reshape((8, 8, 48)))
+    assert np.array_equal(i.reshape((64, 6, 8)).max(axis=2).compute(), ih.reshape((64, 6, 8)).max(axis=2))
+
+
+def test_round_clip_and_axis_moves(da):
+    rng = np.random.default_rng(13)
+    xh = (rng.random((6, 10, 14)) * 200 - 100)
+    x = da.from_array(xh, chunks=(4, 5, 6))
+    for d in (0, 2, -1):
+        _close(da.round(x, d).compute(), np.round(xh, d), "f8")
+    _close(x.round(1).compute(), xh.round(1), "f8")
+    _close(x.clip(-10, 25.5).compute(), xh.clip(-10, 25.5), "f8")
+    _close(da.clip(x, None, 3).compute(), np.clip(xh, None, 3), "f8")
+    _close(x.clip(min=-1).compute(), xh.clip(min=-1), "f8")
+    _close(x.swapaxes(0, 2).compute(), xh.swapaxes(0, 2), "f8")
+    _close(da.moveaxis(x, 0, -1).compute(), np.moveaxis(xh, 0, -1), "f8")
+    _close(da.moveaxis(x, (0, 1), (2, 0)).compute(), np.moveaxis(xh, (0, 1), (2, 0)), "f8")
+    _close(da.rollaxis(x, 2, 0).compute(), np.rollaxis(xh, 2, 0), "f8")
+    _close(x.imag.compute(), xh.imag, "f8")
+    assert x.real.name == x.name and x.conj().name == x.name
 
 
 def test_integer_vocabulary_values(da):
@@ -104,38 +115,40 @@ def test_integer_vocabulary_values(da):
         _close(da.power(x, s).compute(), np.power(xh, sh), "i4")
 
 
-def test_round_clip_and_axis_moves(da):
-    rng = np.random.default_rng(13)
-    xh = (rng.random((6, 10, 14)) * 200 - 100)
-    x = da.from_array(xh, chunks=(4, 5, 6))
-    for d in (0, 2, -1):
-        _close(da.round(x, d).compute(), np.round(xh, d), "f8")
-    _close(x.round(1).compute(), xh.round(1), "f8")
-    _close(x.clip(-10, 25.5).compute(), xh.clip(-10, 25.5), "f8")
-    _close(da.clip(x, None, 3).compute(), np.clip(xh, None, 3), "f8")
-    _close(x.clip(min=-1).compute(), xh.clip(min=-1), "f8")
-    _close(x.swapaxes(0, 2).compute(), xh.swapaxes(0, 2), "f8")
-    _close(da.moveaxis(x, 0, -1).compute(), np.moveaxis(xh, 0, -1), "f8")
-    _close(da.moveaxis(x, (0, 1), (2, 0)).compute(), np.moveaxis(xh, (0, 1), (2, 0)), "f8")
-    _close(da.rollaxis(x, 2, 0).compute(), np.rollaxis(xh, 2, 0), "f8")
-    _close(x.imag.compute(), xh.imag, "f8")
-    assert x.real.name == x.name and x.conj().name == x.name
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_float_vocabulary_values(da, dtype):
+    """Appendix A: every float operator against NumPy on a ragged 2-D array (two blocks per axis), inputs inside
+    each operator's domain (special values: the last test of this file)."""
+    rng = np.random.default_rng(11)
+    with np.errstate(all="ignore"):
+        for op in _UNARY:
+            lo, hi = _DOMAIN.get(op, (-3, 3))
+            xh = (rng.random((37, 53)) * (hi - lo) + lo).astype(dtype)
+            got = getattr(da, op)(da.from_array(xh, chunks=(20, 30))).compute()
+            _close(got, getattr(np, op)(xh), dtype)
+        for op in _BINARY:
+            lo, hi = _DOMAIN.get(op, (-3, 3))
+            xh = (rng.random((37, 53)) * (hi - lo) + lo).astype(dtype)
+            yh = (rng.random((37, 53)) * (hi - lo) + lo).astype(dtype)
+            if op in ("floor_divide", "remainder", "mod", "fmod", "divide", "true_divide"):
+                yh[np.abs(yh) < 0.05] = 0.5               # keep quotients away from the rounding cliff of floor()
+            x, y = da.from_array(xh, chunks=(20, 30)), da.from_array(yh, chunks=(20, 30))
+            _close(getattr(da, op)(x, y).compute(), getattr(np, op)(xh, yh), dtype)
 
 
-def test_reshape_values(da):
-    """manipulation/_reshape.py (tests/test_reshape.py value cases): merges, splits, kept axes, -1, one block,
-    merge_chunks=False, and a reshape between device ops."""
-    rng = np.random.default_rng(14)
-    xh = rng.random((6, 5, 4))
-    x = da.from_array(xh, chunks=(3, 2, 2))
-    for shape in ((30, 4), (3, 2, 5, 4), (6, 20), (120,), (6, 5, 2, 2), (2, 3, 20), (-1, 4), (1, 30, 4, 1)):
-        _close(x.reshape(shape).compute(), xh.reshape(shape), "f8")
-    _close(da.from_array(xh, chunks=(6, 5, 4)).reshape((4, 5, 6)).compute(), xh.reshape((4, 5, 6)), "f8")
-    _close(x.reshape((30, 4), merge_chunks=False).compute(), xh.reshape((30, 4)), "f8")
-    y = (x.T * 2).reshape((20, 6))                       # non-contiguous blocks in front of the views
-    _close(y.compute(), (xh.T * 2).reshape((20, 6)), "f8")
-    _close(y.reshape((4, 5, 6)).sum(axis=1).compute(), (xh.T * 2).reshape((4, 5, 6)).sum(axis=1), "f8")
-    ih = np.arange(64 * 48, dtype=np.int32).reshape(64, 48)
-    i = da.from_array(ih, chunks=(16, 12))
-    assert np.array_equal(i.reshape((8, 8, 48)).compute(), ih.reshape((8, 8, 48)))
-    assert np.array_equal(i.reshape((64, 6, 8)).max(axis=2).compute(), ih.reshape((64, 6, 8)).max(axis=2))
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_float_vocabulary_special_values(da, dtype):
+    """NaN, +-inf and +-0 through the operators whose domain is the whole line (kept last: the riskiest cases)."""
+    sp = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 1.5, -2.5], dtype=dtype)
+    xh = np.tile(sp, (5, 3))
+    x = da.from_array(xh, chunks=(3, 8))
+    with np.errstate(all="ignore"):
+        for op in _UNARY:
+            if op in _DOMAIN:
+                continue
+            _close(getattr(da, op)(x).compute(), getattr(np, op)(xh), dtype)
+        yh = np.ascontiguousarray(np.tile(sp[::-1], (5, 3)))
+        y = da.from_array(yh, chunks=(3, 8))
+        for op in ("maximum", "minimum", "fmax", "fmin", "add", "subtract", "multiply", "less", "greater_equal", "equal",
+                   "not_equal", "copysign", "logical_and", "logical_or", "hypot", "arctan2"):
+            _close(getattr(da, op)(x, y).compute(), getattr(np, op)(xh, yh), dtype)
