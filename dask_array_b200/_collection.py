@@ -68,6 +68,9 @@ def elemwise(op, *args, out=None, where=True, dtype=None, **kwargs):
     return res
 
 
+_NUMPY_ALIASES = {"amin": "min", "amax": "max", "round_": "round", "concat": "concatenate", "permute_dims": "transpose"}
+
+
 class Array:
     __array_priority__ = 11
 
@@ -176,11 +179,41 @@ class Array:
 
         return matmul(self, other)
 
+    def __array_function__(self, func, types, args, kwargs):
+        """``Array.__array_function__`` (:866-923): a NumPy function applied to an Array runs the same-named function
+        of this package and stays lazy (``np.sum(x, axis=0)``, ``np.clip``, ``np.reshape``, ``np.concatenate`` ...).
+        A function the package does not have is handled like the reference does: a ``FutureWarning``, the Arrays among
+        the arguments are computed, and NumPy runs on the results."""
+        import warnings
+
+        import dask_array_b200 as module
+
+        if not all(issubclass(t, (Array, np.ndarray)) or t.__name__ == "DeviceChunk" for t in types):
+            return NotImplemented
+        name = _NUMPY_ALIASES.get(func.__name__, func.__name__)
+        target = getattr(module, name, None) if getattr(func, "__module__", None) == "numpy" else None
+        if target is None or target is func or not callable(target):
+            warnings.warn(f"The `{getattr(func, '__module__', 'numpy')}.{func.__name__}` function is not implemented by "
+                          "dask_array_b200: the arguments are computed and NumPy runs on the host results.", FutureWarning)
+
+            def host(v):
+                if isinstance(v, Array):
+                    return v.compute()
+                if isinstance(v, (list, tuple)):
+                    return type(v)(host(u) for u in v)
+                return v
+            return func(*host(args), **{k: host(v) for k, v in kwargs.items()})
+        return target(*args, **kwargs)
+
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         """``Array.__array_ufunc__`` (:1702): NumPy ufuncs on Arrays stay lazy (``out=`` / ``where=`` / ``dtype=``
         included; the two-output ufuncs ``frexp / modf / divmod`` return a pair of Arrays)."""
         if method != "__call__" or set(kwargs) - {"out", "where", "dtype"}:
             return NotImplemented
+        if ufunc.__name__ == "matmul":                # a gufunc, not element-wise: the blocked contraction
+            if kwargs:
+                return NotImplemented
+            return matmul(*inputs)
         if ufunc.nout == 2 and ufunc.__name__ in ("frexp", "modf", "divmod") and not kwargs:
             return globals()[ufunc.__name__](*inputs)
         if ufunc.nout != 1:

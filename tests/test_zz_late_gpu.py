@@ -92,6 +92,24 @@ def test_round_clip_and_axis_moves(da):
     assert x.real.name == x.name and x.conj().name == x.name
 
 
+def test_numpy_functions_on_arrays(da):
+    """Array.__array_function__ (_collection.py:866-923): same-named functions stay on the device; an unknown one
+    warns, computes its arguments and runs NumPy on the results, like the reference."""
+    import warnings
+
+    xh = np.random.default_rng(15).random((40, 60))
+    x = da.from_array(xh, chunks=(16, 25))
+    _close(np.sum(x, axis=0).compute(), xh.sum(axis=0), "f8")
+    _close(np.clip(x, 0.2, 0.7).compute(), np.clip(xh, 0.2, 0.7), "f8")
+    _close(np.concatenate([x, x], axis=1).max(axis=0).compute(), np.concatenate([xh, xh], axis=1).max(axis=0), "f8")
+    _close(np.matmul(x, x.T).compute(), xh @ xh.T, "f8")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        got = np.linalg.norm(x)
+    assert any(issubclass(i.category, FutureWarning) for i in w)
+    _close(got, np.linalg.norm(xh), "f8")
+
+
 def test_integer_vocabulary_values(da):
     rng = np.random.default_rng(12)
     xh = rng.integers(-50, 50, (37, 53)).astype(np.int32)
