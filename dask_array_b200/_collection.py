@@ -713,8 +713,35 @@ def from_host_blocks(get_block, shape, chunks, dtype, token=None):
 # ----------------------------------------------------------------------------- creation
 def from_array(x, chunks="auto", **kwargs):
     """``da.from_array`` (``io/_from_array.py``)."""
+    from ._device import DeviceChunk
+
+    if isinstance(x, DeviceChunk):
+        return _from_device(x, chunks)
     x = np.asarray(x)
     return Array(FromArray(x, normalize_chunks(chunks, x.shape, dtype=x.dtype)))
+
+
+def _from_device(x, chunks):
+    """``from_array`` of an array that already lives on the GPU (``io/_from_array.py:148-152`` keeps such chunks in
+    their own type): the blocks this rank owns are cut on the device -- views copied once into their own contiguous
+    blocks, no host round trip -- and handed to the graph as resident blocks, like ``persist()`` leaves them."""
+    from . import _eager
+    from ._exchange import owner_of
+    from ._executor import BlockStore, World
+
+    blocks = normalize_chunks(chunks, x.shape, dtype=x.dtype)
+    geometry = BroadcastTrick(0, tuple(x.shape), blocks, x.dtype.name)      # only its block grid is used
+    store = BlockStore(geometry)
+    world = World()
+    for bid in geometry.block_ids():
+        if owner_of(geometry, bid, world.size) != world.rank:
+            continue
+        start, shape = geometry.block_start(bid), geometry.block_shape(bid)
+        view = x[tuple(slice(s, s + n) for s, n in zip(start, shape))] if x.ndim else x
+        store.blocks[bid] = view if view.is_contiguous else _eager.copy(view)
+    store.keepalive.append(x)
+    token = f"{x.ptr:x}-{id(x):x}-{abs(hash(blocks)):x}"
+    return Array(Resident(store, blocks, x.dtype.name, token))
 
 
 def asarray(x, **kwargs):

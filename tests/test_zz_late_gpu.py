@@ -96,6 +96,22 @@ def test_round_clip_and_axis_moves(da):
     assert x.real.name == x.name and x.conj().name == x.name
 
 
+def test_from_array_of_a_device_chunk(da):
+    """io/_from_array.py:148-152: an array that already lives on the GPU is blocked on the device."""
+    from dask_array_b200 import DeviceChunk
+
+    xh = np.random.default_rng(16).random((96, 80), dtype=np.float32)
+    dev = DeviceChunk.from_numpy(xh)
+    x = da.from_array(dev, chunks=(32, 40))
+    assert type(x.expr).__name__ == "Resident" and x.chunks == ((32,) * 3, (40, 40))
+    _close(x.compute(), xh, "f4")
+    _close((x * 2).sum(axis=0).compute(), (xh * 2).sum(axis=0), "f4")
+    _close((x.T + 1).max(axis=1).compute(), (xh.T + 1).max(axis=1), "f4")
+    one = da.from_array(dev)
+    assert one.numblocks == (1, 1) and one.expr.operand("store").blocks[(0, 0)].ptr == dev.ptr      # zero copy
+    _close(da.asarray(dev).mean().compute(), xh.mean(dtype=np.float32), "f4")
+
+
 def test_numpy_functions_on_arrays(da):
     """Array.__array_function__ (_collection.py:866-923): same-named functions stay on the device; an unknown one
     warns, computes its arguments and runs NumPy on the results, like the reference."""
